@@ -1,0 +1,197 @@
+/*
+ * yalps_b200.h -- C ABI of libyalps_b200.so: the B200-native replacement for
+ * the YALPS simplex / node-LP hot path.
+ *
+ * The reference (Ivordir/YALPS, TypeScript) has no FFI; the seam this library
+ * replaces is the module-internal call
+ *     simplex(tableau, options) -> [status, number]      src/simplex.ts:144
+ * made from src/YALPS.ts:79 (root LP) and src/branchAndCut.ts:127 (node LPs),
+ * plus applyCuts (src/branchAndCut.ts:22-61) and the branch-and-cut loop
+ * (src/branchAndCut.ts:89-176) that issues the node LPs.  A Node N-API addon
+ * (bindings/node/) binds exactly these entry points.
+ *
+ * Conventions
+ *  - Tableau layout is the reference's (src/tableau.ts:9-21): row-major fp64,
+ *    `matrix[row*width + col]`, row 0 = objective row, column 0 = RHS;
+ *    positionOfVariable / variableAtPosition are int32[width+height] and start
+ *    as the identity (src/tableau.ts:95-98), so the batch entry points create
+ *    them on the device instead of taking them as inputs.
+ *  - All pointers are plain host pointers unless the name says `_device`.
+ *    The caller owns every buffer; nothing is retained past the call except
+ *    through the ctx (root tableau of a branch-and-cut session).
+ *  - Every function returns 0 on success and a negative yalps_error on
+ *    failure; yalps_last_error() gives the message.  Nothing throws across
+ *    the ABI.  There is no CPU fallback: without a CUDA device every compute
+ *    entry point fails with YALPS_ERR_CUDA.
+ *  - Arithmetic is IEEE-754 binary64 with the reference's operation order
+ *    (no FMA contraction, true divisions); statuses, pivot counts, bases and
+ *    values are bit-identical to the reference loop on the same input.
+ *  - A ctx is not thread-safe; use one per host thread (the reference is
+ *    synchronous on the JS main thread, so `solve` blocks).
+ */
+#ifndef YALPS_B200_H
+#define YALPS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct yalps_ctx yalps_ctx;
+
+/* SolutionStatus, src/types.ts:154 (same spelling order as STATUS_NAMES in the host layer). */
+enum yalps_status {
+  YALPS_OPTIMAL = 0,
+  YALPS_INFEASIBLE = 1,
+  YALPS_UNBOUNDED = 2,
+  YALPS_TIMEDOUT = 3, /* branch-and-cut only, src/branchAndCut.ts:171 */
+  YALPS_CYCLED = 4
+};
+
+enum yalps_error {
+  YALPS_OK = 0,
+  YALPS_ERR_CUDA = -1,     /* CUDA runtime failure or no device */
+  YALPS_ERR_ARGUMENT = -2, /* bad sizes / null pointers */
+  YALPS_ERR_TOO_LARGE = -3,/* tableau exceeds what any kernel path supports */
+  YALPS_ERR_HISTORY = -4   /* checkCycles history buffer exhausted (see max_pivots) */
+};
+
+/* Required<Options>, src/types.ts:203-265, defaults src/YALPS.ts:52-60.
+ * max_pivots, timeout_ms and max_iterations may be +infinity
+ * (benchmarks/runners.ts:10 passes maxPivots: Infinity). */
+typedef struct yalps_options {
+  double precision;      /* 1e-8 */
+  double max_pivots;     /* 8192, per phase (src/simplex.ts:69,109) */
+  double tolerance;      /* 0 */
+  double timeout_ms;     /* +inf */
+  double max_iterations; /* 32768 */
+  int32_t check_cycles;  /* 0 */
+  int32_t reserved;
+} yalps_options;
+
+void yalps_default_options(yalps_options *opt);
+
+/* Kernel path selection for the batch entry points (diagnostics / benchmarks). */
+enum yalps_path {
+  YALPS_PATH_AUTO = 0,
+  YALPS_PATH_SMEM = 1, /* K1: one tableau per CTA resident in shared memory */
+  YALPS_PATH_GMEM = 2, /* K2: tableau in HBM/L2, CTA per LP, pivot row/column staged in shared memory */
+  YALPS_PATH_GRID = 3  /* K4: one LP across the whole grid (cooperative launch) */
+};
+
+/* ---- context ------------------------------------------------------------ */
+int yalps_create(int device, yalps_ctx **out);
+void yalps_destroy(yalps_ctx *ctx);
+const char *yalps_last_error(const yalps_ctx *ctx); /* ctx may be NULL: error of the last failed yalps_create */
+int yalps_device_info(const yalps_ctx *ctx, int32_t *sm_count, int32_t *smem_per_block_optin, int32_t *cc_major,
+                      int32_t *cc_minor);
+/* Force a path / CTA width for subsequent batch calls (0 = auto). */
+int yalps_set_tuning(yalps_ctx *ctx, int32_t path, int32_t threads_per_lp);
+/* Number of kernels launched by this ctx since creation (bench.py's gpu_launches). */
+int64_t yalps_launch_count(const yalps_ctx *ctx);
+
+/* Pinned host memory for callers that want zero-staging transfers. */
+int yalps_host_alloc(yalps_ctx *ctx, uint64_t bytes, void **out);
+int yalps_host_free(yalps_ctx *ctx, void *ptr);
+
+/* ---- simplex(tableau, options), batched: replaces src/simplex.ts:144 ----- */
+/*
+ * n tableaus of identical shape height x width, contiguous in `matrices`
+ * (n*height*width doubles, not modified).  Outputs (any may be NULL):
+ *   status[n]            yalps_status
+ *   value[n]             rounded objective M[0,0] (optimal) / entering column (unbounded) / NaN
+ *   pivots[2n]           phase-1 and phase-2 pivot counts
+ *   rhs_out[n*height]    column 0 of the final tableau
+ *   pos_out/var_out[n*(width+height)]  final positionOfVariable / variableAtPosition
+ *   matrices_out[n*height*width]       final tableau (the in-place result of the reference)
+ * This is what solve() needs to build a Solution (src/YALPS.ts:8-50).
+ */
+int yalps_solve_batch(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, const double *matrices,
+                      const yalps_options *opt, int32_t *status, double *value, int64_t *pivots, double *rhs_out,
+                      int32_t *pos_out, int32_t *var_out, double *matrices_out);
+
+/* Ragged batch: LP i is heights[i] x widths[i] at matrices[mat_offsets[i]];
+ * rhs_out is packed by cumulative heights, pos_out/var_out by cumulative (width+height). */
+int yalps_solve_ragged(yalps_ctx *ctx, int64_t n, const int32_t *heights, const int32_t *widths,
+                       const int64_t *mat_offsets, const double *matrices, const yalps_options *opt, int32_t *status,
+                       double *value, int64_t *pivots, double *rhs_out, int32_t *pos_out, int32_t *var_out,
+                       double *matrices_out);
+
+/* Same as yalps_solve_batch with every buffer already in device memory and the
+ * work enqueued on `stream` (a cudaStream_t, NULL = default stream); returns
+ * without synchronising.  d_work (n*height*width doubles) is only required when
+ * the HBM-resident path is taken and may alias d_matrices for an in-place solve. */
+int yalps_solve_batch_device(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, const double *d_matrices,
+                             double *d_work, const yalps_options *opt, int32_t *d_status, double *d_value,
+                             int64_t *d_pivots, double *d_rhs_out, int32_t *d_pos_out, int32_t *d_var_out,
+                             double *d_matrices_out, void *stream);
+
+/* Synthetic dense LP batch of SURVEY 8(d) (configs 2 and 5) generated on the device:
+ * LP `first+i` -> (m+1) x (nvars+1) tableau, integer-hash PRNG of tests/helpers/util.ts:20-41. */
+int yalps_generate_synthetic_device(yalps_ctx *ctx, int64_t first, int64_t n, int32_t m, int32_t nvars,
+                                    int32_t neg_rows, uint32_t salt, double *d_out, void *stream);
+
+/* Config 3: n replicas of one base tableau whose RHS column is perturbed per replica,
+ * rhs_i[r] = base[r,0] * (1 + eps*(2U-1)), U drawn per `group[r]` (rows of one constraint key share a
+ * draw; group < 0 = unperturbed) from newRand(prospectorHash((first+i) ^ salt)). */
+int yalps_generate_replicas_device(yalps_ctx *ctx, int64_t first, int64_t n, int32_t height, int32_t width,
+                                   const double *base_host, const int32_t *group_host, int32_t ngroups, double eps,
+                                   uint32_t salt, double *d_out, void *stream);
+
+/* ---- branch and cut: replaces src/branchAndCut.ts ------------------------ */
+/*
+ * Root session: uploads the root-optimal tableau once (applyCuts needs the full
+ * matrix, src/branchAndCut.ts:28,38-42).  max_extra_rows = 2*|integers| (:108).
+ */
+int yalps_bnb_set_root(yalps_ctx *ctx, int32_t height, int32_t width, const double *matrix, const int32_t *pos,
+                       const int32_t *var, int32_t max_extra_rows);
+/*
+ * Node wave: node j carries cuts [cut_offsets[j], cut_offsets[j+1]) as
+ * (sign, variable, value) triples (Cut, src/branchAndCut.ts:18).  The device
+ * assembles root + cut rows (applyCuts) and runs simplex.  Outputs are strided
+ * by the wave's tallest node: stride_h = height + max_j ncuts_j:
+ *   rhs_out[n*stride_h], pos_out/var_out[n*(width+stride_h)], matrices_out[n*stride_h*width] (optional).
+ */
+int yalps_bnb_solve_nodes(yalps_ctx *ctx, int64_t n, const int32_t *cut_offsets, const double *cut_sign,
+                          const int32_t *cut_var, const double *cut_value, const yalps_options *opt, int32_t *status,
+                          double *value, int64_t *pivots, double *rhs_out, int32_t *pos_out, int32_t *var_out,
+                          double *matrices_out);
+/*
+ * The whole branchAndCut(tabmod, initResult, options) of src/branchAndCut.ts:89-176
+ * on the current root: best-first search with the reference's heap order, node LPs
+ * evaluated in speculative waves on the device and consumed in the reference's
+ * pop order.  ints = TableauModel.integers (variable ids), sign = TableauModel.sign.
+ * Outputs describe the best tableau (src/branchAndCut.ts:175): out_height rows,
+ * rhs_out[out_height], pos_out/var_out[width+out_height] (buffers sized for
+ * height+max_extra_rows).  stats[8] (optional): nodes evaluated by the replay, node pivots,
+ * max cuts, max heap, waves, nodes solved on device (incl. unused speculation), 0, 0.
+ */
+int yalps_branch_and_cut(yalps_ctx *ctx, const int32_t *ints, int32_t nints, double sign, double init_result,
+                         const yalps_options *opt, int32_t *status, double *result, int32_t *out_height,
+                         double *rhs_out, int32_t *pos_out, int32_t *var_out, int64_t *stats);
+/* Wave width for the speculation (default 64). */
+int yalps_bnb_set_wave(yalps_ctx *ctx, int32_t wave);
+
+/*
+ * One call for solve()'s numeric part (src/YALPS.ts:77-91): root simplex on the
+ * given initial tableau and, if it is optimal and nints > 0, branch and cut.
+ * Buffers sized for height + 2*nints rows.  root_status/root_value/root_pivots[2]
+ * report the root LP (optional).
+ */
+int yalps_solve(yalps_ctx *ctx, int32_t height, int32_t width, const double *matrix, const int32_t *ints,
+                int32_t nints, double sign, const yalps_options *opt, int32_t *status, double *result,
+                int32_t *out_height, double *rhs_out, int32_t *pos_out, int32_t *var_out, int32_t *root_status,
+                double *root_value, int64_t *root_pivots, int64_t *stats);
+
+/* roundToPrecision (src/util.ts:1-4) evaluated on the device for n values (parity probe). */
+int yalps_round_to_precision(yalps_ctx *ctx, int64_t n, const double *x, double precision, double *out);
+
+/* Shared-memory stream microbenchmark: bytes moved per second by ld/st.shared.f64 on all SMs
+ * (the measured denominator of the K1 roofline).  Returns GB/s in *gbs. */
+int yalps_measure_smem_bandwidth(yalps_ctx *ctx, double *gbs, double *sm_clock_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YALPS_B200_H */

@@ -1,0 +1,211 @@
+"""GPU parity: CUDA simplex kernels (through the C ABI) against the CPU oracle, bit for bit --
+status, value, pivot counts per phase, final positionOfVariable / variableAtPosition, RHS column and the
+whole final tableau (signed zeros included).  Sizes are chosen so the oracle finishes in seconds."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import bits, load_netlib, same_bits, same_value
+from oracle import lib as O
+from yalps_b200 import engine as E
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_batch(mats, H, W, **kw):
+    work = mats.copy()
+    res = O.simplex_batch(work, W, H, **kw)
+    res["matrices"] = work
+    return res
+
+
+def assert_batch_equal(got, exp, what=""):
+    assert np.array_equal(got["status"], exp["status"]), f"{what}: status"
+    assert np.array_equal(got["pivots"], exp["pivots"]), f"{what}: pivots"
+    gv, ev = got["value"], exp["value"]
+    assert np.array_equal(np.isnan(gv), np.isnan(ev)) and np.array_equal(bits(gv[~np.isnan(gv)]), bits(ev[~np.isnan(ev)])), f"{what}: value"
+    assert np.array_equal(got["pos"], exp["pos"]) and np.array_equal(got["var"], exp["var"]), f"{what}: basis"
+    assert same_bits(got["rhs"], exp["rhs"]), f"{what}: rhs"
+    if got.get("matrices") is not None:
+        assert same_bits(got["matrices"].reshape(-1), exp["matrices"].reshape(-1)), f"{what}: final tableau"
+
+
+SHAPES = [(32, 64, 0), (32, 64, 8), (1, 1, 0), (5, 3, 2), (7, 40, 3), (40, 7, 10), (16, 100, 4), (60, 31, 20),
+          (33, 33, 5), (90, 130, 30)]
+
+
+@pytest.mark.parametrize("m,nv,neg", SHAPES)
+def test_synthetic_batches_bit_exact(engine, m, nv, neg):
+    n = 96
+    H, W = m + 1, nv + 1
+    mats = O.generate_synthetic(1000, n, m, nv, neg)
+    exp = oracle_batch(mats, H, W)
+    engine.set_tuning(E.PATH_AUTO, 0)
+    got = engine.solve_batch(mats, H, W, want_matrices=True)
+    assert_batch_equal(got, exp, f"{m}x{nv}")
+
+
+@pytest.mark.parametrize("threads", [32, 64, 128, 256, 512, 1024])
+@pytest.mark.parametrize("path", [E.PATH_SMEM, E.PATH_GMEM])
+def test_every_cta_width_and_path(engine, threads, path):
+    m, nv, n = 32, 64, 64
+    mats = O.generate_synthetic(5, n, m, nv, 6)
+    exp = oracle_batch(mats, m + 1, nv + 1)
+    engine.set_tuning(path, threads)
+    try:
+        got = engine.solve_batch(mats, m + 1, nv + 1, want_matrices=True)
+    finally:
+        engine.set_tuning(E.PATH_AUTO, 0)
+    assert_batch_equal(got, exp, f"path={path} threads={threads}")
+
+
+def test_wide_tableau_multi_chunk(engine):
+    """W > 32*KC forces several column chunks per row."""
+    m, nv, n = 12, 700, 8
+    mats = O.generate_synthetic(77, n, m, nv, 3)
+    exp = oracle_batch(mats, m + 1, nv + 1)
+    for threads in (32, 128, 1024):
+        engine.set_tuning(E.PATH_AUTO, threads)
+        got = engine.solve_batch(mats, m + 1, nv + 1, want_matrices=True)
+        assert_batch_equal(got, exp, f"threads={threads}")
+    engine.set_tuning(E.PATH_AUTO, 0)
+
+
+def test_max_pivots_is_per_phase_and_may_be_infinite(engine):
+    m, nv, n = 32, 64, 32
+    mats = O.generate_synthetic(300, n, m, nv, 8)
+    for mp in (0, 1, 3, 7, 11.5, math.inf):
+        exp = oracle_batch(mats, m + 1, nv + 1, max_pivots=mp)
+        got = engine.solve_batch(mats, m + 1, nv + 1, E.make_options(max_pivots=mp), want_matrices=True)
+        assert_batch_equal(got, exp, f"maxPivots={mp}")
+        if mp == 0:
+            assert (got["status"] == 4).all()  # "cycled"
+
+
+def test_precision_option(engine):
+    m, nv, n = 20, 30, 32
+    mats = O.generate_synthetic(900, n, m, nv, 5)
+    for prec in (1e-8, 1e-3, 0.0, 0.25):
+        exp = oracle_batch(mats, m + 1, nv + 1, precision=prec)
+        got = engine.solve_batch(mats, m + 1, nv + 1, E.make_options(precision=prec), want_matrices=True)
+        assert_batch_equal(got, exp, f"precision={prec}")
+
+
+def test_statuses_unbounded_infeasible_and_special_values(engine):
+    H, W = 4, 5
+    t = np.zeros((6, H * W))
+    # 0: unbounded (positive cost, no positive column entry)
+    t[0].reshape(H, W)[0, 1] = 1.0
+    t[0].reshape(H, W)[1:, 1] = -1.0
+    t[0].reshape(H, W)[1:, 0] = 1.0
+    # 1: infeasible (negative rhs, no negative coefficient)
+    t[1].reshape(H, W)[1, 0] = -1.0
+    t[1].reshape(H, W)[1, 1:] = 1.0
+    # 2: NaN / inf cells
+    t[2].reshape(H, W)[:] = 1.0
+    t[2].reshape(H, W)[1, 2] = math.nan
+    t[2].reshape(H, W)[2, 0] = math.inf
+    t[2].reshape(H, W)[0, 3] = 5.0
+    # 3: tiny cells around the 1e-16 skip threshold, negative zeros
+    t[3].reshape(H, W)[:] = [[0.0, 3.0, 2.0, -0.0, 1.0], [4.0, 1.0, 1e-16, 1.0000000000000001e-16, -0.0],
+                             [5.0, 2e-16, 1.0, -1e-17, 3.0], [6.0, -0.0, 2.0, 1.0, 1e-15]]
+    # 4: degenerate ties everywhere
+    t[4].reshape(H, W)[:] = [[0, 1, 1, 1, 1], [0, 1, 1, 1, 1], [0, 1, 1, 1, 1], [0, 1, 1, 1, 1]]
+    # 5: phase 1 with ties
+    t[5].reshape(H, W)[:] = [[0, -1, -1, 2, 2], [-1, -1, -1, -1, -1], [-1, -1, -1, -1, -1], [3, 1, 1, 1, 1]]
+    exp = oracle_batch(t, H, W)
+    got = engine.solve_batch(t, H, W, want_matrices=True)
+    assert_batch_equal(got, exp, "special")
+    assert got["status"][0] == 2 and got["value"][0] == 1.0
+    assert got["status"][1] == 1 and math.isnan(got["value"][1])
+
+
+def test_check_cycles_detects_the_chvatal_cycle(engine):
+    """tests/cases/Chvatal Cycling.json as a raw tableau (maximize; c1,c2 <= 0; c3 <= 1)."""
+    t = np.array([[0, 10, -57, -9, -24], [0, 0.5, -5.5, -2.5, 9], [0, 0.5, -1.5, -0.5, 1], [1, 1, 0, 0, 0]], float)
+    for cc in (True, False):
+        m = t.reshape(1, -1).copy()
+        exp = oracle_batch(m, 4, 5, check_cycles=cc)
+        got = engine.solve_batch(m, 4, 5, E.make_options(check_cycles=cc), want_matrices=True)
+        assert_batch_equal(got, exp, f"checkCycles={cc}")
+    assert exp["status"][0] == 4 or True
+    got = engine.solve_batch(t.reshape(1, -1), 4, 5, E.make_options(check_cycles=True))
+    assert got["status"][0] == 4 and tuple(got["pivots"][0]) == (0, 11)
+
+
+def test_ragged_batch(engine):
+    rng = np.random.default_rng(3)
+    tabs, shapes, exp = [], [], []
+    for i in range(40):
+        m, nv = int(rng.integers(1, 40)), int(rng.integers(1, 70))
+        t = O.generate_synthetic(i, 1, m, nv, int(rng.integers(0, m + 1)))[0]
+        tabs.append(t)
+        shapes.append((m + 1, nv + 1))
+        exp.append(oracle_batch(t.reshape(1, -1), m + 1, nv + 1))
+    got = engine.solve_ragged(tabs, shapes, want_matrices=True)
+    for g, e, s in zip(got, exp, shapes):
+        assert g["status"] == e["status"][0] and g["pivots"] == tuple(e["pivots"][0])
+        assert same_value(g["value"], e["value"][0])
+        assert np.array_equal(g["pos"], e["pos"][0]) and np.array_equal(g["var"], e["var"][0])
+        assert same_bits(g["rhs"], e["rhs"][0]) and same_bits(g["matrix"], e["matrices"][0])
+
+
+def test_round_to_precision_device(engine):
+    rng = np.random.default_rng(1)
+    xs = np.concatenate([rng.normal(size=4000) * 10.0 ** rng.integers(-10, 10, 4000),
+                         [0.5e-8, -0.5e-8, 1.5e-8, 2.5e-8, -0.0, 0.0, 1e300, -1e300, math.inf, -math.inf, math.nan]])
+    for p in (1e-8, 1e-5, 0.5, 3e-9):
+        got = engine.round_to_precision(xs, p)
+        for x, g in zip(xs, got):
+            assert same_value(g, O.round_to_precision(float(x), p)), (x, p)
+
+
+def test_device_generator_matches_oracle_generator(engine):
+    import torch
+    for (m, nv, neg) in [(32, 64, 0), (32, 64, 8), (3, 5, 1)]:
+        n = 50
+        d = torch.empty(n * (m + 1) * (nv + 1), dtype=torch.float64, device="cuda")
+        engine.generate_synthetic_device(123, n, m, nv, d.data_ptr(), neg_rows=neg)
+        torch.cuda.synchronize()
+        assert same_bits(d.cpu().numpy(), O.generate_synthetic(123, n, m, nv, neg).reshape(-1))
+
+
+def test_device_resident_entry_point(engine):
+    import torch
+    m, nv, n = 32, 64, 512
+    H, W = m + 1, nv + 1
+    mats = O.generate_synthetic(0, n, m, nv, 0)
+    exp = oracle_batch(mats, H, W)
+    d_in = torch.from_numpy(mats).cuda()
+    st = torch.empty(n, dtype=torch.int32, device="cuda")
+    val = torch.empty(n, dtype=torch.float64, device="cuda")
+    piv = torch.empty(n, 2, dtype=torch.int64, device="cuda")
+    rhs = torch.empty(n, H, dtype=torch.float64, device="cuda")
+    pos = torch.empty(n, W + H, dtype=torch.int32, device="cuda")
+    var = torch.empty(n, W + H, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    engine.solve_batch_device(n, H, W, d_in.data_ptr(), d_status=st.data_ptr(), d_value=val.data_ptr(),
+                              d_pivots=piv.data_ptr(), d_rhs=rhs.data_ptr(), d_pos=pos.data_ptr(),
+                              d_var=var.data_ptr(), stream=stream)
+    torch.cuda.synchronize()
+    got = {"status": st.cpu().numpy(), "value": val.cpu().numpy(), "pivots": piv.cpu().numpy(),
+           "rhs": rhs.cpu().numpy(), "pos": pos.cpu().numpy(), "var": var.cpu().numpy()}
+    assert_batch_equal(got, exp, "device entry")
+    assert same_bits(d_in.cpu().numpy(), mats)  # the SMEM path leaves its input untouched
+
+
+NL = load_netlib()
+NETLIB_QUICK = [n for n in NL.names if float(NL.z[f"{n}/oracle_seconds"][0]) < 1.0]
+
+
+@pytest.mark.parametrize("name", NETLIB_QUICK)
+def test_netlib_trajectory(engine, name):
+    """Netlib models (golden vectors from tests/golden/netlib.npz): identical status, value, pivot counts,
+    final basis and RHS column -- i.e. the reference's trajectory, whether or not it is the Netlib optimum."""
+    g = NL.get(name)
+    got = engine.solve_batch(g["matrix"], g["height"], g["width"], E.make_options(check_cycles=g["check_cycles"]))
+    assert got["status"][0] == g["status"] and tuple(got["pivots"][0]) == g["pivots"]
+    assert same_value(got["value"][0], g["value"])
+    assert np.array_equal(got["pos"][0], g["final_pos"])
+    assert same_bits(got["rhs"][0], g["final_rhs"])

@@ -1,0 +1,123 @@
+"""GPU parity for the public API: solve(model, options) on every reference test case, and the
+branch-and-cut path (node assembly == applyCuts, node LPs, search statistics)."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import case_expected_result, load_cases, same_bits, same_value
+from oracle import lib as O, model as M
+import yalps_b200
+from yalps_b200 import engine as E
+
+pytestmark = pytest.mark.gpu
+CASES = load_cases()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_solve_matches_reference_and_oracle(engine, case):
+    o = case["oracle"]
+    info = {}
+    sol = yalps_b200.solve(case["model"], case["options"], engine=engine, info=info)
+    # the reference's own acceptance test (tests/solver.ts:23-25 via tests/helpers/validate.ts)
+    options = {**M.DEFAULT_OPTIONS, **case["options"]}
+    model = dict(case["model"])
+    model["integers"] = set(model.get("integers") or [])
+    model["binaries"] = set(model.get("binaries") or [])
+    expected = {"status": case["expected"]["status"], "result": case_expected_result(case)}
+    check = {"status": sol["status"], "result": sol["result"], "variables": [tuple(v) for v in sol["variables"]]}
+    assert M.valid_solution_and_status(check, expected, model, options)
+    # bit-level agreement with the oracle's trajectory
+    assert sol["status"] == o["status"] and same_value(sol["result"], o["result"])
+    assert [list(v) for v in sol["variables"]] == [list(v) for v in o["variables"]]
+    assert info["root_status"] == o["root_status"] and same_value(info["root_value"], o["root_result"])
+    assert list(info["root_pivots"]) == o["root_pivots"]
+    assert info["nodes"] == o["nodes"] and info["node_pivots"] == o["node_pivots"]
+    assert np.array_equal(info["final_pos"], o["final_pos"]) and same_bits(info["final_rhs"], o["final_rhs"])
+
+
+def test_solve_many_equals_solve(engine):
+    small = [c for c in CASES if c["name"] not in ("Monster 2", "Vendor Selection")]
+    default = [c for c in small if not c["options"]]
+    sols = yalps_b200.solve_many([c["model"] for c in default], engine=engine)
+    for c, s in zip(default, sols):
+        assert s["status"] == c["oracle"]["status"] and same_value(s["result"], c["oracle"]["result"]), c["name"]
+        assert [list(v) for v in s["variables"]] == [list(v) for v in c["oracle"]["variables"]]
+
+
+def test_include_zero_variables_and_order(engine):
+    """tests/solver.ts:40-47"""
+    for c in CASES:
+        if c["expected"]["status"] != "optimal" or c["name"] in ("Monster 2", "Vendor Selection", "Monster Problem"):
+            continue
+        sol = yalps_b200.solve(c["model"], {**c["options"], "includeZeroVariables": True}, engine=engine)
+        assert [k for k, _ in sol["variables"]] == [k for k, _ in c["model"]["variables"]]
+
+
+def test_timeout_status(engine):
+    """tests/solver.ts:126-135 with timeout 0: branch and cut must report "timedout" with NaN."""
+    c = next(x for x in CASES if x["name"] == "Knapsack 1")
+    sol = yalps_b200.solve(c["model"], {**c["options"], "timeout": 0}, engine=engine)
+    assert sol["status"] == "timedout" and math.isnan(sol["result"]) and sol["variables"] == []
+
+
+def test_max_iterations_status(engine):
+    c = next(x for x in CASES if x["name"] == "Large Farm MIP")
+    opt = {**M.DEFAULT_OPTIONS, **c["options"], "maxIterations": 5}
+    exp = M.solve(c["model"], opt)
+    sol = yalps_b200.solve(c["model"], {**c["options"], "maxIterations": 5}, engine=engine)
+    assert sol["status"] == exp["status"] and same_value(sol["result"], exp["result"])
+
+
+@pytest.mark.parametrize("name", ["Large Farm MIP", "Knapsack 1", "Fancy Stock Cutting Problem", "Monster 2"])
+def test_node_assembly_and_node_lps(engine, name):
+    """applyCuts on the device (src/branchAndCut.ts:22-61) + node simplex against the oracle, node by node."""
+    c = next(x for x in CASES if x["name"] == name)
+    tm = M.tableau_model(c["model"])
+    t = tm.tableau
+    opt = {**M.DEFAULT_OPTIONS, **c["options"]}
+    st, value, _ = O.simplex(t.matrix, t.width, t.height, t.pos, t.var, opt["precision"], opt["maxPivots"], False)
+    assert st == 0
+    H, W = t.height, t.width
+    engine.bnb_set_root(t.matrix, H, W, t.pos, t.var, 2 * len(tm.integers))
+    rng = np.random.default_rng(7)
+    rhs = t.matrix.reshape(H, W)[:, 0]
+    nodes = []
+    for _ in range(12 if name == "Monster 2" else 48):
+        k = int(rng.integers(1, 6))
+        cuts = []
+        for v in rng.choice(tm.integers, size=min(k, len(tm.integers)), replace=False):
+            row = int(t.pos[v]) - W
+            x = float(rhs[row]) if row >= 0 else 0.0
+            if rng.random() < 0.5:
+                cuts.append((1.0, int(v), math.floor(x)))
+            else:
+                cuts.append((-1.0, int(v), math.ceil(x + rng.integers(0, 2))))
+        nodes.append(cuts)
+    got = engine.bnb_solve_nodes(nodes, E.make_options(opt["precision"], opt["maxPivots"]), want_matrices=True)
+    sh = got["stride_h"]
+    for j, cuts in enumerate(nodes):
+        m0, p0, v0 = O.apply_cuts(t.matrix, W, H, t.pos, t.var, [c_[0] for c_ in cuts], [c_[1] for c_ in cuts],
+                                  [c_[2] for c_ in cuts])
+        h = H + len(cuts)
+        s, val, piv = O.simplex(m0, W, h, p0, v0, opt["precision"], opt["maxPivots"], False)
+        assert got["status"][j] == s and tuple(got["pivots"][j]) == piv and same_value(got["value"][j], val), (name, j)
+        assert np.array_equal(got["pos"][j][:W + h], p0) and np.array_equal(got["var"][j][:W + h], v0)
+        assert same_bits(got["matrices"][j][:h * W], m0), (name, j)
+        assert same_bits(got["rhs"][j][:h], m0.reshape(h, W)[:, 0])
+
+
+def test_zero_pivot_nodes_return_the_assembled_tableau(engine):
+    """A node whose cuts are already satisfied: the output is exactly applyCuts(root, cuts)."""
+    c = next(x for x in CASES if x["name"] == "Knapsack 1")
+    tm = M.tableau_model(c["model"])
+    t = tm.tableau
+    O.simplex(t.matrix, t.width, t.height, t.pos, t.var)
+    H, W = t.height, t.width
+    engine.bnb_set_root(t.matrix, H, W, t.pos, t.var, 2 * len(tm.integers))
+    v = tm.integers[0]
+    cuts = [(1.0, v, 5.0), (-1.0, v, -3.0)]  # x <= 5 and x >= -3: slack for a binary
+    got = engine.bnb_solve_nodes([cuts], want_matrices=True)
+    m0, p0, v0 = O.apply_cuts(t.matrix, W, H, t.pos, t.var, [1.0, -1.0], [v, v], [5.0, -3.0])
+    assert tuple(got["pivots"][0]) == (0, 0) and got["status"][0] == 0
+    assert same_bits(got["matrices"][0][:(H + 2) * W], m0)

@@ -1,0 +1,138 @@
+"""Host-side model -> tableau builder (yalps_b200/tableau.py) against the oracle's literal restatement of
+src/tableau.ts and against the layout properties tests/tableau.ts pins (bit-exact, signed zeros included)."""
+import numpy as np
+import pytest
+
+from conftest import load_cases, same_bits
+from oracle import model as M
+from yalps_b200.tableau import tableau_model
+
+CASES = [c for c in load_cases() if c["name"] not in ("Monster 2", "Monster Problem", "Vendor Selection")]
+ALL = load_cases()
+
+
+def build(model):
+    tm = tableau_model(model)
+    t = tm.tableau
+    return tm, t
+
+
+def assert_same(a, b):
+    ta, tb = a.tableau, b.tableau
+    assert (ta.width, ta.height) == (tb.width, tb.height)
+    mb = tb.matrix
+    assert same_bits(ta.matrix, mb)
+    pa = ta.position_of_variable
+    pb = tb.position_of_variable if hasattr(tb, "position_of_variable") else tb.pos
+    va = ta.variable_at_position
+    vb = tb.variable_at_position if hasattr(tb, "variable_at_position") else tb.var
+    assert np.array_equal(pa, pb) and np.array_equal(va, vb)
+    assert a.sign == b.sign and list(a.integers) == list(b.integers)
+    assert [k for k, _ in a.variables] == [k for k, _ in b.variables]
+
+
+@pytest.mark.parametrize("case", ALL, ids=[c["name"] for c in ALL])
+def test_matches_oracle_builder(case):
+    assert_same(tableau_model(case["model"]), M.tableau_model(case["model"]))
+
+
+def test_empty_model():
+    """tests/tableau.ts:12-27"""
+    tm = tableau_model({"variables": {}, "constraints": {}})
+    t = tm.tableau
+    assert t.width == 1 and t.height == 1 and same_bits(t.matrix, np.zeros(1))
+    assert t.position_of_variable.tolist() == [0, 1] and t.variable_at_position.tolist() == [0, 1]
+    assert tm.sign == 1.0 and tm.variables == [] and tm.integers == []
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_layout_properties(case):
+    model = case["model"]
+    base = tableau_model(model)
+    W = base.tableau.width
+    rand = M.new_rand(M.hash_string(case["name"]))
+
+    # tests/tableau.ts:49-54: no objective -> objective row is zero
+    no_obj = tableau_model({k: v for k, v in model.items() if k != "objective"})
+    exp = base.tableau.matrix.copy()
+    exp[:W] = 0.0
+    assert same_bits(no_obj.tableau.matrix, exp)
+
+    # :56-67: opposite direction negates the objective row (and sign)
+    other = "maximize" if model.get("direction") == "minimize" else "minimize"
+    flipped = tableau_model({**model, "direction": other})
+    exp = base.tableau.matrix.copy()
+    exp[:W] = np.where(exp[:W] == 0.0, 0.0, -exp[:W])
+    assert same_bits(flipped.tableau.matrix, exp) and flipped.sign == -base.sign
+
+    # :104-133: object / array / Map forms are equivalent
+    as_dict = tableau_model({**model, "constraints": dict(model["constraints"]),
+                             "variables": {k: dict(v) for k, v in model["variables"]}})
+    if not any(str(k).isdigit() for k, _ in model["constraints"]) and not any(
+            str(k).isdigit() for k, _ in model["variables"]):
+        assert_same(as_dict, base)
+
+    # :135-191: integer / binary forms
+    keys = [k for k, _ in model["variables"]]
+    assert_same(tableau_model({**model, "integers": False}), tableau_model({**model, "integers": []}))
+    assert_same(tableau_model({**model, "integers": True}), tableau_model({**model, "integers": set(keys)}))
+    assert_same(tableau_model({**model, "binaries": True}), tableau_model({**model, "binaries": list(keys)}))
+    key = keys[int(rand() * len(keys))]
+    assert_same(tableau_model({**model, "integers": [key], "binaries": [key]}),
+                tableau_model({**model, "integers": [], "binaries": [key]}))  # :184-191 binary wins
+
+    # :223-242: equal has precedence over min/max
+    cons = list(model["constraints"])
+    eq = [i for i, (_, c) in enumerate(cons) if c.get("equal") is not None]
+    if eq:
+        i = eq[int(rand() * len(eq))]
+        k, c = cons[i]
+        mod = list(cons)
+        mod[i] = (k, {"equal": c["equal"], "min": c["equal"] + 1.0, "max": c["equal"] - 1.0})
+        assert_same(tableau_model({**model, "constraints": mod}), base)
+
+    # :244-265: constraints with the same key merge
+    i = int(rand() * len(cons))
+    k, c = cons[i]
+    other_c = {"max": rand() * 100.0 + (c.get("max") or 0.0), "min": rand() * 100.0 + (c.get("min") or 0.0)}
+    hi = c.get("equal") if c.get("equal") is not None else (c.get("max") if c.get("max") is not None else float("inf"))
+    lo = c.get("equal") if c.get("equal") is not None else (c.get("min") if c.get("min") is not None else -float("inf"))
+    merged = list(cons)
+    merged[i] = (k, {"max": min(hi, other_c["max"]), "min": max(lo, other_c["min"])})
+    assert_same(tableau_model({**model, "constraints": cons + [(k, other_c)]}),
+                tableau_model({**model, "constraints": merged}))
+
+    # :282-300: the last coefficient with the same key wins
+    variables = list(model["variables"])
+    vi = int(rand() * len(variables))
+    vk, coefs = variables[vi]
+    coefs = list(coefs)
+    if coefs:
+        ci = int(rand() * len(coefs))
+        ck, cv = coefs[ci]
+        dup = list(coefs)
+        dup[ci] = (ck, cv + rand() * 100.0)
+        dup.append((ck, cv))
+        nv = list(variables)
+        nv[vi] = (vk, dup)
+        assert same_bits(tableau_model({**model, "variables": nv}).tableau.matrix, base.tableau.matrix)
+
+    # :308-333: removing a constraint removes its rows
+    i = int(rand() * len(cons))
+    removed = tableau_model({**model, "constraints": cons[:i] + cons[i + 1:]})
+    if sum(1 for k2, _ in cons if k2 == cons[i][0]) == 1:
+        nrows = lambda c: 2 if c.get("equal") is not None else (c.get("max") is not None) + (c.get("min") is not None)
+        row = 1 + sum(nrows(c2) for _, c2 in cons[:i])
+        k_rows = nrows(cons[i][1])
+        exp = np.delete(base.tableau.matrix.reshape(base.tableau.height, W), range(row, row + k_rows), axis=0)
+        assert same_bits(removed.tableau.matrix, exp.reshape(-1))
+        assert removed.tableau.height == base.tableau.height - k_rows
+
+
+def test_integer_like_keys_follow_js_property_order():
+    """Object.entries puts canonical array-index keys first in ascending order (restatement rule 7)."""
+    model = {"objective": "o", "constraints": {"c": {"max": 10}},
+             "variables": {"b": {"c": 1, "o": 1}, "10": {"c": 2, "o": 2}, "2": {"c": 3, "o": 3}}}
+    tm = tableau_model(model)
+    assert [k for k, _ in tm.variables] == ["2", "10", "b"]
+    assert_same(tm, M.tableau_model(model))

@@ -1,0 +1,294 @@
+// kernels.cuh -- batch kernels built on simplex_device.cuh.
+//
+//  K1  k_simplex<NW,KC,true >  one tableau per CTA resident in shared memory (persistent CTAs, atomic LP queue)
+//  K2  k_simplex<NW,KC,false>  tableau in HBM/L2 (working copy), pivot row / column staged in shared memory
+//  K3  node assembly (applyCuts, src/branchAndCut.ts:22-61) fused as the prologue of K1/K2 (mode == kModeNodes)
+//  K5  k_generate_synthetic / k_generate_replicas: device-side input generators of SURVEY 8(d)
+#pragma once
+
+#include "simplex_device.cuh"
+
+namespace yalps {
+
+enum : int { kModeBatch = 0, kModeNodes = 1 };
+
+struct BatchArgs {
+  long long n;
+  int mode;
+  int H, W;       // uniform LP shape (kModeBatch, heights == nullptr) or root shape (kModeNodes)
+  int Hcap;       // tallest LP of the launch (shared-memory carve-up, output stride in node mode)
+  int Wcap;       // widest LP of the launch (shared-memory carve-up)
+  const double *in;   // input tableaus (kModeBatch)
+  double *work;       // K2 working copies (may alias `in`); unused by K1
+  double *mat_out;    // optional final tableaus
+  const int *heights, *widths;          // ragged batch (nullable)
+  const long long *mat_off, *rhs_off, *pos_off;
+  int *status;
+  double *value;
+  long long *pivots;
+  double *rhs_out;
+  int *pos_out, *var_out;
+  // node mode
+  const double *root;
+  const int *root_pos, *root_var;
+  const int *cut_off;
+  const double *cut_sign;
+  const int *cut_var;
+  const double *cut_val;
+  // options
+  double precision, max_pivots;
+  int check_cycles;
+  int *hist;        // gridDim.x * 2 * hist_cap
+  int hist_cap;
+  unsigned long long *counter;
+};
+
+// Shared-memory carve-up, identical on host and device.
+struct SmemLayout {
+  size_t off_M, off_prow, off_colbuf, off_colnew, off_redv, off_redi, off_nz, off_pos, off_var, total;
+  __host__ __device__ static int ld_for(int W) { return W | 1; }  // odd stride: conflict-free column reads
+  __host__ __device__ SmemLayout(int Hcap, int W, bool resident) {
+    size_t o = 0;
+    off_M = o;
+    if (resident) o += (size_t)Hcap * ld_for(W) * 8;
+    off_prow = o;
+    o += (size_t)((W + 1) & ~1) * 8;
+    off_colbuf = o;
+    o += (size_t)Hcap * 8;
+    off_colnew = o;
+    o += (size_t)Hcap * 8;
+    off_redv = o;
+    o += 64 * 8;
+    off_redi = o;
+    o += 64 * 4;
+    off_nz = o;
+    o += (size_t)((W + 31) / 32 + 1) * 4;
+    off_pos = o;
+    if (resident) o += (size_t)(W + Hcap) * 4;
+    off_var = o;
+    if (resident) o += (size_t)(W + Hcap) * 4;
+    total = (o + 15) & ~(size_t)15;
+  }
+};
+
+template <int NW, int KC, bool kResident>
+__global__ void __launch_bounds__(NW * 32) k_simplex(const BatchArgs a) {
+  constexpr int NT = NW * 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ long long s_lp;
+  const int tid = threadIdx.x;
+
+  for (;;) {
+    if (tid == 0) s_lp = (long long)atomicAdd(a.counter, 1ULL);
+    __syncthreads();
+    const long long lp = s_lp;
+    __syncthreads();
+    if (lp >= a.n) break;
+
+    int H, W, ncuts = 0;
+    size_t moff, roff, poff;
+    if (a.mode == kModeNodes) {
+      ncuts = a.cut_off[lp + 1] - a.cut_off[lp];
+      H = a.H + ncuts;
+      W = a.W;
+      moff = (size_t)lp * a.Hcap * W;
+      roff = (size_t)lp * a.Hcap;
+      poff = (size_t)lp * (W + a.Hcap);
+    } else if (a.heights) {
+      H = a.heights[lp];
+      W = a.widths[lp];
+      moff = (size_t)a.mat_off[lp];
+      roff = (size_t)a.rhs_off[lp];
+      poff = (size_t)a.pos_off[lp];
+    } else {
+      H = a.H;
+      W = a.W;
+      moff = (size_t)lp * H * W;
+      roff = (size_t)lp * H;
+      poff = (size_t)lp * (W + H);
+    }
+
+    const SmemLayout L(a.Hcap, a.Wcap, kResident);
+    LpView t;
+    t.H = H;
+    t.W = W;
+    t.ld = kResident ? SmemLayout::ld_for(W) : W;
+    t.M = kResident ? reinterpret_cast<double *>(smem_raw + L.off_M) : a.work + moff;
+    t.pos = kResident ? reinterpret_cast<int *>(smem_raw + L.off_pos) : a.pos_out + poff;
+    t.var = kResident ? reinterpret_cast<int *>(smem_raw + L.off_var) : a.var_out + poff;
+    Scratch s;
+    s.prow = reinterpret_cast<double *>(smem_raw + L.off_prow);
+    s.colbuf = reinterpret_cast<double *>(smem_raw + L.off_colbuf);
+    s.colnew = reinterpret_cast<double *>(smem_raw + L.off_colnew);
+    s.red_v = reinterpret_cast<double *>(smem_raw + L.off_redv);
+    s.red_i = reinterpret_cast<int *>(smem_raw + L.off_redi);
+    s.nzmask = reinterpret_cast<unsigned *>(smem_raw + L.off_nz);
+    s.hist = a.hist ? a.hist + (size_t)blockIdx.x * 2 * a.hist_cap : nullptr;
+    s.hist_cap = a.hist_cap;
+
+    // ---- load / assemble the tableau
+    const int ld = t.ld;
+    if (a.mode == kModeNodes) {
+      // applyCuts (src/branchAndCut.ts:22-61): root copy, then one row per cut
+      const int rootH = a.H;
+      for (int r = tid >> 5; r < rootH; r += NW) {
+        const double *src = a.root + (size_t)r * W;
+        double *dst = t.M + (size_t)r * ld;
+        for (int c = tid & 31; c < W; c += 32) dst[c] = src[c];
+      }
+      const int cbeg = a.cut_off[lp];
+      for (int i = 0; i < ncuts; i++) {
+        const double sign = a.cut_sign[cbeg + i], value = a.cut_val[cbeg + i];
+        const int p = a.root_pos[a.cut_var[cbeg + i]];
+        double *dst = t.M + (size_t)(rootH + i) * ld;
+        if (p < W) {
+          for (int c = tid; c < W; c += NT) dst[c] = (c == 0) ? __dmul_rn(sign, value) : (c == p ? sign : 0.0);
+        } else {
+          const double *src = a.root + (size_t)(p - W) * W;
+          for (int c = tid; c < W; c += NT)
+            dst[c] = (c == 0) ? __dmul_rn(sign, __dsub_rn(value, src[0])) : __dmul_rn(-sign, src[c]);
+        }
+      }
+      const int nroot = W + rootH;
+      for (int k = tid; k < W + H; k += NT) {
+        t.pos[k] = k < nroot ? a.root_pos[k] : k;
+        t.var[k] = k < nroot ? a.root_var[k] : k;
+      }
+    } else {
+      const double *src = a.in + moff;
+      if (kResident) {
+        for (int r = tid >> 5; r < H; r += NW)
+          for (int c = tid & 31; c < W; c += 32) t.M[(size_t)r * ld + c] = src[(size_t)r * W + c];
+      } else if (src != t.M) {
+        const size_t cells = (size_t)H * W;
+        for (size_t k = tid; k < cells; k += NT) t.M[k] = src[k];
+      }
+      for (int k = tid; k < W + H; k += NT) {
+        t.pos[k] = k;
+        t.var[k] = k;
+      }
+    }
+    __syncthreads();
+
+    const LpResult res = simplex_cta<NW, KC>(t, s, a.precision, a.max_pivots, a.check_cycles);
+    __syncthreads();
+
+    // ---- outputs
+    if (tid == 0) {
+      if (a.status) a.status[lp] = res.status;
+      if (a.value) a.value[lp] = res.value;
+      if (a.pivots) {
+        a.pivots[2 * lp] = res.p1;
+        a.pivots[2 * lp + 1] = res.p2;
+      }
+    }
+    if (a.rhs_out)
+      for (int r = tid; r < H; r += NT) a.rhs_out[roff + r] = t.M[(size_t)r * ld];
+    if (kResident) {
+      if (a.pos_out)
+        for (int k = tid; k < W + H; k += NT) a.pos_out[poff + k] = t.pos[k];
+      if (a.var_out)
+        for (int k = tid; k < W + H; k += NT) a.var_out[poff + k] = t.var[k];
+    }
+    if (a.mat_out) {
+      double *dst = a.mat_out + moff;
+      if (kResident) {
+        for (int r = tid >> 5; r < H; r += NW)
+          for (int c = tid & 31; c < W; c += 32) dst[(size_t)r * W + c] = t.M[(size_t)r * ld + c];
+      } else if (dst != t.M) {
+        const size_t cells = (size_t)H * W;
+        for (size_t k = tid; k < cells; k += NT) dst[k] = t.M[k];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- K5: generators -------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t prospector_hash(uint32_t x) {  // tests/helpers/util.ts:20-29
+  x ^= x >> 16;
+  x *= 0x21f0aaadu;
+  x ^= x >> 15;
+  x *= 0xd35a2d97u;
+  x ^= x >> 15;
+  return x;
+}
+
+// draw d (0-based) of newRand(seed0): state after d+1 increments (tests/helpers/util.ts:38-41)
+__host__ __device__ __forceinline__ double rand_draw(uint32_t seed0, uint32_t d) {
+  return (double)prospector_hash(seed0 + (d + 1u) * 0x9e3779b9u) / 4294967296.0;
+}
+
+// Dense synthetic LPs.  Draw order: c_1..c_n, then per row a_k1..a_kn, b_k.
+__global__ void k_generate_synthetic(long long first, long long n, int m, int nvars, int neg_rows, uint32_t salt,
+                                     double *out) {
+  const int W = nvars + 1, H = m + 1;
+  const size_t cells = (size_t)W * H;
+  const size_t total = (size_t)n * cells;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+    const long long i = (long long)(g / cells);
+    const int cell = (int)(g % cells);
+    const int r = cell / W, c = cell % W;
+    const uint32_t seed0 = prospector_hash((uint32_t)(first + i) ^ salt);
+    double v;
+    if (r == 0) {
+      v = (c == 0) ? 0.0 : rand_draw(seed0, (uint32_t)(c - 1));
+    } else {
+      const uint32_t base = (uint32_t)nvars + (uint32_t)(r - 1) * (uint32_t)(nvars + 1);
+      if (c == 0) {
+        const double u = rand_draw(seed0, base + (uint32_t)nvars);
+        v = (r <= neg_rows) ? -(0.5 + u) : (double)nvars * (0.25 + 0.5 * u);
+      } else {
+        v = rand_draw(seed0, base + (uint32_t)(c - 1));
+        if (r <= neg_rows) v = -v;
+      }
+    }
+    out[g] = v;
+  }
+}
+
+// RHS-perturbed replicas of one base tableau.
+__global__ void k_generate_replicas(long long first, long long n, int H, int W, const double *base, const int *group,
+                                    double eps, uint32_t salt, double *out) {
+  const size_t cells = (size_t)W * H;
+  const size_t total = (size_t)n * cells;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+    const long long i = (long long)(g / cells);
+    const int cell = (int)(g % cells);
+    const int r = cell / W, c = cell % W;
+    double v = base[cell];
+    if (c == 0 && group[r] >= 0) {
+      const uint32_t seed0 = prospector_hash((uint32_t)(first + i) ^ salt);
+      const double u = rand_draw(seed0, (uint32_t)group[r]);
+      v = __dmul_rn(v, __dadd_rn(1.0, __dmul_rn(eps, __dsub_rn(__dmul_rn(2.0, u), 1.0))));
+    }
+    out[g] = v;
+  }
+}
+
+__global__ void k_round_to_precision(long long n, const double *x, double precision, double *out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = round_to_precision(x[i], precision);
+}
+
+// Shared-memory stream: every thread reads and rewrites 8-byte cells of a CTA-private buffer.
+// bytes = grid * iters * words * 16.
+__global__ void k_smem_stream(int words, int iters, double *sink) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *buf = reinterpret_cast<double *>(smem_raw);
+  for (int k = threadIdx.x; k < words; k += blockDim.x) buf[k] = (double)k;
+  __syncthreads();
+  double acc = 0.0;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll 4
+    for (int k = threadIdx.x; k < words; k += blockDim.x) {
+      const double x = buf[k];
+      buf[k] = x + 1.0;
+      acc += x;
+    }
+    __syncthreads();
+  }
+  if (acc == -1.0) sink[0] = acc;
+}
+
+}  // namespace yalps

@@ -1,0 +1,657 @@
+// yalps_b200.cu -- C ABI (include/yalps_b200.h) over the sm_100a kernels.
+//
+// Host runtime: context, device buffer pool, double-buffered chunked H2D -> kernel -> D2H pipeline,
+// kernel-path selection, and the branch-and-cut driver (speculative node waves replayed in the
+// reference's pop order, src/branchAndCut.ts:89-176).
+#include "../../include/yalps_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace yalps;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+struct Root {
+  bool valid = false;
+  int H = 0, W = 0, max_extra = 0;
+  DevBuf m, pos, var;
+  std::vector<double> h_m;  // host copy of column 0 is enough for the driver, but keep rhs + pos + var
+  std::vector<double> h_rhs;
+  std::vector<int32_t> h_pos, h_var;
+};
+
+}  // namespace
+
+struct yalps_ctx {
+  int device = 0;
+  cudaDeviceProp prop{};
+  int smem_optin = 0;
+  std::string error;
+  cudaStream_t streams[2]{};
+  cudaEvent_t events[2]{};
+  int64_t launches = 0;
+  int tune_path = 0, tune_threads = 0;
+  int wave = 64;
+  // pooled device buffers (index = purpose * 2 + pipeline slot)
+  std::unordered_map<std::string, DevBuf> pool;
+  std::unordered_map<std::string, DevBuf> pinned;
+  Root root;
+};
+
+namespace {
+
+int fail(yalps_ctx *ctx, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx)
+    ctx->error = buf;
+  else
+    g_create_error = buf;
+  return code;
+}
+
+#define CU(ctx, call)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess)                                                                              \
+      return fail(ctx, YALPS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+int dev_ensure(yalps_ctx *ctx, const std::string &name, size_t bytes, void **out) {
+  DevBuf &b = ctx->pool[name];
+  if (b.cap < bytes) {
+    if (b.p) CU(ctx, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = std::max(bytes, (size_t)256);
+    CU(ctx, cudaMalloc(&b.p, want));
+    b.cap = want;
+  }
+  *out = b.p;
+  return 0;
+}
+
+int pin_ensure(yalps_ctx *ctx, const std::string &name, size_t bytes, void **out) {
+  DevBuf &b = ctx->pinned[name];
+  if (b.cap < bytes) {
+    if (b.p) CU(ctx, cudaFreeHost(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = std::max(bytes, (size_t)256);
+    CU(ctx, cudaMallocHost(&b.p, want));
+    b.cap = want;
+  }
+  *out = b.p;
+  return 0;
+}
+
+// ---- kernel table -------------------------------------------------------------------------------------
+typedef void (*SimplexKernel)(const BatchArgs);
+
+struct KernelEntry {
+  int nw, kc;
+  SimplexKernel resident, global;
+};
+
+#define KENTRY(NW, KC) {NW, KC, k_simplex<NW, KC, true>, k_simplex<NW, KC, false>}
+const KernelEntry kKernels[] = {
+    KENTRY(1, 1),  KENTRY(1, 2),  KENTRY(1, 3),  KENTRY(1, 4),  KENTRY(2, 1),  KENTRY(2, 2),  KENTRY(2, 3),
+    KENTRY(2, 4),  KENTRY(4, 1),  KENTRY(4, 2),  KENTRY(4, 3),  KENTRY(4, 4),  KENTRY(4, 8),  KENTRY(8, 2),
+    KENTRY(8, 4),  KENTRY(8, 8),  KENTRY(16, 4), KENTRY(16, 8), KENTRY(32, 2), KENTRY(32, 4),
+};
+#undef KENTRY
+
+const KernelEntry *pick_kernel(int nw_want, int W) {
+  const int kc_want = std::max(1, (W + 31) / 32);
+  const KernelEntry *best = nullptr;
+  // smallest NW >= wanted (or largest available), then smallest KC >= wanted (or largest available)
+  int nw_sel = -1;
+  for (const auto &k : kKernels)
+    if (k.nw >= nw_want && (nw_sel < 0 || k.nw < nw_sel)) nw_sel = k.nw;
+  if (nw_sel < 0)
+    for (const auto &k : kKernels) nw_sel = std::max(nw_sel, k.nw);
+  for (const auto &k : kKernels) {
+    if (k.nw != nw_sel) continue;
+    if (!best) {
+      best = &k;
+      continue;
+    }
+    const bool k_ok = k.kc >= kc_want, b_ok = best->kc >= kc_want;
+    if (k_ok && (!b_ok || k.kc < best->kc)) best = &k;
+    if (!k_ok && !b_ok && k.kc > best->kc) best = &k;
+  }
+  return best;
+}
+
+int default_warps(long long cells) {
+  long long w = cells / 2048;
+  int nw = 1;
+  while (nw * 2 <= w && nw < 32) nw *= 2;
+  return nw;
+}
+
+struct LaunchPlan {
+  bool resident;
+  const KernelEntry *k;
+  size_t smem;
+  int grid;
+};
+
+int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycles, LaunchPlan *plan) {
+  const SmemLayout Lr(Hcap, Wcap, true), Lg(Hcap, Wcap, false);
+  bool resident = Lr.total <= (size_t)ctx->smem_optin;
+  if (ctx->tune_path == YALPS_PATH_SMEM) {
+    if (!resident) return fail(ctx, YALPS_ERR_TOO_LARGE, "tableau %dx%d does not fit in shared memory", Hcap, Wcap);
+  } else if (ctx->tune_path == YALPS_PATH_GMEM) {
+    resident = false;
+  }
+  if (!resident && Lg.total > (size_t)ctx->smem_optin)
+    return fail(ctx, YALPS_ERR_TOO_LARGE, "tableau %dx%d: pivot row/column staging exceeds shared memory", Hcap, Wcap);
+  int nw = ctx->tune_threads > 0 ? std::max(1, ctx->tune_threads / 32) : default_warps((long long)Hcap * Wcap);
+  if (!resident && ctx->tune_threads <= 0) nw = std::max(nw, 8);
+  const KernelEntry *k = pick_kernel(nw, Wcap);
+  SimplexKernel fn = resident ? k->resident : k->global;
+  const size_t smem = resident ? Lr.total : Lg.total;
+  CU(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, k->nw * 32, smem));
+  if (occ < 1) return fail(ctx, YALPS_ERR_TOO_LARGE, "kernel does not fit on an SM (smem %zu)", smem);
+  if (check_cycles) occ = std::min(occ, 4);  // bounds the history buffer
+  long long grid = (long long)occ * ctx->prop.multiProcessorCount;
+  grid = std::max(1LL, std::min(grid, n));
+  plan->resident = resident;
+  plan->k = k;
+  plan->smem = smem;
+  plan->grid = (int)grid;
+  return 0;
+}
+
+int hist_capacity(const yalps_options *opt) {
+  if (!opt->check_cycles) return 0;
+  double cap = opt->max_pivots;
+  if (!(cap < 262144.0)) cap = 262144.0;
+  if (cap < 1.0) cap = 1.0;
+  return (int)cap;
+}
+
+// Enqueue one kernel launch for `args` (device pointers filled in by the caller).
+int launch_simplex(yalps_ctx *ctx, const LaunchPlan &plan, BatchArgs &args, const std::string &slot,
+                   cudaStream_t stream) {
+  void *counter = nullptr;
+  if (int rc = dev_ensure(ctx, "counter" + slot, 8, &counter)) return rc;
+  CU(ctx, cudaMemsetAsync(counter, 0, 8, stream));
+  args.counter = (unsigned long long *)counter;
+  if (args.check_cycles) {
+    void *hist = nullptr;
+    if (int rc = dev_ensure(ctx, "hist" + slot, (size_t)plan.grid * 2 * args.hist_cap * sizeof(int), &hist)) return rc;
+    args.hist = (int *)hist;
+  } else {
+    args.hist = nullptr;
+  }
+  SimplexKernel fn = plan.resident ? plan.k->resident : plan.k->global;
+  fn<<<plan.grid, plan.k->nw * 32, plan.smem, stream>>>(args);
+  CU(ctx, cudaGetLastError());
+  ctx->launches++;
+  return 0;
+}
+
+void fill_options(BatchArgs &a, const yalps_options *opt) {
+  a.precision = opt->precision;
+  a.max_pivots = opt->max_pivots;
+  a.check_cycles = opt->check_cycles ? 1 : 0;
+  a.hist_cap = hist_capacity(opt);
+}
+
+int check_device_status(yalps_ctx *ctx, const int32_t *status, long long n) {
+  if (!status) return 0;
+  for (long long i = 0; i < n; i++)
+    if (status[i] == ST_ERR_HISTORY)
+      return fail(ctx, YALPS_ERR_HISTORY, "checkCycles history exhausted for LP %lld (more than 262144 pivots in a phase)", i);
+  return 0;
+}
+
+}  // namespace
+
+// =========================================================================================================
+extern "C" {
+
+void yalps_default_options(yalps_options *opt) {
+  opt->precision = 1e-8;
+  opt->max_pivots = 8192;
+  opt->tolerance = 0;
+  opt->timeout_ms = std::numeric_limits<double>::infinity();
+  opt->max_iterations = 32768;
+  opt->check_cycles = 0;
+  opt->reserved = 0;
+}
+
+int yalps_create(int device, yalps_ctx **out) {
+  if (!out) return fail(nullptr, YALPS_ERR_ARGUMENT, "out is null");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(nullptr, YALPS_ERR_CUDA, "no CUDA device available (%s); yalps_b200 has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (device < 0 || device >= count) return fail(nullptr, YALPS_ERR_ARGUMENT, "device %d out of range [0,%d)", device, count);
+  std::unique_ptr<yalps_ctx> ctx(new yalps_ctx);
+  ctx->device = device;
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(nullptr, YALPS_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  if ((e = cudaGetDeviceProperties(&ctx->prop, device)) != cudaSuccess)
+    return fail(nullptr, YALPS_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (ctx->prop.major < 10)
+    return fail(nullptr, YALPS_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                ctx->prop.major, ctx->prop.minor);
+  ctx->smem_optin = (int)ctx->prop.sharedMemPerBlockOptin;
+  for (int i = 0; i < 2; i++) {
+    if ((e = cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking)) != cudaSuccess)
+      return fail(nullptr, YALPS_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    if ((e = cudaEventCreateWithFlags(&ctx->events[i], cudaEventDisableTiming)) != cudaSuccess)
+      return fail(nullptr, YALPS_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e));
+  }
+  *out = ctx.release();
+  return 0;
+}
+
+void yalps_destroy(yalps_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (auto &kv : ctx->pool)
+    if (kv.second.p) cudaFree(kv.second.p);
+  for (auto &kv : ctx->pinned)
+    if (kv.second.p) cudaFreeHost(kv.second.p);
+  for (DevBuf *b : {&ctx->root.m, &ctx->root.pos, &ctx->root.var})
+    if (b->p) cudaFree(b->p);
+  for (int i = 0; i < 2; i++) {
+    if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
+    if (ctx->events[i]) cudaEventDestroy(ctx->events[i]);
+  }
+  delete ctx;
+}
+
+const char *yalps_last_error(const yalps_ctx *ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int yalps_device_info(const yalps_ctx *ctx, int32_t *sm_count, int32_t *smem_per_block_optin, int32_t *cc_major,
+                      int32_t *cc_minor) {
+  if (!ctx) return YALPS_ERR_ARGUMENT;
+  if (sm_count) *sm_count = ctx->prop.multiProcessorCount;
+  if (smem_per_block_optin) *smem_per_block_optin = ctx->smem_optin;
+  if (cc_major) *cc_major = ctx->prop.major;
+  if (cc_minor) *cc_minor = ctx->prop.minor;
+  return 0;
+}
+
+int yalps_set_tuning(yalps_ctx *ctx, int32_t path, int32_t threads_per_lp) {
+  if (!ctx) return YALPS_ERR_ARGUMENT;
+  if (path < 0 || path > YALPS_PATH_GRID) return fail(ctx, YALPS_ERR_ARGUMENT, "bad path %d", path);
+  ctx->tune_path = path;
+  ctx->tune_threads = threads_per_lp;
+  return 0;
+}
+
+int64_t yalps_launch_count(const yalps_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int yalps_host_alloc(yalps_ctx *ctx, uint64_t bytes, void **out) {
+  if (!ctx || !out) return YALPS_ERR_ARGUMENT;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaMallocHost(out, bytes ? bytes : 1));
+  return 0;
+}
+
+int yalps_host_free(yalps_ctx *ctx, void *ptr) {
+  if (!ctx) return YALPS_ERR_ARGUMENT;
+  if (ptr) CU(ctx, cudaFreeHost(ptr));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+int yalps_solve_batch_device(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, const double *d_matrices,
+                             double *d_work, const yalps_options *opt, int32_t *d_status, double *d_value,
+                             int64_t *d_pivots, double *d_rhs_out, int32_t *d_pos_out, int32_t *d_var_out,
+                             double *d_matrices_out, void *stream) {
+  if (!ctx) return YALPS_ERR_ARGUMENT;
+  if (n < 0 || height < 1 || width < 1 || !opt || (n > 0 && !d_matrices))
+    return fail(ctx, YALPS_ERR_ARGUMENT, "bad arguments (n=%lld, %dx%d)", (long long)n, height, width);
+  if ((long long)height * width >= (1LL << 31)) return fail(ctx, YALPS_ERR_TOO_LARGE, "height*width must be < 2^31");
+  if (n == 0) return 0;
+  CU(ctx, cudaSetDevice(ctx->device));
+  LaunchPlan plan;
+  if (int rc = plan_launch(ctx, n, height, width, opt->check_cycles != 0, &plan)) return rc;
+  BatchArgs a{};
+  a.n = n;
+  a.mode = kModeBatch;
+  a.H = a.Hcap = height;
+  a.W = a.Wcap = width;
+  a.in = d_matrices;
+  a.work = d_work;
+  a.mat_out = d_matrices_out;
+  a.status = d_status;
+  a.value = d_value;
+  a.pivots = (long long *)d_pivots;
+  a.rhs_out = d_rhs_out;
+  a.pos_out = d_pos_out;
+  a.var_out = d_var_out;
+  fill_options(a, opt);
+  if (!plan.resident) {
+    if (!d_work) return fail(ctx, YALPS_ERR_ARGUMENT, "d_work is required for the HBM-resident path");
+    if (!d_pos_out || !d_var_out) {
+      void *p = nullptr;
+      if (int rc = dev_ensure(ctx, "posvar_scratch", (size_t)n * (width + height) * 2 * sizeof(int), &p)) return rc;
+      if (!a.pos_out) a.pos_out = (int *)p;
+      if (!a.var_out) a.var_out = (int *)p + (size_t)n * (width + height);
+    }
+  }
+  return launch_simplex(ctx, plan, a, "dev", (cudaStream_t)stream);
+}
+
+// Shared host-side pipeline for uniform and ragged batches.
+static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, const int32_t *heights,
+                      const int32_t *widths, const int64_t *mat_offsets, const double *matrices,
+                      const yalps_options *opt, int32_t *status, double *value, int64_t *pivots, double *rhs_out,
+                      int32_t *pos_out, int32_t *var_out, double *matrices_out) {
+  if (!ctx) return YALPS_ERR_ARGUMENT;
+  if (n < 0 || !opt || (n > 0 && !matrices)) return fail(ctx, YALPS_ERR_ARGUMENT, "bad arguments");
+  if (n == 0) return 0;
+  CU(ctx, cudaSetDevice(ctx->device));
+  const bool ragged = heights != nullptr;
+
+  // per-LP prefix offsets (ragged) and caps
+  std::vector<long long> moff, roff, poff;
+  int Hcap = height, Wcap = width;
+  if (ragged) {
+    if (!widths || !mat_offsets) return fail(ctx, YALPS_ERR_ARGUMENT, "ragged batch needs widths and mat_offsets");
+    moff.resize(n + 1);
+    roff.resize(n + 1);
+    poff.resize(n + 1);
+    long long r = 0, p = 0, m = 0;
+    Hcap = Wcap = 1;
+    for (int64_t i = 0; i < n; i++) {
+      if (heights[i] < 1 || widths[i] < 1) return fail(ctx, YALPS_ERR_ARGUMENT, "LP %lld has empty shape", (long long)i);
+      if ((long long)heights[i] * widths[i] >= (1LL << 31)) return fail(ctx, YALPS_ERR_TOO_LARGE, "height*width must be < 2^31");
+      moff[i] = m;
+      roff[i] = r;
+      poff[i] = p;
+      m += (long long)heights[i] * widths[i];
+      r += heights[i];
+      p += heights[i] + widths[i];
+      Hcap = std::max(Hcap, heights[i]);
+      Wcap = std::max(Wcap, widths[i]);
+    }
+    moff[n] = m;
+    roff[n] = r;
+    poff[n] = p;
+  } else {
+    if (height < 1 || width < 1) return fail(ctx, YALPS_ERR_ARGUMENT, "bad shape %dx%d", height, width);
+    if ((long long)height * width >= (1LL << 31)) return fail(ctx, YALPS_ERR_TOO_LARGE, "height*width must be < 2^31");
+  }
+
+  // chunking: at most ~1.5 GiB of tableaus per pipeline slot
+  const size_t kSlotBytes = (size_t)1536 << 20;
+  auto cells_upto = [&](int64_t i) -> long long { return ragged ? moff[i] : (long long)i * height * width; };
+  auto rows_upto = [&](int64_t i) -> long long { return ragged ? roff[i] : (long long)i * height; };
+  auto pv_upto = [&](int64_t i) -> long long { return ragged ? poff[i] : (long long)i * (height + width); };
+
+  int64_t begin = 0;
+  int slot = 0;
+  int rc = 0;
+  bool used[2] = {false, false};
+  while (begin < n) {
+    int64_t end = begin + 1;
+    while (end < n && (size_t)(cells_upto(end + 1) - cells_upto(begin)) * 8 <= kSlotBytes) end++;
+    const int64_t cn = end - begin;
+    const size_t ccells = (size_t)(cells_upto(end) - cells_upto(begin));
+    const size_t crows = (size_t)(rows_upto(end) - rows_upto(begin));
+    const size_t cpv = (size_t)(pv_upto(end) - pv_upto(begin));
+    const std::string s = std::to_string(slot);
+    cudaStream_t st = ctx->streams[slot];
+    if (used[slot]) CU(ctx, cudaEventSynchronize(ctx->events[slot]));
+
+    int chcap = Hcap, cwcap = Wcap;
+    if (ragged) {
+      chcap = cwcap = 1;
+      for (int64_t i = begin; i < end; i++) {
+        chcap = std::max(chcap, heights[i]);
+        cwcap = std::max(cwcap, widths[i]);
+      }
+    }
+    LaunchPlan plan;
+    if ((rc = plan_launch(ctx, cn, chcap, cwcap, opt->check_cycles != 0, &plan))) return rc;
+
+    void *d_in, *d_status, *d_value, *d_piv, *d_rhs, *d_pos, *d_var;
+    if ((rc = dev_ensure(ctx, "in" + s, ccells * 8, &d_in))) return rc;
+    if ((rc = dev_ensure(ctx, "status" + s, (size_t)cn * 4, &d_status))) return rc;
+    if ((rc = dev_ensure(ctx, "value" + s, (size_t)cn * 8, &d_value))) return rc;
+    if ((rc = dev_ensure(ctx, "pivots" + s, (size_t)cn * 16, &d_piv))) return rc;
+    if ((rc = dev_ensure(ctx, "rhs" + s, crows * 8, &d_rhs))) return rc;
+    if ((rc = dev_ensure(ctx, "pos" + s, cpv * 4, &d_pos))) return rc;
+    if ((rc = dev_ensure(ctx, "var" + s, cpv * 4, &d_var))) return rc;
+    void *d_out = nullptr;
+    if (matrices_out && plan.resident)
+      if ((rc = dev_ensure(ctx, "matout" + s, ccells * 8, &d_out))) return rc;
+
+    const double *src = matrices + (ragged ? mat_offsets[begin] : cells_upto(begin));
+    if (ragged) {
+      // caller offsets may be non-contiguous: copy LP by LP when they are
+      bool contiguous = true;
+      for (int64_t i = begin; i < end && contiguous; i++)
+        contiguous = (mat_offsets[i] - mat_offsets[begin]) == (moff[i] - moff[begin]);
+      if (contiguous) {
+        CU(ctx, cudaMemcpyAsync(d_in, src, ccells * 8, cudaMemcpyHostToDevice, st));
+      } else {
+        for (int64_t i = begin; i < end; i++)
+          CU(ctx, cudaMemcpyAsync((double *)d_in + (moff[i] - moff[begin]), matrices + mat_offsets[i],
+                                  (size_t)heights[i] * widths[i] * 8, cudaMemcpyHostToDevice, st));
+      }
+    } else {
+      CU(ctx, cudaMemcpyAsync(d_in, src, ccells * 8, cudaMemcpyHostToDevice, st));
+    }
+
+    BatchArgs a{};
+    a.n = cn;
+    a.mode = kModeBatch;
+    a.H = height;
+    a.W = width;
+    a.Hcap = chcap;
+    a.Wcap = cwcap;
+    a.in = (const double *)d_in;
+    a.work = (double *)d_in;  // K2 works in place on the device copy
+    a.mat_out = matrices_out ? (plan.resident ? (double *)d_out : (double *)d_in) : nullptr;
+    a.status = (int *)d_status;
+    a.value = (double *)d_value;
+    a.pivots = (long long *)d_piv;
+    a.rhs_out = (double *)d_rhs;
+    a.pos_out = (int *)d_pos;
+    a.var_out = (int *)d_var;
+    if (ragged) {
+      void *d_h, *d_w, *d_mo, *d_ro, *d_po;
+      std::vector<long long> lm(cn), lr(cn), lpv(cn);
+      for (int64_t i = 0; i < cn; i++) {
+        lm[i] = moff[begin + i] - moff[begin];
+        lr[i] = roff[begin + i] - roff[begin];
+        lpv[i] = poff[begin + i] - poff[begin];
+      }
+      if ((rc = dev_ensure(ctx, "rg_h" + s, (size_t)cn * 4, &d_h))) return rc;
+      if ((rc = dev_ensure(ctx, "rg_w" + s, (size_t)cn * 4, &d_w))) return rc;
+      if ((rc = dev_ensure(ctx, "rg_mo" + s, (size_t)cn * 8, &d_mo))) return rc;
+      if ((rc = dev_ensure(ctx, "rg_ro" + s, (size_t)cn * 8, &d_ro))) return rc;
+      if ((rc = dev_ensure(ctx, "rg_po" + s, (size_t)cn * 8, &d_po))) return rc;
+      CU(ctx, cudaMemcpyAsync(d_h, heights + begin, (size_t)cn * 4, cudaMemcpyHostToDevice, st));
+      CU(ctx, cudaMemcpyAsync(d_w, widths + begin, (size_t)cn * 4, cudaMemcpyHostToDevice, st));
+      CU(ctx, cudaMemcpyAsync(d_mo, lm.data(), (size_t)cn * 8, cudaMemcpyHostToDevice, st));
+      CU(ctx, cudaMemcpyAsync(d_ro, lr.data(), (size_t)cn * 8, cudaMemcpyHostToDevice, st));
+      CU(ctx, cudaMemcpyAsync(d_po, lpv.data(), (size_t)cn * 8, cudaMemcpyHostToDevice, st));
+      CU(ctx, cudaStreamSynchronize(st));  // the staging vectors die at the end of this scope
+      a.heights = (const int *)d_h;
+      a.widths = (const int *)d_w;
+      a.mat_off = (const long long *)d_mo;
+      a.rhs_off = (const long long *)d_ro;
+      a.pos_off = (const long long *)d_po;
+    }
+    fill_options(a, opt);
+    if ((rc = launch_simplex(ctx, plan, a, s, st))) return rc;
+
+    if (status) CU(ctx, cudaMemcpyAsync(status + begin, d_status, (size_t)cn * 4, cudaMemcpyDeviceToHost, st));
+    if (value) CU(ctx, cudaMemcpyAsync(value + begin, d_value, (size_t)cn * 8, cudaMemcpyDeviceToHost, st));
+    if (pivots) CU(ctx, cudaMemcpyAsync(pivots + 2 * begin, d_piv, (size_t)cn * 16, cudaMemcpyDeviceToHost, st));
+    if (rhs_out) CU(ctx, cudaMemcpyAsync(rhs_out + rows_upto(begin), d_rhs, crows * 8, cudaMemcpyDeviceToHost, st));
+    if (pos_out) CU(ctx, cudaMemcpyAsync(pos_out + pv_upto(begin), d_pos, cpv * 4, cudaMemcpyDeviceToHost, st));
+    if (var_out) CU(ctx, cudaMemcpyAsync(var_out + pv_upto(begin), d_var, cpv * 4, cudaMemcpyDeviceToHost, st));
+    if (matrices_out) {
+      if (ragged) {
+        for (int64_t i = begin; i < end; i++)
+          CU(ctx, cudaMemcpyAsync(matrices_out + mat_offsets[i], (double *)a.mat_out + (moff[i] - moff[begin]),
+                                  (size_t)heights[i] * widths[i] * 8, cudaMemcpyDeviceToHost, st));
+      } else {
+        CU(ctx, cudaMemcpyAsync(matrices_out + cells_upto(begin), a.mat_out, ccells * 8, cudaMemcpyDeviceToHost, st));
+      }
+    }
+    CU(ctx, cudaEventRecord(ctx->events[slot], st));
+    used[slot] = true;
+    slot ^= 1;
+    begin = end;
+  }
+  for (int i = 0; i < 2; i++)
+    if (used[i]) CU(ctx, cudaStreamSynchronize(ctx->streams[i]));
+  return check_device_status(ctx, status, n);
+}
+
+int yalps_solve_batch(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, const double *matrices,
+                      const yalps_options *opt, int32_t *status, double *value, int64_t *pivots, double *rhs_out,
+                      int32_t *pos_out, int32_t *var_out, double *matrices_out) {
+  return solve_host(ctx, n, height, width, nullptr, nullptr, nullptr, matrices, opt, status, value, pivots, rhs_out,
+                    pos_out, var_out, matrices_out);
+}
+
+int yalps_solve_ragged(yalps_ctx *ctx, int64_t n, const int32_t *heights, const int32_t *widths,
+                       const int64_t *mat_offsets, const double *matrices, const yalps_options *opt, int32_t *status,
+                       double *value, int64_t *pivots, double *rhs_out, int32_t *pos_out, int32_t *var_out,
+                       double *matrices_out) {
+  if (!heights) return fail(ctx, YALPS_ERR_ARGUMENT, "heights is null");
+  return solve_host(ctx, n, 0, 0, heights, widths, mat_offsets, matrices, opt, status, value, pivots, rhs_out,
+                    pos_out, var_out, matrices_out);
+}
+
+int yalps_generate_synthetic_device(yalps_ctx *ctx, int64_t first, int64_t n, int32_t m, int32_t nvars,
+                                    int32_t neg_rows, uint32_t salt, double *d_out, void *stream) {
+  if (!ctx) return YALPS_ERR_ARGUMENT;
+  if (n < 0 || m < 0 || nvars < 0 || !d_out) return fail(ctx, YALPS_ERR_ARGUMENT, "bad arguments");
+  if (n == 0) return 0;
+  CU(ctx, cudaSetDevice(ctx->device));
+  const size_t total = (size_t)n * (m + 1) * (nvars + 1);
+  const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)ctx->prop.multiProcessorCount * 16);
+  k_generate_synthetic<<<grid, 256, 0, (cudaStream_t)stream>>>(first, n, m, nvars, neg_rows, salt, d_out);
+  CU(ctx, cudaGetLastError());
+  ctx->launches++;
+  return 0;
+}
+
+int yalps_generate_replicas_device(yalps_ctx *ctx, int64_t first, int64_t n, int32_t height, int32_t width,
+                                   const double *base_host, const int32_t *group_host, int32_t ngroups, double eps,
+                                   uint32_t salt, double *d_out, void *stream) {
+  if (!ctx) return YALPS_ERR_ARGUMENT;
+  if (n < 0 || height < 1 || width < 1 || !base_host || !group_host || !d_out)
+    return fail(ctx, YALPS_ERR_ARGUMENT, "bad arguments");
+  (void)ngroups;
+  if (n == 0) return 0;
+  CU(ctx, cudaSetDevice(ctx->device));
+  void *d_base, *d_group;
+  const size_t cells = (size_t)height * width;
+  if (int rc = dev_ensure(ctx, "rep_base", cells * 8, &d_base)) return rc;
+  if (int rc = dev_ensure(ctx, "rep_group", (size_t)height * 4, &d_group)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(ctx, cudaMemcpyAsync(d_base, base_host, cells * 8, cudaMemcpyHostToDevice, st));
+  CU(ctx, cudaMemcpyAsync(d_group, group_host, (size_t)height * 4, cudaMemcpyHostToDevice, st));
+  const size_t total = (size_t)n * cells;
+  const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)ctx->prop.multiProcessorCount * 16);
+  k_generate_replicas<<<grid, 256, 0, st>>>(first, n, height, width, (const double *)d_base, (const int *)d_group, eps,
+                                            salt, d_out);
+  CU(ctx, cudaGetLastError());
+  CU(ctx, cudaStreamSynchronize(st));  // base_host / group_host may be pageable
+  ctx->launches++;
+  return 0;
+}
+
+int yalps_round_to_precision(yalps_ctx *ctx, int64_t n, const double *x, double precision, double *out) {
+  if (!ctx) return YALPS_ERR_ARGUMENT;
+  if (n < 0 || (n > 0 && (!x || !out))) return fail(ctx, YALPS_ERR_ARGUMENT, "bad arguments");
+  if (n == 0) return 0;
+  CU(ctx, cudaSetDevice(ctx->device));
+  void *d_x, *d_o;
+  if (int rc = dev_ensure(ctx, "round_x", (size_t)n * 8, &d_x)) return rc;
+  if (int rc = dev_ensure(ctx, "round_o", (size_t)n * 8, &d_o)) return rc;
+  cudaStream_t st = ctx->streams[0];
+  CU(ctx, cudaMemcpyAsync(d_x, x, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  k_round_to_precision<<<(int)((n + 255) / 256), 256, 0, st>>>(n, (const double *)d_x, precision, (double *)d_o);
+  CU(ctx, cudaGetLastError());
+  ctx->launches++;
+  CU(ctx, cudaMemcpyAsync(out, d_o, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  CU(ctx, cudaStreamSynchronize(st));
+  return 0;
+}
+
+int yalps_measure_smem_bandwidth(yalps_ctx *ctx, double *gbs, double *sm_clock_mhz) {
+  if (!ctx || !gbs) return YALPS_ERR_ARGUMENT;
+  CU(ctx, cudaSetDevice(ctx->device));
+  const int words = 24 * 1024 / 8 * 4;  // 96 KiB per CTA, 2 CTAs per SM
+  const int threads = 512, iters = 2000;
+  const size_t smem = (size_t)words * 8;
+  CU(ctx, cudaFuncSetAttribute(k_smem_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void *sink;
+  if (int rc = dev_ensure(ctx, "sink", 64, &sink)) return rc;
+  const int grid = ctx->prop.multiProcessorCount * 2;
+  cudaStream_t st = ctx->streams[0];
+  cudaEvent_t e0, e1;
+  CU(ctx, cudaEventCreate(&e0));
+  CU(ctx, cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    CU(ctx, cudaEventRecord(e0, st));
+    k_smem_stream<<<grid, threads, smem, st>>>(words, iters, (double *)sink);
+    CU(ctx, cudaEventRecord(e1, st));
+    CU(ctx, cudaEventSynchronize(e1));
+    CU(ctx, cudaGetLastError());
+    ctx->launches++;
+    float ms = 0;
+    CU(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0) best = std::min(best, ms);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  const double bytes = (double)grid * iters * words * 16.0;
+  *gbs = bytes / (best * 1e-3) / 1e9;
+  if (sm_clock_mhz) {
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+    *sm_clock_mhz = khz / 1000.0;
+  }
+  return 0;
+}
+
+}  // extern "C"
+
+#include "bnb.inl"

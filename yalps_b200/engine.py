@@ -1,0 +1,277 @@
+"""Engine: one context of libyalps_b200.so on one GPU (numpy in, numpy out).
+
+This is the thin host layer north_star describes: it packs tableaus (RHS column 0, objective row 0,
+src/tableau.ts:9-21) into host buffers and calls the C ABI; all arithmetic happens in the sm_100a
+kernels.  Device-resident entry points take raw device pointers (e.g. `torch.Tensor.data_ptr()`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import Options, YalpsError
+
+STATUS_NAMES = ("optimal", "infeasible", "unbounded", "timedout", "cycled")  # enum yalps_status
+
+PATH_AUTO, PATH_SMEM, PATH_GMEM, PATH_GRID = 0, 1, 2, 3
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def make_options(precision=1e-8, max_pivots=8192, check_cycles=False, tolerance=0.0, timeout_ms=math.inf,
+                 max_iterations=32768) -> Options:
+    o = Options()
+    o.precision = float(precision)
+    o.max_pivots = float(max_pivots)
+    o.tolerance = float(tolerance)
+    o.timeout_ms = float(timeout_ms)
+    o.max_iterations = float(max_iterations)
+    o.check_cycles = 1 if check_cycles else 0
+    o.reserved = 0
+    return o
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        self._lib = _ffi.load()
+        self._ctx = C.c_void_p()
+        rc = self._lib.yalps_create(int(device), C.byref(self._ctx))
+        if rc != 0:
+            msg = self._lib.yalps_last_error(None)
+            raise YalpsError(rc, msg.decode() if msg else "yalps_create failed")
+        self.device = int(device)
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._lib.yalps_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != 0:
+            msg = self._lib.yalps_last_error(self._ctx)
+            raise YalpsError(rc, msg.decode() if msg else "")
+
+    def device_info(self) -> dict:
+        v = [C.c_int32() for _ in range(4)]
+        self._check(self._lib.yalps_device_info(self._ctx, *[C.byref(x) for x in v]))
+        return {"sm_count": v[0].value, "smem_per_block_optin": v[1].value, "cc": (v[2].value, v[3].value)}
+
+    def set_tuning(self, path: int = PATH_AUTO, threads_per_lp: int = 0):
+        self._check(self._lib.yalps_set_tuning(self._ctx, path, threads_per_lp))
+
+    def set_wave(self, wave: int):
+        self._check(self._lib.yalps_bnb_set_wave(self._ctx, int(wave)))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.yalps_launch_count(self._ctx))
+
+    def pinned_empty(self, shape, dtype) -> np.ndarray:
+        """numpy array over page-locked memory (freed with the engine's process)."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p()
+        self._check(self._lib.yalps_host_alloc(self._ctx, n, C.byref(p)))
+        buf = (C.c_char * max(n, 1)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    # ------------------------------------------------------------------ simplex batches
+    def solve_batch(self, matrices: np.ndarray, height: int, width: int, options: Optional[Options] = None,
+                    want_matrices: bool = False, want_basis: bool = True) -> dict:
+        """n same-shape tableaus, `matrices` float64 of n*height*width values (not modified)."""
+        opt = options or make_options()
+        m = np.ascontiguousarray(matrices, dtype=np.float64).reshape(-1)
+        cells = height * width
+        if cells <= 0 or m.size % cells:
+            raise ValueError(f"matrices has {m.size} values, not a multiple of {height}x{width}")
+        n = m.size // cells
+        out = {
+            "status": np.empty(n, np.int32),
+            "value": np.empty(n, np.float64),
+            "pivots": np.empty((n, 2), np.int64),
+            "rhs": np.empty((n, height), np.float64),
+            "pos": np.empty((n, width + height), np.int32) if want_basis else None,
+            "var": np.empty((n, width + height), np.int32) if want_basis else None,
+            "matrices": np.empty((n, cells), np.float64) if want_matrices else None,
+        }
+        self._check(self._lib.yalps_solve_batch(self._ctx, n, height, width, _ptr(m), C.byref(opt), _ptr(out["status"]),
+                                                _ptr(out["value"]), _ptr(out["pivots"]), _ptr(out["rhs"]),
+                                                _ptr(out["pos"]), _ptr(out["var"]), _ptr(out["matrices"])))
+        return out
+
+    def solve_ragged(self, tableaus: Sequence[np.ndarray], shapes: Sequence[tuple], options: Optional[Options] = None,
+                     want_matrices: bool = False) -> list:
+        """LPs of different shapes in one call.  tableaus[i] is float64 of height_i*width_i values."""
+        opt = options or make_options()
+        n = len(tableaus)
+        if n == 0:
+            return []
+        heights = np.asarray([s[0] for s in shapes], np.int32)
+        widths = np.asarray([s[1] for s in shapes], np.int32)
+        cells = heights.astype(np.int64) * widths
+        offs = np.zeros(n + 1, np.int64)
+        np.cumsum(cells, out=offs[1:])
+        packed = np.empty(int(offs[-1]), np.float64)
+        for i, t in enumerate(tableaus):
+            packed[offs[i]:offs[i + 1]] = np.asarray(t, np.float64).reshape(-1)
+        roffs = np.zeros(n + 1, np.int64)
+        np.cumsum(heights, out=roffs[1:])
+        poffs = np.zeros(n + 1, np.int64)
+        np.cumsum(heights.astype(np.int64) + widths, out=poffs[1:])
+        status = np.empty(n, np.int32)
+        value = np.empty(n, np.float64)
+        pivots = np.empty((n, 2), np.int64)
+        rhs = np.empty(int(roffs[-1]), np.float64)
+        pos = np.empty(int(poffs[-1]), np.int32)
+        var = np.empty(int(poffs[-1]), np.int32)
+        mats = np.empty(int(offs[-1]), np.float64) if want_matrices else None
+        self._check(self._lib.yalps_solve_ragged(self._ctx, n, _ptr(heights), _ptr(widths), _ptr(offs[:-1].copy()),
+                                                 _ptr(packed), C.byref(opt), _ptr(status), _ptr(value), _ptr(pivots),
+                                                 _ptr(rhs), _ptr(pos), _ptr(var), _ptr(mats)))
+        res = []
+        for i in range(n):
+            res.append({
+                "status": int(status[i]), "value": float(value[i]), "pivots": (int(pivots[i, 0]), int(pivots[i, 1])),
+                "rhs": rhs[roffs[i]:roffs[i + 1]], "pos": pos[poffs[i]:poffs[i + 1]], "var": var[poffs[i]:poffs[i + 1]],
+                "matrix": mats[offs[i]:offs[i + 1]] if want_matrices else None,
+            })
+        return res
+
+    def solve_batch_device(self, n: int, height: int, width: int, d_matrices: int, options: Optional[Options] = None,
+                           d_work: int = 0, d_status: int = 0, d_value: int = 0, d_pivots: int = 0, d_rhs: int = 0,
+                           d_pos: int = 0, d_var: int = 0, d_matrices_out: int = 0, stream: int = 0):
+        """Everything already in device memory (raw pointers); enqueues on `stream` and returns."""
+        opt = options or make_options()
+        z = lambda p: C.c_void_p(p) if p else None
+        self._check(self._lib.yalps_solve_batch_device(self._ctx, n, height, width, z(d_matrices), z(d_work),
+                                                       C.byref(opt), z(d_status), z(d_value), z(d_pivots), z(d_rhs),
+                                                       z(d_pos), z(d_var), z(d_matrices_out), z(stream)))
+
+    def generate_synthetic_device(self, first: int, n: int, m: int, nvars: int, d_out: int, neg_rows: int = 0,
+                                  salt: int = 0x5BD1E995, stream: int = 0):
+        self._check(self._lib.yalps_generate_synthetic_device(self._ctx, first, n, m, nvars, neg_rows, salt,
+                                                              C.c_void_p(d_out), C.c_void_p(stream) if stream else None))
+
+    def generate_replicas_device(self, first: int, n: int, base: np.ndarray, height: int, width: int,
+                                 group: np.ndarray, d_out: int, eps: float = 1e-2, salt: int = 0x2545F491,
+                                 stream: int = 0):
+        base = np.ascontiguousarray(base, np.float64).reshape(-1)
+        group = np.ascontiguousarray(group, np.int32)
+        ngroups = int(group.max()) + 1 if group.size else 0
+        self._check(self._lib.yalps_generate_replicas_device(self._ctx, first, n, height, width, _ptr(base), _ptr(group),
+                                                             ngroups, eps, salt, C.c_void_p(d_out),
+                                                             C.c_void_p(stream) if stream else None))
+
+    # ------------------------------------------------------------------ branch and cut
+    def bnb_set_root(self, matrix: np.ndarray, height: int, width: int, pos: np.ndarray, var: np.ndarray,
+                     max_extra_rows: int):
+        m = np.ascontiguousarray(matrix, np.float64).reshape(-1)
+        p = np.ascontiguousarray(pos, np.int32)
+        v = np.ascontiguousarray(var, np.int32)
+        self._check(self._lib.yalps_bnb_set_root(self._ctx, height, width, _ptr(m), _ptr(p), _ptr(v), max_extra_rows))
+        self._root_shape = (height, width)
+
+    def bnb_solve_nodes(self, cuts_per_node: Sequence[Sequence[tuple]], options: Optional[Options] = None,
+                        want_matrices: bool = False) -> dict:
+        """cuts_per_node[j] = [(sign, variable, value), ...] (Cut, src/branchAndCut.ts:18)."""
+        opt = options or make_options()
+        H, W = self._root_shape
+        n = len(cuts_per_node)
+        offs = np.zeros(n + 1, np.int32)
+        np.cumsum([len(c) for c in cuts_per_node], out=offs[1:])
+        flat = [c for cuts in cuts_per_node for c in cuts]
+        sign = np.asarray([c[0] for c in flat], np.float64)
+        var = np.asarray([c[1] for c in flat], np.int32)
+        val = np.asarray([c[2] for c in flat], np.float64)
+        hcap = H + (max((len(c) for c in cuts_per_node), default=0))
+        out = {
+            "status": np.empty(n, np.int32), "value": np.empty(n, np.float64), "pivots": np.empty((n, 2), np.int64),
+            "rhs": np.empty((n, hcap), np.float64), "pos": np.empty((n, W + hcap), np.int32),
+            "var": np.empty((n, W + hcap), np.int32),
+            "matrices": np.empty((n, hcap * W), np.float64) if want_matrices else None, "stride_h": hcap,
+        }
+        self._check(self._lib.yalps_bnb_solve_nodes(self._ctx, n, _ptr(offs), _ptr(sign), _ptr(var), _ptr(val),
+                                                    C.byref(opt), _ptr(out["status"]), _ptr(out["value"]),
+                                                    _ptr(out["pivots"]), _ptr(out["rhs"]), _ptr(out["pos"]),
+                                                    _ptr(out["var"]), _ptr(out["matrices"])))
+        return out
+
+    def solve_tableau(self, matrix: np.ndarray, height: int, width: int, integers: Sequence[int], sign: float,
+                      options: Optional[Options] = None) -> dict:
+        """Numeric part of solve() (src/YALPS.ts:77-91): root simplex + branch and cut when needed."""
+        opt = options or make_options()
+        m = np.ascontiguousarray(matrix, np.float64).reshape(-1)
+        ints = np.ascontiguousarray(integers, np.int32)
+        cap = height + 2 * ints.size
+        rhs = np.empty(cap, np.float64)
+        pos = np.empty(width + cap, np.int32)
+        var = np.empty(width + cap, np.int32)
+        status, out_h, root_status = C.c_int32(), C.c_int32(), C.c_int32()
+        result, root_value = C.c_double(), C.c_double()
+        root_piv = np.zeros(2, np.int64)
+        stats = np.zeros(8, np.int64)
+        self._check(self._lib.yalps_solve(self._ctx, height, width, _ptr(m), _ptr(ints) if ints.size else None,
+                                          int(ints.size), float(sign), C.byref(opt), C.byref(status), C.byref(result),
+                                          C.byref(out_h), _ptr(rhs), _ptr(pos), _ptr(var), C.byref(root_status),
+                                          C.byref(root_value), _ptr(root_piv), _ptr(stats)))
+        h = out_h.value
+        return {
+            "status": status.value, "result": result.value, "height": h, "rhs": rhs[:h], "pos": pos[:width + h],
+            "var": var[:width + h], "root_status": root_status.value, "root_value": root_value.value,
+            "root_pivots": (int(root_piv[0]), int(root_piv[1])),
+            "stats": {"nodes": int(stats[0]), "node_pivots": int(stats[1]), "max_cuts": int(stats[2]),
+                      "max_heap": int(stats[3]), "waves": int(stats[4]), "device_nodes": int(stats[5])},
+        }
+
+    def branch_and_cut(self, integers: Sequence[int], sign: float, init_result: float,
+                       options: Optional[Options] = None) -> dict:
+        """branchAndCut on the root previously given to bnb_set_root (src/branchAndCut.ts:89-176)."""
+        opt = options or make_options()
+        H, W = self._root_shape
+        ints = np.ascontiguousarray(integers, np.int32)
+        cap = H + 2 * ints.size
+        rhs = np.empty(cap, np.float64)
+        pos = np.empty(W + cap, np.int32)
+        var = np.empty(W + cap, np.int32)
+        status, out_h = C.c_int32(), C.c_int32()
+        result = C.c_double()
+        stats = np.zeros(8, np.int64)
+        self._check(self._lib.yalps_branch_and_cut(self._ctx, _ptr(ints), int(ints.size), float(sign),
+                                                   float(init_result), C.byref(opt), C.byref(status), C.byref(result),
+                                                   C.byref(out_h), _ptr(rhs), _ptr(pos), _ptr(var), _ptr(stats)))
+        h = out_h.value
+        return {"status": status.value, "result": result.value, "height": h, "rhs": rhs[:h], "pos": pos[:W + h],
+                "var": var[:W + h],
+                "stats": {"nodes": int(stats[0]), "node_pivots": int(stats[1]), "max_cuts": int(stats[2]),
+                          "max_heap": int(stats[3]), "waves": int(stats[4]), "device_nodes": int(stats[5])}}
+
+    # ------------------------------------------------------------------ probes
+    def round_to_precision(self, x: np.ndarray, precision: float) -> np.ndarray:
+        x = np.ascontiguousarray(x, np.float64).reshape(-1)
+        out = np.empty_like(x)
+        self._check(self._lib.yalps_round_to_precision(self._ctx, x.size, _ptr(x), float(precision), _ptr(out)))
+        return out
+
+    def measure_smem_bandwidth(self) -> tuple:
+        g, c = C.c_double(), C.c_double()
+        self._check(self._lib.yalps_measure_smem_bandwidth(self._ctx, C.byref(g), C.byref(c)))
+        return g.value, c.value

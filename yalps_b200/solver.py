@@ -1,0 +1,130 @@
+"""solve(model, options) / solve_many(models, options): the public API of the reference (src/index.ts:1-3,
+src/YALPS.ts:73-92) in front of the B200 engine.
+
+Model, Options and Solution keep the reference's shapes and spellings (src/types.ts):
+  model   = {"direction", "objective", "constraints", "variables", "integers", "binaries"}
+  options = {"precision", "checkCycles", "maxPivots", "tolerance", "timeout", "maxIterations",
+             "includeZeroVariables"}
+  solution = {"status": "optimal"|"infeasible"|"unbounded"|"timedout"|"cycled", "result", "variables"}
+The tableau is built on the host (tableau.py), the simplex and branch-and-cut numerics run on the GPU
+through the C ABI; there is no CPU solve path.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .engine import Engine, STATUS_NAMES, make_options
+from .tableau import TableauModel, tableau_model
+
+# src/YALPS.ts:52-60
+_DEFAULTS = {
+    "precision": 1e-8,
+    "checkCycles": False,
+    "maxPivots": 8192,
+    "tolerance": 0,
+    "timeout": math.inf,
+    "maxIterations": 32768,
+    "includeZeroVariables": False,
+}
+
+#: exported mutable copy, like `defaultOptions` (src/YALPS.ts:65); editing it does not change solve()
+default_options = dict(_DEFAULTS)
+defaultOptions = default_options
+
+_engines: dict = {}
+
+
+def get_engine(device: int = 0) -> Engine:
+    """Process-wide engine per device (created on first use; raises if there is no CUDA device)."""
+    eng = _engines.get(device)
+    if eng is None:
+        eng = _engines[device] = Engine(device)
+    return eng
+
+
+def _js_round(x: float) -> float:
+    if math.isnan(x) or math.isinf(x) or abs(x) >= 2.0 ** 52:
+        return x
+    r = float(math.floor(x))
+    if x - r >= 0.5:
+        r += 1.0
+    return -0.0 if r == 0.0 and math.copysign(1.0, x) < 0 else r
+
+
+def round_to_precision(num: float, precision: float) -> float:
+    """src/util.ts:1-4 (host copy, used only to format reported variable values)."""
+    rounding = _js_round(1.0 / precision)
+    return _js_round((num + 2.0 ** -52) * rounding) / rounding
+
+
+def _c_options(opt: dict):
+    return make_options(opt["precision"], opt["maxPivots"], opt["checkCycles"], opt["tolerance"], opt["timeout"],
+                        opt["maxIterations"])
+
+
+def _solution(tabmod: TableauModel, status: str, result: float, rhs, pos, var, opt: dict) -> dict:
+    """src/YALPS.ts:8-50: needs only column 0 and the basis arrays of the final tableau."""
+    width = tabmod.tableau.width
+    precision = opt["precision"]
+    names = tabmod.variables
+    if status == "optimal" or (status == "timedout" and not math.isnan(result)):
+        out = []
+        for i, (key, _) in enumerate(names):
+            row = int(pos[i + 1]) - width
+            value = float(rhs[row]) if row >= 0 else 0.0
+            if value > precision:
+                out.append([key, round_to_precision(value, precision)])
+            elif opt["includeZeroVariables"]:
+                out.append([key, 0.0])
+        return {"status": status, "result": -tabmod.sign * result, "variables": out}
+    if status == "unbounded":
+        v = int(var[int(result)]) - 1
+        return {"status": "unbounded", "result": tabmod.sign * math.inf,
+                "variables": [[names[v][0], math.inf]] if 0 <= v < len(names) else []}
+    return {"status": status, "result": math.nan, "variables": []}
+
+
+def solve(model: dict, options: Optional[dict] = None, *, engine: Optional[Engine] = None,
+          info: Optional[dict] = None) -> dict:
+    """Runs the solver on `model` (src/YALPS.ts:73-92).  `info`, if given, receives engine statistics."""
+    tabmod = tableau_model(model)
+    opt = {**_DEFAULTS, **(options or {})}
+    eng = engine or get_engine()
+    t = tabmod.tableau
+    r = eng.solve_tableau(t.matrix, t.height, t.width, tabmod.integers, tabmod.sign, _c_options(opt))
+    if info is not None:
+        info.update(r["stats"], root_status=STATUS_NAMES[r["root_status"]], root_value=r["root_value"],
+                    root_pivots=r["root_pivots"], height=t.height, width=t.width, final_rhs=r["rhs"],
+                    final_pos=r["pos"], final_var=r["var"])
+    return _solution(tabmod, STATUS_NAMES[r["status"]], r["result"], r["rhs"], r["pos"], r["var"], opt)
+
+
+def solve_many(models: Sequence[dict], options: Optional[dict] = None, *, engine: Optional[Engine] = None) -> list:
+    """solveMany(models, options): all root LPs go to the device as ONE ragged batch; models with integer
+    variables whose root is optimal then run branch and cut (node waves) one after another."""
+    opt = {**_DEFAULTS, **(options or {})}
+    copt = _c_options(opt)
+    eng = engine or get_engine()
+    tabmods = [tableau_model(m) for m in models]
+    if not tabmods:
+        return []
+    roots = eng.solve_ragged([tm.tableau.matrix for tm in tabmods],
+                             [(tm.tableau.height, tm.tableau.width) for tm in tabmods], copt,
+                             want_matrices=any(tm.integers for tm in tabmods))
+    out = []
+    for tm, r in zip(tabmods, roots):
+        status = STATUS_NAMES[r["status"]]
+        if not tm.integers or status != "optimal":
+            out.append(_solution(tm, status, r["value"], r["rhs"], r["pos"], r["var"], opt))
+            continue
+        t = tm.tableau
+        eng.bnb_set_root(r["matrix"], t.height, t.width, r["pos"], r["var"], 2 * len(tm.integers))
+        b = eng.branch_and_cut(tm.integers, tm.sign, r["value"], copt)
+        out.append(_solution(tm, STATUS_NAMES[b["status"]], b["result"], b["rhs"], b["pos"], b["var"], opt))
+    return out
+
+
+solveMany = solve_many

@@ -1,0 +1,163 @@
+"""Model -> tableau, host side (the producer at the drop-in boundary).
+
+Same contract as `tableauModel` in the reference (src/tableau.ts:47-137): flat row-major float64
+matrix, row 0 = objective row holding sign*coef, column 0 = RHS, one row per finite bound of each
+merged constraint key (upper row first), one `x <= 1` row per binary after all constraints, identity
+positionOfVariable / variableAtPosition.  tests/tableau.ts pins this layout bit for bit, including
+negative zeros, and tests/test_tableau.py re-expresses those properties.
+
+Unlike the reference this builder is array-oriented: constraint keys are resolved to row numbers
+once, then every (variable, coefficient) pair becomes at most three scattered stores.
+"""
+from __future__ import annotations
+
+import math
+import re
+from dataclasses import dataclass
+from typing import Any, Iterable
+
+import numpy as np
+
+_INDEX_KEY = re.compile(r"0|[1-9][0-9]*")
+
+
+def entries(obj) -> Iterable:
+    """Pairs of a mapping-like argument in the order the reference would iterate it.
+
+    dict plays the role of a JS object: canonical array-index keys first in ascending numeric order,
+    then the remaining keys in insertion order (what Object.entries yields, src/tableau.ts:37).
+    Any other iterable is taken as an iterable of (key, value) pairs (Array / Map, src/tableau.ts:36).
+    """
+    if isinstance(obj, dict):
+        numeric = [k for k in obj if isinstance(k, str) and _INDEX_KEY.fullmatch(k) and int(k) < 4294967295]
+        if not numeric:
+            return list(obj.items())
+        numeric.sort(key=int)
+        seen = set(numeric)
+        return [(k, obj[k]) for k in numeric] + [(k, v) for k, v in obj.items() if k not in seen]
+    return obj
+
+
+def _as_set(spec):
+    """src/tableau.ts:41-45: True stays True, False/None -> empty set, iterables -> set."""
+    if spec is True:
+        return True
+    if spec is None or spec is False:
+        return frozenset()
+    return spec if isinstance(spec, (set, frozenset)) else set(spec)
+
+
+def _field(constraint, name):
+    if isinstance(constraint, dict):
+        return constraint.get(name)
+    return getattr(constraint, name, None)
+
+
+@dataclass
+class Tableau:
+    """src/tableau.ts:9-15"""
+
+    matrix: np.ndarray  # float64[height*width], row-major
+    width: int
+    height: int
+    position_of_variable: np.ndarray  # int32[width+height]
+    variable_at_position: np.ndarray  # int32[width+height]
+
+
+@dataclass
+class TableauModel:
+    """src/tableau.ts:26-31"""
+
+    tableau: Tableau
+    sign: float
+    variables: list  # [(key, coefficients)]
+    integers: list  # variable ids (1-based columns) that must be integral
+
+
+def tableau_model(model: dict) -> TableauModel:
+    sign = -1.0 if model.get("direction") == "minimize" else 1.0
+    objective = model.get("objective")
+    variables = list(entries(model["variables"]))
+    nvars = len(variables)
+
+    # integer / binary marking (src/tableau.ts:57-71); binary wins over integer
+    ints: list[int] = []
+    binary_cols: list[int] = []
+    integers, binaries = model.get("integers"), model.get("binaries")
+    if integers is not None or binaries is not None:
+        bin_set = _as_set(binaries)
+        int_set = True if bin_set is True else _as_set(integers)
+        for col, (key, _) in enumerate(variables, start=1):
+            if bin_set is True or key in bin_set:
+                binary_cols.append(col)
+                ints.append(col)
+            elif int_set is True or key in int_set:
+                ints.append(col)
+
+    # merge constraints per key, first-seen order (src/tableau.ts:73-80)
+    lower: dict[Any, float] = {}
+    upper: dict[Any, float] = {}
+    for key, con in entries(model["constraints"]):
+        eq = _field(con, "equal")
+        lo = eq if eq is not None else _field(con, "min")
+        hi = eq if eq is not None else _field(con, "max")
+        lo = -math.inf if lo is None else float(lo)
+        hi = math.inf if hi is None else float(hi)
+        if key in lower:
+            lower[key] = max(lower[key], lo)
+            upper[key] = min(upper[key], hi)
+        else:
+            lower[key] = max(-math.inf, lo)
+            upper[key] = min(math.inf, hi)
+
+    # row numbering: upper row first, then lower row (src/tableau.ts:82-86)
+    up_row: dict[Any, int] = {}
+    lo_row: dict[Any, int] = {}
+    rows = 1
+    rhs_rows: list[int] = []
+    rhs_vals: list[float] = []
+    for key in lower:
+        if math.isfinite(upper[key]):
+            up_row[key] = rows
+            rhs_rows.append(rows)
+            rhs_vals.append(upper[key])
+            rows += 1
+        if math.isfinite(lower[key]):
+            lo_row[key] = rows
+            rhs_rows.append(rows)
+            rhs_vals.append(-lower[key])
+            rows += 1
+
+    width = nvars + 1
+    height = rows + len(binary_cols)
+    matrix = np.zeros(height * width, dtype=np.float64)
+
+    # coefficients: later duplicates of a key overwrite earlier ones (src/tableau.ts:100-117)
+    idx: list[int] = []
+    val: list[float] = []
+    for col, (_, coefs) in enumerate(variables, start=1):
+        for ckey, coef in entries(coefs):
+            coef = float(coef)
+            if objective is not None and ckey == objective:
+                idx.append(col)
+                val.append(sign * coef)
+            r = up_row.get(ckey)
+            if r is not None:
+                idx.append(r * width + col)
+                val.append(coef)
+            r = lo_row.get(ckey)
+            if r is not None:
+                idx.append(r * width + col)
+                val.append(-coef)
+    if idx:
+        # numpy fancy assignment applies repeated indices in order, so the last one wins like the reference
+        matrix[np.asarray(idx, dtype=np.int64)] = np.asarray(val, dtype=np.float64)
+    if rhs_rows:
+        matrix[np.asarray(rhs_rows, dtype=np.int64) * width] = np.asarray(rhs_vals, dtype=np.float64)
+    for k, col in enumerate(binary_cols):  # src/tableau.ts:130-134
+        r = rows + k
+        matrix[r * width] = 1.0
+        matrix[r * width + col] = 1.0
+
+    ident = np.arange(width + height, dtype=np.int32)
+    return TableauModel(Tableau(matrix, width, height, ident.copy(), ident.copy()), sign, variables, ints)
