@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the batched simplex hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload config2|...]
+
+A "step" is one pass of the hot path (the batched simplex kernel) over one batch of synthetic LPs.
+N=1 workload = BASELINE.json configs[1]: 65,536 synthetic feasible dense LPs 32x64 (tableau 33x65 fp64),
+generated on the device with the integer-hash PRNG of the reference's test helpers.
+For N>1 (torchrun, one rank per GPU) every rank solves its own 65,536 LPs (weak scaling, no data-path
+collective: LPs are independent); the time is the max over ranks, the value the sum of all ranks' pivots.
+
+`value`     pivots/s with the tableaus already resident in HBM (device entry point of the C ABI)
+`e2e`       pivots/s through the host C-ABI call (yalps_solve_batch) from pinned host buffers, H2D of the
+            tableaus and D2H of status/value/pivots/RHS/basis inside the timed region
+`roofline`  SURVEY 8(d): algorithmic bytes = 16*H*W per pivot, against the shared-memory stream bandwidth
+            measured live (K1 keeps the tableau in shared memory) -- the HBM view is reported alongside
+`cpu_baseline` the CPU restatement of the reference loop (oracle/, C -O2 -ffp-contract=off; Node is not
+            available) on the box's host cores, bounded sample of the same workload
+
+--impl reference times that CPU restatement alone (all host threads) and prints the same JSON shape.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n LPs per GPU, m rows, n vars, neg rows)
+    "config2": (65536, 32, 64, 0),
+    "config2_phase1": (65536, 32, 64, 8),
+    "small": (4096, 32, 64, 0),
+}
+METRIC = "batched_simplex_pivots_per_s"
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(n_lp, m, nv, neg, first, threads, salt=0x5BD1E995):
+    """Times the oracle (CPU restatement of the reference loop) on n_lp LPs of the workload."""
+    import numpy as np
+    from oracle import lib as O
+    mats = O.generate_synthetic(first, n_lp, m, nv, neg, salt)
+    t0 = time.perf_counter()
+    res = O.simplex_batch(mats, nv + 1, m + 1, nthreads=threads, want_pos=False)
+    dt = time.perf_counter() - t0
+    piv = int(res["pivots"].sum())
+    assert (res["status"] == 0).all() or neg > 0
+    return piv / dt, n_lp / dt, piv, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n, m, nv, neg = WORKLOADS[args.workload]
+    cores = host_cores()
+    sample = min(n, 16384)
+    for _ in range(args.warmup):
+        cpu_baseline(min(sample, 2048), m, nv, neg, 0, cores)
+    tot_piv, tot_t, tot_lp = 0, 0.0, 0
+    for s in range(args.steps):
+        _, _, piv, dt = cpu_baseline(sample, m, nv, neg, (s * sample) % n, cores)
+        tot_piv += piv
+        tot_t += dt
+        tot_lp += sample
+    value = tot_piv / tot_t
+    one_thread = cpu_baseline(2048, m, nv, neg, 0, 1)[0]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "pivots/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload, n, m, nv, neg), "l2": "inputs larger than L2"},
+        "lps_per_s": tot_lp / tot_t,
+        "cpu_baseline": {"value": value, "unit": "pivots/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} LPs of the workload per step, {cores} threads; single thread: "
+                                   f"{one_thread:.4g} pivots/s",
+                         "note": "C restatement of src/simplex.ts (oracle/), not Node/V8: no JS engine in this image"},
+        "e2e": {"value": value, "unit": "pivots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_name(name, n, m, nv, neg):
+    return (f"{name}: {n} synthetic dense LPs {m}x{nv} fp64 per GPU (tableau {m + 1}x{nv + 1}, "
+            f"{'feasible start' if not neg else str(neg) + ' infeasible rows'}), one tableau per CTA in shared memory")
+
+
+def run_native(args):
+    import numpy as np
+    import torch
+    import yalps_b200
+    from yalps_b200.engine import make_options
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    n, m, nv, neg = WORKLOADS[args.workload]
+    H, W = m + 1, nv + 1
+    cells = H * W
+    eng = yalps_b200.Engine(local)
+    if args.threads or args.path:
+        eng.set_tuning(args.path, args.threads)
+    opt = make_options()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # ---- inputs resident in HBM (LP ids are disjoint per rank)
+    d_in = torch.empty(n * cells, dtype=torch.float64, device=dev)
+    eng.generate_synthetic_device(rank * n, n, m, nv, d_in.data_ptr(), neg_rows=neg, stream=stream)
+    d_status = torch.empty(n, dtype=torch.int32, device=dev)
+    d_value = torch.empty(n, dtype=torch.float64, device=dev)
+    d_piv = torch.empty(n, 2, dtype=torch.int64, device=dev)
+    d_rhs = torch.empty(n, H, dtype=torch.float64, device=dev)
+    d_pos = torch.empty(n, W + H, dtype=torch.int32, device=dev)
+    d_var = torch.empty(n, W + H, dtype=torch.int32, device=dev)
+
+    def step():
+        eng.solve_batch_device(n, H, W, d_in.data_ptr(), opt, d_status=d_status.data_ptr(),
+                               d_value=d_value.data_ptr(), d_pivots=d_piv.data_ptr(), d_rhs=d_rhs.data_ptr(),
+                               d_pos=d_pos.data_ptr(), d_var=d_var.data_ptr(), stream=stream)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    pivots_per_step = int(d_piv.sum().item())
+    statuses = torch.bincount(d_status.to(torch.int64), minlength=5).tolist()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_begin = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_begin.record()
+    for e0, e1 in evs:
+        e0.record()
+        step()
+        e1.record()
+    t_end.record()
+    barrier()
+    launches = eng.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = t_begin.elapsed_time(t_end)
+    kernel_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs) / args.steps
+
+    # ---- e2e: host buffers through the reference-facing C-ABI call
+    h_in = eng.pinned_empty((n * cells,), np.float64)
+    torch.cuda.synchronize()
+    h_in[:] = d_in.cpu().numpy()
+    e2e_steps = max(1, min(args.steps, 5))
+    out = eng.solve_batch(h_in, H, W, opt)  # warm-up (allocates the staging pool)
+    assert int(out["pivots"].sum()) == pivots_per_step
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        out = eng.solve_batch(h_in, H, W, opt)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    h2d = n * cells * 8
+    d2h = n * (4 + 8 + 16 + H * 8 + 2 * (W + H) * 4)
+
+    # ---- max over ranks, sum of work
+    t = torch.tensor([elapsed_ms, e2e_s * 1e3, kernel_ms], dtype=torch.float64, device=dev)
+    work = torch.tensor([float(pivots_per_step)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+    elapsed_ms, e2e_ms, kernel_ms_max = (float(x) for x in t.tolist())
+    total_pivots_step = float(work.item())
+
+    if rank == 0:
+        value = total_pivots_step * args.steps / (elapsed_ms * 1e-3)
+        bytes_per_pivot = 16 * H * W  # SURVEY 8(d), dense tableau
+        achieved = pivots_per_step * bytes_per_pivot / (kernel_ms * 1e-3) / 1e9
+        smem_gbs, _ = eng.measure_smem_bandwidth()
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        hbm_alg = n * (cells * 8 + 4 + 8 + 16 + H * 8 + 2 * (W + H) * 4) / (kernel_ms * 1e-3) / 1e9
+        cores = host_cores()
+        cpu_n = min(n, 16384)
+        cpu_v, cpu_lps, _, cpu_dt = cpu_baseline(cpu_n, m, nv, neg, 0, cores)
+        cpu_1, _, _, _ = cpu_baseline(min(n, 4096), m, nv, neg, 0, 1)
+        line = {
+            "metric": METRIC, "value": value, "unit": "pivots/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload, n, m, nv, neg),
+                       "l2": f"inputs larger than L2 ({n * cells * 8 / 1e6:.0f} MB per GPU read every step)",
+                       "parallelism": f"{world} x independent LP shards, no collective on the data path",
+                       "pivots_per_step_per_gpu": pivots_per_step, "status_counts": statuses},
+            "lps_per_s": n * world * args.steps / (elapsed_ms * 1e-3),
+            "e2e": {"value": total_pivots_step / (e2e_ms * 1e-3), "unit": "pivots/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "lps_per_s": n * world / (e2e_ms * 1e-3),
+                    "api": "yalps_solve_batch (host pointers, pinned input)"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "smem", "achieved": achieved, "peak": smem_gbs, "unit": "GB/s",
+                         "frac": achieved / smem_gbs, "traffic": None,
+                         "peak_source": "measured live: ld/st.shared.f64 stream on all SMs (yalps_measure_smem_bandwidth)",
+                         "bytes_per_unit": bytes_per_pivot, "units_per_launch": pivots_per_step,
+                         "kernel_ms": kernel_ms, "kernel": "k_simplex<NW,KC,resident>",
+                         "hbm": {"achieved": hbm_alg, "peak": hbm_peak, "frac": hbm_alg / hbm_peak,
+                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                                 "note": "tableau read once + results written once per LP"}},
+            "cpu_baseline": {"value": cpu_v, "unit": "pivots/s", "cores": cores, "kind": "port",
+                             "sample": f"first {cpu_n} LPs of the workload, {cores} threads, {cpu_dt:.2f} s; "
+                                       f"single thread {cpu_1:.4g} pivots/s",
+                             "lps_per_s": cpu_lps,
+                             "note": "C restatement of src/simplex.ts (oracle/), not Node/V8"},
+        }
+        print(json.dumps(line))
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["native", "reference"], default="native")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="config2")
+    ap.add_argument("--threads", type=int, default=0, help="threads per LP (0 = auto)")
+    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 smem, 2 gmem")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_native(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -45,35 +45,47 @@ struct BatchArgs {
 
 // Shared-memory carve-up, identical on host and device.
 struct SmemLayout {
-  size_t off_M, off_prow, off_colbuf, off_colnew, off_redv, off_redi, off_nz, off_pos, off_var, total;
-  __host__ __device__ static int ld_for(int W) { return W | 1; }  // odd stride: conflict-free column reads
-  __host__ __device__ SmemLayout(int Hcap, int W, bool resident) {
+  size_t off_A, off_b, off_colbuf, off_colnew, off_misc, off_red, off_var, total;
+  int ldA;
+  // Resident layout: A rows 16-byte aligned (even ldA) with ldA/2 odd so that the strided pivot-column
+  // reads spread over the banks.
+  __host__ __device__ static int ld_for(int W) {
+    int ld = (W - 1 + 1) & ~1;
+    if (ld < 2) ld = 2;
+    if (((ld >> 1) & 1) == 0) ld += 2;
+    return ld;
+  }
+  __host__ __device__ SmemLayout(int Hcap, int Wcap, bool resident) {
     size_t o = 0;
-    off_M = o;
-    if (resident) o += (size_t)Hcap * ld_for(W) * 8;
-    off_prow = o;
-    o += (size_t)((W + 1) & ~1) * 8;
+    ldA = ld_for(Wcap);
+    off_A = o;
+    if (resident) o += (size_t)Hcap * ldA * 8;
+    off_b = o;
+    if (resident) o += (size_t)((Hcap + 1) & ~1) * 8;
     off_colbuf = o;
-    o += (size_t)Hcap * 8;
+    o += (size_t)((Hcap + 3) & ~3) * 8;
     off_colnew = o;
-    o += (size_t)Hcap * 8;
-    off_redv = o;
-    o += 64 * 8;
-    off_redi = o;
-    o += 64 * 4;
-    off_nz = o;
-    o += (size_t)((W + 31) / 32 + 1) * 4;
-    off_pos = o;
-    if (resident) o += (size_t)(W + Hcap) * 4;
+    o += (size_t)((Hcap + 1) & ~1) * 8;
+    off_misc = o;
+    o += 16;
+    off_red = o;
+    o += 192 * 4;
     off_var = o;
-    if (resident) o += (size_t)(W + Hcap) * 4;
+    if (resident) o += (size_t)(Wcap + Hcap) * 4;
     total = (o + 15) & ~(size_t)15;
   }
 };
 
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <int NW, int KC, bool kResident>
 __global__ void __launch_bounds__(NW * 32) k_simplex(const BatchArgs a) {
   constexpr int NT = NW * 32;
+  constexpr int VW = kResident ? 2 : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ long long s_lp;
   const int tid = threadIdx.x;
@@ -112,65 +124,89 @@ __global__ void __launch_bounds__(NW * 32) k_simplex(const BatchArgs a) {
     LpView t;
     t.H = H;
     t.W = W;
-    t.ld = kResident ? SmemLayout::ld_for(W) : W;
-    t.M = kResident ? reinterpret_cast<double *>(smem_raw + L.off_M) : a.work + moff;
-    t.pos = kResident ? reinterpret_cast<int *>(smem_raw + L.off_pos) : a.pos_out + poff;
-    t.var = kResident ? reinterpret_cast<int *>(smem_raw + L.off_var) : a.var_out + poff;
+    if (kResident) {
+      t.A = reinterpret_cast<double *>(smem_raw + L.off_A);
+      t.b = reinterpret_cast<double *>(smem_raw + L.off_b);
+      t.ldA = SmemLayout::ld_for(W);
+      t.ldb = 1;
+      t.var = reinterpret_cast<int *>(smem_raw + L.off_var);
+    } else {
+      t.A = a.work + moff + 1;
+      t.b = a.work + moff;
+      t.ldA = t.ldb = W;
+      t.var = a.var_out + poff;
+    }
     Scratch s;
-    s.prow = reinterpret_cast<double *>(smem_raw + L.off_prow);
     s.colbuf = reinterpret_cast<double *>(smem_raw + L.off_colbuf);
     s.colnew = reinterpret_cast<double *>(smem_raw + L.off_colnew);
-    s.red_v = reinterpret_cast<double *>(smem_raw + L.off_redv);
-    s.red_i = reinterpret_cast<int *>(smem_raw + L.off_redi);
-    s.nzmask = reinterpret_cast<unsigned *>(smem_raw + L.off_nz);
+    s.misc = reinterpret_cast<double *>(smem_raw + L.off_misc);
+    s.red = reinterpret_cast<unsigned *>(smem_raw + L.off_red);
     s.hist = a.hist ? a.hist + (size_t)blockIdx.x * 2 * a.hist_cap : nullptr;
     s.hist_cap = a.hist_cap;
 
-    // ---- load / assemble the tableau
-    const int ld = t.ld;
-    if (a.mode == kModeNodes) {
-      // applyCuts (src/branchAndCut.ts:22-61): root copy, then one row per cut
-      const int rootH = a.H;
-      for (int r = tid >> 5; r < rootH; r += NW) {
-        const double *src = a.root + (size_t)r * W;
-        double *dst = t.M + (size_t)r * ld;
-        for (int c = tid & 31; c < W; c += 32) dst[c] = src[c];
+    // ---- load / assemble the tableau (reference layout, row stride W) into the (A, b) view
+    const int ldA = t.ldA, ldb = t.ldb;
+    const int rootH = a.mode == kModeNodes ? a.H : H;
+    const double *src = a.mode == kModeNodes ? a.root : a.in + moff;
+    if (kResident) {
+      // asynchronous 8-byte copies (LDGSTS) straight into the (A, b) layout: every copy of the tableau is in
+      // flight before the first one is waited for, so the load costs one memory latency, not one per row
+      const int qd = NT / W, rm = NT % W;
+      int r = tid / W, c = tid % W;
+      const int total = rootH * W;
+      for (int k = tid; k < total; k += NT) {
+        double *dst = (c == 0) ? (t.b + r) : (t.A + (size_t)r * ldA + (c - 1));
+        cp_async8(dst, src + k);
+        r += qd;
+        c += rm;
+        if (c >= W) {
+          c -= W;
+          r++;
+        }
       }
+    } else if (src != a.work + moff) {
+      const size_t cells = (size_t)rootH * W;
+      double *dst = a.work + moff;
+      for (size_t k = tid; k < cells; k += NT) dst[k] = src[k];
+    }
+    if (a.mode == kModeNodes) {
+      // applyCuts (src/branchAndCut.ts:22-61): one row per cut below the root rows
       const int cbeg = a.cut_off[lp];
       for (int i = 0; i < ncuts; i++) {
         const double sign = a.cut_sign[cbeg + i], value = a.cut_val[cbeg + i];
         const int p = a.root_pos[a.cut_var[cbeg + i]];
-        double *dst = t.M + (size_t)(rootH + i) * ld;
+        const int r = rootH + i;
+        double *dA = t.A + (size_t)r * ldA - 1;
         if (p < W) {
-          for (int c = tid; c < W; c += NT) dst[c] = (c == 0) ? __dmul_rn(sign, value) : (c == p ? sign : 0.0);
+          for (int c = tid; c < W; c += NT) {
+            if (c == 0)
+              t.b[(size_t)r * ldb] = __dmul_rn(sign, value);
+            else
+              dA[c] = (c == p) ? sign : 0.0;
+          }
         } else {
-          const double *src = a.root + (size_t)(p - W) * W;
-          for (int c = tid; c < W; c += NT)
-            dst[c] = (c == 0) ? __dmul_rn(sign, __dsub_rn(value, src[0])) : __dmul_rn(-sign, src[c]);
+          const double *sr = a.root + (size_t)(p - W) * W;
+          for (int c = tid; c < W; c += NT) {
+            if (c == 0)
+              t.b[(size_t)r * ldb] = __dmul_rn(sign, __dsub_rn(value, sr[0]));
+            else
+              dA[c] = __dmul_rn(-sign, sr[c]);
+          }
         }
       }
       const int nroot = W + rootH;
-      for (int k = tid; k < W + H; k += NT) {
-        t.pos[k] = k < nroot ? a.root_pos[k] : k;
-        t.var[k] = k < nroot ? a.root_var[k] : k;
-      }
+      for (int k = tid; k < W + H; k += NT) t.var[k] = k < nroot ? a.root_var[k] : k;
     } else {
-      const double *src = a.in + moff;
-      if (kResident) {
-        for (int r = tid >> 5; r < H; r += NW)
-          for (int c = tid & 31; c < W; c += 32) t.M[(size_t)r * ld + c] = src[(size_t)r * W + c];
-      } else if (src != t.M) {
-        const size_t cells = (size_t)H * W;
-        for (size_t k = tid; k < cells; k += NT) t.M[k] = src[k];
-      }
-      for (int k = tid; k < W + H; k += NT) {
-        t.pos[k] = k;
-        t.var[k] = k;
-      }
+      for (int k = tid; k < W + H; k += NT) t.var[k] = k;
     }
+    if (kResident) {  // zero the padding columns so that vector loads past W-1 read defined values
+      const int pad = ldA - (W - 1);
+      for (int k = tid; k < H * pad; k += NT) t.A[(size_t)(k / pad) * ldA + (W - 1) + (k % pad)] = 0.0;
+    }
+    if (kResident) cp_async_wait_all();
     __syncthreads();
 
-    const LpResult res = simplex_cta<NW, KC>(t, s, a.precision, a.max_pivots, a.check_cycles);
+    const LpResult res = simplex_cta<NW, KC, VW>(t, s, a.precision, a.max_pivots, a.check_cycles);
     __syncthreads();
 
     // ---- outputs
@@ -183,21 +219,19 @@ __global__ void __launch_bounds__(NW * 32) k_simplex(const BatchArgs a) {
       }
     }
     if (a.rhs_out)
-      for (int r = tid; r < H; r += NT) a.rhs_out[roff + r] = t.M[(size_t)r * ld];
-    if (kResident) {
-      if (a.pos_out)
-        for (int k = tid; k < W + H; k += NT) a.pos_out[poff + k] = t.pos[k];
-      if (a.var_out)
-        for (int k = tid; k < W + H; k += NT) a.var_out[poff + k] = t.var[k];
-    }
+      for (int r = tid; r < H; r += NT) a.rhs_out[roff + r] = t.b[(size_t)r * ldb];
+    if (a.pos_out)  // positionOfVariable is the inverse permutation of variableAtPosition
+      for (int k = tid; k < W + H; k += NT) a.pos_out[poff + t.var[k]] = k;
+    if (kResident && a.var_out)
+      for (int k = tid; k < W + H; k += NT) a.var_out[poff + k] = t.var[k];
     if (a.mat_out) {
       double *dst = a.mat_out + moff;
-      if (kResident) {
-        for (int r = tid >> 5; r < H; r += NW)
-          for (int c = tid & 31; c < W; c += 32) dst[(size_t)r * W + c] = t.M[(size_t)r * ld + c];
-      } else if (dst != t.M) {
-        const size_t cells = (size_t)H * W;
-        for (size_t k = tid; k < cells; k += NT) dst[k] = t.M[k];
+      if (kResident || dst != a.work + moff) {
+        for (int r = tid >> 5; r < H; r += NW) {
+          const double *sA = t.A + (size_t)r * ldA - 1;
+          double *dr = dst + (size_t)r * W;
+          for (int c = tid & 31; c < W; c += 32) dr[c] = (c == 0) ? t.b[(size_t)r * ldb] : sA[c];
+        }
       }
     }
     __syncthreads();

@@ -5,10 +5,24 @@
 // The reference is a sequential scalar loop; here every selection is a
 // lexicographic (value, index) arg-reduction that reproduces the sequential
 // "strict comparison, first index wins" outcome, and the Gauss-Jordan update is a
-// row-parallel rank-1 update.  Arithmetic is IEEE binary64 with the reference's
+// column-parallel rank-1 update.  Arithmetic is IEEE binary64 with the reference's
 // rounding sequence: products and differences are separate roundings
 // (__dmul_rn / __dsub_rn are never contracted to FMA) and every quotient is a
 // true division (__ddiv_rn), so trajectories are bit-identical.
+//
+// Data layout of one LP (LpView): the RHS column (column 0 of the reference
+// tableau) is split from the coefficient block,
+//     b[r*ldb]          = M[r, 0]
+//     A[r*ldA + (c-1)]  = M[r, c],  1 <= c < W
+// so that for the shared-memory resident kernel A rows are 16-byte aligned and a
+// lane updates two adjacent cells per ld/st.shared.v2.f64 (VW = 2).  The HBM
+// resident kernel views the reference layout in place (A = M+1, b = M, ldA = ldb
+// = W) with 8-byte accesses (VW = 1).
+//
+// Work split: thread t owns the vector-columns t, t+NT, ... (KC of them, pivot-row
+// values kept in registers from the normalisation to the update) and walks down
+// ALL rows, so the per-row pivot-column coefficient is one broadcast load per
+// warp and the inner loop is  ld - mul - sub - st  with no index arithmetic.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -16,7 +30,7 @@
 
 namespace yalps {
 
-constexpr double kTiny = 1e-16;      // sparsity threshold of src/simplex.ts:18,31
+constexpr double kTiny = 1e-16;  // sparsity threshold of src/simplex.ts:18,31
 constexpr int kNone = 0x7fffffff;
 
 enum : int {
@@ -47,32 +61,6 @@ __device__ __forceinline__ double round_to_precision(double num, double precisio
   return __ddiv_rn(js_round(__dmul_rn(shifted, rounding)), rounding);
 }
 
-struct Arg {
-  double v;
-  int i;
-};
-
-// "candidate (v,i) beats incumbent (bv,bi)": strict comparison on the value, lowest index on ties --
-// the parallel equivalent of the reference's ascending scans with `>` / `<`.
-template <bool kMax>
-__device__ __forceinline__ bool beats(double v, int i, double bv, int bi) {
-  return kMax ? (v > bv || (v == bv && i < bi)) : (v < bv || (v == bv && i < bi));
-}
-
-template <bool kMax>
-__device__ __forceinline__ Arg warp_arg(Arg a) {
-#pragma unroll
-  for (int off = 16; off; off >>= 1) {
-    const double v = __shfl_xor_sync(0xffffffffu, a.v, off);
-    const int i = __shfl_xor_sync(0xffffffffu, a.i, off);
-    if (beats<kMax>(v, i, a.v, a.i)) {
-      a.v = v;
-      a.i = i;
-    }
-  }
-  return a;
-}
-
 template <int NW>
 __device__ __forceinline__ void cta_sync() {
   if (NW == 1)
@@ -81,43 +69,75 @@ __device__ __forceinline__ void cta_sync() {
     __syncthreads();
 }
 
-// CTA-wide arg-reduction; every thread returns the same winner.  red_v/red_i hold 2x32 slots and are
-// used alternately (parity) so that one barrier per reduction is enough.
+// ---- arg-reductions on order-preserving integer keys ---------------------------------------------------
+// key(x) is monotone in x with key(-0) == key(+0); a lane without a candidate carries kNoKey and kNone.
+// "Best" = largest (kMax) or smallest key, lowest index on ties: the parallel equivalent of the reference's
+// ascending scans with strict `>` / `<`.  Three redux.sync per warp instead of a 5-step shuffle butterfly.
+__device__ __forceinline__ unsigned long long order_key(double x) {
+  const long long bits = __double_as_longlong(__dadd_rn(x, 0.0));  // -0 -> +0
+  return bits < 0 ? ~(unsigned long long)bits : ((unsigned long long)bits | 0x8000000000000000ULL);
+}
+
+template <bool kMax>
+__device__ __forceinline__ unsigned long long no_key() {
+  return kMax ? 0ULL : ~0ULL;
+}
+
+struct Best {
+  unsigned hi, lo;
+  int idx;
+};
+
+template <bool kMax>
+__device__ __forceinline__ Best warp_best(unsigned hi, unsigned lo, int idx) {
+  Best w;
+  if (kMax) {
+    w.hi = __reduce_max_sync(0xffffffffu, hi);
+    w.lo = __reduce_max_sync(0xffffffffu, hi == w.hi ? lo : 0u);
+  } else {
+    w.hi = __reduce_min_sync(0xffffffffu, hi);
+    w.lo = __reduce_min_sync(0xffffffffu, hi == w.hi ? lo : 0xffffffffu);
+  }
+  w.idx = (int)__reduce_min_sync(0xffffffffu, (hi == w.hi && lo == w.lo) ? (unsigned)idx : (unsigned)kNone);
+  return w;
+}
+
+// CTA-wide: every thread returns the winning index (kNone if no lane had a candidate).
+// red holds 2 x 3 x 32 words, used alternately (parity) so that one barrier per reduction suffices.
 template <bool kMax, int NW>
-__device__ __forceinline__ Arg block_arg(Arg a, double *red_v, int *red_i, int &parity) {
-  a = warp_arg<kMax>(a);
-  if (NW == 1) return a;
+__device__ __forceinline__ int block_best(unsigned long long key, int idx, unsigned *red, int &parity) {
+  Best w = warp_best<kMax>((unsigned)(key >> 32), (unsigned)key, idx);
+  if (NW == 1) return w.idx;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double *rv = red_v + parity * 32;
-  int *ri = red_i + parity * 32;
+  unsigned *r = red + parity * 96;
   parity ^= 1;
   if (lane == 0) {
-    rv[warp] = a.v;
-    ri[warp] = a.i;
+    r[warp] = w.hi;
+    r[32 + warp] = w.lo;
+    r[64 + warp] = (unsigned)w.idx;
   }
   __syncthreads();
-  Arg b;
-  b.v = lane < NW ? rv[lane] : (kMax ? -d_inf() : d_inf());
-  b.i = lane < NW ? ri[lane] : kNone;
-  return warp_arg<kMax>(b);
+  const unsigned long long nk = no_key<kMax>();
+  const unsigned hi = lane < NW ? r[lane] : (unsigned)(nk >> 32);
+  const unsigned lo = lane < NW ? r[32 + lane] : (unsigned)nk;
+  const int id = lane < NW ? (int)r[64 + lane] : kNone;
+  return warp_best<kMax>(hi, lo, id).idx;
 }
 
 struct LpView {
-  double *M;  // tableau, row stride ld (shared or global memory)
-  int ld;
-  int H, W;
-  int *pos;  // positionOfVariable[W+H]
-  int *var;  // variableAtPosition[W+H]
+  double *A;  // coefficient block, A[r*ldA + j] = M[r, j+1]
+  double *b;  // RHS column, b[r*ldb] = M[r, 0]
+  int ldA, ldb;
+  int H, W;   // reference tableau shape (W counts the RHS column)
+  int *var;   // variableAtPosition[W+H]; positionOfVariable is its inverse and is rebuilt on output
 };
 
 struct Scratch {
-  double *prow;      // [W]  normalised pivot row
-  double *colbuf;    // [H]  pivot column before the update
-  double *colnew;    // [H]  -coef/q
-  double *red_v;     // [64]
-  int *red_i;        // [64]
-  unsigned *nzmask;  // [ceil(W/32)] bit c%32 of word c/32: |old pivot-row cell| > 1e-16
-  int *hist;         // [2*hist_cap] (leaving var, entering var) pairs, checkCycles only
+  double *colbuf;  // [H]  pivot column before the update; 0 for rows the update must not touch
+  double *colnew;  // [H]  -coef/q
+  double *misc;    // [2]  normalised RHS of the pivot row, its non-zero flag
+  unsigned *red;   // [192]
+  int *hist;       // [2*hist_cap] (leaving var, entering var) pairs, checkCycles only
   int hist_cap;
 };
 
@@ -145,93 +165,197 @@ __device__ __forceinline__ bool history_has_cycle(const int *hist, int len) {
   return __syncthreads_or(found) != 0;
 }
 
-// src/simplex.ts:5-39.  NW warps, KC pivot-row cells per lane kept in registers per column chunk.
-template <int NW, int KC>
+template <int VW>
+struct Cells;
+template <>
+struct Cells<1> {
+  double x;
+  __device__ __forceinline__ void load(const double *p) { x = *p; }
+  __device__ __forceinline__ double get(int) const { return x; }
+};
+template <>
+struct Cells<2> {
+  double2 v;
+  __device__ __forceinline__ void load(const double *p) { v = *reinterpret_cast<const double2 *>(p); }
+  __device__ __forceinline__ double get(int e) const { return e ? v.y : v.x; }
+};
+
+// RU rows of the rank-1 update for this thread's KC vector-columns, as one straight-line block: all loads are
+// issued before the arithmetic so that RU*KC independent ld-mul-sub-st chains are in flight per thread.
+//   p     normalised pivot-row cells (0.0 where the old cell was flushed)
+//   st    bit k*VW+e: cell e of vector-column k is rewritten (old pivot-row cell > 1e-16, or padding)
+//   full  bit k: all VW cells of vector-column k are rewritten
+//   act   bit i: row i of the group is active (pivot-column coefficient > 1e-16 and not the pivot row)
+// kPartial = some thread of the CTA has a vector-column with only one of its two cells rewritten.
+template <int NT, int KC, int VW, int RU, bool kPartial>
+__device__ __forceinline__ void update_rows(double *__restrict__ Ar, int ldA, const double (&p)[KC][VW], unsigned st,
+                                            unsigned full, const double (&coef)[RU], unsigned act) {
+  Cells<VW> x[RU][KC];
+#pragma unroll
+  for (int i = 0; i < RU; i++)
+#pragma unroll
+    for (int k = 0; k < KC; k++) {
+      const bool need = kPartial ? (((st >> (k * VW)) & ((1u << VW) - 1u)) != 0u) : (((full >> k) & 1u) != 0u);
+      if (((act >> i) & 1u) && need) x[i][k].load(Ar + (size_t)i * ldA + (size_t)VW * NT * k);
+    }
+#pragma unroll
+  for (int i = 0; i < RU; i++)
+#pragma unroll
+    for (int k = 0; k < KC; k++) {
+      double *dst = Ar + (size_t)i * ldA + (size_t)VW * NT * k;
+      const bool on = (act >> i) & 1u;
+      if (VW == 2) {
+        const double t0 = __dsub_rn(x[i][k].get(0), __dmul_rn(coef[i], p[k][0]));
+        const double t1 = __dsub_rn(x[i][k].get(1), __dmul_rn(coef[i], p[k][VW - 1]));
+        if (on && ((full >> k) & 1u)) {
+          *reinterpret_cast<double2 *>(dst) = make_double2(t0, t1);
+        } else if (kPartial && on) {
+          if ((st >> (k * VW)) & 1u) dst[0] = t0;
+          if ((st >> (k * VW + 1)) & 1u) dst[1] = t1;
+        }
+      } else {
+        const double t0 = __dsub_rn(x[i][k].get(0), __dmul_rn(coef[i], p[k][0]));
+        if (on && ((full >> k) & 1u)) dst[0] = t0;
+      }
+    }
+}
+
+template <int NT, int KC, int VW, int RU, bool kPartial>
+__device__ __forceinline__ void update_all(double *__restrict__ Abase, int ldA, int H, const double *colbuf,
+                                           const double (&p)[KC][VW], unsigned st, unsigned full) {
+  int r = 0;
+  for (; r + RU <= H; r += RU) {
+    double coef[RU];
+    unsigned act = 0;
+#pragma unroll
+    for (int i = 0; i < RU; i++) {
+      coef[i] = colbuf[r + i];
+      if (coef[i] != 0.0) act |= 1u << i;
+    }
+    if (act) update_rows<NT, KC, VW, RU, kPartial>(Abase + (size_t)r * ldA, ldA, p, st, full, coef, act);
+  }
+  for (; r < H; r++) {
+    double coef[1] = {colbuf[r]};
+    if (coef[0] != 0.0) update_rows<NT, KC, VW, 1, kPartial>(Abase + (size_t)r * ldA, ldA, p, st, full, coef, 1u);
+  }
+}
+
+// src/simplex.ts:5-39.
+template <int NW, int KC, int VW>
 __device__ __forceinline__ void pivot_cta(const LpView &t, const Scratch &s, int row, int col) {
   constexpr int NT = NW * 32;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double *__restrict__ M = t.M;
-  const int ld = t.ld, H = t.H, W = t.W;
-  const double q = M[(size_t)row * ld + col];
+  constexpr int RU = KC <= 2 ? 4 : (KC <= 4 ? 2 : 1);
+  const int tid = threadIdx.x;
+  double *__restrict__ A = t.A;
+  double *__restrict__ b = t.b;
+  const int ldA = t.ldA, ldb = t.ldb, H = t.H, Wm1 = t.W - 1;
+  const int jc = col - 1;
+  const double q = A[(size_t)row * ldA + jc];
 
-  // ---- snapshot: normalised pivot row, old pivot column, -coef/q (M itself is not modified here)
-  for (int cbase = warp * 32; cbase < W; cbase += NT) {
-    const int c = cbase + lane;
-    bool nz = false;
-    if (c < W) {
-      const double v = M[(size_t)row * ld + c];
-      nz = fabs(v) > kTiny;
-      s.prow[c] = nz ? __ddiv_rn(v, q) : 0.0;
+  // ---- normalise the pivot row into registers (:16-25); A and b are only read in this phase.
+  // The pivot cell itself becomes 1/q (:25): same division code path with numerator 1.
+  double p[KC][VW];
+  unsigned st = 0, full = 0, valid = 0, partial = 0;
+  {
+    const double *Arow = A + (size_t)row * ldA + VW * tid;
+#pragma unroll
+    for (int k = 0; k < KC; k++) {
+      const int j0 = VW * (tid + NT * k);
+      Cells<VW> v;
+      if (j0 < Wm1) v.load(Arow + (size_t)VW * NT * k);
+#pragma unroll
+      for (int e = 0; e < VW; e++) {
+        p[k][e] = 0.0;
+        const int j = j0 + e;
+        if (j < Wm1) {
+          valid |= 1u << (k * VW + e);
+          const double x = (j == jc) ? 1.0 : v.get(e);
+          if (fabs(x) > kTiny) {
+            p[k][e] = __ddiv_rn(x, q);
+            st |= 1u << (k * VW + e);  // the pivot column is rewritten too and fixed up after the update
+          }
+        } else if (VW == 2 && j0 < Wm1) {
+          st |= 1u << (k * VW + e);    // padding cell next to the last column: rewriting it is harmless
+        }
+      }
+      const unsigned m = (st >> (k * VW)) & ((1u << VW) - 1u);
+      if (m == (1u << VW) - 1u)
+        full |= 1u << k;
+      else if (m)
+        partial = 1u;
     }
-    const unsigned m = __ballot_sync(0xffffffffu, nz);
-    if (lane == 0) s.nzmask[cbase >> 5] = m;
   }
+  const bool any_partial = (VW == 2) && (NW == 1 ? __any_sync(0xffffffffu, partial) : __syncthreads_or((int)partial));
+  // old pivot column, -coef/q, and the RHS cell of the pivot row (:19 for c = 0, :28-36): one division each
   for (int r = tid; r < H; r += NT) {
-    const double coef = M[(size_t)r * ld + col];
-    s.colbuf[r] = coef;
-    if (r != row && fabs(coef) > kTiny) s.colnew[r] = __ddiv_rn(-coef, q);
+    const double coef = A[(size_t)r * ldA + jc];
+    const double num = (r == row) ? b[(size_t)row * ldb] : -coef;
+    const bool nz = fabs(num) > kTiny;  // also false for NaN, as in the reference
+    const double quo = nz ? __ddiv_rn(num, q) : 0.0;
+    if (r == row) {
+      s.misc[0] = quo;
+      s.misc[1] = nz ? 1.0 : 0.0;
+      s.colbuf[r] = 0.0;  // the pivot row is not updated by the rank-1 pass
+    } else {
+      s.colbuf[r] = nz ? coef : 0.0;  // row skip (:31)
+      s.colnew[r] = quo;
+    }
   }
-  if (tid == 0) {  // basis bookkeeping, src/simplex.ts:7-12
-    const int leaving = t.var[W + row];
-    const int entering = t.var[col];
-    t.var[W + row] = entering;
+  if (tid == 0) {  // basis bookkeeping (:7-12)
+    const int leaving = t.var[t.W + row];
+    t.var[t.W + row] = t.var[col];
     t.var[col] = leaving;
-    t.pos[leaving] = col;
-    t.pos[entering] = W + row;
   }
   cta_sync<NW>();
 
-  // ---- update: warp w owns rows w, w+NW, ...; lanes span the columns of the chunk
-  const double qinv = __ddiv_rn(1.0, q);
-  for (int cb = 0; cb < W; cb += 32 * KC) {
-    double p[KC];
-    unsigned nzb = 0, vb = 0;
-    int kcol = -1;
+  // ---- rank-1 update of every active row (the pivot-column cells get a throw-away value here)
+  if (any_partial)
+    update_all<NT, KC, VW, RU, true>(A + VW * tid, ldA, H, s.colbuf, p, st, full);
+  else
+    update_all<NT, KC, VW, RU, false>(A + VW * tid, ldA, H, s.colbuf, p, st, full);
+  // pivot row (:19,22,25)
+  {
+    double *Arow = A + (size_t)row * ldA + VW * tid;
 #pragma unroll
     for (int k = 0; k < KC; k++) {
-      const int c = cb + lane + 32 * k;
-      p[k] = 0.0;
-      if (c < W) {
-        p[k] = s.prow[c];
-        vb |= 1u << k;
-        if (c == col)
-          kcol = k;
-        else if ((s.nzmask[c >> 5] >> lane) & 1u)
-          nzb |= 1u << k;
+      double *dst = Arow + (size_t)VW * NT * k;
+      if (VW == 2) {
+        if ((valid >> (k * VW)) & 1u) *reinterpret_cast<double2 *>(dst) = make_double2(p[k][0], p[k][VW - 1]);
+      } else {
+        if ((valid >> k) & 1u) dst[0] = p[k][0];
       }
     }
-    const bool colchunk = (col >= cb) && (col < cb + 32 * KC);
-    for (int r = warp; r < H; r += NW) {
-      double *__restrict__ Mr = M + (size_t)r * ld + cb + lane;
-      if (r == row) {
-#pragma unroll
-        for (int k = 0; k < KC; k++)
-          if ((vb >> k) & 1u) Mr[32 * k] = (k == kcol) ? qinv : p[k];
-        continue;
-      }
+  }
+  cta_sync<NW>();
+  // RHS column (:34 for c = 0) and pivot column (:36)
+  {
+    const double p0 = s.misc[0];
+    const bool nz0 = s.misc[1] != 0.0;
+    for (int r = tid; r < H; r += NT) {
       const double coef = s.colbuf[r];
-      if (!(fabs(coef) > kTiny)) continue;  // row skip, src/simplex.ts:31
-#pragma unroll
-      for (int k = 0; k < KC; k++) {
-        if ((nzb >> k) & 1u) {
-          const double x = Mr[32 * k];
-          Mr[32 * k] = __dsub_rn(x, __dmul_rn(coef, p[k]));
+      if (r == row) {
+        b[(size_t)r * ldb] = p0;
+      } else if (coef != 0.0) {
+        if (nz0) {
+          const double x = b[(size_t)r * ldb];
+          b[(size_t)r * ldb] = __dsub_rn(x, __dmul_rn(coef, p0));
         }
+        A[(size_t)r * ldA + jc] = s.colnew[r];
       }
-      if (colchunk && kcol >= 0) Mr[32 * kcol] = s.colnew[r];
     }
   }
   cta_sync<NW>();
 }
 
-// src/simplex.ts:106-142 (phase1) falling through to 66-103 (phase2); whole CTA executes this uniformly.
-template <int NW, int KC>
+// src/simplex.ts:106-142 (phase1) falling through to 66-103 (phase2); the whole CTA executes this uniformly.
+template <int NW, int KC, int VW>
 __device__ __forceinline__ LpResult simplex_cta(const LpView &t, const Scratch &s, double precision, double max_pivots,
                                                 int check_cycles) {
   constexpr int NT = NW * 32;
   const int tid = threadIdx.x;
-  const double *__restrict__ M = t.M;
-  const int ld = t.ld, H = t.H, W = t.W;
+  const double *__restrict__ A = t.A;
+  const double *__restrict__ b = t.b;
+  const int ldA = t.ldA, ldb = t.ldb, H = t.H, Wm1 = t.W - 1;
   const double INF = d_inf();
 
   LpResult res;
@@ -246,80 +370,106 @@ __device__ __forceinline__ LpResult simplex_cta(const LpView &t, const Scratch &
     int row, col;
     if (phase == 1) {
       // leaving row: first index of the most negative RHS below -precision (:111-119)
-      Arg a = {INF, kNone};
+      double bv = INF;
+      int bi = kNone;
       for (int r = 1 + tid; r < H; r += NT) {
-        const double v = M[(size_t)r * ld];
-        if (v < -precision && v < a.v) {
-          a.v = v;
-          a.i = r;
+        const double v = b[(size_t)r * ldb];
+        if (v < -precision && v < bv) {
+          bv = v;
+          bi = r;
         }
       }
-      a = block_arg<false, NW>(a, s.red_v, s.red_i, parity);
-      if (a.i == kNone) {  // feasible: phase 2 with a fresh counter and history (:120, :67-69)
+      row = block_best<false, NW>(bi == kNone ? no_key<false>() : order_key(bv), bi, s.red, parity);
+      if (row == kNone) {  // feasible: phase 2 with a fresh counter and history (:120, :67-69)
         phase = 2;
         iter = 0;
         hist_len = 0;
         continue;
       }
-      row = a.i;
       // entering column: first index of max -M[0,c]/M[row,c] over M[row,c] < -precision (:123-134)
-      Arg b = {-INF, kNone};
-      for (int c = 1 + tid; c < W; c += NT) {
-        const double coef = M[(size_t)row * ld + c];
-        if (coef < -precision) {
-          const double ratio = __ddiv_rn(-M[c], coef);
-          if (ratio > b.v) {  // b.v starts at -inf: -inf and NaN ratios never win, as in the reference
-            b.v = ratio;
-            b.i = c;
-          }
-        }
-      }
-      b = block_arg<true, NW>(b, s.red_v, s.red_i, parity);
-      if (b.i == kNone) {
-        res.status = ST_INFEASIBLE;
-        break;
-      }
-      col = b.i;
-    } else {
-      // entering column: first index of the largest reduced cost above precision (:71-79)
-      Arg a = {-INF, kNone};
-      for (int c = 1 + tid; c < W; c += NT) {
-        const double v = M[c];
-        if (v > precision && v > a.v) {
-          a.v = v;
-          a.i = c;
-        }
-      }
-      a = block_arg<true, NW>(a, s.red_v, s.red_i, parity);
-      if (a.i == kNone) {
-        res.status = ST_OPTIMAL;
-        res.value = round_to_precision(M[0], precision);
-        break;
-      }
-      col = a.i;
-      // leaving row: ratio test with the reference's early break (:83-95) == lowest r whose ratio is
-      // <= precision if any, else first index of the minimum ratio.  Ratios <= precision get key -inf.
-      Arg b = {INF, kNone};
-      for (int r = 1 + tid; r < H; r += NT) {
-        const double v = M[(size_t)r * ld + col];
-        if (v > precision) {
-          const double ratio = __ddiv_rn(M[(size_t)r * ld], v);
-          if (ratio < INF) {  // +inf and NaN never win (`ratio < minRatio` with minRatio = Infinity)
-            const double key = (ratio <= precision) ? -INF : ratio;
-            if (b.i == kNone || key < b.v) {
-              b.v = key;
-              b.i = r;
+      bv = -INF;
+      bi = kNone;
+      {
+        const double *Arow = A + (size_t)row * ldA + VW * tid;
+        const double *A0 = A + VW * tid;
+#pragma unroll
+        for (int k = 0; k < KC; k++) {
+          const int j0 = VW * (tid + NT * k);
+          if (j0 < Wm1) {
+            Cells<VW> cf, ob;
+            cf.load(Arow + (size_t)VW * NT * k);
+            ob.load(A0 + (size_t)VW * NT * k);
+#pragma unroll
+            for (int e = 0; e < VW; e++) {
+              const double coef = cf.get(e);
+              if (j0 + e < Wm1 && coef < -precision) {
+                const double ratio = __ddiv_rn(-ob.get(e), coef);
+                if (ratio > bv) {  // bv starts at -inf: -inf and NaN ratios never win, as in the reference
+                  bv = ratio;
+                  bi = j0 + e + 1;
+                }
+              }
             }
           }
         }
       }
-      b = block_arg<false, NW>(b, s.red_v, s.red_i, parity);
-      if (b.i == kNone) {
+      col = block_best<true, NW>(bi == kNone ? no_key<true>() : order_key(bv), bi, s.red, parity);
+      if (col == kNone) {
+        res.status = ST_INFEASIBLE;
+        break;
+      }
+    } else {
+      // entering column: first index of the largest reduced cost above precision (:71-79)
+      double bv = -INF;
+      int bi = kNone;
+      {
+        const double *A0 = A + VW * tid;
+#pragma unroll
+        for (int k = 0; k < KC; k++) {
+          const int j0 = VW * (tid + NT * k);
+          if (j0 < Wm1) {
+            Cells<VW> ob;
+            ob.load(A0 + (size_t)VW * NT * k);
+#pragma unroll
+            for (int e = 0; e < VW; e++) {
+              const double v = ob.get(e);
+              if (j0 + e < Wm1 && v > precision && v > bv) {
+                bv = v;
+                bi = j0 + e + 1;
+              }
+            }
+          }
+        }
+      }
+      col = block_best<true, NW>(bi == kNone ? no_key<true>() : order_key(bv), bi, s.red, parity);
+      if (col == kNone) {
+        res.status = ST_OPTIMAL;
+        res.value = round_to_precision(b[0], precision);
+        break;
+      }
+      // leaving row: ratio test with the reference's early break (:83-95) == lowest r whose ratio is
+      // <= precision if any, else first index of the minimum ratio.  Ratios <= precision get key -inf.
+      bv = INF;
+      bi = kNone;
+      for (int r = 1 + tid; r < H; r += NT) {
+        const double v = A[(size_t)r * ldA + (col - 1)];
+        if (v > precision) {
+          const double ratio = __ddiv_rn(b[(size_t)r * ldb], v);
+          if (ratio < INF) {  // +inf and NaN never win (`ratio < minRatio` with minRatio = Infinity)
+            const double key = (ratio <= precision) ? -INF : ratio;
+            if (bi == kNone || key < bv) {
+              bv = key;
+              bi = r;
+            }
+          }
+        }
+      }
+      row = block_best<false, NW>(bi == kNone ? no_key<false>() : order_key(bv), bi, s.red, parity);
+      if (row == kNone) {
         res.status = ST_UNBOUNDED;
         res.value = (double)col;
         break;
       }
-      row = b.i;
     }
 
     if (check_cycles) {  // (:98, :137)
@@ -328,7 +478,7 @@ __device__ __forceinline__ LpResult simplex_cta(const LpView &t, const Scratch &
         break;
       }
       if (tid == 0) {
-        s.hist[2 * hist_len] = t.var[W + row];
+        s.hist[2 * hist_len] = t.var[t.W + row];
         s.hist[2 * hist_len + 1] = t.var[col];
       }
       hist_len++;
@@ -336,7 +486,7 @@ __device__ __forceinline__ LpResult simplex_cta(const LpView &t, const Scratch &
       if (history_has_cycle<NT>(s.hist, hist_len)) break;  // "cycled", NaN
     }
 
-    pivot_cta<NW, KC>(t, s, row, col);
+    pivot_cta<NW, KC, VW>(t, s, row, col);
     if (phase == 1)
       res.p1++;
     else

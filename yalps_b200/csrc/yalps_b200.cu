@@ -119,30 +119,35 @@ struct KernelEntry {
 
 #define KENTRY(NW, KC) {NW, KC, k_simplex<NW, KC, true>, k_simplex<NW, KC, false>}
 const KernelEntry kKernels[] = {
-    KENTRY(1, 1),  KENTRY(1, 2),  KENTRY(1, 3),  KENTRY(1, 4),  KENTRY(2, 1),  KENTRY(2, 2),  KENTRY(2, 3),
-    KENTRY(2, 4),  KENTRY(4, 1),  KENTRY(4, 2),  KENTRY(4, 3),  KENTRY(4, 4),  KENTRY(4, 8),  KENTRY(8, 2),
-    KENTRY(8, 4),  KENTRY(8, 8),  KENTRY(16, 4), KENTRY(16, 8), KENTRY(32, 2), KENTRY(32, 4),
+    KENTRY(1, 1), KENTRY(1, 2),  KENTRY(1, 3),  KENTRY(1, 4),  KENTRY(2, 1),  KENTRY(2, 2),  KENTRY(2, 3),
+    KENTRY(2, 4), KENTRY(4, 1),  KENTRY(4, 2),  KENTRY(4, 4),  KENTRY(8, 1),  KENTRY(8, 2),  KENTRY(8, 4),
+    KENTRY(8, 8), KENTRY(16, 1), KENTRY(16, 2), KENTRY(16, 4), KENTRY(32, 1), KENTRY(32, 2), KENTRY(32, 4),
+    KENTRY(32, 8),
 };
 #undef KENTRY
 
-const KernelEntry *pick_kernel(int nw_want, int W) {
-  const int kc_want = std::max(1, (W + 31) / 32);
+// Thread t keeps the pivot-row cells of vector-columns t, t+NT, ... in registers: NT*KC*VW >= W-1 is required.
+// Smallest NW >= nw_want whose widest KC covers the row, then the smallest covering KC.
+const KernelEntry *pick_kernel(int nw_want, int W, bool resident) {
+  const int vw = resident ? 2 : 1;
+  const int wm1 = std::max(W - 1, 1);
   const KernelEntry *best = nullptr;
-  // smallest NW >= wanted (or largest available), then smallest KC >= wanted (or largest available)
-  int nw_sel = -1;
-  for (const auto &k : kKernels)
-    if (k.nw >= nw_want && (nw_sel < 0 || k.nw < nw_sel)) nw_sel = k.nw;
-  if (nw_sel < 0)
-    for (const auto &k : kKernels) nw_sel = std::max(nw_sel, k.nw);
   for (const auto &k : kKernels) {
-    if (k.nw != nw_sel) continue;
+    if ((long long)k.nw * 32 * k.kc * vw < wm1) continue;
     if (!best) {
       best = &k;
       continue;
     }
-    const bool k_ok = k.kc >= kc_want, b_ok = best->kc >= kc_want;
-    if (k_ok && (!b_ok || k.kc < best->kc)) best = &k;
-    if (!k_ok && !b_ok && k.kc > best->kc) best = &k;
+    const bool k_ok = k.nw >= nw_want, b_ok = best->nw >= nw_want;
+    if (k_ok != b_ok) {
+      if (k_ok) best = &k;
+      continue;
+    }
+    if (k_ok) {  // both at least as wide as wanted: prefer the narrower CTA, then the smaller KC
+      if (k.nw < best->nw || (k.nw == best->nw && k.kc < best->kc)) best = &k;
+    } else {     // both narrower than wanted: prefer the wider CTA, then the smaller KC
+      if (k.nw > best->nw || (k.nw == best->nw && k.kc < best->kc)) best = &k;
+    }
   }
   return best;
 }
@@ -173,7 +178,8 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
     return fail(ctx, YALPS_ERR_TOO_LARGE, "tableau %dx%d: pivot row/column staging exceeds shared memory", Hcap, Wcap);
   int nw = ctx->tune_threads > 0 ? std::max(1, ctx->tune_threads / 32) : default_warps((long long)Hcap * Wcap);
   if (!resident && ctx->tune_threads <= 0) nw = std::max(nw, 8);
-  const KernelEntry *k = pick_kernel(nw, Wcap);
+  const KernelEntry *k = pick_kernel(nw, Wcap, resident);
+  if (!k) return fail(ctx, YALPS_ERR_TOO_LARGE, "tableau width %d exceeds the widest kernel", Wcap);
   SimplexKernel fn = resident ? k->resident : k->global;
   const size_t smem = resident ? Lr.total : Lg.total;
   CU(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
