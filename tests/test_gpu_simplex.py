@@ -209,3 +209,56 @@ def test_netlib_trajectory(engine, name):
     assert same_value(got["value"][0], g["value"])
     assert np.array_equal(got["pos"][0], g["final_pos"])
     assert same_bits(got["rhs"][0], g["final_rhs"])
+
+
+# ---------------------------------------------------------------------------------------------- K4 grid kernel
+@pytest.mark.parametrize("m,nv,neg", [(32, 64, 6), (5, 3, 2), (100, 300, 40), (300, 90, 100), (1, 1, 0)])
+def test_grid_kernel_bit_exact(engine, m, nv, neg):
+    """One LP across the whole grid (cooperative launch), forced on small inputs so the oracle is quick."""
+    n = 4
+    mats = O.generate_synthetic(4000, n, m, nv, neg)
+    exp = oracle_batch(mats, m + 1, nv + 1)
+    engine.set_tuning(E.PATH_GRID, 0)
+    try:
+        got = engine.solve_batch(mats, m + 1, nv + 1, want_matrices=True)
+    finally:
+        engine.set_tuning(E.PATH_AUTO, 0)
+    assert_batch_equal(got, exp, f"grid {m}x{nv}")
+
+
+def test_grid_kernel_check_cycles_and_budget(engine):
+    t = np.array([[0, 10, -57, -9, -24], [0, 0.5, -5.5, -2.5, 9], [0, 0.5, -1.5, -0.5, 1], [1, 1, 0, 0, 0]], float)
+    engine.set_tuning(E.PATH_GRID, 0)
+    try:
+        for kw in ({"check_cycles": True}, {"check_cycles": False, "max_pivots": 9}, {"max_pivots": 0}):
+            m = t.reshape(1, -1).copy()
+            exp = oracle_batch(m, 4, 5, **kw)
+            got = engine.solve_batch(m, 4, 5, E.make_options(**kw), want_matrices=True)
+            assert_batch_equal(got, exp, f"grid {kw}")
+    finally:
+        engine.set_tuning(E.PATH_AUTO, 0)
+
+
+def test_large_dense_lp_takes_the_grid_path(engine):
+    """A tableau beyond shared memory with n = 1 (config 5 in miniature): auto path == K4."""
+    m, nv = 400, 900
+    mats = O.generate_synthetic(9, 1, m, nv, 60)
+    exp = oracle_batch(mats, m + 1, nv + 1)
+    got = engine.solve_batch(mats, m + 1, nv + 1, want_matrices=True)
+    assert_batch_equal(got, exp, "400x900")
+    assert got["pivots"].sum() > 100
+
+
+NETLIB_LONG = [n for n in NL.names if float(NL.z[f"{n}/oracle_seconds"][0]) >= 1.0]
+
+
+@pytest.mark.parametrize("name", NETLIB_LONG)
+def test_netlib_long_trajectories(engine, name):
+    """The reference's 'cannot handle' list (benchmarks/netlib/read.ts:55-58): thousands of pivots on dense,
+    ill-conditioned tableaus.  Status / value / pivot counts / final basis must still be the reference's."""
+    g = NL.get(name)
+    got = engine.solve_batch(g["matrix"], g["height"], g["width"], E.make_options(check_cycles=g["check_cycles"]))
+    assert got["status"][0] == g["status"] and tuple(got["pivots"][0]) == g["pivots"]
+    assert same_value(got["value"][0], g["value"])
+    assert np.array_equal(got["pos"][0], g["final_pos"])
+    assert same_bits(got["rhs"][0], g["final_rhs"])

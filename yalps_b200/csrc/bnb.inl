@@ -242,7 +242,30 @@ int yalps_bnb_solve_nodes(yalps_ctx *ctx, int64_t n, const int32_t *cut_offsets,
   a.cut_var = (const int *)d_var;
   a.cut_val = (const double *)d_val;
   fill_options(a, opt);
-  if ((rc = launch_simplex(ctx, plan, a, "nd", st))) return rc;
+  if (use_grid_path(ctx, n, plan)) {
+    // few large nodes: assemble them in HBM (K3), then give each node the whole grid (K4)
+    if (!d_work) {
+      if ((rc = dev_ensure(ctx, "nd_work", mat_bytes, &d_work))) return rc;
+      if (matrices_out) d_out = d_work;
+    }
+    const int gx = std::max(1, std::min(ctx->prop.multiProcessorCount * 4, (int)(((size_t)R.H * W + 255) / 256)));
+    const int gy = (int)std::min<int64_t>(n, 65535);
+    k_assemble_nodes<<<dim3(gx, gy), 256, 0, st>>>(n, R.H, W, Hcap, (const double *)R.m.p, (const int *)R.pos.p,
+                                                   (const int *)d_off, (const double *)d_sign, (const int *)d_var,
+                                                   (const double *)d_val, (double *)d_work);
+    CU(ctx, cudaGetLastError());
+    ctx->launches++;
+    for (int64_t j = 0; j < n; j++) {
+      const int hj = R.H + (cut_offsets[j + 1] - cut_offsets[j]);
+      if ((rc = launch_grid(ctx, hj, W, (double *)d_work + (size_t)j * Hcap * W, opt, (int *)d_status + j,
+                            (double *)d_value + j, (long long *)d_piv + 2 * j, (double *)d_rhs + (size_t)j * Hcap,
+                            (int *)d_pos + (size_t)j * (W + Hcap), (int *)d_vr + (size_t)j * (W + Hcap), st,
+                            (const int *)R.var.p, W + R.H)))
+        return rc;
+    }
+  } else if ((rc = launch_simplex(ctx, plan, a, "nd", st))) {
+    return rc;
+  }
   if (status) CU(ctx, cudaMemcpyAsync(status, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
   if (value) CU(ctx, cudaMemcpyAsync(value, d_value, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
   if (pivots) CU(ctx, cudaMemcpyAsync(pivots, d_piv, (size_t)n * 16, cudaMemcpyDeviceToHost, st));

@@ -1,0 +1,266 @@
+// grid_kernel.cuh -- K4: ONE large LP spread over the whole GPU (cooperative persistent launch).
+//
+// Same algorithm and rounding sequence as simplex_device.cuh (src/simplex.ts:5-142), different work split:
+//   * the tableau stays in HBM/L2 in the reference layout (row stride W, column 0 = RHS), updated in place;
+//   * every CTA recomputes the pivot choice redundantly from the (L2-resident) objective row / RHS column /
+//     pivot column, so all CTAs agree on (row, col) without exchanging partial results;
+//   * every CTA stages the normalised pivot row (and its non-zero flags) in its own shared memory;
+//   * rows are dealt to warps round-robin over the whole grid; a warp streams its row with coalesced 8-byte
+//     accesses, several loads in flight per lane, and skips rows whose pivot-column cell is below 1e-16;
+//   * two grid barriers per pivot: one after every CTA has finished reading (pivot choice + staging of the old
+//     pivot row) and one after the update, so that no CTA ever selects from a half-updated tableau.
+#pragma once
+
+#include "simplex_device.cuh"
+
+namespace yalps {
+
+// Grid-wide barrier for a cooperative launch (all CTAs co-resident): monotonically increasing arrival counter,
+// release on arrival / acquire on the spin so that every CTA's tableau writes are visible to every other CTA.
+__device__ __forceinline__ void grid_barrier(unsigned long long *counter, unsigned long long &epoch) {
+  __syncthreads();
+  epoch++;
+  if (threadIdx.x == 0) {
+    const unsigned long long goal = epoch * gridDim.x;
+    __threadfence();
+    asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(counter) : "memory");
+    unsigned long long seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(counter) : "memory");
+    } while (seen < goal);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+struct GridArgs {
+  double *M;  // H x W, reference layout, updated in place
+  int H, W;
+  int *var;   // variableAtPosition[W+H] (global), maintained by CTA 0
+  const int *init_var;  // node mode: root variableAtPosition (first init_n entries), identity beyond
+  int init_n;
+  int *pos_out;
+  double *rhs_out;
+  int *status;
+  double *value;
+  long long *pivots;
+  double precision, max_pivots;
+  int check_cycles;
+  int *hist;
+  int hist_cap;
+  int *flags;                  // [2] cycle / history-overflow verdict of CTA 0, by iteration parity
+  unsigned long long *barrier; // grid barrier arrival counter, zeroed before the launch
+};
+
+constexpr int kGridThreads = 1024;
+constexpr int kGridWarps = kGridThreads / 32;
+
+// shared memory: prow[W] doubles, nz bitmask words, reduction scratch
+struct GridSmem {
+  size_t off_prow, off_nz, off_red, total;
+  __host__ __device__ explicit GridSmem(int W) {
+    size_t o = 0;
+    off_prow = o;
+    o += (size_t)((W + 1) & ~1) * 8;
+    off_nz = o;
+    o += (size_t)((W + 31) / 32 + 1) * 4;
+    o = (o + 15) & ~(size_t)15;
+    off_red = o;
+    o += 192 * 4;
+    total = (o + 15) & ~(size_t)15;
+  }
+};
+
+__global__ void __launch_bounds__(kGridThreads, 1) k_simplex_grid(const GridArgs a) {
+  constexpr int NT = kGridThreads, NW = kGridWarps;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long epoch = 0;
+  const GridSmem L(a.W);
+  double *prow = reinterpret_cast<double *>(smem_raw + L.off_prow);
+  unsigned *nzmask = reinterpret_cast<unsigned *>(smem_raw + L.off_nz);
+  unsigned *red = reinterpret_cast<unsigned *>(smem_raw + L.off_red);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int H = a.H, W = a.W;
+  double *__restrict__ M = a.M;
+  const double precision = a.precision, INF = d_inf();
+  const int gwarp = blockIdx.x * NW + warp, gwarps = gridDim.x * NW;
+
+  for (int k = blockIdx.x * NT + tid; k < W + H; k += gridDim.x * NT)
+    a.var[k] = (a.init_var && k < a.init_n) ? a.init_var[k] : k;
+  grid_barrier(a.barrier, epoch);
+
+  int status = ST_CYCLED;
+  double value = d_nan();
+  long long p1 = 0, p2 = 0, iter = 0;
+  int phase = 1, parity = 0, hist_len = 0;
+
+  for (;;) {
+    if (!((double)iter < a.max_pivots)) break;
+    int row, col;
+    if (phase == 1) {
+      double bv = INF;
+      int bi = kNone;
+      for (int r = 1 + tid; r < H; r += NT) {
+        const double v = M[(size_t)r * W];
+        if (v < -precision && v < bv) {
+          bv = v;
+          bi = r;
+        }
+      }
+      row = block_best<false, NW>(bi == kNone ? no_key<false>() : order_key(bv), bi, red, parity);
+      if (row == kNone) {
+        phase = 2;
+        iter = 0;
+        hist_len = 0;
+        continue;
+      }
+      bv = -INF;
+      bi = kNone;
+      for (int c = 1 + tid; c < W; c += NT) {
+        const double coef = M[(size_t)row * W + c];
+        if (coef < -precision) {
+          const double ratio = __ddiv_rn(-M[c], coef);
+          if (ratio > bv) {
+            bv = ratio;
+            bi = c;
+          }
+        }
+      }
+      col = block_best<true, NW>(bi == kNone ? no_key<true>() : order_key(bv), bi, red, parity);
+      if (col == kNone) {
+        status = ST_INFEASIBLE;
+        break;
+      }
+    } else {
+      double bv = -INF;
+      int bi = kNone;
+      for (int c = 1 + tid; c < W; c += NT) {
+        const double v = M[c];
+        if (v > precision && v > bv) {
+          bv = v;
+          bi = c;
+        }
+      }
+      col = block_best<true, NW>(bi == kNone ? no_key<true>() : order_key(bv), bi, red, parity);
+      if (col == kNone) {
+        status = ST_OPTIMAL;
+        value = round_to_precision(M[0], precision);
+        break;
+      }
+      bv = INF;
+      bi = kNone;
+      for (int r = 1 + tid; r < H; r += NT) {
+        const double v = M[(size_t)r * W + col];
+        if (v > precision) {
+          const double ratio = __ddiv_rn(M[(size_t)r * W], v);
+          if (ratio < INF) {
+            const double key = (ratio <= precision) ? -INF : ratio;
+            if (bi == kNone || key < bv) {
+              bv = key;
+              bi = r;
+            }
+          }
+        }
+      }
+      row = block_best<false, NW>(bi == kNone ? no_key<false>() : order_key(bv), bi, red, parity);
+      if (row == kNone) {
+        status = ST_UNBOUNDED;
+        value = (double)col;
+        break;
+      }
+    }
+
+    if (a.check_cycles) {  // CTA 0 keeps the history; its verdict reaches the other CTAs through a grid barrier
+      if (blockIdx.x == 0) {
+        int verdict = 0;
+        if (hist_len >= a.hist_cap) {
+          verdict = 2;
+        } else {
+          if (tid == 0) {
+            a.hist[2 * hist_len] = a.var[W + row];
+            a.hist[2 * hist_len + 1] = a.var[col];
+          }
+          __syncthreads();
+          if (history_has_cycle<NT>(a.hist, hist_len + 1)) verdict = 1;
+        }
+        if (tid == 0) a.flags[iter & 1] = verdict;
+        __threadfence();
+      }
+      hist_len++;
+      grid_barrier(a.barrier, epoch);
+      const int verdict = *reinterpret_cast<volatile int *>(a.flags + (iter & 1));
+      if (verdict == 2) status = ST_ERR_HISTORY;
+      if (verdict) break;
+    }
+
+    // ---- stage the normalised pivot row (src/simplex.ts:16-25) in shared memory
+    const double q = M[(size_t)row * W + col];
+    for (int cbase = warp * 32; cbase < W; cbase += NT) {
+      const int c = cbase + lane;
+      bool nz = false;
+      if (c < W) {
+        const double v = (c == col) ? 1.0 : M[(size_t)row * W + c];
+        nz = fabs(v) > kTiny;
+        prow[c] = nz ? __ddiv_rn(v, q) : 0.0;
+        if (c == col) nz = false;  // the pivot column gets -coef/q instead (:36)
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, nz);
+      if (lane == 0) nzmask[cbase >> 5] = m;
+    }
+    if (blockIdx.x == 0 && tid == 0) {  // basis bookkeeping (:7-12)
+      const int leaving = a.var[W + row];
+      a.var[W + row] = a.var[col];
+      a.var[col] = leaving;
+    }
+    grid_barrier(a.barrier, epoch);  // every CTA has made its choice and staged the old pivot row: the tableau may change now
+
+    // ---- rank-1 update, rows dealt round-robin to the warps of the grid (:28-38)
+    for (int r = gwarp; r < H; r += gwarps) {
+      double *__restrict__ Mr = M + (size_t)r * W;
+      if (r == row) {
+        for (int c = lane; c < W; c += 32) Mr[c] = prow[c];
+        continue;
+      }
+      const double coef = Mr[col];
+      if (!(fabs(coef) > kTiny)) continue;  // row skip (:31)
+      int c = lane;
+      for (; c + 7 * 32 < W; c += 8 * 32) {
+        double x[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) x[u] = Mr[c + 32 * u];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int cc = c + 32 * u;
+          if ((nzmask[cc >> 5] >> lane) & 1u) Mr[cc] = __dsub_rn(x[u], __dmul_rn(coef, prow[cc]));
+        }
+      }
+      for (; c < W; c += 32)
+        if ((nzmask[c >> 5] >> lane) & 1u) Mr[c] = __dsub_rn(Mr[c], __dmul_rn(coef, prow[c]));
+      if (lane == 0) Mr[col] = __ddiv_rn(-coef, q);
+    }
+    grid_barrier(a.barrier, epoch);
+
+    if (phase == 1)
+      p1++;
+    else
+      p2++;
+    iter++;
+  }
+
+  // ---- outputs (all CTAs leave the loop in the same iteration with the same verdict)
+  if (blockIdx.x == 0 && tid == 0) {
+    if (a.status) a.status[0] = status;
+    if (a.value) a.value[0] = value;
+    if (a.pivots) {
+      a.pivots[0] = p1;
+      a.pivots[1] = p2;
+    }
+  }
+  if (a.rhs_out)
+    for (int r = blockIdx.x * NT + tid; r < H; r += gridDim.x * NT) a.rhs_out[r] = M[(size_t)r * W];
+  if (a.pos_out)
+    for (int k = blockIdx.x * NT + tid; k < W + H; k += gridDim.x * NT) a.pos_out[a.var[k]] = k;
+}
+
+}  // namespace yalps

@@ -151,18 +151,11 @@ __global__ void __launch_bounds__(NW * 32) k_simplex(const BatchArgs a) {
     if (kResident) {
       // asynchronous 8-byte copies (LDGSTS) straight into the (A, b) layout: every copy of the tableau is in
       // flight before the first one is waited for, so the load costs one memory latency, not one per row
-      const int qd = NT / W, rm = NT % W;
-      int r = tid / W, c = tid % W;
-      const int total = rootH * W;
-      for (int k = tid; k < total; k += NT) {
-        double *dst = (c == 0) ? (t.b + r) : (t.A + (size_t)r * ldA + (c - 1));
-        cp_async8(dst, src + k);
-        r += qd;
-        c += rm;
-        if (c >= W) {
-          c -= W;
-          r++;
-        }
+      for (int r = tid >> 5; r < rootH; r += NW) {
+        const double *sr = src + (size_t)r * W;
+        double *dA = t.A + (size_t)r * ldA - 1;
+        if ((tid & 31) == 0) cp_async8(t.b + r, sr);
+        for (int c = 1 + (tid & 31); c < W; c += 32) cp_async8(dA + c, sr + c);
       }
     } else if (src != a.work + moff) {
       const size_t cells = (size_t)rootH * W;
@@ -235,6 +228,32 @@ __global__ void __launch_bounds__(NW * 32) k_simplex(const BatchArgs a) {
       }
     }
     __syncthreads();
+  }
+}
+
+// K3 standalone: applyCuts (src/branchAndCut.ts:22-61) for a wave of nodes into HBM working copies
+// (row stride W, node stride Hcap*W) -- used in front of the grid kernel; K1/K2 fuse the same assembly.
+__global__ void k_assemble_nodes(long long n, int rootH, int W, int Hcap, const double *root, const int *root_pos,
+                                 const int *cut_off, const double *cut_sign, const int *cut_var, const double *cut_val,
+                                 double *work) {
+  const size_t root_cells = (size_t)rootH * W;
+  for (long long node = blockIdx.y; node < n; node += gridDim.y) {
+    double *dst = work + (size_t)node * Hcap * W;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < root_cells; k += (size_t)gridDim.x * blockDim.x)
+      dst[k] = root[k];
+    const int cbeg = cut_off[node], ncuts = cut_off[node + 1] - cbeg;
+    for (int i = blockIdx.x; i < ncuts; i += gridDim.x) {
+      const double sign = cut_sign[cbeg + i], value = cut_val[cbeg + i];
+      const int p = root_pos[cut_var[cbeg + i]];
+      double *dr = dst + (size_t)(rootH + i) * W;
+      if (p < W) {
+        for (int c = threadIdx.x; c < W; c += blockDim.x) dr[c] = (c == 0) ? __dmul_rn(sign, value) : (c == p ? sign : 0.0);
+      } else {
+        const double *sr = root + (size_t)(p - W) * W;
+        for (int c = threadIdx.x; c < W; c += blockDim.x)
+          dr[c] = (c == 0) ? __dmul_rn(sign, __dsub_rn(value, sr[0])) : __dmul_rn(-sign, sr[c]);
+      }
+    }
   }
 }
 

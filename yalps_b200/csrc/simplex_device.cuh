@@ -227,11 +227,20 @@ __device__ __forceinline__ void update_all(double *__restrict__ Abase, int ldA, 
   for (; r + RU <= H; r += RU) {
     double coef[RU];
     unsigned act = 0;
+    if (RU % 2 == 0) {  // colbuf is 16-byte aligned and r is a multiple of RU: two coefficients per load
 #pragma unroll
-    for (int i = 0; i < RU; i++) {
-      coef[i] = colbuf[r + i];
-      if (coef[i] != 0.0) act |= 1u << i;
+      for (int i = 0; i < RU; i += 2) {
+        const double2 c2 = *reinterpret_cast<const double2 *>(colbuf + r + i);
+        coef[i] = c2.x;
+        coef[i + (RU > 1 ? 1 : 0)] = c2.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < RU; i++) coef[i] = colbuf[r + i];
     }
+#pragma unroll
+    for (int i = 0; i < RU; i++)
+      if (coef[i] != 0.0) act |= 1u << i;
     if (act) update_rows<NT, KC, VW, RU, kPartial>(Abase + (size_t)r * ldA, ldA, p, st, full, coef, act);
   }
   for (; r < H; r++) {
@@ -244,7 +253,7 @@ __device__ __forceinline__ void update_all(double *__restrict__ Abase, int ldA, 
 template <int NW, int KC, int VW>
 __device__ __forceinline__ void pivot_cta(const LpView &t, const Scratch &s, int row, int col) {
   constexpr int NT = NW * 32;
-  constexpr int RU = KC <= 2 ? 4 : (KC <= 4 ? 2 : 1);
+  constexpr int RU = KC == 1 ? 8 : (KC == 2 ? 4 : (KC <= 4 ? 2 : 1));
   const int tid = threadIdx.x;
   double *__restrict__ A = t.A;
   double *__restrict__ b = t.b;

@@ -13,6 +13,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <limits>
 #include <memory>
 #include <string>
@@ -20,6 +21,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "grid_kernel.cuh"
 
 using namespace yalps;
 
@@ -174,12 +176,22 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
   } else if (ctx->tune_path == YALPS_PATH_GMEM) {
     resident = false;
   }
-  if (!resident && Lg.total > (size_t)ctx->smem_optin)
+  const bool grid_ok = ctx->tune_path == YALPS_PATH_GRID || (ctx->tune_path == YALPS_PATH_AUTO && n <= 16);
+  plan->resident = resident;
+  plan->k = nullptr;
+  plan->smem = 0;
+  plan->grid = 0;
+  if (!resident && Lg.total > (size_t)ctx->smem_optin) {
+    if (grid_ok) return 0;  // only the grid kernel (K4) can take it
     return fail(ctx, YALPS_ERR_TOO_LARGE, "tableau %dx%d: pivot row/column staging exceeds shared memory", Hcap, Wcap);
+  }
   int nw = ctx->tune_threads > 0 ? std::max(1, ctx->tune_threads / 32) : default_warps((long long)Hcap * Wcap);
   if (!resident && ctx->tune_threads <= 0) nw = std::max(nw, 8);
   const KernelEntry *k = pick_kernel(nw, Wcap, resident);
-  if (!k) return fail(ctx, YALPS_ERR_TOO_LARGE, "tableau width %d exceeds the widest kernel", Wcap);
+  if (!k) {
+    if (grid_ok) return 0;
+    return fail(ctx, YALPS_ERR_TOO_LARGE, "tableau width %d exceeds the widest kernel", Wcap);
+  }
   SimplexKernel fn = resident ? k->resident : k->global;
   const size_t smem = resident ? Lr.total : Lg.total;
   CU(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -194,6 +206,14 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
   plan->smem = smem;
   plan->grid = (int)grid;
   return 0;
+}
+
+// K4 (whole grid per LP, LPs one after another) beats K2 (one CTA per LP) when the tableaus do not fit in
+// shared memory and there are too few of them to give every SM its own LP.
+bool use_grid_path(const yalps_ctx *ctx, long long n, const LaunchPlan &plan) {
+  if (ctx->tune_path == YALPS_PATH_GRID || plan.k == nullptr) return true;
+  if (ctx->tune_path != YALPS_PATH_AUTO) return false;
+  return !plan.resident && n <= 16;
 }
 
 int hist_capacity(const yalps_options *opt) {
@@ -335,6 +355,61 @@ int yalps_host_free(yalps_ctx *ctx, void *ptr) {
   return 0;
 }
 
+// K4: one LP over the whole grid.  d_M (H*W doubles, reference layout) is solved in place.
+static int launch_grid(yalps_ctx *ctx, int H, int W, double *d_M, const yalps_options *opt, int *d_status,
+                       double *d_value, long long *d_pivots, double *d_rhs, int *d_pos, int *d_var,
+                       cudaStream_t stream, const int *d_init_var = nullptr, int init_n = 0) {
+  const GridSmem L(W);
+  if (L.total > (size_t)ctx->smem_optin)
+    return fail(ctx, YALPS_ERR_TOO_LARGE, "tableau width %d: pivot row staging exceeds shared memory", W);
+  int coop = 0;
+  CU(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
+  if (!coop) return fail(ctx, YALPS_ERR_CUDA, "device does not support cooperative launches");
+  CU(ctx, cudaFuncSetAttribute(k_simplex_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  int occ = 0;
+  CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_simplex_grid, kGridThreads, L.total));
+  if (occ < 1) return fail(ctx, YALPS_ERR_TOO_LARGE, "grid kernel does not fit on an SM");
+  // enough CTAs to stream the tableau, not more than can be co-resident, not more warps than rows
+  int grid = ctx->prop.multiProcessorCount;
+  const long long bytes = (long long)H * W * 8;
+  grid = (int)std::max(1LL, std::min<long long>(grid, bytes / (256 << 10) + 1));
+  grid = std::min(grid, std::max(1, (H + kGridWarps - 1) / kGridWarps));
+  if (const char *env = getenv("YALPS_GRID_CTAS")) grid = std::max(1, std::min(atoi(env), ctx->prop.multiProcessorCount * occ));
+  GridArgs a{};
+  a.M = d_M;
+  a.H = H;
+  a.W = W;
+  a.status = d_status;
+  a.value = d_value;
+  a.pivots = d_pivots;
+  a.rhs_out = d_rhs;
+  a.pos_out = d_pos;
+  a.precision = opt->precision;
+  a.max_pivots = opt->max_pivots;
+  a.check_cycles = opt->check_cycles ? 1 : 0;
+  a.hist_cap = hist_capacity(opt);
+  void *p = nullptr;
+  if (!d_var) {
+    if (int rc = dev_ensure(ctx, "grid_var", (size_t)(W + H) * 4, &p)) return rc;
+    d_var = (int *)p;
+  }
+  a.var = d_var;
+  a.init_var = d_init_var;
+  a.init_n = init_n;
+  if (int rc = dev_ensure(ctx, "grid_flags", 64, &p)) return rc;
+  a.flags = (int *)p;
+  a.barrier = (unsigned long long *)((char *)p + 32);
+  CU(ctx, cudaMemsetAsync(p, 0, 64, stream));
+  if (a.check_cycles) {
+    if (int rc = dev_ensure(ctx, "grid_hist", (size_t)2 * a.hist_cap * sizeof(int), &p)) return rc;
+    a.hist = (int *)p;
+  }
+  void *params[] = {&a};
+  CU(ctx, cudaLaunchCooperativeKernel((void *)k_simplex_grid, dim3(grid), dim3(kGridThreads), params, L.total, stream));
+  ctx->launches++;
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 int yalps_solve_batch_device(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, const double *d_matrices,
                              double *d_work, const yalps_options *opt, int32_t *d_status, double *d_value,
@@ -363,6 +438,24 @@ int yalps_solve_batch_device(yalps_ctx *ctx, int64_t n, int32_t height, int32_t 
   a.pos_out = d_pos_out;
   a.var_out = d_var_out;
   fill_options(a, opt);
+  if (use_grid_path(ctx, n, plan)) {
+    if (!d_work) return fail(ctx, YALPS_ERR_ARGUMENT, "d_work is required for the grid path");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t cells = (size_t)height * width;
+    if (d_work != d_matrices)
+      CU(ctx, cudaMemcpyAsync(d_work, d_matrices, (size_t)n * cells * 8, cudaMemcpyDeviceToDevice, st));
+    for (int64_t i = 0; i < n; i++) {
+      if (int rc = launch_grid(ctx, height, width, d_work + i * cells, opt, d_status ? d_status + i : nullptr,
+                               d_value ? d_value + i : nullptr, d_pivots ? (long long *)d_pivots + 2 * i : nullptr,
+                               d_rhs_out ? d_rhs_out + i * height : nullptr,
+                               d_pos_out ? d_pos_out + i * (width + height) : nullptr,
+                               d_var_out ? d_var_out + i * (width + height) : nullptr, st))
+        return rc;
+    }
+    if (d_matrices_out && d_matrices_out != d_work)
+      CU(ctx, cudaMemcpyAsync(d_matrices_out, d_work, (size_t)n * cells * 8, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
   if (!plan.resident) {
     if (!d_work) return fail(ctx, YALPS_ERR_ARGUMENT, "d_work is required for the HBM-resident path");
     if (!d_pos_out || !d_var_out) {
@@ -416,11 +509,14 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
     if ((long long)height * width >= (1LL << 31)) return fail(ctx, YALPS_ERR_TOO_LARGE, "height*width must be < 2^31");
   }
 
-  // chunking: at most ~1.5 GiB of tableaus per pipeline slot
-  const size_t kSlotBytes = (size_t)1536 << 20;
   auto cells_upto = [&](int64_t i) -> long long { return ragged ? moff[i] : (long long)i * height * width; };
   auto rows_upto = [&](int64_t i) -> long long { return ragged ? roff[i] : (long long)i * height; };
   auto pv_upto = [&](int64_t i) -> long long { return ragged ? poff[i] : (long long)i * (height + width); };
+
+  // chunking: two pipeline slots; a large batch is cut into ~8 chunks (64 MiB .. 1.5 GiB each) so that the
+  // H2D copy of chunk k+1 overlaps the kernel and the D2H copies of chunk k
+  const size_t total_bytes = (size_t)cells_upto(n) * 8;
+  const size_t kSlotBytes = std::min((size_t)1536 << 20, std::max((size_t)64 << 20, total_bytes / 8 + 4096));
 
   int64_t begin = 0;
   int slot = 0;
@@ -519,7 +615,20 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
       a.pos_off = (const long long *)d_po;
     }
     fill_options(a, opt);
-    if ((rc = launch_simplex(ctx, plan, a, s, st))) return rc;
+    if (use_grid_path(ctx, cn, plan)) {
+      for (int64_t i = 0; i < cn; i++) {
+        const int hi = ragged ? heights[begin + i] : height, wi = ragged ? widths[begin + i] : width;
+        const long long mo = cells_upto(begin + i) - cells_upto(begin), ro = rows_upto(begin + i) - rows_upto(begin),
+                        po = pv_upto(begin + i) - pv_upto(begin);
+        if ((rc = launch_grid(ctx, hi, wi, (double *)d_in + mo, opt, (int *)d_status + i, (double *)d_value + i,
+                              (long long *)d_piv + 2 * i, (double *)d_rhs + ro, (int *)d_pos + po, (int *)d_var + po,
+                              st)))
+          return rc;
+      }
+      a.mat_out = matrices_out ? (double *)d_in : nullptr;
+    } else if ((rc = launch_simplex(ctx, plan, a, s, st))) {
+      return rc;
+    }
 
     if (status) CU(ctx, cudaMemcpyAsync(status + begin, d_status, (size_t)cn * 4, cudaMemcpyDeviceToHost, st));
     if (value) CU(ctx, cudaMemcpyAsync(value + begin, d_value, (size_t)cn * 8, cudaMemcpyDeviceToHost, st));

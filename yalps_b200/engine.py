@@ -95,24 +95,34 @@ class Engine:
         return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
     # ------------------------------------------------------------------ simplex batches
+    def batch_outputs(self, n: int, height: int, width: int, want_matrices: bool = False, want_basis: bool = True,
+                      pinned: bool = False) -> dict:
+        """Output buffers for solve_batch; pinned=True allocates them page-locked (reusable across calls)."""
+        mk = self.pinned_empty if pinned else (lambda shape, dtype: np.empty(shape, dtype))
+        return {
+            "status": mk((n,), np.int32),
+            "value": mk((n,), np.float64),
+            "pivots": mk((n, 2), np.int64),
+            "rhs": mk((n, height), np.float64),
+            "pos": mk((n, width + height), np.int32) if want_basis else None,
+            "var": mk((n, width + height), np.int32) if want_basis else None,
+            "matrices": mk((n, height * width), np.float64) if want_matrices else None,
+        }
+
     def solve_batch(self, matrices: np.ndarray, height: int, width: int, options: Optional[Options] = None,
-                    want_matrices: bool = False, want_basis: bool = True) -> dict:
-        """n same-shape tableaus, `matrices` float64 of n*height*width values (not modified)."""
+                    want_matrices: bool = False, want_basis: bool = True, out: Optional[dict] = None) -> dict:
+        """n same-shape tableaus, `matrices` float64 of n*height*width values (not modified).
+        `out` may be a dict from batch_outputs() to reuse (pinned) result buffers."""
         opt = options or make_options()
         m = np.ascontiguousarray(matrices, dtype=np.float64).reshape(-1)
         cells = height * width
         if cells <= 0 or m.size % cells:
             raise ValueError(f"matrices has {m.size} values, not a multiple of {height}x{width}")
         n = m.size // cells
-        out = {
-            "status": np.empty(n, np.int32),
-            "value": np.empty(n, np.float64),
-            "pivots": np.empty((n, 2), np.int64),
-            "rhs": np.empty((n, height), np.float64),
-            "pos": np.empty((n, width + height), np.int32) if want_basis else None,
-            "var": np.empty((n, width + height), np.int32) if want_basis else None,
-            "matrices": np.empty((n, cells), np.float64) if want_matrices else None,
-        }
+        if out is None:
+            out = self.batch_outputs(n, height, width, want_matrices, want_basis)
+        elif out["status"].shape[0] != n:
+            raise ValueError("out was allocated for a different batch size")
         self._check(self._lib.yalps_solve_batch(self._ctx, n, height, width, _ptr(m), C.byref(opt), _ptr(out["status"]),
                                                 _ptr(out["value"]), _ptr(out["pivots"]), _ptr(out["rhs"]),
                                                 _ptr(out["pos"]), _ptr(out["var"]), _ptr(out["matrices"])))
