@@ -121,3 +121,26 @@ def test_zero_pivot_nodes_return_the_assembled_tableau(engine):
     m0, p0, v0 = O.apply_cuts(t.matrix, W, H, t.pos, t.var, [1.0, -1.0], [v, v], [5.0, -3.0])
     assert tuple(got["pivots"][0]) == (0, 0) and got["status"][0] == 0
     assert same_bits(got["matrices"][0][:(H + 2) * W], m0)
+
+
+@pytest.mark.parametrize("name", ["Knapsack 1", "Large Farm MIP"])
+def test_python_wave_driver_matches_native_driver(engine, name):
+    """yalps_b200.distributed.branch_and_cut_sharded (the multi-GPU host driver, here with one rank) against the
+    C++ driver and the oracle: same search, node for node."""
+    from yalps_b200 import distributed as D
+    c = next(x for x in CASES if x["name"] == name)
+    opt = {**M.DEFAULT_OPTIONS, **c["options"]}
+    tm = yalps_b200.tableau_model(c["model"])
+    t = tm.tableau
+    copt = E.make_options(opt["precision"], opt["maxPivots"], opt["checkCycles"], opt["tolerance"], opt["timeout"],
+                          opt["maxIterations"])
+    root = engine.solve_batch(t.matrix, t.height, t.width, copt, want_matrices=True)
+    assert root["status"][0] == 0
+    engine.bnb_set_root(root["matrices"][0], t.height, t.width, root["pos"][0], root["var"][0], 2 * len(tm.integers))
+    res = D.branch_and_cut_sharded(D.engine_node_evaluator(engine, copt), root["rhs"][0], root["pos"][0],
+                                   root["var"][0], t.width, t.height, tm.integers, tm.sign, float(root["value"][0]),
+                                   opt, wave=32)
+    o = c["oracle"]
+    assert res["status"] == o["status"] and same_value(-tm.sign * res["result"], o["result"])
+    assert res["stats"]["nodes"] == o["nodes"] and res["stats"]["node_pivots"] == o["node_pivots"]
+    assert np.array_equal(res["pos"], o["final_pos"]) and same_bits(res["rhs"], o["final_rhs"])
