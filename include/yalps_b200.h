@@ -165,7 +165,8 @@ int yalps_bnb_solve_nodes(yalps_ctx *ctx, int64_t n, const int32_t *cut_offsets,
  * Outputs describe the best tableau (src/branchAndCut.ts:175): out_height rows,
  * rhs_out[out_height], pos_out/var_out[width+out_height] (buffers sized for
  * height+max_extra_rows).  stats[8] (optional): nodes evaluated by the replay, node pivots,
- * max cuts, max heap, waves, nodes solved on device (incl. unused speculation), 0, 0.
+ * max cuts, max heap, waves, nodes solved on device (incl. unused speculation),
+ * microseconds spent in device waves, microseconds total.
  */
 int yalps_branch_and_cut(yalps_ctx *ctx, const int32_t *ints, int32_t nints, double sign, double init_result,
                          const yalps_options *opt, int32_t *status, double *result, int32_t *out_height,

@@ -130,10 +130,11 @@ class Tableau:
 
 
 class TableauModel:
-    __slots__ = ("tableau", "sign", "variables", "integers")
+    __slots__ = ("tableau", "sign", "variables", "integers", "row_groups")
 
-    def __init__(self, tableau, sign, variables, integers):
+    def __init__(self, tableau, sign, variables, integers, row_groups=None):
         self.tableau, self.sign, self.variables, self.integers = tableau, sign, variables, integers
+        self.row_groups = row_groups  # row -> index of the constraint key it came from (-1: objective / binary rows)
 
 
 def _get(con, key):
@@ -217,7 +218,11 @@ def tableau_model(model: dict) -> TableauModel:
         matrix[row * width] = 1.0
         matrix[row * width + col] = 1.0
 
-    return TableauModel(Tableau(matrix, width, height, pos, var), sign, variables, ints)
+    groups = np.full(height, -1, dtype=np.int32)
+    for g, b in enumerate(constraints.values()):
+        nrows = (1 if math.isfinite(b[1]) else 0) + (1 if math.isfinite(b[2]) else 0)
+        groups[b[0]:b[0] + nrows] = g
+    return TableauModel(Tableau(matrix, width, height, pos, var), sign, variables, ints, groups)
 
 
 # --------------------------------------------------------------------------- solve (src/YALPS.ts)

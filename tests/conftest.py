@@ -89,6 +89,7 @@ class NetlibGolden:
             "pivots": tuple(int(x) for x in z[f"{name}/pivots"]), "final_pos": z[f"{name}/final_pos"],
             "final_rhs": z[f"{name}/final_rhs"], "list": int(z[f"{name}/list"][0]),
             "oracle_seconds": float(z[f"{name}/oracle_seconds"][0]),
+            "row_groups": z[f"{name}/row_groups"],
         }
 
 

@@ -98,6 +98,7 @@ def netlib():
         data[f"{name}/nz_idx"] = nzi.astype(np.int64)
         data[f"{name}/nz_val"] = init[nzi]
         data[f"{name}/neg_zero_idx"] = np.flatnonzero((init == 0) & np.signbit(init)).astype(np.int64)
+        data[f"{name}/row_groups"] = tm.row_groups
         data[f"{name}/check_cycles"] = np.asarray([1 if opt["checkCycles"] else 0], np.int32)
         data[f"{name}/index_value"] = np.asarray([math.nan if e["value"] is None else e["value"]], np.float64)
         data[f"{name}/status"] = np.asarray([st], np.int32)

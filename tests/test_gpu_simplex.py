@@ -262,3 +262,73 @@ def test_netlib_long_trajectories(engine, name):
     assert same_value(got["value"][0], g["value"])
     assert np.array_equal(got["pos"][0], g["final_pos"])
     assert same_bits(got["rhs"][0], g["final_rhs"])
+
+
+def _replica_rhs(base_rhs, groups, first, n, eps=1e-2, salt=0x2545F491):
+    """numpy statement of the config-3 perturbation: one U per constraint key."""
+    from oracle import model as M
+    out = np.tile(base_rhs, (n, 1))
+    for i in range(n):
+        seed0 = M.prospector_hash((first + i) ^ salt)
+        for r, g in enumerate(groups):
+            if g >= 0:
+                u = M.prospector_hash((seed0 + (int(g) + 1) * 0x9E3779B9) & 0xFFFFFFFF) / 4294967296.0
+                out[i, r] = base_rhs[r] * (1.0 + eps * (2.0 * u - 1.0))
+    return out
+
+
+def test_replica_generator_and_config3_parity(engine):
+    """Config 3: RHS-perturbed replicas of SC105 / ADLITTLE generated on the device, solved on both memory paths,
+    against the oracle on the same replicas."""
+    import torch
+    for name, n in (("ADLITTLE", 24), ("SC105", 12)):
+        g = NL.get(name)
+        H, W = g["height"], g["width"]
+        d = torch.empty(n * H * W, dtype=torch.float64, device="cuda")
+        engine.generate_replicas_device(7, n, g["matrix"], H, W, g["row_groups"], d.data_ptr())
+        torch.cuda.synchronize()
+        mats = d.cpu().numpy().reshape(n, H * W)
+        exp_mats = np.tile(g["matrix"], (n, 1))
+        exp_mats.reshape(n, H, W)[:, :, 0] = _replica_rhs(g["matrix"].reshape(H, W)[:, 0], g["row_groups"], 7, n)
+        assert same_bits(mats, exp_mats)
+        exp = oracle_batch(mats, H, W)
+        assert (exp["status"] == 0).all()
+        for path in (E.PATH_SMEM, E.PATH_GMEM):
+            engine.set_tuning(path, 0)
+            got = engine.solve_batch(mats, H, W, want_matrices=True)
+            assert_batch_equal(got, exp, f"{name} path={path}")
+        engine.set_tuning(E.PATH_AUTO, 0)
+
+
+def test_full_size_batch_properties(engine):
+    """BASELINE.json config 2 at full size (65,536 LPs, too many for the oracle in a unit test): size-independent
+    properties -- every LP optimal (feasible start, bounded), the basis arrays are inverse permutations, the
+    reported value is roundToPrecision of the final M[0,0], final RHS is non-negative, and an oracle spot check
+    on a random sample of 512 LPs is bit-exact."""
+    import torch
+    n, m, nv = 65536, 32, 64
+    H, W = m + 1, nv + 1
+    d = torch.empty(n * H * W, dtype=torch.float64, device="cuda")
+    engine.generate_synthetic_device(0, n, m, nv, d.data_ptr())
+    st = torch.empty(n, dtype=torch.int32, device="cuda")
+    val = torch.empty(n, dtype=torch.float64, device="cuda")
+    piv = torch.empty(n, 2, dtype=torch.int64, device="cuda")
+    rhs = torch.empty(n, H, dtype=torch.float64, device="cuda")
+    pos = torch.empty(n, W + H, dtype=torch.int32, device="cuda")
+    var = torch.empty(n, W + H, dtype=torch.int32, device="cuda")
+    engine.solve_batch_device(n, H, W, d.data_ptr(), d_status=st.data_ptr(), d_value=val.data_ptr(),
+                              d_pivots=piv.data_ptr(), d_rhs=rhs.data_ptr(), d_pos=pos.data_ptr(), d_var=var.data_ptr(),
+                              stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert bool((st == 0).all())
+    assert bool((piv[:, 0] == 0).all()) and int(piv[:, 1].min()) >= 1
+    idx = torch.arange(W + H, device="cuda", dtype=torch.int64).expand(n, -1)
+    assert bool((torch.gather(pos.long(), 1, var.long()) == idx).all())  # pos[var[p]] == p
+    assert bool((rhs[:, 1:] >= -1e-8).all())  # primal feasible at the optimum
+    r0 = engine.round_to_precision(rhs[:, 0].cpu().numpy(), 1e-8)
+    assert same_bits(r0, val.cpu().numpy())
+    sample = np.random.default_rng(0).choice(n, 512, replace=False)
+    mats = d.view(n, H * W)[torch.from_numpy(sample).cuda()].cpu().numpy()
+    exp = oracle_batch(mats, H, W)
+    assert np.array_equal(exp["pivots"], piv.cpu().numpy()[sample])
+    assert same_bits(exp["rhs"], rhs.cpu().numpy()[sample]) and np.array_equal(exp["pos"], pos.cpu().numpy()[sample])

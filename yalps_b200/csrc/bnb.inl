@@ -20,18 +20,19 @@ struct Cut {
 struct Branch {
   double eval;
   std::vector<Cut> cuts;
-  int64_t id;
 };
 
 // npm heap@0.2.7 (package.json:157) == CPython heapq; comparator x[0]-y[0] (src/branchAndCut.ts:100).
+// The heap holds indices into the branch arena (copying it for the wave look-ahead is a memcpy).
 struct BranchHeap {
-  std::vector<std::shared_ptr<Branch>> a;
-  static bool lt(const Branch &x, const Branch &y) { return x.eval - y.eval < 0; }
+  const std::vector<Branch> *arena;
+  std::vector<int32_t> a;
+  bool lt(int32_t x, int32_t y) const { return (*arena)[x].eval - (*arena)[y].eval < 0; }
   void sift_toward_root(size_t start, size_t pos) {
-    auto item = a[pos];
+    const int32_t item = a[pos];
     while (pos > start) {
       const size_t parent = (pos - 1) >> 1;
-      if (!lt(*item, *a[parent])) break;
+      if (!lt(item, a[parent])) break;
       a[pos] = a[parent];
       pos = parent;
     }
@@ -39,11 +40,11 @@ struct BranchHeap {
   }
   void sift_to_leaf(size_t pos) {
     const size_t end = a.size(), start = pos;
-    auto item = a[pos];
+    const int32_t item = a[pos];
     size_t child = 2 * pos + 1;
     while (child < end) {
       const size_t right = child + 1;
-      if (right < end && !lt(*a[child], *a[right])) child = right;
+      if (right < end && !lt(a[child], a[right])) child = right;
       a[pos] = a[child];
       pos = child;
       child = 2 * pos + 1;
@@ -51,15 +52,15 @@ struct BranchHeap {
     a[pos] = item;
     sift_toward_root(start, pos);
   }
-  void push(std::shared_ptr<Branch> b) {
-    a.push_back(std::move(b));
+  void push(int32_t b) {
+    a.push_back(b);
     sift_toward_root(0, a.size() - 1);
   }
-  std::shared_ptr<Branch> pop() {
-    auto last = a.back();
+  int32_t pop() {
+    const int32_t last = a.back();
     a.pop_back();
     if (a.empty()) return last;
-    auto top = a[0];
+    const int32_t top = a[0];
     a[0] = last;
     sift_to_leaf(0);
     return top;
@@ -67,13 +68,16 @@ struct BranchHeap {
   bool empty() const { return a.empty(); }
 };
 
-struct NodeResult {
-  int32_t status;
-  double value;
-  int64_t pivots;
-  int32_t height;
+// Results of one device wave, kept as downloaded; nodes are read in place (no per-node copies).
+struct WaveBuf {
+  int n = 0, Hcap = 0;
+  std::vector<int32_t> ids;
+  std::vector<int32_t> status;
+  std::vector<double> value;
+  std::vector<int64_t> piv;
   std::vector<double> rhs;
   std::vector<int32_t> pos, var;
+  size_t bytes() const { return rhs.size() * 8 + (pos.size() + var.size()) * 4; }
 };
 
 double host_js_round(double x) {
@@ -192,19 +196,32 @@ int yalps_bnb_solve_nodes(yalps_ctx *ctx, int64_t n, const int32_t *cut_offsets,
   if (int rc = plan_launch(ctx, n, Hcap, W, opt->check_cycles != 0, &plan)) return rc;
 
   cudaStream_t st = ctx->streams[0];
-  void *d_off, *d_sign, *d_var, *d_val, *d_status, *d_value, *d_piv, *d_rhs, *d_pos, *d_vr;
   int rc;
-  const size_t nc = (size_t)std::max(ncut_total, 1);
-  if ((rc = dev_ensure(ctx, "nd_off", (size_t)(n + 1) * 4, &d_off))) return rc;
-  if ((rc = dev_ensure(ctx, "nd_sign", nc * 8, &d_sign))) return rc;
-  if ((rc = dev_ensure(ctx, "nd_var", nc * 4, &d_var))) return rc;
-  if ((rc = dev_ensure(ctx, "nd_val", nc * 8, &d_val))) return rc;
-  if ((rc = dev_ensure(ctx, "nd_status", (size_t)n * 4, &d_status))) return rc;
-  if ((rc = dev_ensure(ctx, "nd_value", (size_t)n * 8, &d_value))) return rc;
-  if ((rc = dev_ensure(ctx, "nd_piv", (size_t)n * 16, &d_piv))) return rc;
-  if ((rc = dev_ensure(ctx, "nd_rhs", (size_t)n * Hcap * 8, &d_rhs))) return rc;
-  if ((rc = dev_ensure(ctx, "nd_pos", (size_t)n * (W + Hcap) * 4, &d_pos))) return rc;
-  if ((rc = dev_ensure(ctx, "nd_vr", (size_t)n * (W + Hcap) * 4, &d_vr))) return rc;
+  // One pinned staging buffer and ONE copy per direction: a wave is latency-bound, and every extra
+  // cudaMemcpyAsync from pageable memory costs more than the node kernel itself.
+  auto up8 = [](size_t x) { return (x + 7) & ~(size_t)7; };
+  const size_t nc = (size_t)std::max(ncut_total, 0);
+  const size_t in_off = 0, in_var = up8((size_t)(n + 1) * 4), in_sign = in_var + up8(nc * 4), in_val = in_sign + nc * 8,
+               in_bytes = in_val + nc * 8;
+  const size_t o_status = 0, o_piv = up8((size_t)n * 4), o_value = o_piv + (size_t)n * 16, o_rhs = o_value + (size_t)n * 8,
+               o_pos = o_rhs + (size_t)n * Hcap * 8, o_var = o_pos + up8((size_t)n * (W + Hcap) * 4),
+               out_bytes = o_var + up8((size_t)n * (W + Hcap) * 4);
+  void *h_in, *h_out, *d_inb, *d_outb;
+  if ((rc = pin_ensure(ctx, "nd_h_in", in_bytes + 8, &h_in))) return rc;
+  if ((rc = pin_ensure(ctx, "nd_h_out", out_bytes + 8, &h_out))) return rc;
+  if ((rc = dev_ensure(ctx, "nd_d_in", in_bytes + 8, &d_inb))) return rc;
+  if ((rc = dev_ensure(ctx, "nd_d_out", out_bytes + 8, &d_outb))) return rc;
+  std::memcpy((char *)h_in + in_off, cut_offsets, (size_t)(n + 1) * 4);
+  if (nc) {
+    std::memcpy((char *)h_in + in_var, cut_var, nc * 4);
+    std::memcpy((char *)h_in + in_sign, cut_sign, nc * 8);
+    std::memcpy((char *)h_in + in_val, cut_value, nc * 8);
+  }
+  CU(ctx, cudaMemcpyAsync(d_inb, h_in, in_bytes, cudaMemcpyHostToDevice, st));
+  void *d_off = (char *)d_inb + in_off, *d_var = (char *)d_inb + in_var, *d_sign = (char *)d_inb + in_sign,
+       *d_val = (char *)d_inb + in_val;
+  void *d_status = (char *)d_outb + o_status, *d_piv = (char *)d_outb + o_piv, *d_value = (char *)d_outb + o_value,
+       *d_rhs = (char *)d_outb + o_rhs, *d_pos = (char *)d_outb + o_pos, *d_vr = (char *)d_outb + o_var;
   void *d_work = nullptr, *d_out = nullptr;
   const size_t mat_bytes = (size_t)n * Hcap * W * 8;
   if (!plan.resident) {
@@ -212,12 +229,6 @@ int yalps_bnb_solve_nodes(yalps_ctx *ctx, int64_t n, const int32_t *cut_offsets,
     d_out = matrices_out ? d_work : nullptr;
   } else if (matrices_out) {
     if ((rc = dev_ensure(ctx, "nd_out", mat_bytes, &d_out))) return rc;
-  }
-  CU(ctx, cudaMemcpyAsync(d_off, cut_offsets, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, st));
-  if (ncut_total > 0) {
-    CU(ctx, cudaMemcpyAsync(d_sign, cut_sign, (size_t)ncut_total * 8, cudaMemcpyHostToDevice, st));
-    CU(ctx, cudaMemcpyAsync(d_var, cut_var, (size_t)ncut_total * 4, cudaMemcpyHostToDevice, st));
-    CU(ctx, cudaMemcpyAsync(d_val, cut_value, (size_t)ncut_total * 8, cudaMemcpyHostToDevice, st));
   }
   BatchArgs a{};
   a.n = n;
@@ -266,14 +277,16 @@ int yalps_bnb_solve_nodes(yalps_ctx *ctx, int64_t n, const int32_t *cut_offsets,
   } else if ((rc = launch_simplex(ctx, plan, a, "nd", st))) {
     return rc;
   }
-  if (status) CU(ctx, cudaMemcpyAsync(status, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-  if (value) CU(ctx, cudaMemcpyAsync(value, d_value, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-  if (pivots) CU(ctx, cudaMemcpyAsync(pivots, d_piv, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
-  if (rhs_out) CU(ctx, cudaMemcpyAsync(rhs_out, d_rhs, (size_t)n * Hcap * 8, cudaMemcpyDeviceToHost, st));
-  if (pos_out) CU(ctx, cudaMemcpyAsync(pos_out, d_pos, (size_t)n * (W + Hcap) * 4, cudaMemcpyDeviceToHost, st));
-  if (var_out) CU(ctx, cudaMemcpyAsync(var_out, d_vr, (size_t)n * (W + Hcap) * 4, cudaMemcpyDeviceToHost, st));
+  CU(ctx, cudaMemcpyAsync(h_out, d_outb, out_bytes, cudaMemcpyDeviceToHost, st));
   if (matrices_out) CU(ctx, cudaMemcpyAsync(matrices_out, d_out, mat_bytes, cudaMemcpyDeviceToHost, st));
   CU(ctx, cudaStreamSynchronize(st));
+  const char *ho = (const char *)h_out;
+  if (status) std::memcpy(status, ho + o_status, (size_t)n * 4);
+  if (value) std::memcpy(value, ho + o_value, (size_t)n * 8);
+  if (pivots) std::memcpy(pivots, ho + o_piv, (size_t)n * 16);
+  if (rhs_out) std::memcpy(rhs_out, ho + o_rhs, (size_t)n * Hcap * 8);
+  if (pos_out) std::memcpy(pos_out, ho + o_pos, (size_t)n * (W + Hcap) * 4);
+  if (var_out) std::memcpy(var_out, ho + o_var, (size_t)n * (W + Hcap) * 4);
   return check_device_status(ctx, status, n);
 }
 
@@ -287,7 +300,8 @@ int yalps_branch_and_cut(yalps_ctx *ctx, const int32_t *ints, int32_t nints, dou
     return fail(ctx, YALPS_ERR_ARGUMENT, "bad arguments");
   const int W = R.W, H = R.H;
   const double precision = opt->precision;
-  int64_t st_nodes = 0, st_pivots = 0, st_maxcuts = 0, st_maxheap = 0, st_waves = 0, st_devnodes = 0;
+  int64_t st_nodes = 0, st_pivots = 0, st_maxcuts = 0, st_maxheap = 0, st_waves = 0, st_devnodes = 0, st_wave_us = 0;
+  const auto t_begin = std::chrono::steady_clock::now();
 
   auto write_best = [&](const double *rhs, const int32_t *pos, const int32_t *var, int h) {
     *out_height = h;
@@ -303,7 +317,8 @@ int yalps_branch_and_cut(yalps_ctx *ctx, const int32_t *ints, int32_t nints, dou
     stats[3] = st_maxheap;
     stats[4] = st_waves;
     stats[5] = st_devnodes;
-    stats[6] = stats[7] = 0;
+    stats[6] = st_wave_us;
+    stats[7] = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_begin).count();
   };
 
   int32_t init_var;
@@ -319,138 +334,161 @@ int yalps_branch_and_cut(yalps_ctx *ctx, const int32_t *ints, int32_t nints, dou
   if (2 * nints > R.max_extra)
     return fail(ctx, YALPS_ERR_ARGUMENT, "root was set with max_extra_rows=%d < 2*|integers|=%d", R.max_extra, 2 * nints);
 
-  int64_t next_id = 0;
+  std::vector<Branch> arena;
+  arena.reserve(4096);
   BranchHeap heap;
-  {
-    auto b1 = std::make_shared<Branch>();
-    b1->eval = init_result;
-    b1->cuts = {Cut{-1.0, init_var, std::ceil(init_val)}};
-    b1->id = next_id++;
-    auto b2 = std::make_shared<Branch>();
-    b2->eval = init_result;
-    b2->cuts = {Cut{1.0, init_var, std::floor(init_val)}};
-    b2->id = next_id++;
-    heap.push(b1);
-    heap.push(b2);
-  }
+  heap.arena = &arena;
+  arena.push_back(Branch{init_result, {Cut{-1.0, init_var, std::ceil(init_val)}}});
+  arena.push_back(Branch{init_result, {Cut{1.0, init_var, std::floor(init_val)}}});
+  heap.push(0);
+  heap.push(1);
 
-  std::unordered_map<int64_t, NodeResult> cache;
+  // branch id -> (wave, slot) of its cached node result, -1 = not evaluated
+  std::vector<int32_t> res_wave, res_slot;
+  std::vector<std::unique_ptr<WaveBuf>> waves;
+  size_t cached_bytes = 0, oldest_wave = 0;
+  const size_t kCacheBudget = (size_t)768 << 20;
+  auto cached = [&](int32_t id) { return (size_t)id < res_wave.size() && res_wave[id] >= 0; };
+
   const double threshold = init_result * (1.0 - sign * opt->tolerance);
   const double stop_time = opt->timeout_ms + now_ms();
   bool timedout = now_ms() >= stop_time;
   bool found = false;
   double best_eval = std::numeric_limits<double>::infinity();
-  NodeResult best;
+  int best_height = 0;
+  std::vector<double> best_rhs;
+  std::vector<int32_t> best_pos, best_var;
   double iter = 0;
 
-  // wave staging
   std::vector<int32_t> w_off;
   std::vector<double> w_sign, w_val;
   std::vector<int32_t> w_var;
-  std::vector<int32_t> w_status;
-  std::vector<double> w_value;
-  std::vector<int64_t> w_piv;
-  std::vector<double> w_rhs;
-  std::vector<int32_t> w_pos, w_vr;
+  BranchHeap peek;
+  peek.arena = &arena;
 
-  auto run_wave = [&](const std::shared_ptr<Branch> &needed) -> int {
-    // the needed branch first, then the branches the heap would pop next (on a copy of the heap)
-    std::vector<std::shared_ptr<Branch>> wave{needed};
-    BranchHeap peek = heap;
-    while ((int)wave.size() < ctx->wave && !peek.empty()) {
-      auto b = peek.pop();
-      if (b->eval > best_eval) break;  // would be pruned (:124)
-      if (cache.find(b->id) == cache.end()) wave.push_back(b);
+  auto run_wave = [&](int32_t needed) -> int {
+    // the needed branch first, then the branches the heap would pop next (on a copy of the index heap)
+    auto wb = std::make_unique<WaveBuf>();
+    wb->ids.push_back(needed);
+    peek.a = heap.a;
+    while ((int)wb->ids.size() < ctx->wave && !peek.empty()) {
+      const int32_t b = peek.pop();
+      if (arena[b].eval > best_eval) break;  // would be pruned (:124)
+      if (!cached(b)) wb->ids.push_back(b);
     }
-    const int64_t n = (int64_t)wave.size();
+    const int64_t n = (int64_t)wb->ids.size();
     w_off.assign(1, 0);
     w_sign.clear();
     w_var.clear();
     w_val.clear();
     int maxcuts = 0;
-    for (auto &b : wave) {
-      for (auto &c : b->cuts) {
+    for (int32_t id : wb->ids) {
+      for (const Cut &c : arena[id].cuts) {
         w_sign.push_back(c.sign);
         w_var.push_back(c.variable);
         w_val.push_back(c.value);
       }
       w_off.push_back((int32_t)w_sign.size());
-      maxcuts = std::max(maxcuts, (int)b->cuts.size());
+      maxcuts = std::max(maxcuts, (int)arena[id].cuts.size());
     }
-    const int Hcap = H + maxcuts;
-    w_status.resize(n);
-    w_value.resize(n);
-    w_piv.resize(2 * n);
-    w_rhs.resize((size_t)n * Hcap);
-    w_pos.resize((size_t)n * (W + Hcap));
-    w_vr.resize((size_t)n * (W + Hcap));
+    wb->n = (int)n;
+    wb->Hcap = H + maxcuts;
+    wb->status.resize(n);
+    wb->value.resize(n);
+    wb->piv.resize(2 * n);
+    wb->rhs.resize((size_t)n * wb->Hcap);
+    wb->pos.resize((size_t)n * (W + wb->Hcap));
+    wb->var.resize((size_t)n * (W + wb->Hcap));
+    const auto t0 = std::chrono::steady_clock::now();
     if (int rc = yalps_bnb_solve_nodes(ctx, n, w_off.data(), w_sign.data(), w_var.data(), w_val.data(), opt,
-                                       w_status.data(), w_value.data(), w_piv.data(), w_rhs.data(), w_pos.data(),
-                                       w_vr.data(), nullptr))
+                                       wb->status.data(), wb->value.data(), wb->piv.data(), wb->rhs.data(),
+                                       wb->pos.data(), wb->var.data(), nullptr))
       return rc;
+    st_wave_us += std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
     st_waves++;
     st_devnodes += n;
+    if (res_wave.size() < arena.size()) {
+      res_wave.resize(arena.capacity() > arena.size() ? arena.capacity() : arena.size() * 2, -1);
+      res_slot.resize(res_wave.size(), -1);
+    }
     for (int64_t j = 0; j < n; j++) {
-      NodeResult nr;
-      nr.status = w_status[j];
-      nr.value = w_value[j];
-      nr.pivots = w_piv[2 * j] + w_piv[2 * j + 1];
-      nr.height = H + (int)wave[j]->cuts.size();
-      nr.rhs.assign(w_rhs.begin() + (size_t)j * Hcap, w_rhs.begin() + (size_t)j * Hcap + nr.height);
-      nr.pos.assign(w_pos.begin() + (size_t)j * (W + Hcap), w_pos.begin() + (size_t)j * (W + Hcap) + W + nr.height);
-      nr.var.assign(w_vr.begin() + (size_t)j * (W + Hcap), w_vr.begin() + (size_t)j * (W + Hcap) + W + nr.height);
-      cache.emplace(wave[j]->id, std::move(nr));
+      res_wave[wb->ids[j]] = (int32_t)waves.size();
+      res_slot[wb->ids[j]] = (int32_t)j;
+    }
+    cached_bytes += wb->bytes();
+    waves.push_back(std::move(wb));
+    // bounded cache: forget the oldest waves (their unused speculation is recomputed if it is ever needed)
+    while (cached_bytes > kCacheBudget && oldest_wave + 1 < waves.size()) {
+      WaveBuf &old = *waves[oldest_wave];
+      for (int32_t id : old.ids)
+        if (res_wave[id] == (int32_t)oldest_wave) res_wave[id] = -1;
+      cached_bytes -= old.bytes();
+      waves[oldest_wave].reset();
+      oldest_wave++;
     }
     return 0;
   };
 
   while (iter < opt->max_iterations && !heap.empty() && best_eval >= threshold && !timedout) {  // :122
     st_maxheap = std::max<int64_t>(st_maxheap, (int64_t)heap.a.size());
-    auto br = heap.pop();
-    if (br->eval > best_eval) break;  // :124
+    const int32_t br = heap.pop();
+    if (arena[br].eval > best_eval) break;  // :124
 
-    auto it = cache.find(br->id);
-    if (it == cache.end()) {
+    if (!cached(br))
       if (int rc = run_wave(br)) return rc;
-      it = cache.find(br->id);
-    }
-    NodeResult nr = std::move(it->second);
-    cache.erase(it);
+    const WaveBuf &wb = *waves[res_wave[br]];
+    const int slot = res_slot[br];
+    res_wave[br] = -1;  // consumed
+    const int32_t n_status = wb.status[slot];
+    const double n_value = wb.value[slot];
+    const int n_height = H + (int)arena[br].cuts.size();
+    const double *n_rhs = wb.rhs.data() + (size_t)slot * wb.Hcap;
+    const int32_t *n_pos = wb.pos.data() + (size_t)slot * (W + wb.Hcap);
+    const int32_t *n_var = wb.var.data() + (size_t)slot * (W + wb.Hcap);
     st_nodes++;
-    st_pivots += nr.pivots;
-    st_maxcuts = std::max<int64_t>(st_maxcuts, (int64_t)br->cuts.size());
+    st_pivots += wb.piv[2 * slot] + wb.piv[2 * slot + 1];
+    st_maxcuts = std::max<int64_t>(st_maxcuts, (int64_t)arena[br].cuts.size());
 
-    if (nr.status == YALPS_OPTIMAL && nr.value < best_eval) {  // :130
+    if (n_status == YALPS_OPTIMAL && n_value < best_eval) {  // :130
       int32_t variable;
       double value, frac;
-      most_fractional(nr.rhs.data(), nr.pos.data(), W, ints, nints, &variable, &value, &frac);
+      most_fractional(n_rhs, n_pos, W, ints, nints, &variable, &value, &frac);
       if (frac <= precision) {  // integer solution, new incumbent (:132-139)
         found = true;
-        best_eval = nr.value;
-        best = std::move(nr);
+        best_eval = n_value;
+        best_height = n_height;
+        best_rhs.assign(n_rhs, n_rhs + n_height);
+        best_pos.assign(n_pos, n_pos + W + n_height);
+        best_var.assign(n_var, n_var + W + n_height);
       } else {  // branch (:141-156)
-        auto upper = std::make_shared<Branch>();
-        auto lower = std::make_shared<Branch>();
-        for (const Cut &cut : br->cuts) {
+        Branch upper, lower;
+        upper.cuts.reserve(arena[br].cuts.size() + 1);
+        lower.cuts.reserve(arena[br].cuts.size() + 1);
+        for (const Cut &cut : arena[br].cuts) {
           if (cut.variable == variable) {
             if (cut.sign < 0)
-              lower->cuts.push_back(cut);
+              lower.cuts.push_back(cut);
             else
-              upper->cuts.push_back(cut);
+              upper.cuts.push_back(cut);
           } else {
-            upper->cuts.push_back(cut);
-            lower->cuts.push_back(cut);
+            upper.cuts.push_back(cut);
+            lower.cuts.push_back(cut);
           }
         }
-        lower->cuts.push_back(Cut{1.0, variable, std::floor(value)});
-        upper->cuts.push_back(Cut{-1.0, variable, std::ceil(value)});
-        upper->eval = lower->eval = nr.value;
-        upper->id = next_id++;
-        lower->id = next_id++;
-        heap.push(upper);
-        heap.push(lower);
+        lower.cuts.push_back(Cut{1.0, variable, std::floor(value)});
+        upper.cuts.push_back(Cut{-1.0, variable, std::ceil(value)});
+        upper.eval = lower.eval = n_value;
+        arena.push_back(std::move(upper));
+        heap.push((int32_t)arena.size() - 1);
+        arena.push_back(std::move(lower));
+        heap.push((int32_t)arena.size() - 1);
+        if (res_wave.size() < arena.size()) {
+          res_wave.resize(arena.size() * 2, -1);
+          res_slot.resize(res_wave.size(), -1);
+        }
       }
     }
+    std::vector<Cut>().swap(arena[br].cuts);  // the cut list of a consumed branch is no longer needed
     timedout = now_ms() >= stop_time;  // :162
     iter++;
   }
@@ -459,7 +497,7 @@ int yalps_branch_and_cut(yalps_ctx *ctx, const int32_t *ints, int32_t nints, dou
   *status = unfinished ? YALPS_TIMEDOUT : (!found ? YALPS_INFEASIBLE : YALPS_OPTIMAL);
   *result = found ? best_eval : std::numeric_limits<double>::quiet_NaN();
   if (found)
-    write_best(best.rhs.data(), best.pos.data(), best.var.data(), best.height);
+    write_best(best_rhs.data(), best_pos.data(), best_var.data(), best_height);
   else
     write_best(R.h_rhs.data(), R.h_pos.data(), R.h_var.data(), H);  // bestTableau = root (:119)
   write_stats();

@@ -154,11 +154,21 @@ const KernelEntry *pick_kernel(int nw_want, int W, bool resident) {
   return best;
 }
 
-int default_warps(long long cells) {
-  long long w = cells / 2048;
-  int nw = 1;
-  while (nw * 2 <= w && nw < 32) nw *= 2;
-  return nw;
+// CTA width by tableau size, from scripts/sweep_paths.py on B200 (profiles/r01_sweep_paths.jsonl).
+int default_warps(long long cells, bool resident) {
+  if (resident) {
+    if (cells < 3000) return 1;
+    if (cells < 12000) return 2;
+    if (cells < 40000) return 4;
+    if (cells < 120000) return 8;
+    return 16;
+  }
+  if (cells < 5000) return 1;
+  if (cells < 12000) return 2;
+  if (cells < 25000) return 4;
+  if (cells < 50000) return 8;
+  if (cells < 400000) return 16;
+  return 32;
 }
 
 struct LaunchPlan {
@@ -168,9 +178,14 @@ struct LaunchPlan {
   int grid;
 };
 
-int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycles, LaunchPlan *plan) {
+// density: fraction of non-zero cells of a sample of the input (< 0 = unknown).  Sparse tableaus skip most of
+// the rank-1 update, their pivots are latency-bound, and the HBM/L2-resident kernel wins because it needs no
+// shared memory for the tableau and therefore runs many more LPs per SM (profiles/r01_sweep_paths.jsonl).
+int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycles, LaunchPlan *plan,
+                double density = -1.0) {
   const SmemLayout Lr(Hcap, Wcap, true), Lg(Hcap, Wcap, false);
   bool resident = Lr.total <= (size_t)ctx->smem_optin;
+  if (resident && ctx->tune_path == YALPS_PATH_AUTO && density >= 0.0 && density < 0.35 && n > 64) resident = false;
   if (ctx->tune_path == YALPS_PATH_SMEM) {
     if (!resident) return fail(ctx, YALPS_ERR_TOO_LARGE, "tableau %dx%d does not fit in shared memory", Hcap, Wcap);
   } else if (ctx->tune_path == YALPS_PATH_GMEM) {
@@ -185,8 +200,8 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
     if (grid_ok) return 0;  // only the grid kernel (K4) can take it
     return fail(ctx, YALPS_ERR_TOO_LARGE, "tableau %dx%d: pivot row/column staging exceeds shared memory", Hcap, Wcap);
   }
-  int nw = ctx->tune_threads > 0 ? std::max(1, ctx->tune_threads / 32) : default_warps((long long)Hcap * Wcap);
-  if (!resident && ctx->tune_threads <= 0) nw = std::max(nw, 8);
+  const int nw = ctx->tune_threads > 0 ? std::max(1, ctx->tune_threads / 32)
+                                      : default_warps((long long)Hcap * Wcap, resident);
   const KernelEntry *k = pick_kernel(nw, Wcap, resident);
   if (!k) {
     if (grid_ok) return 0;
@@ -521,6 +536,7 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
   int64_t begin = 0;
   int slot = 0;
   int rc = 0;
+  double density = -1.0;
   bool used[2] = {false, false};
   while (begin < n) {
     int64_t end = begin + 1;
@@ -542,7 +558,15 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
       }
     }
     LaunchPlan plan;
-    if ((rc = plan_launch(ctx, cn, chcap, cwcap, opt->check_cycles != 0, &plan))) return rc;
+    if (density < 0.0) {  // sample the first tableau once
+      const double *m0 = matrices + (ragged ? mat_offsets[0] : 0);
+      const long long c0 = ragged ? (long long)heights[0] * widths[0] : (long long)height * width;
+      const long long step = std::max(1LL, c0 / 4096);
+      long long seen = 0, nz = 0;
+      for (long long k = 0; k < c0; k += step, seen++) nz += m0[k] != 0.0;
+      density = seen ? (double)nz / (double)seen : 1.0;
+    }
+    if ((rc = plan_launch(ctx, cn, chcap, cwcap, opt->check_cycles != 0, &plan, density))) return rc;
 
     void *d_in, *d_status, *d_value, *d_piv, *d_rhs, *d_pos, *d_var;
     if ((rc = dev_ensure(ctx, "in" + s, ccells * 8, &d_in))) return rc;

@@ -249,7 +249,8 @@ class Engine:
             "var": var[:width + h], "root_status": root_status.value, "root_value": root_value.value,
             "root_pivots": (int(root_piv[0]), int(root_piv[1])),
             "stats": {"nodes": int(stats[0]), "node_pivots": int(stats[1]), "max_cuts": int(stats[2]),
-                      "max_heap": int(stats[3]), "waves": int(stats[4]), "device_nodes": int(stats[5])},
+                      "max_heap": int(stats[3]), "waves": int(stats[4]), "device_nodes": int(stats[5]),
+                      "wave_us": int(stats[6]), "bnb_us": int(stats[7])},
         }
 
     def branch_and_cut(self, integers: Sequence[int], sign: float, init_result: float,
@@ -272,7 +273,8 @@ class Engine:
         return {"status": status.value, "result": result.value, "height": h, "rhs": rhs[:h], "pos": pos[:W + h],
                 "var": var[:W + h],
                 "stats": {"nodes": int(stats[0]), "node_pivots": int(stats[1]), "max_cuts": int(stats[2]),
-                          "max_heap": int(stats[3]), "waves": int(stats[4]), "device_nodes": int(stats[5])}}
+                          "max_heap": int(stats[3]), "waves": int(stats[4]), "device_nodes": int(stats[5]),
+                          "wave_us": int(stats[6]), "bnb_us": int(stats[7])}}
 
     # ------------------------------------------------------------------ probes
     def round_to_precision(self, x: np.ndarray, precision: float) -> np.ndarray:
