@@ -209,15 +209,23 @@ int yalps_bnb_solve_nodes(yalps_ctx *ctx, int64_t n, const int32_t *cut_offsets,
   void *h_in, *h_out, *d_inb, *d_outb;
   if ((rc = pin_ensure(ctx, "nd_h_in", in_bytes + 8, &h_in))) return rc;
   if ((rc = pin_ensure(ctx, "nd_h_out", out_bytes + 8, &h_out))) return rc;
-  if ((rc = dev_ensure(ctx, "nd_d_in", in_bytes + 8, &d_inb))) return rc;
-  if ((rc = dev_ensure(ctx, "nd_d_out", out_bytes + 8, &d_outb))) return rc;
+  // small waves: the kernel reads the cut lists and writes its results straight through the mapped pinned
+  // buffers (zero-copy), so a wave is launch + synchronise; big waves use one explicit copy per direction
+  const bool zero_copy = in_bytes + out_bytes <= ((size_t)1 << 20);
+  if (zero_copy) {
+    if ((rc = pin_device_ptr(ctx, h_in, &d_inb))) return rc;
+    if ((rc = pin_device_ptr(ctx, h_out, &d_outb))) return rc;
+  } else {
+    if ((rc = dev_ensure(ctx, "nd_d_in", in_bytes + 8, &d_inb))) return rc;
+    if ((rc = dev_ensure(ctx, "nd_d_out", out_bytes + 8, &d_outb))) return rc;
+  }
   std::memcpy((char *)h_in + in_off, cut_offsets, (size_t)(n + 1) * 4);
   if (nc) {
     std::memcpy((char *)h_in + in_var, cut_var, nc * 4);
     std::memcpy((char *)h_in + in_sign, cut_sign, nc * 8);
     std::memcpy((char *)h_in + in_val, cut_value, nc * 8);
   }
-  CU(ctx, cudaMemcpyAsync(d_inb, h_in, in_bytes, cudaMemcpyHostToDevice, st));
+  if (!zero_copy) CU(ctx, cudaMemcpyAsync(d_inb, h_in, in_bytes, cudaMemcpyHostToDevice, st));
   void *d_off = (char *)d_inb + in_off, *d_var = (char *)d_inb + in_var, *d_sign = (char *)d_inb + in_sign,
        *d_val = (char *)d_inb + in_val;
   void *d_status = (char *)d_outb + o_status, *d_piv = (char *)d_outb + o_piv, *d_value = (char *)d_outb + o_value,
@@ -277,7 +285,7 @@ int yalps_bnb_solve_nodes(yalps_ctx *ctx, int64_t n, const int32_t *cut_offsets,
   } else if ((rc = launch_simplex(ctx, plan, a, "nd", st))) {
     return rc;
   }
-  CU(ctx, cudaMemcpyAsync(h_out, d_outb, out_bytes, cudaMemcpyDeviceToHost, st));
+  if (!zero_copy) CU(ctx, cudaMemcpyAsync(h_out, d_outb, out_bytes, cudaMemcpyDeviceToHost, st));
   if (matrices_out) CU(ctx, cudaMemcpyAsync(matrices_out, d_out, mat_bytes, cudaMemcpyDeviceToHost, st));
   CU(ctx, cudaStreamSynchronize(st));
   const char *ho = (const char *)h_out;

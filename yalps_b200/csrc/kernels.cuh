@@ -90,11 +90,14 @@ __global__ void __launch_bounds__(NW * 32) k_simplex(const BatchArgs a) {
   __shared__ long long s_lp;
   const int tid = threadIdx.x;
 
-  for (;;) {
-    if (tid == 0) s_lp = (long long)atomicAdd(a.counter, 1ULL);
-    __syncthreads();
-    const long long lp = s_lp;
-    __syncthreads();
+  for (long long static_lp = blockIdx.x;; static_lp += gridDim.x) {
+    long long lp = static_lp;  // small launches (node waves): LPs dealt statically, no queue to reset
+    if (a.counter) {           // big batches: persistent CTAs pull the next LP from an atomic queue
+      if (tid == 0) s_lp = (long long)atomicAdd(a.counter, 1ULL);
+      __syncthreads();
+      lp = s_lp;
+      __syncthreads();
+    }
     if (lp >= a.n) break;
 
     int H, W, ncuts = 0;

@@ -58,6 +58,8 @@ struct yalps_ctx {
   // pooled device buffers (index = purpose * 2 + pipeline slot)
   std::unordered_map<std::string, DevBuf> pool;
   std::unordered_map<std::string, DevBuf> pinned;
+  std::unordered_map<std::string, int> occ_cache;
+  std::unordered_map<void *, int> smem_attr;
   Root root;
 };
 
@@ -103,11 +105,17 @@ int pin_ensure(yalps_ctx *ctx, const std::string &name, size_t bytes, void **out
     if (b.p) CU(ctx, cudaFreeHost(b.p));
     b.p = nullptr;
     b.cap = 0;
-    size_t want = std::max(bytes, (size_t)256);
-    CU(ctx, cudaMallocHost(&b.p, want));
+    size_t want = std::max(bytes * 2, (size_t)4096);
+    CU(ctx, cudaHostAlloc(&b.p, want, cudaHostAllocMapped | cudaHostAllocPortable));
     b.cap = want;
   }
   *out = b.p;
+  return 0;
+}
+
+// Device-side alias of a buffer from pin_ensure (zero-copy access over PCIe for latency-bound small launches).
+int pin_device_ptr(yalps_ctx *ctx, void *host, void **dev) {
+  CU(ctx, cudaHostGetDevicePointer(dev, host, 0));
   return 0;
 }
 
@@ -203,16 +211,43 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
   const int nw = ctx->tune_threads > 0 ? std::max(1, ctx->tune_threads / 32)
                                       : default_warps((long long)Hcap * Wcap, resident);
   const KernelEntry *k = pick_kernel(nw, Wcap, resident);
+  if (k) {  // the attribute / occupancy queries cost microseconds: remember them per (kernel, shared memory size)
+    const size_t smem_c = resident ? Lr.total : Lg.total;
+    const std::string key = std::to_string((size_t)(resident ? (void *)k->resident : (void *)k->global)) + ":" + std::to_string(smem_c);
+    auto it = ctx->occ_cache.find(key);
+    if (it != ctx->occ_cache.end()) {
+      int &attr = ctx->smem_attr[(void *)(resident ? k->resident : k->global)];
+      if ((int)smem_c > attr) {  // the opt-in limit is per function and only ever raised
+        CU(ctx, cudaFuncSetAttribute(resident ? k->resident : k->global, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+        attr = (int)smem_c;
+      }
+      int occ_c = it->second;
+      if (check_cycles) occ_c = std::min(occ_c, 4);
+      long long grid_c = std::max(1LL, std::min((long long)occ_c * ctx->prop.multiProcessorCount, n));
+      plan->resident = resident;
+      plan->k = k;
+      plan->smem = smem_c;
+      plan->grid = (int)grid_c;
+      return 0;
+    }
+  }
   if (!k) {
     if (grid_ok) return 0;
     return fail(ctx, YALPS_ERR_TOO_LARGE, "tableau width %d exceeds the widest kernel", Wcap);
   }
   SimplexKernel fn = resident ? k->resident : k->global;
   const size_t smem = resident ? Lr.total : Lg.total;
-  CU(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    int &attr = ctx->smem_attr[(void *)fn];
+    if ((int)smem > attr) {
+      CU(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = (int)smem;
+    }
+  }
   int occ = 0;
   CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, k->nw * 32, smem));
   if (occ < 1) return fail(ctx, YALPS_ERR_TOO_LARGE, "kernel does not fit on an SM (smem %zu)", smem);
+  ctx->occ_cache[std::to_string((size_t)(void *)fn) + ":" + std::to_string(smem)] = occ;
   if (check_cycles) occ = std::min(occ, 4);  // bounds the history buffer
   long long grid = (long long)occ * ctx->prop.multiProcessorCount;
   grid = std::max(1LL, std::min(grid, n));
@@ -242,10 +277,13 @@ int hist_capacity(const yalps_options *opt) {
 // Enqueue one kernel launch for `args` (device pointers filled in by the caller).
 int launch_simplex(yalps_ctx *ctx, const LaunchPlan &plan, BatchArgs &args, const std::string &slot,
                    cudaStream_t stream) {
-  void *counter = nullptr;
-  if (int rc = dev_ensure(ctx, "counter" + slot, 8, &counter)) return rc;
-  CU(ctx, cudaMemsetAsync(counter, 0, 8, stream));
-  args.counter = (unsigned long long *)counter;
+  args.counter = nullptr;
+  if (args.n > plan.grid) {  // more LPs than CTAs: dynamic queue (pivot counts vary per LP)
+    void *counter = nullptr;
+    if (int rc = dev_ensure(ctx, "counter" + slot, 8, &counter)) return rc;
+    CU(ctx, cudaMemsetAsync(counter, 0, 8, stream));
+    args.counter = (unsigned long long *)counter;
+  }
   if (args.check_cycles) {
     void *hist = nullptr;
     if (int rc = dev_ensure(ctx, "hist" + slot, (size_t)plan.grid * 2 * args.hist_cap * sizeof(int), &hist)) return rc;
@@ -527,6 +565,90 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
   auto cells_upto = [&](int64_t i) -> long long { return ragged ? moff[i] : (long long)i * height * width; };
   auto rows_upto = [&](int64_t i) -> long long { return ragged ? roff[i] : (long long)i * height; };
   auto pv_upto = [&](int64_t i) -> long long { return ragged ? poff[i] : (long long)i * (height + width); };
+
+  // ---- small calls (a single LP, a handful of models): latency-bound.  Stage through one mapped pinned buffer,
+  // let the kernel read the tableaus and write the results zero-copy: launch + synchronise, no memcpy calls.
+  {
+    const size_t in_b = (size_t)cells_upto(n) * 8, rows_b = (size_t)rows_upto(n) * 8, pv_b = (size_t)pv_upto(n) * 4;
+    const size_t out_b = (size_t)n * 32 + rows_b + 2 * pv_b + 64 + (matrices_out ? in_b : 0);
+    const size_t desc_b = ragged ? (size_t)n * 32 + 64 : 0;
+    LaunchPlan plan;
+    if (in_b + out_b + desc_b <= ((size_t)768 << 10) && ctx->tune_path != YALPS_PATH_GRID &&
+        plan_launch(ctx, n, Hcap, Wcap, opt->check_cycles != 0, &plan) == 0 && plan.k && plan.resident) {
+      auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+      size_t o = 0;
+      const size_t o_in = o; o += up16(in_b);
+      const size_t o_h = o; o += ragged ? up16((size_t)n * 4) : 0;
+      const size_t o_w = o; o += ragged ? up16((size_t)n * 4) : 0;
+      const size_t o_mo = o; o += ragged ? up16((size_t)n * 8) : 0;
+      const size_t o_ro = o; o += ragged ? up16((size_t)n * 8) : 0;
+      const size_t o_po = o; o += ragged ? up16((size_t)n * 8) : 0;
+      const size_t o_st = o; o += up16((size_t)n * 4);
+      const size_t o_val = o; o += up16((size_t)n * 8);
+      const size_t o_piv = o; o += up16((size_t)n * 16);
+      const size_t o_rhs = o; o += up16(rows_b);
+      const size_t o_pos = o; o += up16(pv_b);
+      const size_t o_var = o; o += up16(pv_b);
+      const size_t o_mat = o; o += matrices_out ? up16(in_b) : 0;
+      void *hb, *db;
+      int rc;
+      if ((rc = pin_ensure(ctx, "small_io", o + 16, &hb))) return rc;
+      if ((rc = pin_device_ptr(ctx, hb, &db))) return rc;
+      char *h = (char *)hb, *d = (char *)db;
+      if (ragged) {
+        for (int64_t i = 0; i < n; i++)
+          std::memcpy(h + o_in + (size_t)moff[i] * 8, matrices + mat_offsets[i], (size_t)heights[i] * widths[i] * 8);
+        std::memcpy(h + o_h, heights, (size_t)n * 4);
+        std::memcpy(h + o_w, widths, (size_t)n * 4);
+        std::memcpy(h + o_mo, moff.data(), (size_t)n * 8);
+        std::memcpy(h + o_ro, roff.data(), (size_t)n * 8);
+        std::memcpy(h + o_po, poff.data(), (size_t)n * 8);
+      } else {
+        std::memcpy(h + o_in, matrices, in_b);
+      }
+      BatchArgs a{};
+      a.n = n;
+      a.mode = kModeBatch;
+      a.H = height;
+      a.W = width;
+      a.Hcap = Hcap;
+      a.Wcap = Wcap;
+      a.in = (const double *)(d + o_in);
+      a.work = nullptr;
+      a.mat_out = matrices_out ? (double *)(d + o_mat) : nullptr;
+      a.status = (int *)(d + o_st);
+      a.value = (double *)(d + o_val);
+      a.pivots = (long long *)(d + o_piv);
+      a.rhs_out = (double *)(d + o_rhs);
+      a.pos_out = (int *)(d + o_pos);
+      a.var_out = (int *)(d + o_var);
+      if (ragged) {
+        a.heights = (const int *)(d + o_h);
+        a.widths = (const int *)(d + o_w);
+        a.mat_off = (const long long *)(d + o_mo);
+        a.rhs_off = (const long long *)(d + o_ro);
+        a.pos_off = (const long long *)(d + o_po);
+      }
+      fill_options(a, opt);
+      cudaStream_t st = ctx->streams[0];
+      if ((rc = launch_simplex(ctx, plan, a, "small", st))) return rc;
+      CU(ctx, cudaStreamSynchronize(st));
+      if (status) std::memcpy(status, h + o_st, (size_t)n * 4);
+      if (value) std::memcpy(value, h + o_val, (size_t)n * 8);
+      if (pivots) std::memcpy(pivots, h + o_piv, (size_t)n * 16);
+      if (rhs_out) std::memcpy(rhs_out, h + o_rhs, rows_b);
+      if (pos_out) std::memcpy(pos_out, h + o_pos, pv_b);
+      if (var_out) std::memcpy(var_out, h + o_var, pv_b);
+      if (matrices_out) {
+        if (ragged)
+          for (int64_t i = 0; i < n; i++)
+            std::memcpy(matrices_out + mat_offsets[i], h + o_mat + (size_t)moff[i] * 8, (size_t)heights[i] * widths[i] * 8);
+        else
+          std::memcpy(matrices_out, h + o_mat, in_b);
+      }
+      return check_device_status(ctx, status, n);
+    }
+  }
 
   // chunking: two pipeline slots; a large batch is cut into ~8 chunks (64 MiB .. 1.5 GiB each) so that the
   // H2D copy of chunk k+1 overlaps the kernel and the D2H copies of chunk k
