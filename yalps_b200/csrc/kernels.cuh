@@ -44,32 +44,30 @@ struct BatchArgs {
 };
 
 // Shared-memory carve-up, identical on host and device.
+// Resident layout: every tableau row is  [ A(0..W-2) | pad | b | -coef/q ]  with an even row stride ldA
+// (16-byte aligned rows -> v2.f64 accesses) whose half is odd (strided column reads spread over the banks);
+// the RHS cell and the per-pivot -coef/q scratch cell of a row live in its last two slots.
 struct SmemLayout {
-  size_t off_A, off_b, off_colbuf, off_colnew, off_misc, off_red, off_var, total;
+  size_t off_A, off_colbuf, off_colnew, off_misc, off_red, off_var, total;
   int ldA;
-  // Resident layout: A rows 16-byte aligned (even ldA) with ldA/2 odd so that the strided pivot-column
-  // reads spread over the banks.
   __host__ __device__ static int ld_for(int W) {
-    int ld = (W - 1 + 1) & ~1;
-    if (ld < 2) ld = 2;
+    int ld = (W - 1 + 2 + 1) & ~1;
     if (((ld >> 1) & 1) == 0) ld += 2;
     return ld;
   }
-  __host__ __device__ SmemLayout(int Hcap, int Wcap, bool resident) {
+  __host__ __device__ SmemLayout(int Hcap, int Wcap, bool resident, int nw) {
     size_t o = 0;
     ldA = ld_for(Wcap);
     off_A = o;
     if (resident) o += (size_t)Hcap * ldA * 8;
-    off_b = o;
-    if (resident) o += (size_t)((Hcap + 1) & ~1) * 8;
     off_colbuf = o;
-    o += (size_t)((Hcap + 3) & ~3) * 8;
+    o += (size_t)((Hcap + 7) & ~7) * 8;
     off_colnew = o;
-    o += (size_t)((Hcap + 1) & ~1) * 8;
+    if (!resident) o += (size_t)((Hcap + 1) & ~1) * 8;
     off_misc = o;
     o += 16;
     off_red = o;
-    o += 192 * 4;
+    if (nw > 1) o += 192 * 4;
     off_var = o;
     if (resident) o += (size_t)(Wcap + Hcap) * 4;
     total = (o + 15) & ~(size_t)15;
@@ -82,8 +80,11 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) 
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// min CTAs/SM in the launch bounds caps the register count so that shared memory, not registers, limits residency
+// (one-warp CTAs: 12 per SM -> <= 168 registers per thread).
 template <int NW, int KC, bool kResident>
-__global__ void __launch_bounds__(NW * 32) k_simplex(const BatchArgs a) {
+__global__ void __launch_bounds__(NW * 32, NW == 1 ? 12 : (NW == 2 ? 6 : (NW == 4 ? 3 : (NW == 8 ? 2 : 1))))
+    k_simplex(const BatchArgs a) {
   constexpr int NT = NW * 32;
   constexpr int VW = kResident ? 2 : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -123,25 +124,27 @@ __global__ void __launch_bounds__(NW * 32) k_simplex(const BatchArgs a) {
       poff = (size_t)lp * (W + H);
     }
 
-    const SmemLayout L(a.Hcap, a.Wcap, kResident);
+    const SmemLayout L(a.Hcap, a.Wcap, kResident, NW);
     LpView t;
     t.H = H;
     t.W = W;
+    Scratch s;
     if (kResident) {
       t.A = reinterpret_cast<double *>(smem_raw + L.off_A);
-      t.b = reinterpret_cast<double *>(smem_raw + L.off_b);
-      t.ldA = SmemLayout::ld_for(W);
-      t.ldb = 1;
+      t.ldA = t.ldb = SmemLayout::ld_for(W);
+      t.b = t.A + (t.ldA - 2);
+      s.colnew = t.A + (t.ldA - 1);
+      s.ldc = t.ldA;
       t.var = reinterpret_cast<int *>(smem_raw + L.off_var);
     } else {
+      s.colnew = reinterpret_cast<double *>(smem_raw + L.off_colnew);
+      s.ldc = 1;
       t.A = a.work + moff + 1;
       t.b = a.work + moff;
       t.ldA = t.ldb = W;
       t.var = a.var_out + poff;
     }
-    Scratch s;
     s.colbuf = reinterpret_cast<double *>(smem_raw + L.off_colbuf);
-    s.colnew = reinterpret_cast<double *>(smem_raw + L.off_colnew);
     s.misc = reinterpret_cast<double *>(smem_raw + L.off_misc);
     s.red = reinterpret_cast<unsigned *>(smem_raw + L.off_red);
     s.hist = a.hist ? a.hist + (size_t)blockIdx.x * 2 * a.hist_cap : nullptr;
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(NW * 32) k_simplex(const BatchArgs a) {
       for (int r = tid >> 5; r < rootH; r += NW) {
         const double *sr = src + (size_t)r * W;
         double *dA = t.A + (size_t)r * ldA - 1;
-        if ((tid & 31) == 0) cp_async8(t.b + r, sr);
+        if ((tid & 31) == 0) cp_async8(t.b + (size_t)r * ldb, sr);
         for (int c = 1 + (tid & 31); c < W; c += 32) cp_async8(dA + c, sr + c);
       }
     } else if (src != a.work + moff) {
@@ -196,7 +199,7 @@ __global__ void __launch_bounds__(NW * 32) k_simplex(const BatchArgs a) {
       for (int k = tid; k < W + H; k += NT) t.var[k] = k;
     }
     if (kResident) {  // zero the padding columns so that vector loads past W-1 read defined values
-      const int pad = ldA - (W - 1);
+      const int pad = ldA - 2 - (W - 1);
       for (int k = tid; k < H * pad; k += NT) t.A[(size_t)(k / pad) * ldA + (W - 1) + (k % pad)] = 0.0;
     }
     if (kResident) cp_async_wait_all();

@@ -133,10 +133,11 @@ struct LpView {
 };
 
 struct Scratch {
-  double *colbuf;  // [H]  pivot column before the update; 0 for rows the update must not touch
-  double *colnew;  // [H]  -coef/q
-  double *misc;    // [2]  normalised RHS of the pivot row, its non-zero flag
-  unsigned *red;   // [192]
+  double *colbuf;     // [H]  pivot column before the update; 0 for rows the update must not touch
+  double *colnew;     // [H]  -coef/q, element r at colnew[r*ldc]
+  int ldc;
+  double *misc;       // [2]  normalised RHS of the pivot row, its non-zero flag
+  unsigned *red;      // [192] cross-warp reduction scratch (NW > 1 only)
   int *hist;       // [2*hist_cap] (leaving var, entering var) pairs, checkCycles only
   int hist_cap;
 };
@@ -307,7 +308,7 @@ __device__ __forceinline__ void pivot_cta(const LpView &t, const Scratch &s, int
       s.colbuf[r] = 0.0;  // the pivot row is not updated by the rank-1 pass
     } else {
       s.colbuf[r] = nz ? coef : 0.0;  // row skip (:31)
-      s.colnew[r] = quo;
+      s.colnew[(size_t)r * s.ldc] = quo;
     }
   }
   if (tid == 0) {  // basis bookkeeping (:7-12)
@@ -349,7 +350,7 @@ __device__ __forceinline__ void pivot_cta(const LpView &t, const Scratch &s, int
           const double x = b[(size_t)r * ldb];
           b[(size_t)r * ldb] = __dsub_rn(x, __dmul_rn(coef, p0));
         }
-        A[(size_t)r * ldA + jc] = s.colnew[r];
+        A[(size_t)r * ldA + jc] = s.colnew[(size_t)r * s.ldc];
       }
     }
   }

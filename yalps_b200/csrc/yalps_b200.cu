@@ -191,7 +191,7 @@ struct LaunchPlan {
 // shared memory for the tableau and therefore runs many more LPs per SM (profiles/r01_sweep_paths.jsonl).
 int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycles, LaunchPlan *plan,
                 double density = -1.0) {
-  const SmemLayout Lr(Hcap, Wcap, true), Lg(Hcap, Wcap, false);
+  SmemLayout Lr(Hcap, Wcap, true, 32), Lg(Hcap, Wcap, false, 32);
   bool resident = Lr.total <= (size_t)ctx->smem_optin;
   if (resident && ctx->tune_path == YALPS_PATH_AUTO && density >= 0.0 && density < 0.35 && n > 64) resident = false;
   if (ctx->tune_path == YALPS_PATH_SMEM) {
@@ -211,6 +211,10 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
   const int nw = ctx->tune_threads > 0 ? std::max(1, ctx->tune_threads / 32)
                                       : default_warps((long long)Hcap * Wcap, resident);
   const KernelEntry *k = pick_kernel(nw, Wcap, resident);
+  if (k) {
+    Lr = SmemLayout(Hcap, Wcap, true, k->nw);
+    Lg = SmemLayout(Hcap, Wcap, false, k->nw);
+  }
   if (k) {  // the attribute / occupancy queries cost microseconds: remember them per (kernel, shared memory size)
     const size_t smem_c = resident ? Lr.total : Lg.total;
     const std::string key = std::to_string((size_t)(resident ? (void *)k->resident : (void *)k->global)) + ":" + std::to_string(smem_c);
