@@ -347,6 +347,9 @@ def model_from_mps(text: str, direction: str | None = None) -> dict:
     def section():
         return lines[state["i"]].rstrip() if state["i"] < len(lines) else None
 
+    def got(sec):  # sectionErr, benchmarks/mps.ts:62-63
+        return "end of file" if sec is None else f"'{sec}'"
+
     def parse_num(value, what):
         if value == "":
             fail(f"Missing {what} value")
@@ -364,7 +367,7 @@ def model_from_mps(text: str, direction: str | None = None) -> dict:
 
     # ROWS (:70-98)
     if section() != "ROWS":
-        fail(f"Expected section ROWS but got {section()!r}")
+        fail(f"Expected section ROWS but got {got(section())}")
     line = next_line()
     while not_end(line):
         name = f2(line)
@@ -392,7 +395,7 @@ def model_from_mps(text: str, direction: str | None = None) -> dict:
 
     # COLUMNS (:114-162)
     if section() != "COLUMNS":
-        fail(f"Expected section COLUMNS but got {section()!r}")
+        fail(f"Expected section COLUMNS but got {got(section())}")
 
     def add_coef(variable, row, value):
         if row == "":
@@ -438,7 +441,7 @@ def model_from_mps(text: str, direction: str | None = None) -> dict:
 
     # RHS (:164-209)
     if section() != "RHS":
-        fail(f"Expected section RHS but got {section()!r}")
+        fail(f"Expected section RHS but got {got(section())}")
 
     def add_constraint(row, value):
         if row == "":
@@ -489,9 +492,9 @@ def model_from_mps(text: str, direction: str | None = None) -> dict:
             line = next_line()
         sec = section()
         if sec not in ("BOUNDS", "ENDATA"):
-            fail(f"Expected section BOUNDS or ENDATA but got {sec!r}")
+            fail(f"Expected section BOUNDS or ENDATA but got {got(sec)}")
     elif sec not in ("BOUNDS", "ENDATA"):
-        fail(f"Expected section RANGES, BOUNDS, or ENDATA but got {sec!r}")
+        fail(f"Expected section RANGES, BOUNDS, or ENDATA but got {got(sec)}")
 
     if sec == "BOUNDS":  # :254-302
         def set_bounds(name, lower, upper):
@@ -540,7 +543,7 @@ def model_from_mps(text: str, direction: str | None = None) -> dict:
                 fail(f"Unexpected bound type '{typ}'")
             line = next_line()
         if section() != "ENDATA":
-            fail(f"Expected section ENDATA but got {section()!r}")
+            fail(f"Expected section ENDATA but got {got(section())}")
     return model
 
 

@@ -1,0 +1,207 @@
+"""Fixed-column MPS reader (host side; SURVEY 8f-1: the data format in front of the hot path).
+
+Same accepted dialect and error behaviour as the reference's benchmark reader `modelFromMps`
+(benchmarks/mps.ts:304-325): sections NAME, ROWS, COLUMNS (with MARKER INTORG/INTEND), RHS, optional RANGES and
+BOUNDS, ENDATA; fields at the fixed columns of benchmarks/mps.ts:31-36; `*` comment lines; the first N row is the
+objective and RHS entries on N rows are ignored; numbers are parsed like JS parseFloat (longest numeric prefix).
+`netlib_model` applies the Netlib conversion of benchmarks/netlib/read.ts:16-28 (min == max -> equal, free rows
+dropped, direction "minimize") and returns a model dict for `yalps_b200.solve`.
+
+Implementation note: a table-driven single pass over the lines (section -> handler), not the reference's chain of
+reader functions.
+"""
+from __future__ import annotations
+
+import math
+import re
+from typing import Optional
+
+INF = math.inf
+_FIELDS = ((1, 3), (4, 12), (14, 22), (24, 36), (39, 47), (49, 61))  # benchmarks/mps.ts:31-36
+_FLOAT = re.compile(r"\s*([+-]?(?:Infinity|(?:\d+\.?\d*|\.\d+)(?:[eE][+-]?\d+)?))")
+
+
+class MpsError(ValueError):
+    pass
+
+
+def _parse_float(text: str) -> float:
+    m = _FLOAT.match(text)
+    return float(m.group(1).replace("Infinity", "inf")) if m else math.nan
+
+
+def _fields(line: str):
+    return tuple(line[a:b].strip() for a, b in _FIELDS)
+
+
+def model_from_mps(text: str, direction: Optional[str] = None) -> dict:
+    lines = re.split(r"\r?\n", text)
+    start = next((i for i, l in enumerate(lines) if l.startswith("NAME")), None)
+    if start is None:
+        raise MpsError("Line 1: No NAME section was found")
+    model = {"name": _fields(lines[start])[2], "direction": direction, "objective": None, "constraints": {},
+             "variables": {}, "bounds": {}, "integers": set(), "binaries": set()}
+    row_type: dict = {}
+    state = {"section": None, "int": False, "col": None, "lineno": start + 1}
+
+    def fail(msg):
+        raise MpsError(f"Line {state['lineno'] + 1}: {msg}")
+
+    def number(value, what):
+        if value == "":
+            fail(f"Missing {what} value")
+        v = _parse_float(value)
+        if math.isnan(v):
+            fail(f"Failed to parse number '{value}'")
+        return v
+
+    def known_row(row):
+        if row == "":
+            fail("Missing row name")
+        if row not in row_type:
+            fail(f"The row '{row}' was not defined in the ROWS section")
+        return row_type[row]
+
+    def on_rows(f):
+        typ, name = f[0], f[1]
+        if name == "":
+            fail("Missing row name")
+        if name in row_type:
+            fail(f"The row '{name}' was already defined")
+        if typ == "":
+            fail("Missing row type")
+        if typ not in ("L", "G", "E", "N"):
+            fail(f"Unexpected row type '{typ}'")
+        model["constraints"][name] = {"L": [-INF, 0.0], "G": [0.0, INF], "E": [0.0, 0.0], "N": [-INF, INF]}[typ]
+        if typ == "N" and model["objective"] is None:
+            model["objective"] = name
+        row_type[name] = typ
+
+    def on_columns(f):
+        if f[2] == "'MARKER'":
+            if f[3] not in ("'INTORG'", "'INTEND'"):
+                fail(f"Unexpected MARKER '{f[3]}'")
+            state["int"] = f[3] == "'INTORG'"
+            state["col"] = None
+            return
+        name = f[1]
+        if name == "":
+            fail("Missing column name")
+        if name != state["col"]:
+            if name in model["variables"]:
+                fail(f"Values for the column '{name}' were previously provided -- all values for a column must come "
+                     "consecutively")
+            model["variables"][name] = {}
+            if state["int"]:
+                model["integers"].add(name)
+            state["col"] = name
+        coefs = model["variables"][name]
+        for row, value in ((f[2], f[3]), (f[4], f[5])):
+            if (row, value) == ("", "") and row is f[4]:
+                continue
+            if row == "":
+                fail("Missing row name")
+            if value == "":
+                fail("Missing coefficient value")
+            known_row(row)
+            if row in coefs:
+                fail(f"The coefficient for row '{row}' was previously set for this column")
+            coefs[row] = number(value, "coefficient")
+
+    def on_rhs(f):
+        for row, value in ((f[2], f[3]), (f[4], f[5])):
+            if (row, value) == ("", "") and row is f[4]:
+                continue
+            typ = known_row(row)
+            v = number(value, "rhs")
+            con = model["constraints"][row]
+            if typ in ("L", "E"):
+                con[1] = v
+            if typ in ("G", "E"):
+                con[0] = v
+
+    def on_ranges(f):
+        for row, value in ((f[2], f[3]), (f[4], f[5])):
+            if (row, value) == ("", "") and row is f[4]:
+                continue
+            typ = known_row(row)
+            v = number(value, "range")
+            b = model["constraints"][row]
+            if typ == "L" or (typ == "E" and v < 0.0):
+                b[0] = b[1] - abs(v)
+            if typ == "G" or (typ == "E" and v > 0.0):
+                b[1] = b[0] + abs(v)
+
+    def on_bounds(f):
+        typ, col = f[0], f[2]
+        if col == "":
+            fail("Missing column name")
+        if col not in model["variables"]:
+            fail(f"The column '{col}' was not defined in the COLUMNS section")
+        v = number(f[3], "bound") if typ in ("LO", "UP", "FX", "LI", "UI") else math.nan
+        lo_hi = {"LO": (v, INF), "UP": (0.0, v), "FX": (v, v), "FR": (-INF, INF), "MI": (-INF, 0.0), "PL": (0.0, INF),
+                 "LI": (v, INF), "UI": (0.0, v)}
+        if typ == "BV":
+            model["binaries"].add(col)
+            return
+        if typ == "SC":
+            fail("SC bound type is unsupported")
+        if typ == "":
+            fail("Missing bound type")
+        if typ not in lo_hi:
+            fail(f"Unexpected bound type '{typ}'")
+        if typ in ("LI", "UI"):
+            model["integers"].add(col)
+        b = model["bounds"].setdefault(col, [0.0, INF])
+        lo, hi = lo_hi[typ]
+        if not math.isnan(lo):
+            b[0] = lo
+        if not math.isnan(hi):
+            b[1] = hi
+
+    handlers = {"ROWS": on_rows, "COLUMNS": on_columns, "RHS": on_rhs, "RANGES": on_ranges, "BOUNDS": on_bounds}
+    order = {"ROWS": ("COLUMNS",), "COLUMNS": ("RHS",), "RHS": ("RANGES", "BOUNDS", "ENDATA"),
+             "RANGES": ("BOUNDS", "ENDATA"), "BOUNDS": ("ENDATA",)}
+    wording = {("ROWS",): "ROWS", ("COLUMNS",): "COLUMNS", ("RHS",): "RHS",
+               ("RANGES", "BOUNDS", "ENDATA"): "RANGES, BOUNDS, or ENDATA", ("BOUNDS", "ENDATA"): "BOUNDS or ENDATA",
+               ("ENDATA",): "ENDATA"}
+    expected = ("ROWS",)
+    last = None  # last non-comment line seen: what the reference reports as the "section" at end of file
+    for i in range(start + 1, len(lines)):
+        line = lines[i]
+        if line.startswith("*"):
+            continue
+        state["lineno"] = last = i
+        if line.startswith(" "):
+            if state["section"] is None:
+                fail(f"Expected section {wording[expected]} but got '{line.rstrip()}'")
+            handlers[state["section"]](_fields(line))
+            continue
+        name = line.rstrip()
+        if name not in expected:
+            fail(f"Expected section {wording[expected]} but got '{name}'")
+        if name == "ENDATA":
+            return model
+        state["section"] = name
+        expected = order[name]
+    if last is None:
+        state["lineno"] = start + 1
+        fail(f"Expected section {wording[expected]} but got end of file")
+    state["lineno"] = last
+    fail(f"Expected section {wording[expected]} but got '{lines[last].rstrip()}'")
+
+
+def netlib_model(text: str) -> dict:
+    """benchmarks/netlib/read.ts:16-28,38-41: the model dict solve() takes (pair lists keep MPS order)."""
+    mps = model_from_mps(text, "minimize")
+    constraints = []
+    for key, (lo, hi) in mps["constraints"].items():
+        if math.isfinite(lo) and math.isfinite(hi):
+            constraints.append((key, {"equal": lo} if lo == hi else {"min": lo, "max": hi}))
+        elif math.isfinite(lo):
+            constraints.append((key, {"min": lo}))
+        elif math.isfinite(hi):
+            constraints.append((key, {"max": hi}))
+    return {"name": mps["name"], "direction": "minimize", "objective": mps["objective"], "constraints": constraints,
+            "variables": [(k, list(v.items())) for k, v in mps["variables"].items()], "integers": mps["integers"],
+            "binaries": mps["binaries"], "bounds": mps["bounds"]}
