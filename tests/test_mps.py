@@ -49,30 +49,27 @@ def test_error_behaviour_matches_the_reference_reader(bad, msg):
     assert msg in str(e2.value)
 
 
+def _line(f1="", f2="", f3="", f4="", f5="", f6=""):
+    """One fixed-column MPS line with the fields at the offsets of benchmarks/mps.ts:31-36."""
+    buf = [" "] * 61
+    for (a, b), v in zip(((1, 3), (4, 12), (14, 22), (24, 36), (39, 47), (49, 61)), (f1, f2, f3, f4, f5, f6)):
+        buf[a:a + len(v)] = list(v)
+        assert len(v) <= b - a
+    return "".join(buf).rstrip()
+
+
 def test_ranges_bounds_and_markers():
-    text = """NAME          TINY
-ROWS
- N  COST
- L  LIM1
- G  LIM2
- E  EQ1
-COLUMNS
-    MARKER                 'MARKER'                 'INTORG'
-    X1        COST               1.0   LIM1               1.0
-    X1        LIM2               1.0
-    MARKER                 'MARKER'                 'INTEND'
-    X2        COST               2.0   LIM1               1.0
-    X2        EQ1               -1.0
-RHS
-    RHS       LIM1               4.0   LIM2               1.0
-    RHS       EQ1                7.0
-RANGES
-    RNG       LIM1               2.5   EQ1               -3.0
-BOUNDS
- UP BND       X1                 4.0
- BV BND       X2
-ENDATA
-"""
+    text = "\n".join([
+        "NAME          TINY", "ROWS", _line("N", "COST"), _line("L", "LIM1"), _line("G", "LIM2"), _line("E", "EQ1"),
+        "COLUMNS",
+        _line("", "MARKER", "'MARKER'", "'INTORG'"),
+        _line("", "X1", "COST", "1.0", "LIM1", "1.0"), _line("", "X1", "LIM2", "1.0"),
+        _line("", "MARKER", "'MARKER'", "'INTEND'"),
+        _line("", "X2", "COST", "2.0", "LIM1", "1.0"), _line("", "X2", "EQ1", "-1.0"),
+        "RHS", _line("", "RHS", "LIM1", "4.0", "LIM2", "1.0"), _line("", "RHS", "EQ1", "7.0"),
+        "RANGES", _line("", "RNG", "LIM1", "2.5", "EQ1", "-3.0"),
+        "BOUNDS", _line("UP", "BND", "X1", "4.0"), _line("BV", "BND", "X2"),
+        "ENDATA", ""])
     a, b = P.model_from_mps(text), M.model_from_mps(text)
     _same_model(a, b)
     assert a["constraints"]["LIM1"] == [1.5, 4.0] and a["constraints"]["EQ1"] == [4.0, 7.0]
