@@ -186,25 +186,25 @@ struct Cells<2> {
 //   p     normalised pivot-row cells (0.0 where the old cell was flushed)
 //   st    bit k*VW+e: cell e of vector-column k is rewritten (old pivot-row cell > 1e-16, or padding)
 //   full  bit k: all VW cells of vector-column k are rewritten
-//   act   bit i: row i of the group is active (pivot-column coefficient > 1e-16 and not the pivot row)
+//   coef  pivot-column coefficient of each row of the block; 0.0 marks a row the update must not touch
 // kPartial = some thread of the CTA has a vector-column with only one of its two cells rewritten.
 template <int NT, int KC, int VW, int RU, bool kPartial>
 __device__ __forceinline__ void update_rows(double *__restrict__ Ar, int ldA, const double (&p)[KC][VW], unsigned st,
-                                            unsigned full, const double (&coef)[RU], unsigned act) {
+                                            unsigned full, const double (&coef)[RU]) {
   Cells<VW> x[RU][KC];
 #pragma unroll
   for (int i = 0; i < RU; i++)
 #pragma unroll
     for (int k = 0; k < KC; k++) {
       const bool need = kPartial ? (((st >> (k * VW)) & ((1u << VW) - 1u)) != 0u) : (((full >> k) & 1u) != 0u);
-      if (((act >> i) & 1u) && need) x[i][k].load(Ar + (size_t)i * ldA + (size_t)VW * NT * k);
+      if (coef[i] != 0.0 && need) x[i][k].load(Ar + (size_t)i * ldA + (size_t)VW * NT * k);
     }
 #pragma unroll
   for (int i = 0; i < RU; i++)
 #pragma unroll
     for (int k = 0; k < KC; k++) {
       double *dst = Ar + (size_t)i * ldA + (size_t)VW * NT * k;
-      const bool on = (act >> i) & 1u;
+      const bool on = coef[i] != 0.0;
       if (VW == 2) {
         const double t0 = __dsub_rn(x[i][k].get(0), __dmul_rn(coef[i], p[k][0]));
         const double t1 = __dsub_rn(x[i][k].get(1), __dmul_rn(coef[i], p[k][VW - 1]));
@@ -227,7 +227,6 @@ __device__ __forceinline__ void update_all(double *__restrict__ Abase, int ldA, 
   int r = 0;
   for (; r + RU <= H; r += RU) {
     double coef[RU];
-    unsigned act = 0;
     if (RU % 2 == 0) {  // colbuf is 16-byte aligned and r is a multiple of RU: two coefficients per load
 #pragma unroll
       for (int i = 0; i < RU; i += 2) {
@@ -239,14 +238,14 @@ __device__ __forceinline__ void update_all(double *__restrict__ Abase, int ldA, 
 #pragma unroll
       for (int i = 0; i < RU; i++) coef[i] = colbuf[r + i];
     }
+    bool any = false;
 #pragma unroll
-    for (int i = 0; i < RU; i++)
-      if (coef[i] != 0.0) act |= 1u << i;
-    if (act) update_rows<NT, KC, VW, RU, kPartial>(Abase + (size_t)r * ldA, ldA, p, st, full, coef, act);
+    for (int i = 0; i < RU; i++) any |= coef[i] != 0.0;
+    if (any) update_rows<NT, KC, VW, RU, kPartial>(Abase + (size_t)r * ldA, ldA, p, st, full, coef);
   }
   for (; r < H; r++) {
     double coef[1] = {colbuf[r]};
-    if (coef[0] != 0.0) update_rows<NT, KC, VW, 1, kPartial>(Abase + (size_t)r * ldA, ldA, p, st, full, coef, 1u);
+    if (coef[0] != 0.0) update_rows<NT, KC, VW, 1, kPartial>(Abase + (size_t)r * ldA, ldA, p, st, full, coef);
   }
 }
 
