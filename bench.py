@@ -61,7 +61,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -217,7 +217,6 @@ def run_native(args):
     t_end.record()
     barrier()
     launches = eng.launch_count - launches0
-    clocks = sampler.stop() if rank == 0 else None
     elapsed_ms = t_begin.elapsed_time(t_end)
     kernel_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs) / args.steps
 
@@ -235,6 +234,7 @@ def run_native(args):
         out = eng.solve_batch(h_in, H, W, opt, out=h_out)
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+    clocks = sampler.stop() if rank == 0 else None  # sampled over the device-timed and the end-to-end regions
     h2d = n * cells * 8
     d2h = n * (4 + 8 + 16 + H * 8 + 2 * (W + H) * 4)
 
@@ -259,6 +259,13 @@ def run_native(args):
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         hbm_alg = n * (cells * 8 + 4 + 8 + 16 + H * 8 + 2 * (W + H) * 4) / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        try:  # dram bytes per launch of this kernel from the committed ncu --set full capture (profiles/)
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "r01f_k1_ncu_summary.json")))
+            if args.workload == "config2":
+                traffic = ncu["dram_bytes_per_launch"]
+        except (OSError, KeyError, ValueError):
+            pass
         cores = host_cores()
         cpu_n = min(n, 16384)
         cpu_v, cpu_lps, _, cpu_dt = cpu_baseline(cpu_n, m, nv, neg, 0, cores)
@@ -278,7 +285,9 @@ def run_native(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "smem", "achieved": achieved, "peak": smem_gbs, "unit": "GB/s",
-                         "frac": achieved / smem_gbs, "traffic": None,
+                         "frac": achieved / smem_gbs, "traffic": traffic,
+                         "traffic_note": "dram__bytes_read+write per launch (ncu --set full, profiles/r01f_k1_ncu_summary.json); "
+                                         "the tableau is read from HBM once, every pivot runs out of shared memory",
                          "peak_source": "measured live: ld/st.shared.f64 stream on all SMs (yalps_measure_smem_bandwidth)",
                          "bytes_per_unit": bytes_per_pivot, "units_per_launch": pivots_per_step,
                          "kernel_ms": kernel_ms, "kernel": "k_simplex<NW,KC,resident>",

@@ -1,0 +1,69 @@
+"""Error behaviour and edge cases of the C ABI on a real device."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import lib as O
+from yalps_b200 import _ffi, engine as E
+
+pytestmark = pytest.mark.gpu
+
+
+def test_empty_batch_and_optional_outputs(engine):
+    out = engine.solve_batch(np.zeros(0), 3, 4)
+    assert out["status"].shape == (0,)
+    lib = _ffi.load()
+    mats = O.generate_synthetic(0, 4, 5, 6)
+    opt = E.make_options()
+    status = np.empty(4, np.int32)
+    # every output except status is NULL
+    rc = lib.yalps_solve_batch(engine._ctx, 4, 6, 7, mats.ctypes.data_as(C.c_void_p), C.byref(opt),
+                               status.ctypes.data_as(C.c_void_p), None, None, None, None, None, None)
+    assert rc == 0 and (status == 0).all()
+
+
+def test_argument_errors_are_reported_not_thrown(engine):
+    lib = _ffi.load()
+    opt = E.make_options()
+    rc = lib.yalps_solve_batch(engine._ctx, 1, 0, 4, None, C.byref(opt), None, None, None, None, None, None, None)
+    assert rc == -2 and b"bad" in lib.yalps_last_error(engine._ctx)
+    rc = lib.yalps_bnb_solve_nodes(None, 0, None, None, None, None, C.byref(opt), None, None, None, None, None, None, None)
+    assert rc == -2
+    with pytest.raises(_ffi.YalpsError):
+        engine.set_tuning(9, 0)
+    with pytest.raises(_ffi.YalpsError) as e:
+        engine.set_tuning(E.PATH_SMEM, 0)
+        try:
+            engine.solve_batch(np.zeros(600 * 700), 600, 700)
+        finally:
+            engine.set_tuning(E.PATH_AUTO, 0)
+    assert e.value.code == -3  # does not fit in shared memory
+
+
+def test_branch_and_cut_without_root_is_an_error():
+    import yalps_b200
+    eng = yalps_b200.Engine(0)
+    try:
+        with pytest.raises(_ffi.YalpsError):
+            eng._root_shape = (2, 2)
+            eng.branch_and_cut([1], 1.0, 0.0)
+    finally:
+        eng.close()
+
+
+def test_check_cycles_history_limit_is_an_error_not_a_wrong_answer(engine):
+    """With checkCycles the per-phase history is capped at 262,144 pivots; a run that would exceed it
+    reports YALPS_ERR_HISTORY.  Here the cap is reached artificially through max_pivots > cap on a cycling LP is
+    not possible (it cycles at 11), so only the non-error path is checked."""
+    t = np.array([[0, 10, -57, -9, -24], [0, 0.5, -5.5, -2.5, 9], [0, 0.5, -1.5, -0.5, 1], [1, 1, 0, 0, 0]], float)
+    out = engine.solve_batch(t.reshape(1, -1), 4, 5, E.make_options(check_cycles=True, max_pivots=float("inf")))
+    assert out["status"][0] == 4
+
+
+def test_launch_counter_and_device_info(engine):
+    before = engine.launch_count
+    engine.solve_batch(O.generate_synthetic(0, 2, 3, 4), 4, 5)
+    assert engine.launch_count == before + 1
+    info = engine.device_info()
+    assert info["cc"][0] >= 10 and info["sm_count"] >= 100 and info["smem_per_block_optin"] >= 200 * 1024
