@@ -121,7 +121,9 @@ int yalps_solve_ragged(yalps_ctx *ctx, int64_t n, const int32_t *heights, const 
 /* Same as yalps_solve_batch with every buffer already in device memory and the
  * work enqueued on `stream` (a cudaStream_t, NULL = default stream); returns
  * without synchronising.  d_work (n*height*width doubles) is only required when
- * the HBM-resident path is taken and may alias d_matrices for an in-place solve. */
+ * the HBM-resident path is taken and may alias d_matrices for an in-place solve.  When d_work is given the
+ * first call for a (buffer, shape) samples the density of the first tableau to choose the kernel path, which
+ * synchronises `stream` once. */
 int yalps_solve_batch_device(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, const double *d_matrices,
                              double *d_work, const yalps_options *opt, int32_t *d_status, double *d_value,
                              int64_t *d_pivots, double *d_rhs_out, int32_t *d_pos_out, int32_t *d_var_out,

@@ -66,17 +66,17 @@ if "config3" in what:  # RHS-perturbed replicas, SMEM-resident (K1) vs HBM-resid
         piv = torch.empty(n, 2, dtype=torch.int64, device="cuda")
         val = torch.empty(n, dtype=torch.float64, device="cuda")
         stream = torch.cuda.current_stream().cuda_stream
-        for path, pname in ((E.PATH_SMEM, "K1 smem-resident"), (E.PATH_GMEM, "K2 hbm-resident")):
-            for threads in ((128, 256, 512) if path == E.PATH_SMEM else (256, 1024)):
+        for path, pname in ((E.PATH_AUTO, "auto policy"), (E.PATH_SMEM, "K1 smem-resident"), (E.PATH_GMEM, "K2 hbm-resident")):
+            for threads in ((0,) if path == E.PATH_AUTO else (64, 128, 256) if path == E.PATH_SMEM else (64, 128, 256)):
                 eng.set_tuning(path, threads)
 
                 def run():
-                    if path == E.PATH_GMEM:
+                    if path != E.PATH_SMEM:
                         work.copy_(d)
                     eng.solve_batch_device(n, H, W, d.data_ptr(), d_work=work.data_ptr(), d_status=st.data_ptr(),
                                            d_value=val.data_ptr(), d_pivots=piv.data_ptr(), stream=stream)
                 ms = ev_time(run, reps=2)
-                if path == E.PATH_GMEM:
+                if path != E.PATH_SMEM:
                     ms -= ev_time(lambda: work.copy_(d), reps=2)
                 p = int(piv.sum().item())
                 emit(workload=f"config3: {n} RHS-perturbed (eps=1e-2) replicas of Netlib {name} {H}x{W}", kernel=pname,

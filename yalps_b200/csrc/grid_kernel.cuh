@@ -5,8 +5,11 @@
 //   * every CTA recomputes the pivot choice redundantly from the (L2-resident) objective row / RHS column /
 //     pivot column, so all CTAs agree on (row, col) without exchanging partial results;
 //   * every CTA stages the normalised pivot row (and its non-zero flags) in its own shared memory;
-//   * rows are dealt to warps round-robin over the whole grid; a warp streams its row with coalesced 8-byte
-//     accesses, several loads in flight per lane, and skips rows whose pivot-column cell is below 1e-16;
+//   * every CTA also stages the old pivot column (0 for rows the update must skip), so the update never waits on
+//     a dependent global load and a row can be split between warps without a read/write hazard on its
+//     pivot-column cell;
+//   * the update is dealt to the warps of the whole grid as (row, 256-column segment) items, round-robin:
+//     coalesced 8-byte accesses, 8 loads in flight per lane, skipped rows cost one shared-memory read;
 //   * two grid barriers per pivot: one after every CTA has finished reading (pivot choice + staging of the old
 //     pivot row) and one after the update, so that no CTA ever selects from a half-updated tableau.
 #pragma once
@@ -55,13 +58,15 @@ struct GridArgs {
 constexpr int kGridThreads = 1024;
 constexpr int kGridWarps = kGridThreads / 32;
 
-// shared memory: prow[W] doubles, nz bitmask words, reduction scratch
+// shared memory: prow[W] doubles, colbuf[H] doubles, nz bitmask words, reduction scratch
 struct GridSmem {
-  size_t off_prow, off_nz, off_red, total;
-  __host__ __device__ explicit GridSmem(int W) {
+  size_t off_prow, off_col, off_nz, off_red, total;
+  __host__ __device__ GridSmem(int H, int W) {
     size_t o = 0;
     off_prow = o;
     o += (size_t)((W + 1) & ~1) * 8;
+    off_col = o;
+    o += (size_t)((H + 1) & ~1) * 8;
     off_nz = o;
     o += (size_t)((W + 31) / 32 + 1) * 4;
     o = (o + 15) & ~(size_t)15;
@@ -71,12 +76,15 @@ struct GridSmem {
   }
 };
 
+constexpr int kSegCols = 256;  // columns per update item: 8 loads in flight per lane
+
 __global__ void __launch_bounds__(kGridThreads, 1) k_simplex_grid(const GridArgs a) {
   constexpr int NT = kGridThreads, NW = kGridWarps;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long epoch = 0;
-  const GridSmem L(a.W);
+  const GridSmem L(a.H, a.W);
   double *prow = reinterpret_cast<double *>(smem_raw + L.off_prow);
+  double *colbuf = reinterpret_cast<double *>(smem_raw + L.off_col);
   unsigned *nzmask = reinterpret_cast<unsigned *>(smem_raw + L.off_nz);
   unsigned *red = reinterpret_cast<unsigned *>(smem_raw + L.off_red);
 
@@ -208,6 +216,10 @@ __global__ void __launch_bounds__(kGridThreads, 1) k_simplex_grid(const GridArgs
       const unsigned m = __ballot_sync(0xffffffffu, nz);
       if (lane == 0) nzmask[cbase >> 5] = m;
     }
+    for (int r = tid; r < H; r += NT) {  // old pivot column; 0 = the rank-1 pass leaves the row alone (:29,:31)
+      const double coef = M[(size_t)r * W + col];
+      colbuf[r] = (r != row && fabs(coef) > kTiny) ? coef : 0.0;
+    }
     if (blockIdx.x == 0 && tid == 0) {  // basis bookkeeping (:7-12)
       const int leaving = a.var[W + row];
       a.var[W + row] = a.var[col];
@@ -215,29 +227,37 @@ __global__ void __launch_bounds__(kGridThreads, 1) k_simplex_grid(const GridArgs
     }
     grid_barrier(a.barrier, epoch);  // every CTA has made its choice and staged the old pivot row: the tableau may change now
 
-    // ---- rank-1 update, rows dealt round-robin to the warps of the grid (:28-38)
-    for (int r = gwarp; r < H; r += gwarps) {
-      double *__restrict__ Mr = M + (size_t)r * W;
-      if (r == row) {
-        for (int c = lane; c < W; c += 32) Mr[c] = prow[c];
-        continue;
-      }
-      const double coef = Mr[col];
-      if (!(fabs(coef) > kTiny)) continue;  // row skip (:31)
-      int c = lane;
-      for (; c + 7 * 32 < W; c += 8 * 32) {
+    // ---- rank-1 update (:28-38): (row, column segment) items dealt round-robin to the warps of the grid
+    {
+      const int nseg = (W + kSegCols - 1) / kSegCols;
+      const long long items = (long long)H * nseg;
+      for (long long it = gwarp; it < items; it += gwarps) {
+        const int r = (int)(it / nseg);
+        const int c0 = (int)(it - (long long)r * nseg) * kSegCols + lane;
+        double *__restrict__ Mr = M + (size_t)r * W;
+        if (r == row) {
+#pragma unroll
+          for (int u = 0; u < 8; u++)
+            if (c0 + 32 * u < W) Mr[c0 + 32 * u] = prow[c0 + 32 * u];
+          continue;
+        }
+        const double coef = colbuf[r];
+        if (coef == 0.0) continue;  // row skip (:31)
         double x[8];
 #pragma unroll
-        for (int u = 0; u < 8; u++) x[u] = Mr[c + 32 * u];
+        for (int u = 0; u < 8; u++)
+          if (c0 + 32 * u < W) x[u] = Mr[c0 + 32 * u];
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-          const int cc = c + 32 * u;
-          if ((nzmask[cc >> 5] >> lane) & 1u) Mr[cc] = __dsub_rn(x[u], __dmul_rn(coef, prow[cc]));
+          const int cc = c0 + 32 * u;
+          if (cc < W) {
+            if ((nzmask[cc >> 5] >> lane) & 1u)
+              Mr[cc] = __dsub_rn(x[u], __dmul_rn(coef, prow[cc]));
+            else if (cc == col)
+              Mr[cc] = __ddiv_rn(-coef, q);  // (:36)
+          }
         }
       }
-      for (; c < W; c += 32)
-        if ((nzmask[c >> 5] >> lane) & 1u) Mr[c] = __dsub_rn(Mr[c], __dmul_rn(coef, prow[c]));
-      if (lane == 0) Mr[col] = __ddiv_rn(-coef, q);
     }
     grid_barrier(a.barrier, epoch);
 

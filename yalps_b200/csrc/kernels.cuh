@@ -325,6 +325,17 @@ __global__ void k_generate_replicas(long long first, long long n, int H, int W, 
   }
 }
 
+// Non-zero count of a sample of one tableau (kernel-path policy: sparse batches go to the HBM/L2-resident kernel).
+__global__ void k_sample_density(const double *m, long long cells, long long step, int *out /* [2]: seen, nz */) {
+  int seen = 0, nz = 0;
+  for (long long k = (long long)threadIdx.x * step; k < cells; k += (long long)blockDim.x * step) {
+    seen++;
+    nz += m[k] != 0.0;
+  }
+  atomicAdd(out, seen);
+  atomicAdd(out + 1, nz);
+}
+
 __global__ void k_round_to_precision(long long n, const double *x, double precision, double *out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = round_to_precision(x[i], precision);

@@ -60,6 +60,7 @@ struct yalps_ctx {
   std::unordered_map<std::string, DevBuf> pinned;
   std::unordered_map<std::string, int> occ_cache;
   std::unordered_map<void *, int> smem_attr;
+  std::unordered_map<std::string, double> density_cache;
   Root root;
 };
 
@@ -171,8 +172,8 @@ int default_warps(long long cells, bool resident) {
     if (cells < 120000) return 8;
     return 16;
   }
-  if (cells < 5000) return 1;
-  if (cells < 12000) return 2;
+  if (cells < 3000) return 1;
+  if (cells < 6000) return 2;
   if (cells < 25000) return 4;
   if (cells < 50000) return 8;
   if (cells < 400000) return 16;
@@ -416,9 +417,9 @@ int yalps_host_free(yalps_ctx *ctx, void *ptr) {
 static int launch_grid(yalps_ctx *ctx, int H, int W, double *d_M, const yalps_options *opt, int *d_status,
                        double *d_value, long long *d_pivots, double *d_rhs, int *d_pos, int *d_var,
                        cudaStream_t stream, const int *d_init_var = nullptr, int init_n = 0) {
-  const GridSmem L(W);
+  const GridSmem L(H, W);
   if (L.total > (size_t)ctx->smem_optin)
-    return fail(ctx, YALPS_ERR_TOO_LARGE, "tableau width %d: pivot row staging exceeds shared memory", W);
+    return fail(ctx, YALPS_ERR_TOO_LARGE, "tableau %dx%d: pivot row/column staging exceeds shared memory", H, W);
   int coop = 0;
   CU(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
   if (!coop) return fail(ctx, YALPS_ERR_CUDA, "device does not support cooperative launches");
@@ -430,7 +431,10 @@ static int launch_grid(yalps_ctx *ctx, int H, int W, double *d_M, const yalps_op
   int grid = ctx->prop.multiProcessorCount;
   const long long bytes = (long long)H * W * 8;
   grid = (int)std::max(1LL, std::min<long long>(grid, bytes / (256 << 10) + 1));
-  grid = std::min(grid, std::max(1, (H + kGridWarps - 1) / kGridWarps));
+  {
+    const long long items = (long long)H * ((W + kSegCols - 1) / kSegCols);
+    grid = (int)std::min<long long>(grid, std::max(1LL, (items + kGridWarps - 1) / kGridWarps));
+  }
   if (const char *env = getenv("YALPS_GRID_CTAS")) grid = std::max(1, std::min(atoi(env), ctx->prop.multiProcessorCount * occ));
   GridArgs a{};
   a.M = d_M;
@@ -478,8 +482,31 @@ int yalps_solve_batch_device(yalps_ctx *ctx, int64_t n, int32_t height, int32_t 
   if ((long long)height * width >= (1LL << 31)) return fail(ctx, YALPS_ERR_TOO_LARGE, "height*width must be < 2^31");
   if (n == 0) return 0;
   CU(ctx, cudaSetDevice(ctx->device));
+  // density probe for the path policy, once per (buffer, shape): synchronises `stream` the first time only
+  double density = -1.0;
+  if (ctx->tune_path == YALPS_PATH_AUTO && n > 64 && d_work) {
+    const std::string key = std::to_string((size_t)d_matrices) + ":" + std::to_string(height) + "x" + std::to_string(width);
+    auto it = ctx->density_cache.find(key);
+    if (it == ctx->density_cache.end()) {
+      void *hp, *dp;
+      if (int rc = pin_ensure(ctx, "density_probe", 64, &hp)) return rc;
+      if (int rc = pin_device_ptr(ctx, hp, &dp)) return rc;
+      ((int *)hp)[0] = ((int *)hp)[1] = 0;
+      const long long cells = (long long)height * width;
+      k_sample_density<<<1, 256, 0, (cudaStream_t)stream>>>(d_matrices, cells, std::max(1LL, cells / 4096), (int *)dp);
+      CU(ctx, cudaGetLastError());
+      CU(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+      ctx->launches++;
+      const int seen = ((int *)hp)[0], nz = ((int *)hp)[1];
+      density = seen ? (double)nz / seen : 1.0;
+      if (ctx->density_cache.size() > 64) ctx->density_cache.clear();
+      ctx->density_cache[key] = density;
+    } else {
+      density = it->second;
+    }
+  }
   LaunchPlan plan;
-  if (int rc = plan_launch(ctx, n, height, width, opt->check_cycles != 0, &plan)) return rc;
+  if (int rc = plan_launch(ctx, n, height, width, opt->check_cycles != 0, &plan, density)) return rc;
   BatchArgs a{};
   a.n = n;
   a.mode = kModeBatch;
