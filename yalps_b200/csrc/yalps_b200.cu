@@ -22,6 +22,7 @@
 
 #include "kernels.cuh"
 #include "grid_kernel.cuh"
+#include "reg_kernel.cuh"
 
 using namespace yalps;
 
@@ -181,6 +182,7 @@ int default_warps(long long cells, bool resident) {
 }
 
 struct LaunchPlan {
+  bool reg = false;  // K1r: tableau in registers (small LPs)
   bool resident;
   const KernelEntry *k;
   size_t smem;
@@ -191,7 +193,7 @@ struct LaunchPlan {
 // the rank-1 update, their pivots are latency-bound, and the HBM/L2-resident kernel wins because it needs no
 // shared memory for the tableau and therefore runs many more LPs per SM (profiles/r01_sweep_paths.jsonl).
 int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycles, LaunchPlan *plan,
-                double density = -1.0) {
+                double density = -1.0, bool allow_reg = false) {
   SmemLayout Lr(Hcap, Wcap, true, 32), Lg(Hcap, Wcap, false, 32);
   bool resident = Lr.total <= (size_t)ctx->smem_optin;
   if (resident && ctx->tune_path == YALPS_PATH_AUTO && density >= 0.0 && density < 0.35 && n > 64) resident = false;
@@ -201,6 +203,29 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
     resident = false;
   }
   const bool grid_ok = ctx->tune_path == YALPS_PATH_GRID || (ctx->tune_path == YALPS_PATH_AUTO && n <= 16);
+  plan->reg = false;
+  if (allow_reg && Hcap <= kRegMaxRows && Wcap <= kRegMaxCols && !check_cycles &&
+      ctx->tune_path == YALPS_PATH_REG) {  // explicit only: measured slower than K1 (see reg_kernel.cuh)
+    auto it = ctx->occ_cache.find("reg33");
+    int occ = 0;
+    if (it == ctx->occ_cache.end()) {
+      CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_simplex_reg<kRegMaxRows>, 32, 0));
+      ctx->occ_cache["reg33"] = occ;
+    } else {
+      occ = it->second;
+    }
+    if (occ >= 1) {
+      plan->reg = true;
+      plan->resident = true;
+      plan->k = nullptr;
+      plan->smem = 0;
+      plan->grid = (int)std::max(1LL, std::min((long long)occ * ctx->prop.multiProcessorCount, n));
+      return 0;
+    }
+  }
+  if (ctx->tune_path == YALPS_PATH_REG)
+    return fail(ctx, YALPS_ERR_TOO_LARGE, "tableau %dx%d does not fit the register-resident kernel (max %dx%d, no checkCycles)",
+                Hcap, Wcap, kRegMaxRows, kRegMaxCols);
   plan->resident = resident;
   plan->k = nullptr;
   plan->smem = 0;
@@ -266,6 +291,7 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
 // K4 (whole grid per LP, LPs one after another) beats K2 (one CTA per LP) when the tableaus do not fit in
 // shared memory and there are too few of them to give every SM its own LP.
 bool use_grid_path(const yalps_ctx *ctx, long long n, const LaunchPlan &plan) {
+  if (plan.reg) return false;
   if (ctx->tune_path == YALPS_PATH_GRID || plan.k == nullptr) return true;
   if (ctx->tune_path != YALPS_PATH_AUTO) return false;
   return !plan.resident && n <= 16;
@@ -295,6 +321,12 @@ int launch_simplex(yalps_ctx *ctx, const LaunchPlan &plan, BatchArgs &args, cons
     args.hist = (int *)hist;
   } else {
     args.hist = nullptr;
+  }
+  if (plan.reg) {
+    k_simplex_reg<kRegMaxRows><<<plan.grid, 32, 0, stream>>>(args);
+    CU(ctx, cudaGetLastError());
+    ctx->launches++;
+    return 0;
   }
   SimplexKernel fn = plan.resident ? plan.k->resident : plan.k->global;
   fn<<<plan.grid, plan.k->nw * 32, plan.smem, stream>>>(args);
@@ -392,7 +424,7 @@ int yalps_device_info(const yalps_ctx *ctx, int32_t *sm_count, int32_t *smem_per
 
 int yalps_set_tuning(yalps_ctx *ctx, int32_t path, int32_t threads_per_lp) {
   if (!ctx) return YALPS_ERR_ARGUMENT;
-  if (path < 0 || path > YALPS_PATH_GRID) return fail(ctx, YALPS_ERR_ARGUMENT, "bad path %d", path);
+  if (path < 0 || path > YALPS_PATH_REG) return fail(ctx, YALPS_ERR_ARGUMENT, "bad path %d", path);
   ctx->tune_path = path;
   ctx->tune_threads = threads_per_lp;
   return 0;
@@ -506,7 +538,7 @@ int yalps_solve_batch_device(yalps_ctx *ctx, int64_t n, int32_t height, int32_t 
     }
   }
   LaunchPlan plan;
-  if (int rc = plan_launch(ctx, n, height, width, opt->check_cycles != 0, &plan, density)) return rc;
+  if (int rc = plan_launch(ctx, n, height, width, opt->check_cycles != 0, &plan, density, true)) return rc;
   BatchArgs a{};
   a.n = n;
   a.mode = kModeBatch;
@@ -605,7 +637,7 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
     const size_t desc_b = ragged ? (size_t)n * 32 + 64 : 0;
     LaunchPlan plan;
     if (in_b + out_b + desc_b <= ((size_t)768 << 10) && ctx->tune_path != YALPS_PATH_GRID &&
-        plan_launch(ctx, n, Hcap, Wcap, opt->check_cycles != 0, &plan) == 0 && plan.k && plan.resident) {
+        plan_launch(ctx, n, Hcap, Wcap, opt->check_cycles != 0, &plan, -1.0, true) == 0 && (plan.k || plan.reg) && plan.resident) {
       auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
       size_t o = 0;
       const size_t o_in = o; o += up16(in_b);
@@ -719,7 +751,7 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
       for (long long k = 0; k < c0; k += step, seen++) nz += m0[k] != 0.0;
       density = seen ? (double)nz / (double)seen : 1.0;
     }
-    if ((rc = plan_launch(ctx, cn, chcap, cwcap, opt->check_cycles != 0, &plan, density))) return rc;
+    if ((rc = plan_launch(ctx, cn, chcap, cwcap, opt->check_cycles != 0, &plan, density, true))) return rc;
 
     void *d_in, *d_status, *d_value, *d_piv, *d_rhs, *d_pos, *d_var;
     if ((rc = dev_ensure(ctx, "in" + s, ccells * 8, &d_in))) return rc;
