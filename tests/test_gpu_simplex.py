@@ -374,3 +374,23 @@ def test_register_kernel_options_and_special_values(engine):
             engine.solve_batch(np.zeros(34 * 65), 34, 65)  # one row too many for the register kernel
     finally:
         engine.set_tuning(E.PATH_AUTO, 0)
+
+
+def test_ragged_batch_mixed_sizes_are_grouped(engine):
+    """A ragged batch with tiny, medium and beyond-shared-memory tableaus: each size class gets its own kernel
+    configuration (K1 of several widths, K2/K4), results come back in the caller's order."""
+    rng = np.random.default_rng(11)
+    shapes_mn = [(3, 4), (32, 64), (200, 260), (5, 9), (90, 130), (250, 300), (32, 64), (1, 1), (60, 200)] * 3
+    rng.shuffle(shapes_mn)
+    tabs, shapes, exp = [], [], []
+    for i, (m, nv) in enumerate(shapes_mn):
+        t = O.generate_synthetic(100 + i, 1, m, nv, min(m, 3))[0]
+        tabs.append(t)
+        shapes.append((m + 1, nv + 1))
+        exp.append(oracle_batch(t.reshape(1, -1), m + 1, nv + 1))
+    got = engine.solve_ragged(tabs, shapes, want_matrices=True)
+    for g, e, s in zip(got, exp, shapes):
+        assert g["status"] == e["status"][0] and g["pivots"] == tuple(e["pivots"][0]), s
+        assert same_value(g["value"], e["value"][0])
+        assert np.array_equal(g["pos"], e["pos"][0]) and np.array_equal(g["var"], e["var"][0])
+        assert same_bits(g["rhs"], e["rhs"][0]) and same_bits(g["matrix"], e["matrices"][0]), s

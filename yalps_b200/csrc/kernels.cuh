@@ -23,6 +23,7 @@ struct BatchArgs {
   double *mat_out;    // optional final tableaus
   const int *heights, *widths;          // ragged batch (nullable)
   const long long *mat_off, *rhs_off, *pos_off;
+  const int *index;                     // ragged groups: launch-local LP -> LP id within the chunk (nullable)
   int *status;
   double *value;
   long long *pivots;
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 1 ? 12 : (NW == 2 ? 6 : (NW == 
       __syncthreads();
     }
     if (lp >= a.n) break;
+    if (a.index) lp = a.index[lp];
 
     int H, W, ncuts = 0;
     size_t moff, roff, poff;

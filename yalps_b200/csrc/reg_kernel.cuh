@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(32, 10) k_simplex_reg(const BatchArgs a) {
       __syncwarp();
     }
     if (lp >= a.n) break;
+    if (a.index) lp = a.index[lp];
     int H, W;
     size_t moff, roff, poff;
     if (a.heights) {

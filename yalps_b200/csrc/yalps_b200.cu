@@ -762,7 +762,7 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
     if ((rc = dev_ensure(ctx, "pos" + s, cpv * 4, &d_pos))) return rc;
     if ((rc = dev_ensure(ctx, "var" + s, cpv * 4, &d_var))) return rc;
     void *d_out = nullptr;
-    if (matrices_out && plan.resident)
+    if (matrices_out && (plan.resident || ragged))
       if ((rc = dev_ensure(ctx, "matout" + s, ccells * 8, &d_out))) return rc;
 
     const double *src = matrices + (ragged ? mat_offsets[begin] : cells_upto(begin));
@@ -824,19 +824,78 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
       a.pos_off = (const long long *)d_po;
     }
     fill_options(a, opt);
-    if (use_grid_path(ctx, cn, plan)) {
-      for (int64_t i = 0; i < cn; i++) {
-        const int hi = ragged ? heights[begin + i] : height, wi = ragged ? widths[begin + i] : width;
-        const long long mo = cells_upto(begin + i) - cells_upto(begin), ro = rows_upto(begin + i) - rows_upto(begin),
-                        po = pv_upto(begin + i) - pv_upto(begin);
-        if ((rc = launch_grid(ctx, hi, wi, (double *)d_in + mo, opt, (int *)d_status + i, (double *)d_value + i,
-                              (long long *)d_piv + 2 * i, (double *)d_rhs + ro, (int *)d_pos + po, (int *)d_var + po,
-                              st)))
-          return rc;
+    if (!ragged) {
+      if (use_grid_path(ctx, cn, plan)) {
+        for (int64_t i = 0; i < cn; i++) {
+          const long long mo = (long long)i * height * width;
+          if ((rc = launch_grid(ctx, height, width, (double *)d_in + mo, opt, (int *)d_status + i, (double *)d_value + i,
+                                (long long *)d_piv + 2 * i, (double *)d_rhs + (size_t)i * height,
+                                (int *)d_pos + (size_t)i * (width + height), (int *)d_var + (size_t)i * (width + height),
+                                st)))
+            return rc;
+        }
+        a.mat_out = matrices_out ? (double *)d_in : nullptr;
+      } else if ((rc = launch_simplex(ctx, plan, a, s, st))) {
+        return rc;
       }
-      a.mat_out = matrices_out ? (double *)d_in : nullptr;
-    } else if ((rc = launch_simplex(ctx, plan, a, s, st))) {
-      return rc;
+    } else {
+      // Ragged chunk: LPs of very different sizes must not share one launch configuration (one large model would
+      // push a thousand small ones onto the HBM-resident kernel).  Group by (fits in shared memory, CTA width) and
+      // launch each group with its own plan through an index indirection.
+      if (matrices_out) a.mat_out = (double *)d_out;
+      std::vector<std::vector<int>> groups;
+      std::vector<std::pair<int, int>> caps;  // (Hcap, Wcap) per group
+      std::unordered_map<int, int> group_of;
+      for (int64_t i = 0; i < cn; i++) {
+        const int hi = heights[begin + i], wi = widths[begin + i];
+        const bool res = SmemLayout(hi, wi, true, 32).total <= (size_t)ctx->smem_optin;
+        const int key = (res ? 0 : 64) + default_warps((long long)hi * wi, res);
+        auto it = group_of.find(key);
+        if (it == group_of.end()) {
+          it = group_of.emplace(key, (int)groups.size()).first;
+          groups.emplace_back();
+          caps.emplace_back(1, 1);
+        }
+        groups[it->second].push_back((int)i);
+        caps[it->second].first = std::max(caps[it->second].first, hi);
+        caps[it->second].second = std::max(caps[it->second].second, wi);
+      }
+      std::vector<int> flat;
+      for (auto &g : groups) flat.insert(flat.end(), g.begin(), g.end());
+      void *d_index;
+      if ((rc = dev_ensure(ctx, "rg_index" + s, flat.size() * 4, &d_index))) return rc;
+      CU(ctx, cudaMemcpyAsync(d_index, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, st));
+      CU(ctx, cudaStreamSynchronize(st));
+      size_t at = 0;
+      for (size_t g = 0; g < groups.size(); g++) {
+        const long long gn = (long long)groups[g].size();
+        LaunchPlan gp;
+        if ((rc = plan_launch(ctx, gn, caps[g].first, caps[g].second, opt->check_cycles != 0, &gp,
+                              groups.size() == 1 ? density : -1.0, true)))
+          return rc;
+        if (use_grid_path(ctx, gn, gp)) {
+          for (int id : groups[g]) {
+            const int hi = heights[begin + id], wi = widths[begin + id];
+            const long long mo = moff[begin + id] - moff[begin], ro = roff[begin + id] - roff[begin],
+                            po = poff[begin + id] - poff[begin];
+            if ((rc = launch_grid(ctx, hi, wi, (double *)d_in + mo, opt, (int *)d_status + id, (double *)d_value + id,
+                                  (long long *)d_piv + 2 * id, (double *)d_rhs + ro, (int *)d_pos + po, (int *)d_var + po,
+                                  st)))
+              return rc;
+            if (matrices_out)
+              CU(ctx, cudaMemcpyAsync((double *)d_out + mo, (double *)d_in + mo, (size_t)hi * wi * 8,
+                                      cudaMemcpyDeviceToDevice, st));
+          }
+        } else {
+          BatchArgs ga = a;
+          ga.n = gn;
+          ga.Hcap = caps[g].first;
+          ga.Wcap = caps[g].second;
+          ga.index = (const int *)d_index + at;
+          if ((rc = launch_simplex(ctx, gp, ga, s, st))) return rc;
+        }
+        at += groups[g].size();
+      }
     }
 
     if (status) CU(ctx, cudaMemcpyAsync(status + begin, d_status, (size_t)cn * 4, cudaMemcpyDeviceToHost, st));
