@@ -144,3 +144,20 @@ def test_python_wave_driver_matches_native_driver(engine, name):
     assert res["status"] == o["status"] and same_value(-tm.sign * res["result"], o["result"])
     assert res["stats"]["nodes"] == o["nodes"] and res["stats"]["node_pivots"] == o["node_pivots"]
     assert np.array_equal(res["pos"], o["final_pos"]) and same_bits(res["rhs"], o["final_rhs"])
+
+
+def test_solve_many_concurrent_milps(engine):
+    """Many MILPs: root LPs in one ragged batch, branch-and-cut searches on concurrent contexts of the same GPU."""
+    import time
+    names = ["Knapsack 1", "Fancy Stock Cutting Problem", "Integer Wood Shop Problem", "Taco Party", "Cutting Stock"]
+    picked = [c for c in CASES if c["name"] in names and not c["options"]]
+    models = [c["model"] for c in picked] * 6
+    oracle = [c["oracle"] for c in picked] * 6
+    for workers in (1, 4):
+        t0 = time.perf_counter()
+        sols = yalps_b200.solve_many(models, engine=engine, milp_workers=workers)
+        dt = time.perf_counter() - t0
+        for s, o in zip(sols, oracle):
+            assert s["status"] == o["status"] and same_value(s["result"], o["result"])
+            assert [list(v) for v in s["variables"]] == [list(v) for v in o["variables"]]
+        print(f"solve_many: {len(models)} MILPs, {workers} worker(s): {dt * 1e3:.1f} ms")

@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <limits>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -29,6 +30,20 @@ using namespace yalps;
 namespace {
 
 thread_local std::string g_create_error;
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the function on the device, shared by every ctx of
+// the process: it is only ever raised, under a lock (several contexts may run on different host threads).
+std::mutex g_attr_mutex;
+std::unordered_map<std::string, int> g_smem_attr;
+
+cudaError_t raise_smem_limit(int device, const void *fn, int bytes) {
+  std::lock_guard<std::mutex> lock(g_attr_mutex);
+  int &cur = g_smem_attr[std::to_string(device) + ":" + std::to_string((size_t)fn)];
+  if (bytes <= cur) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) cur = bytes;
+  return e;
+}
 
 struct DevBuf {
   void *p = nullptr;
@@ -60,7 +75,6 @@ struct yalps_ctx {
   std::unordered_map<std::string, DevBuf> pool;
   std::unordered_map<std::string, DevBuf> pinned;
   std::unordered_map<std::string, int> occ_cache;
-  std::unordered_map<void *, int> smem_attr;
   std::unordered_map<std::string, double> density_cache;
   Root root;
 };
@@ -246,11 +260,7 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
     const std::string key = std::to_string((size_t)(resident ? (void *)k->resident : (void *)k->global)) + ":" + std::to_string(smem_c);
     auto it = ctx->occ_cache.find(key);
     if (it != ctx->occ_cache.end()) {
-      int &attr = ctx->smem_attr[(void *)(resident ? k->resident : k->global)];
-      if ((int)smem_c > attr) {  // the opt-in limit is per function and only ever raised
-        CU(ctx, cudaFuncSetAttribute(resident ? k->resident : k->global, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-        attr = (int)smem_c;
-      }
+      CU(ctx, raise_smem_limit(ctx->device, (const void *)(resident ? k->resident : k->global), (int)smem_c));
       int occ_c = it->second;
       if (check_cycles) occ_c = std::min(occ_c, 4);
       long long grid_c = std::max(1LL, std::min((long long)occ_c * ctx->prop.multiProcessorCount, n));
@@ -267,13 +277,7 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
   }
   SimplexKernel fn = resident ? k->resident : k->global;
   const size_t smem = resident ? Lr.total : Lg.total;
-  {
-    int &attr = ctx->smem_attr[(void *)fn];
-    if ((int)smem > attr) {
-      CU(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr = (int)smem;
-    }
-  }
+  CU(ctx, raise_smem_limit(ctx->device, (const void *)fn, (int)smem));
   int occ = 0;
   CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, k->nw * 32, smem));
   if (occ < 1) return fail(ctx, YALPS_ERR_TOO_LARGE, "kernel does not fit on an SM (smem %zu)", smem);
@@ -455,7 +459,7 @@ static int launch_grid(yalps_ctx *ctx, int H, int W, double *d_M, const yalps_op
   int coop = 0;
   CU(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
   if (!coop) return fail(ctx, YALPS_ERR_CUDA, "device does not support cooperative launches");
-  CU(ctx, cudaFuncSetAttribute(k_simplex_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  CU(ctx, raise_smem_limit(ctx->device, (const void *)k_simplex_grid, (int)L.total));
   int occ = 0;
   CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_simplex_grid, kGridThreads, L.total));
   if (occ < 1) return fail(ctx, YALPS_ERR_TOO_LARGE, "grid kernel does not fit on an SM");
@@ -1003,7 +1007,7 @@ int yalps_measure_smem_bandwidth(yalps_ctx *ctx, double *gbs, double *sm_clock_m
   const int words = 24 * 1024 / 8 * 4;  // 96 KiB per CTA, 2 CTAs per SM
   const int threads = 512, iters = 2000;
   const size_t smem = (size_t)words * 8;
-  CU(ctx, cudaFuncSetAttribute(k_smem_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CU(ctx, raise_smem_limit(ctx->device, (const void *)k_smem_stream, (int)smem));
   void *sink;
   if (int rc = dev_ensure(ctx, "sink", 64, &sink)) return rc;
   const int grid = ctx->prop.multiProcessorCount * 2;

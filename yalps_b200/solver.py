@@ -102,9 +102,25 @@ def solve(model: dict, options: Optional[dict] = None, *, engine: Optional[Engin
     return _solution(tabmod, STATUS_NAMES[r["status"]], r["result"], r["rhs"], r["pos"], r["var"], opt)
 
 
-def solve_many(models: Sequence[dict], options: Optional[dict] = None, *, engine: Optional[Engine] = None) -> list:
-    """solveMany(models, options): all root LPs go to the device as ONE ragged batch; models with integer
-    variables whose root is optimal then run branch and cut (node waves) one after another."""
+def _worker_engines(device: int, count: int) -> list:
+    """Extra engines (one ctx each, same GPU) for concurrent branch-and-cut searches; a ctx is single-threaded."""
+    out = []
+    for k in range(count):
+        key = (device, "milp", k)
+        eng = _engines.get(key)
+        if eng is None:
+            eng = _engines[key] = Engine(device)
+        out.append(eng)
+    return out
+
+
+def solve_many(models: Sequence[dict], options: Optional[dict] = None, *, engine: Optional[Engine] = None,
+               milp_workers: int = 4) -> list:
+    """solveMany(models, options): all root LPs go to the device as ONE ragged batch (LPs of different sizes are
+    grouped per kernel configuration by the library).  Models with integer variables whose root is optimal then
+    run branch and cut; their searches are latency-bound node waves, so up to `milp_workers` of them run
+    concurrently, each on its own context / streams of the same GPU (the C ABI releases the GIL for a whole search).
+    Results are identical to calling solve() per model."""
     opt = {**_DEFAULTS, **(options or {})}
     copt = _c_options(opt)
     eng = engine or get_engine()
@@ -114,16 +130,53 @@ def solve_many(models: Sequence[dict], options: Optional[dict] = None, *, engine
     roots = eng.solve_ragged([tm.tableau.matrix for tm in tabmods],
                              [(tm.tableau.height, tm.tableau.width) for tm in tabmods], copt,
                              want_matrices=any(tm.integers for tm in tabmods))
-    out = []
-    for tm, r in zip(tabmods, roots):
+    out: list = [None] * len(tabmods)
+    milp = []
+    for i, (tm, r) in enumerate(zip(tabmods, roots)):
         status = STATUS_NAMES[r["status"]]
         if not tm.integers or status != "optimal":
-            out.append(_solution(tm, status, r["value"], r["rhs"], r["pos"], r["var"], opt))
-            continue
+            out[i] = _solution(tm, status, r["value"], r["rhs"], r["pos"], r["var"], opt)
+        else:
+            milp.append(i)
+
+    def search(e: Engine, i: int):
+        tm, r = tabmods[i], roots[i]
         t = tm.tableau
-        eng.bnb_set_root(r["matrix"], t.height, t.width, r["pos"], r["var"], 2 * len(tm.integers))
-        b = eng.branch_and_cut(tm.integers, tm.sign, r["value"], copt)
-        out.append(_solution(tm, STATUS_NAMES[b["status"]], b["result"], b["rhs"], b["pos"], b["var"], opt))
+        e.bnb_set_root(r["matrix"], t.height, t.width, r["pos"], r["var"], 2 * len(tm.integers))
+        b = e.branch_and_cut(tm.integers, tm.sign, r["value"], copt)
+        out[i] = _solution(tm, STATUS_NAMES[b["status"]], b["result"], b["rhs"], b["pos"], b["var"], opt)
+
+    workers = max(1, min(int(milp_workers), len(milp)))
+    if workers <= 1:
+        for i in milp:
+            search(eng, i)
+    else:
+        import queue
+        import threading
+        todo: "queue.SimpleQueue[int]" = queue.SimpleQueue()
+        for i in milp:
+            todo.put(i)
+        errors: list = []
+
+        def run(e: Engine):
+            while True:
+                try:
+                    i = todo.get_nowait()
+                except queue.Empty:
+                    return
+                try:
+                    search(e, i)
+                except Exception as exc:  # surfaced after the join
+                    errors.append(exc)
+                    return
+
+        threads = [threading.Thread(target=run, args=(e,)) for e in _worker_engines(eng.device, workers)]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        if errors:
+            raise errors[0]
     return out
 
 
