@@ -1,0 +1,28 @@
+"""One mid-size dense LP through the grid kernel (K4), for profiling: python scripts/k4_case.py [m] [n] [max_pivots]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import yalps_b200
+from yalps_b200 import engine as E
+m = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+nv = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
+cap = float(sys.argv[3]) if len(sys.argv) > 3 else 200.0
+eng = yalps_b200.Engine(0)
+H, W = m + 1, nv + 1
+d = torch.empty(H * W, dtype=torch.float64, device="cuda")
+work = torch.empty_like(d)
+piv = torch.empty(1, 2, dtype=torch.int64, device="cuda")
+eng.generate_synthetic_device(0, 1, m, nv, d.data_ptr())
+opt = E.make_options(max_pivots=cap)
+stream = torch.cuda.current_stream().cuda_stream
+for _ in range(2):
+    work.copy_(d)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eng.solve_batch_device(1, H, W, d.data_ptr(), opt, d_work=work.data_ptr(), d_pivots=piv.data_ptr(), stream=stream)
+    e1.record()
+    torch.cuda.synchronize()
+    p = int(piv.sum().item())
+    print(f"{H}x{W}: {p} pivots, {e0.elapsed_time(e1) * 1e3 / max(p, 1):.2f} us/pivot")
+eng.close()

@@ -4,6 +4,10 @@
 //   * the tableau stays in HBM/L2 in the reference layout (row stride W, column 0 = RHS), updated in place;
 //   * every CTA recomputes the pivot choice redundantly from the (L2-resident) objective row / RHS column /
 //     pivot column, so all CTAs agree on (row, col) without exchanging partial results;
+//   * every CTA keeps private shared-memory copies of the objective row and of the RHS column and applies the
+//     same rank-1 update to them as the owners of those cells apply in HBM (same operands, same operations, so
+//     the copies stay bit-identical): the first selection of every pivot reads shared memory only, and a pivot
+//     costs two dependent trips to L2/HBM (pivot row, pivot column) instead of four or five;
 //   * every CTA stages the normalised pivot row (and its non-zero flags) in its own shared memory;
 //   * every CTA also stages the old pivot column (0 for rows the update must skip), so the update never waits on
 //     a dependent global load and a row can be split between warps without a read/write hazard on its
@@ -58,17 +62,22 @@ struct GridArgs {
 constexpr int kGridThreads = 1024;
 constexpr int kGridWarps = kGridThreads / 32;
 
-// shared memory: prow[W] doubles, colbuf[H] doubles, nz bitmask words, reduction scratch
+// shared memory: prow[W], row0[W] (objective row copy), colbuf[H], bcol[H] (RHS column copy), nz bitmask, scratch
 struct GridSmem {
-  size_t off_prow, off_col, off_nz, off_red, total;
+  size_t off_prow, off_row0, off_col, off_b, off_nz, off_red, total;
   __host__ __device__ GridSmem(int H, int W) {
     size_t o = 0;
     off_prow = o;
     o += (size_t)((W + 1) & ~1) * 8;
+    off_row0 = o;
+    o += (size_t)((W + 1) & ~1) * 8;
     off_col = o;
     o += (size_t)((H + 1) & ~1) * 8;
+    off_b = o;
+    o += (size_t)((H + 1) & ~1) * 8;
+    o = (o + 15) & ~(size_t)15;
     off_nz = o;
-    o += (size_t)((W + 31) / 32 + 1) * 4;
+    o += (size_t)(((W + 31) / 32 + 8 + 7) & ~7) * 4;
     o = (o + 15) & ~(size_t)15;
     off_red = o;
     o += 192 * 4;
@@ -84,7 +93,9 @@ __global__ void __launch_bounds__(kGridThreads, 1) k_simplex_grid(const GridArgs
   unsigned long long epoch = 0;
   const GridSmem L(a.H, a.W);
   double *prow = reinterpret_cast<double *>(smem_raw + L.off_prow);
+  double *row0 = reinterpret_cast<double *>(smem_raw + L.off_row0);
   double *colbuf = reinterpret_cast<double *>(smem_raw + L.off_col);
+  double *bcol = reinterpret_cast<double *>(smem_raw + L.off_b);
   unsigned *nzmask = reinterpret_cast<unsigned *>(smem_raw + L.off_nz);
   unsigned *red = reinterpret_cast<unsigned *>(smem_raw + L.off_red);
 
@@ -96,6 +107,8 @@ __global__ void __launch_bounds__(kGridThreads, 1) k_simplex_grid(const GridArgs
 
   for (int k = blockIdx.x * NT + tid; k < W + H; k += gridDim.x * NT)
     a.var[k] = (a.init_var && k < a.init_n) ? a.init_var[k] : k;
+  for (int c = tid; c < W; c += NT) row0[c] = M[c];
+  for (int r = tid; r < H; r += NT) bcol[r] = M[(size_t)r * W];
   grid_barrier(a.barrier, epoch);
 
   int status = ST_CYCLED;
@@ -107,10 +120,11 @@ __global__ void __launch_bounds__(kGridThreads, 1) k_simplex_grid(const GridArgs
     if (!((double)iter < a.max_pivots)) break;
     int row, col;
     if (phase == 1) {
+      // leaving row from the private RHS copy (:111-119)
       double bv = INF;
       int bi = kNone;
       for (int r = 1 + tid; r < H; r += NT) {
-        const double v = M[(size_t)r * W];
+        const double v = bcol[r];
         if (v < -precision && v < bv) {
           bv = v;
           bi = r;
@@ -123,12 +137,14 @@ __global__ void __launch_bounds__(kGridThreads, 1) k_simplex_grid(const GridArgs
         hist_len = 0;
         continue;
       }
+      // trip 1: the pivot row (raw) into shared memory, entering column from it and the private objective row
       bv = -INF;
       bi = kNone;
-      for (int c = 1 + tid; c < W; c += NT) {
+      for (int c = tid; c < W; c += NT) {
         const double coef = M[(size_t)row * W + c];
-        if (coef < -precision) {
-          const double ratio = __ddiv_rn(-M[c], coef);
+        prow[c] = coef;
+        if (c >= 1 && coef < -precision) {
+          const double ratio = __ddiv_rn(-row0[c], coef);
           if (ratio > bv) {
             bv = ratio;
             bi = c;
@@ -140,11 +156,14 @@ __global__ void __launch_bounds__(kGridThreads, 1) k_simplex_grid(const GridArgs
         status = ST_INFEASIBLE;
         break;
       }
+      // trip 2: the pivot column (raw)
+      for (int r = tid; r < H; r += NT) colbuf[r] = M[(size_t)r * W + col];
     } else {
+      // entering column from the private objective row (:71-79)
       double bv = -INF;
       int bi = kNone;
       for (int c = 1 + tid; c < W; c += NT) {
-        const double v = M[c];
+        const double v = row0[c];
         if (v > precision && v > bv) {
           bv = v;
           bi = c;
@@ -153,15 +172,17 @@ __global__ void __launch_bounds__(kGridThreads, 1) k_simplex_grid(const GridArgs
       col = block_best<true, NW>(bi == kNone ? no_key<true>() : order_key(bv), bi, red, parity);
       if (col == kNone) {
         status = ST_OPTIMAL;
-        value = round_to_precision(M[0], precision);
+        value = round_to_precision(row0[0], precision);
         break;
       }
+      // trip 1: the pivot column (raw) into shared memory, ratio test against the private RHS copy (:83-95)
       bv = INF;
       bi = kNone;
-      for (int r = 1 + tid; r < H; r += NT) {
+      for (int r = tid; r < H; r += NT) {
         const double v = M[(size_t)r * W + col];
-        if (v > precision) {
-          const double ratio = __ddiv_rn(M[(size_t)r * W], v);
+        colbuf[r] = v;
+        if (r >= 1 && v > precision) {
+          const double ratio = __ddiv_rn(bcol[r], v);
           if (ratio < INF) {
             const double key = (ratio <= precision) ? -INF : ratio;
             if (bi == kNone || key < bv) {
@@ -177,7 +198,10 @@ __global__ void __launch_bounds__(kGridThreads, 1) k_simplex_grid(const GridArgs
         value = (double)col;
         break;
       }
+      // trip 2: the pivot row (raw)
+      for (int c = tid; c < W; c += NT) prow[c] = M[(size_t)row * W + c];
     }
+    __syncthreads();  // raw pivot row and column are complete in shared memory
 
     if (a.check_cycles) {  // CTA 0 keeps the history; its verdict reaches the other CTAs through a grid barrier
       if (blockIdx.x == 0) {
@@ -202,13 +226,15 @@ __global__ void __launch_bounds__(kGridThreads, 1) k_simplex_grid(const GridArgs
       if (verdict) break;
     }
 
-    // ---- stage the normalised pivot row (src/simplex.ts:16-25) in shared memory
-    const double q = M[(size_t)row * W + col];
+    // ---- normalise the staged pivot row in place (src/simplex.ts:16-25); column: 0 = row left alone (:29,:31)
+    const double q = prow[col];
+    const double coef0 = colbuf[0];  // objective-row cell of the pivot column, before colbuf is rewritten
+    __syncthreads();
     for (int cbase = warp * 32; cbase < W; cbase += NT) {
       const int c = cbase + lane;
       bool nz = false;
       if (c < W) {
-        const double v = (c == col) ? 1.0 : M[(size_t)row * W + c];
+        const double v = (c == col) ? 1.0 : prow[c];
         nz = fabs(v) > kTiny;
         prow[c] = nz ? __ddiv_rn(v, q) : 0.0;
         if (c == col) nz = false;  // the pivot column gets -coef/q instead (:36)
@@ -216,9 +242,34 @@ __global__ void __launch_bounds__(kGridThreads, 1) k_simplex_grid(const GridArgs
       const unsigned m = __ballot_sync(0xffffffffu, nz);
       if (lane == 0) nzmask[cbase >> 5] = m;
     }
-    for (int r = tid; r < H; r += NT) {  // old pivot column; 0 = the rank-1 pass leaves the row alone (:29,:31)
-      const double coef = M[(size_t)r * W + col];
+    for (int r = tid; r < H; r += NT) {
+      const double coef = colbuf[r];
       colbuf[r] = (r != row && fabs(coef) > kTiny) ? coef : 0.0;
+    }
+    __syncthreads();
+    // ---- the same rank-1 update on the private objective row / RHS column copies
+    {
+      const bool act0 = fabs(coef0) > kTiny;  // row 0 is never the pivot row
+      const double p0 = prow[0];
+      const bool nz0 = (nzmask[0] & 1u) != 0u;  // column 0 is never the pivot column
+      if (act0) {
+        for (int c = tid; c < W; c += NT) {
+          if ((nzmask[c >> 5] >> (c & 31)) & 1u)
+            row0[c] = __dsub_rn(row0[c], __dmul_rn(coef0, prow[c]));
+          else if (c == col)
+            row0[c] = __ddiv_rn(-coef0, q);
+        }
+      }
+      for (int r = 1 + tid; r < H; r += NT) {
+        if (r == row) {
+          bcol[r] = p0;
+        } else {
+          const double coef = colbuf[r];
+          if (coef != 0.0 && nz0) bcol[r] = __dsub_rn(bcol[r], __dmul_rn(coef, p0));
+        }
+      }
+      __syncthreads();
+      if (tid == 0) bcol[0] = row0[0];  // the corner cell belongs to both copies
     }
     if (blockIdx.x == 0 && tid == 0) {  // basis bookkeeping (:7-12)
       const int leaving = a.var[W + row];
@@ -227,35 +278,54 @@ __global__ void __launch_bounds__(kGridThreads, 1) k_simplex_grid(const GridArgs
     }
     grid_barrier(a.barrier, epoch);  // every CTA has made its choice and staged the old pivot row: the tableau may change now
 
-    // ---- rank-1 update (:28-38): (row, column segment) items dealt round-robin to the warps of the grid
+    // ---- rank-1 update (:28-38): (row, column segment) items dealt round-robin to the warps of the grid.
+    // Item decomposition is incremental 32-bit arithmetic; a full segment runs without bounds checks, with the
+    // eight non-zero flags of the lane gathered from two 16-byte shared-memory loads.
     {
       const int nseg = (W + kSegCols - 1) / kSegCols;
-      const long long items = (long long)H * nseg;
-      for (long long it = gwarp; it < items; it += gwarps) {
-        const int r = (int)(it / nseg);
-        const int c0 = (int)(it - (long long)r * nseg) * kSegCols + lane;
-        double *__restrict__ Mr = M + (size_t)r * W;
+      const int step_r = gwarps / nseg, step_s = gwarps - step_r * nseg;
+      int r = gwarp / nseg, seg = gwarp - r * nseg;
+      while (r < H) {
+        const int c0 = seg * kSegCols + lane;
+        double *__restrict__ Mr = M + (size_t)r * W + c0;
+        const double coef = colbuf[r];
+        const bool full_seg = (seg + 1) * kSegCols <= W;
         if (r == row) {
 #pragma unroll
           for (int u = 0; u < 8; u++)
-            if (c0 + 32 * u < W) Mr[c0 + 32 * u] = prow[c0 + 32 * u];
-          continue;
-        }
-        const double coef = colbuf[r];
-        if (coef == 0.0) continue;  // row skip (:31)
-        double x[8];
+            if (full_seg || c0 + 32 * u < W) Mr[32 * u] = prow[c0 + 32 * u];
+        } else if (coef != 0.0) {  // else: row skip (:31)
+          // nz flags of my 8 columns: words seg*8 .. seg*8+7 (the mask array is padded to a multiple of 8 words)
+          const uint4 w0 = *reinterpret_cast<const uint4 *>(nzmask + seg * 8);
+          const uint4 w1 = *reinterpret_cast<const uint4 *>(nzmask + seg * 8 + 4);
+          const unsigned bits = ((w0.x >> lane) & 1u) | (((w0.y >> lane) & 1u) << 1) | (((w0.z >> lane) & 1u) << 2) |
+                                (((w0.w >> lane) & 1u) << 3) | (((w1.x >> lane) & 1u) << 4) |
+                                (((w1.y >> lane) & 1u) << 5) | (((w1.z >> lane) & 1u) << 6) |
+                                (((w1.w >> lane) & 1u) << 7);
+          double x[8];
+          if (full_seg) {
 #pragma unroll
-        for (int u = 0; u < 8; u++)
-          if (c0 + 32 * u < W) x[u] = Mr[c0 + 32 * u];
+            for (int u = 0; u < 8; u++) x[u] = Mr[32 * u];
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-          const int cc = c0 + 32 * u;
-          if (cc < W) {
-            if ((nzmask[cc >> 5] >> lane) & 1u)
-              Mr[cc] = __dsub_rn(x[u], __dmul_rn(coef, prow[cc]));
-            else if (cc == col)
-              Mr[cc] = __ddiv_rn(-coef, q);  // (:36)
+            for (int u = 0; u < 8; u++)
+              if ((bits >> u) & 1u) Mr[32 * u] = __dsub_rn(x[u], __dmul_rn(coef, prow[c0 + 32 * u]));
+          } else {
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+              if (c0 + 32 * u < W) x[u] = Mr[32 * u];
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+              if (c0 + 32 * u < W && ((bits >> u) & 1u)) Mr[32 * u] = __dsub_rn(x[u], __dmul_rn(coef, prow[c0 + 32 * u]));
           }
+          // the pivot-column cell of this row (:36), by the lane that owns it
+          if (col >= seg * kSegCols && col < (seg + 1) * kSegCols && ((col - lane) & 31) == 0)
+            M[(size_t)r * W + col] = __ddiv_rn(-coef, q);
+        }
+        r += step_r;
+        seg += step_s;
+        if (seg >= nseg) {
+          seg -= nseg;
+          r++;
         }
       }
     }

@@ -463,13 +463,11 @@ static int launch_grid(yalps_ctx *ctx, int H, int W, double *d_M, const yalps_op
   int occ = 0;
   CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_simplex_grid, kGridThreads, L.total));
   if (occ < 1) return fail(ctx, YALPS_ERR_TOO_LARGE, "grid kernel does not fit on an SM");
-  // enough CTAs to stream the tableau, not more than can be co-resident, not more warps than rows
+  // at most ~2 update items (row x 256-column segment) per warp, never more CTAs than can be co-resident
   int grid = ctx->prop.multiProcessorCount;
-  const long long bytes = (long long)H * W * 8;
-  grid = (int)std::max(1LL, std::min<long long>(grid, bytes / (256 << 10) + 1));
   {
     const long long items = (long long)H * ((W + kSegCols - 1) / kSegCols);
-    grid = (int)std::min<long long>(grid, std::max(1LL, (items + kGridWarps - 1) / kGridWarps));
+    grid = (int)std::min<long long>(grid, std::max(1LL, (items + 2 * kGridWarps - 1) / (2 * kGridWarps)));
   }
   if (const char *env = getenv("YALPS_GRID_CTAS")) grid = std::max(1, std::min(atoi(env), ctx->prop.multiProcessorCount * occ));
   GridArgs a{};
