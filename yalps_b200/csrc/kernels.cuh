@@ -159,11 +159,29 @@ __global__ void __launch_bounds__(NW * 32, NW == 1 ? 12 : (NW == 2 ? 6 : (NW == 
     if (kResident) {
       // asynchronous 8-byte copies (LDGSTS) straight into the (A, b) layout: every copy of the tableau is in
       // flight before the first one is waited for, so the load costs one memory latency, not one per row
-      for (int r = tid >> 5; r < rootH; r += NW) {
-        const double *sr = src + (size_t)r * W;
-        double *dA = t.A + (size_t)r * ldA - 1;
-        if ((tid & 31) == 0) cp_async8(t.b + (size_t)r * ldb, sr);
-        for (int c = 1 + (tid & 31); c < W; c += 32) cp_async8(dA + c, sr + c);
+      // (addresses advance incrementally: one 32-bit shared address and one global pointer per lane)
+      {
+        const int lane = tid & 31;
+        const unsigned sA0 = (unsigned)__cvta_generic_to_shared(t.A) + 8u * (unsigned)lane;  // A[r][lane]
+        const unsigned sB0 = (unsigned)__cvta_generic_to_shared(t.b);
+        const unsigned row_bytes = 8u * (unsigned)ldA;
+        const int full = (W - 1) / 32, tail = (W - 1) - 32 * full;  // coefficient columns per lane
+        unsigned sA = sA0 + row_bytes * (unsigned)(tid >> 5), sB = sB0 + 8u * (unsigned)ldb * (unsigned)(tid >> 5);
+        const double *g = src + (size_t)(tid >> 5) * W;
+        for (int r = tid >> 5; r < rootH; r += NW) {
+          if (lane == 0) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sB), "l"(g) : "memory");
+          const double *gc = g + 1 + lane;
+          unsigned d = sA;
+          for (int k = 0; k < full; k++) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gc) : "memory");
+            gc += 32;
+            d += 256u;
+          }
+          if (lane < tail) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gc) : "memory");
+          g += (size_t)NW * W;
+          sA += row_bytes * NW;
+          sB += 8u * (unsigned)ldb * NW;
+        }
       }
     } else if (src != a.work + moff) {
       const size_t cells = (size_t)rootH * W;
