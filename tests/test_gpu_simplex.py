@@ -394,3 +394,35 @@ def test_ragged_batch_mixed_sizes_are_grouped(engine):
         assert same_value(g["value"], e["value"][0])
         assert np.array_equal(g["pos"], e["pos"][0]) and np.array_equal(g["var"], e["var"][0])
         assert same_bits(g["rhs"], e["rhs"][0]) and same_bits(g["matrix"], e["matrices"][0]), s
+
+
+@pytest.mark.parametrize("m,nv,cap", [(1024, 2048, 60), (4096, 8192, 12)])
+def test_config5_full_size_capped_pivots_against_oracle(engine, m, nv, cap):
+    """BASELINE.json config 5 at full size (4097 x 8193 tableau, 268 MB): the first `cap` pivots of the grid-wide
+    kernel against the oracle, bit for bit over the whole tableau (a full solve is too slow for the CPU oracle in a
+    unit test; `maxPivots` is part of the reference's interface, so a capped run is a legitimate trajectory prefix)."""
+    import torch
+    H, W = m + 1, nv + 1
+    d = torch.empty(H * W, dtype=torch.float64, device="cuda")
+    engine.generate_synthetic_device(0, 1, m, nv, d.data_ptr())
+    torch.cuda.synchronize()
+    mats = d.cpu().numpy().reshape(1, -1)
+    exp = oracle_batch(mats, H, W, max_pivots=cap)
+    got = engine.solve_batch(mats, H, W, E.make_options(max_pivots=cap), want_matrices=True)
+    assert_batch_equal(got, exp, f"config5 {m}x{nv}")
+    assert got["status"][0] == 4 and int(got["pivots"][0].sum()) == cap
+
+
+def test_kernel_paths_agree_on_a_mid_size_batch(engine):
+    """K1, K2 and K4 are independent formulations: on the same inputs they must agree bit for bit with each other
+    (and with the oracle) -- 24 LPs of 120 x 200."""
+    m, nv, n = 120, 200, 24
+    mats = O.generate_synthetic(31, n, m, nv, 25)
+    exp = oracle_batch(mats, m + 1, nv + 1)
+    outs = {}
+    for name, path in (("K1", E.PATH_SMEM), ("K2", E.PATH_GMEM), ("K4", E.PATH_GRID)):
+        engine.set_tuning(path, 0)
+        outs[name] = engine.solve_batch(mats, m + 1, nv + 1, want_matrices=True)
+    engine.set_tuning(E.PATH_AUTO, 0)
+    for name, got in outs.items():
+        assert_batch_equal(got, exp, name)
