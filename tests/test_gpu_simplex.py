@@ -426,3 +426,14 @@ def test_kernel_paths_agree_on_a_mid_size_batch(engine):
     engine.set_tuning(E.PATH_AUTO, 0)
     for name, got in outs.items():
         assert_batch_equal(got, exp, name)
+
+
+def test_host_pipeline_with_several_chunks(engine):
+    """The host entry point cuts large batches into double-buffered chunks (H2D / kernel / D2H overlap): 4,400 LPs of
+    33 x 65 (75 MB) span two chunks; every LP must come back in order and bit-exact."""
+    n, m, nv = 4400, 32, 64
+    mats = O.generate_synthetic(123456, n, m, nv, 3)
+    exp = oracle_batch(mats, m + 1, nv + 1)
+    got = engine.solve_batch(mats, m + 1, nv + 1)
+    got["matrices"] = None
+    assert_batch_equal(got, exp, "chunked host pipeline")

@@ -161,3 +161,17 @@ def test_solve_many_concurrent_milps(engine):
             assert s["status"] == o["status"] and same_value(s["result"], o["result"])
             assert [list(v) for v in s["variables"]] == [list(v) for v in o["variables"]]
         print(f"solve_many: {len(models)} MILPs, {workers} worker(s): {dt * 1e3:.1f} ms")
+
+
+def test_afiro_from_mps_end_to_end(engine):
+    """BASELINE.json config 1: Netlib AFIRO read by the host-side MPS reader, converted like benchmarks/netlib/read.ts,
+    solved through solve(): the index.json objective, 14 + 6 pivots."""
+    import os
+    from conftest import GOLDEN
+    from yalps_b200.mps import netlib_model
+    model = netlib_model(open(os.path.join(GOLDEN, "afiro.mps")).read())
+    info = {}
+    sol = yalps_b200.solve(model, engine=engine, info=info)
+    assert sol["status"] == "optimal" and sol["result"] == -464.75314286
+    assert info["root_pivots"] == (14, 6) and (info["height"], info["width"]) == (36, 33)
+    assert abs(sol["result"] - (-464.75314286)) <= 1e-5 * 464.75314286  # benchmarks/netlib/index.json
