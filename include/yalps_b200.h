@@ -90,6 +90,9 @@ int yalps_device_info(const yalps_ctx *ctx, int32_t *sm_count, int32_t *smem_per
                       int32_t *cc_minor);
 /* Force a path / CTA width for subsequent batch calls (0 = auto). */
 int yalps_set_tuning(yalps_ctx *ctx, int32_t path, int32_t threads_per_lp);
+/* Row groups per CTA for the shared-memory / HBM paths: > 1 selects the row-split latency kernels
+ * (csrc/simplex_split.cuh: threads_per_lp / row_groups column threads x row_groups), 0 = automatic. */
+int yalps_set_row_groups(yalps_ctx *ctx, int32_t row_groups);
 /* Number of kernels launched by this ctx since creation (bench.py's gpu_launches). */
 int64_t yalps_launch_count(const yalps_ctx *ctx);
 
@@ -192,6 +195,11 @@ int yalps_solve(yalps_ctx *ctx, int32_t height, int32_t width, const double *mat
 /* roundToPrecision (src/util.ts:1-4) evaluated on the device for n values (parity probe). */
 int yalps_round_to_precision(yalps_ctx *ctx, int64_t n, const double *x, double precision, double *out);
 
+/* Probe: the shared-reciprocal division of csrc/fastdiv.cuh against __ddiv_rn on n hash-generated operand pairs
+ * (mode 0..4: random bit patterns, tableau-like values, special values, exact quotients, exponent extremes).
+ * The kernels must divide exactly like the reference's JS `/` (src/simplex.ts:19,25,36,89,128). */
+int yalps_probe_division(yalps_ctx *ctx, int64_t n, uint64_t seed, int32_t mode, uint64_t *mismatches,
+                         uint64_t *first_bad_bits /* [2]: numerator, divisor; may be NULL */);
 /* Shared-memory stream microbenchmark: bytes moved per second by ld/st.shared.f64 on all SMs
  * (the measured denominator of the K1 roofline).  Returns GB/s in *gbs. */
 int yalps_measure_smem_bandwidth(yalps_ctx *ctx, double *gbs, double *sm_clock_mhz);

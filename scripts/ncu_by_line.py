@@ -18,8 +18,9 @@ root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(root, "yalps_b200", "libyalps_b200.so")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
-cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+dis = ""  # the library has one cubin per translation unit: search them all
+for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
+    dis += subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout + "\n"
 lines, cur, on = [], None, False
 for ln in dis.split("\n"):
     if ln.startswith("//---") and ".text." in ln:

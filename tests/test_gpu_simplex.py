@@ -60,6 +60,81 @@ def test_every_cta_width_and_path(engine, threads, path):
     assert_batch_equal(got, exp, f"path={path} threads={threads}")
 
 
+SPLIT_SHAPES = [(32, 64, 6), (5, 3, 2), (40, 7, 10), (16, 100, 4), (90, 130, 30), (12, 700, 3), (150, 103, 40)]
+
+
+@pytest.mark.parametrize("rows", [2, 4, 8, 16])
+@pytest.mark.parametrize("path", [E.PATH_SMEM, E.PATH_GMEM])
+@pytest.mark.parametrize("m,nv,neg", SPLIT_SHAPES)
+def test_row_split_kernels_bit_exact(engine, m, nv, neg, path, rows):
+    """simplex_split.cuh: NWR row groups x NWC column warps, compacted active-row list."""
+    n = 24
+    H, W = m + 1, nv + 1
+    mats = O.generate_synthetic(4242 + m, n, m, nv, neg)
+    exp = oracle_batch(mats, H, W)
+    for threads in (64 * rows, 512):
+        engine.set_tuning(path, threads, rows)
+        try:
+            got = engine.solve_batch(mats, H, W, want_matrices=True)
+        finally:
+            engine.set_tuning(E.PATH_AUTO, 0)
+        assert_batch_equal(got, exp, f"{m}x{nv} path={path} rows={rows} threads={threads}")
+
+
+@pytest.mark.parametrize("rows", [2, 8])
+def test_row_split_special_values_options_and_cycles(engine, rows):
+    H, W = 4, 5
+    t = np.zeros((4, H * W))
+    t[0].reshape(H, W)[:] = [[0.0, 3.0, 2.0, -0.0, 1.0], [4.0, 1.0, 1e-16, 1.0000000000000001e-16, -0.0],
+                             [5.0, 2e-16, 1.0, -1e-17, 3.0], [6.0, -0.0, 2.0, 1.0, 1e-15]]
+    t[1].reshape(H, W)[:] = [[0, 1, 1, 1, 1], [0, 1, 1, 1, 1], [0, 1, 1, 1, 1], [0, 1, 1, 1, 1]]
+    t[2].reshape(H, W)[:] = [[0, -1, -1, 2, 2], [-1, -1, -1, -1, -1], [-1, -1, -1, -1, -1], [3, 1, 1, 1, 1]]
+    t[3].reshape(H, W)[:] = 1.0
+    t[3].reshape(H, W)[1, 2] = math.nan
+    t[3].reshape(H, W)[2, 0] = math.inf
+    t[3].reshape(H, W)[0, 3] = 5.0
+    chv = np.array([[0, 10, -57, -9, -24], [0, 0.5, -5.5, -2.5, 9], [0, 0.5, -1.5, -0.5, 1], [1, 1, 0, 0, 0]], float)
+    m, nv = 32, 64
+    mats = O.generate_synthetic(300, 16, m, nv, 8)
+    try:
+        for path in (E.PATH_SMEM, E.PATH_GMEM):
+            engine.set_tuning(path, 64 * rows, rows)
+            assert_batch_equal(engine.solve_batch(t, H, W, want_matrices=True), oracle_batch(t, H, W), "special")
+            for cc in (True, False):
+                c = chv.reshape(1, -1).copy()
+                assert_batch_equal(engine.solve_batch(c, 4, 5, E.make_options(check_cycles=cc), want_matrices=True),
+                                   oracle_batch(c, 4, 5, check_cycles=cc), f"chvatal cc={cc}")
+            for mp in (0, 1, 7, 11.5, math.inf):
+                assert_batch_equal(engine.solve_batch(mats, m + 1, nv + 1, E.make_options(max_pivots=mp), want_matrices=True),
+                                   oracle_batch(mats, m + 1, nv + 1, max_pivots=mp), f"maxPivots={mp}")
+            for prec in (1e-3, 0.0, 0.25):
+                assert_batch_equal(engine.solve_batch(mats, m + 1, nv + 1, E.make_options(precision=prec), want_matrices=True),
+                                   oracle_batch(mats, m + 1, nv + 1, precision=prec), f"precision={prec}")
+    finally:
+        engine.set_tuning(E.PATH_AUTO, 0)
+
+
+@pytest.mark.parametrize("name", ["AFIRO", "ADLITTLE", "SC105", "BLEND", "KLEIN1", "SHARE2B", "SC205", "ISRAEL"])
+def test_row_split_netlib_sparse(engine, name):
+    """Sparse Netlib tableaus: the compacted row list is short and changes every pivot."""
+    g = load_netlib().get(name)
+    H, W = g["height"], g["width"]
+    mats = np.asarray(g["matrix"], np.float64).reshape(1, -1)
+    exp = oracle_batch(mats, H, W)
+    try:
+        for path in (E.PATH_SMEM, E.PATH_GMEM):
+            for rows, threads in ((4, 256), (8, 512), (16, 512)):
+                engine.set_tuning(path, threads, rows)
+                try:
+                    got = engine.solve_batch(mats, H, W, want_matrices=True)
+                except E.YalpsError:
+                    assert path == E.PATH_SMEM  # does not fit in shared memory
+                    continue
+                assert_batch_equal(got, exp, f"{name} path={path} rows={rows}")
+    finally:
+        engine.set_tuning(E.PATH_AUTO, 0)
+
+
 def test_wide_tableau_multi_chunk(engine):
     """W > 32*KC forces several column chunks per row."""
     m, nv, n = 12, 700, 8

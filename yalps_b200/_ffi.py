@@ -46,6 +46,8 @@ SIGNATURES = {
     "yalps_last_error": (C.c_char_p, [_vp]),
     "yalps_device_info": (C.c_int, [_vp, _ip, _ip, _ip, _ip]),
     "yalps_set_tuning": (C.c_int, [_vp, C.c_int32, C.c_int32]),
+    "yalps_set_row_groups": (C.c_int, [_vp, C.c_int32]),
+    "yalps_probe_division": (C.c_int, [_vp, C.c_int64, C.c_uint64, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "yalps_launch_count": (C.c_int64, [_vp]),
     "yalps_host_alloc": (C.c_int, [_vp, C.c_uint64, C.POINTER(_vp)]),
     "yalps_host_free": (C.c_int, [_vp, _vp]),

@@ -3,10 +3,11 @@
 //  K1  k_simplex<NW,KC,true >  one tableau per CTA resident in shared memory (persistent CTAs, atomic LP queue)
 //  K2  k_simplex<NW,KC,false>  tableau in HBM/L2 (working copy), pivot row / column staged in shared memory
 //  K3  node assembly (applyCuts, src/branchAndCut.ts:22-61) fused as the prologue of K1/K2 (mode == kModeNodes)
-//  K5  k_generate_synthetic / k_generate_replicas: device-side input generators of SURVEY 8(d)
+//  K5  generators and the other non-template kernels live in aux_kernels.cuh
 #pragma once
 
 #include "simplex_device.cuh"
+#include "simplex_split.cuh"
 
 namespace yalps {
 
@@ -48,23 +49,34 @@ struct BatchArgs {
 // Resident layout: every tableau row is  [ A(0..W-2) | pad | b | -coef/q ]  with an even row stride ldA
 // (16-byte aligned rows -> v2.f64 accesses) whose half is odd (strided column reads spread over the banks);
 // the RHS cell and the per-pivot -coef/q scratch cell of a row live in its last two slots.
+// Split kernels (row groups, simplex_split.cuh) replace colbuf/colnew by the compacted active-row list.
 struct SmemLayout {
-  size_t off_A, off_colbuf, off_colnew, off_misc, off_red, off_var, total;
+  size_t off_A, off_colbuf, off_colnew, off_misc, off_red, off_var, off_cc, off_list, off_cnt, total;
   int ldA;
   __host__ __device__ static int ld_for(int W) {
     int ld = (W - 1 + 2 + 1) & ~1;
     if (((ld >> 1) & 1) == 0) ld += 2;
     return ld;
   }
-  __host__ __device__ SmemLayout(int Hcap, int Wcap, bool resident, int nw) {
+  __host__ __device__ SmemLayout(int Hcap, int Wcap, bool resident, int nw, bool split = false) {
     size_t o = 0;
     ldA = ld_for(Wcap);
     off_A = o;
     if (resident) o += (size_t)Hcap * ldA * 8;
-    off_colbuf = o;
-    o += (size_t)((Hcap + 7) & ~7) * 8;
-    off_colnew = o;
-    if (!resident) o += (size_t)((Hcap + 1) & ~1) * 8;
+    off_colbuf = off_colnew = off_cc = off_list = off_cnt = o;
+    if (split) {
+      off_cc = o;
+      o += (size_t)(Hcap + 8) * 16;
+      off_list = o;
+      o += (size_t)((Hcap + 3) & ~3) * 4;
+      off_cnt = o;
+      o += 16;
+    } else {
+      off_colbuf = o;
+      o += (size_t)((Hcap + 7) & ~7) * 8;
+      off_colnew = o;
+      if (!resident) o += (size_t)((Hcap + 1) & ~1) * 8;
+    }
     off_misc = o;
     o += 16;
     off_red = o;
@@ -83,10 +95,17 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // min CTAs/SM in the launch bounds caps the register count so that shared memory, not registers, limits residency
 // (one-warp CTAs: 12 per SM -> <= 168 registers per thread).
-template <int NW, int KC, bool kResident>
-__global__ void __launch_bounds__(NW * 32, NW == 1 ? 12 : (NW == 2 ? 6 : (NW == 4 ? 3 : (NW == 8 ? 2 : 1))))
-    k_simplex(const BatchArgs a) {
+// NWR > 1: split kernel, NWC column warps x NWR row groups, registers capped at 128 per thread.
+constexpr int min_ctas_per_sm(int nwc, int nwr) {
+  return nwr == 1 ? (nwc == 1 ? 12 : (nwc == 2 ? 6 : (nwc == 4 ? 3 : (nwc == 8 ? 2 : 1))))
+                  : (nwc * nwr >= 16 ? 1 : 16 / (nwc * nwr));
+}
+
+template <int NWC, int KC, bool kResident, int NWR = 1>
+__global__ void __launch_bounds__(NWC *NWR * 32, min_ctas_per_sm(NWC, NWR)) k_simplex(const BatchArgs a) {
+  constexpr int NW = NWC * NWR;
   constexpr int NT = NW * 32;
+  constexpr bool kSplit = NWR > 1;
   constexpr int VW = kResident ? 2 : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ long long s_lp;
@@ -126,11 +145,12 @@ __global__ void __launch_bounds__(NW * 32, NW == 1 ? 12 : (NW == 2 ? 6 : (NW == 
       poff = (size_t)lp * (W + H);
     }
 
-    const SmemLayout L(a.Hcap, a.Wcap, kResident, NW);
+    const SmemLayout L(a.Hcap, a.Wcap, kResident, NW, kSplit);
     LpView t;
     t.H = H;
     t.W = W;
     Scratch s;
+    SplitScratch ss;
     if (kResident) {
       t.A = reinterpret_cast<double *>(smem_raw + L.off_A);
       t.ldA = t.ldb = SmemLayout::ld_for(W);
@@ -151,6 +171,20 @@ __global__ void __launch_bounds__(NW * 32, NW == 1 ? 12 : (NW == 2 ? 6 : (NW == 
     s.red = reinterpret_cast<unsigned *>(smem_raw + L.off_red);
     s.hist = a.hist ? a.hist + (size_t)blockIdx.x * 2 * a.hist_cap : nullptr;
     s.hist_cap = a.hist_cap;
+    ss.cc = reinterpret_cast<double *>(smem_raw + L.off_cc);
+    ss.list = reinterpret_cast<int *>(smem_raw + L.off_list);
+    ss.cnt = reinterpret_cast<int *>(smem_raw + L.off_cnt);
+    ss.misc = s.misc;
+    ss.red = s.red;
+    ss.hist = s.hist;
+    ss.hist_cap = s.hist_cap;
+    if (kSplit && tid == 0) *ss.cnt = 0;
+#ifdef YALPS_TIMING
+    long long yt_local[16];
+    for (int k = 0; k < 16; k++) yt_local[k] = 0;
+    yt_local[15] = clock64();
+    ss.yt = yt_local;
+#endif
 
     // ---- load / assemble the tableau (reference layout, row stride W) into the (A, b) view
     const int ldA = t.ldA, ldb = t.ldb;
@@ -225,10 +259,12 @@ __global__ void __launch_bounds__(NW * 32, NW == 1 ? 12 : (NW == 2 ? 6 : (NW == 
     if (kResident) cp_async_wait_all();
     __syncthreads();
 
-    const LpResult res = simplex_cta<NW, KC, VW>(t, s, a.precision, a.max_pivots, a.check_cycles);
+    LpResult res;
+    if constexpr (kSplit)
+      res = simplex_cta_split<NWC, KC, NWR, VW>(t, ss, a.precision, a.max_pivots, a.check_cycles);
+    else
+      res = simplex_cta<NW, KC, VW>(t, s, a.precision, a.max_pivots, a.check_cycles);
     __syncthreads();
-
-    // ---- outputs
     if (tid == 0) {
       if (a.status) a.status[lp] = res.status;
       if (a.value) a.value[lp] = res.value;
@@ -239,6 +275,15 @@ __global__ void __launch_bounds__(NW * 32, NW == 1 ? 12 : (NW == 2 ? 6 : (NW == 
     }
     if (a.rhs_out)
       for (int r = tid; r < H; r += NT) a.rhs_out[roff + r] = t.b[(size_t)r * ldb];
+#ifdef YALPS_TIMING
+    __syncthreads();
+    if (kSplit && a.rhs_out && (tid == 0 || tid == NT - 1 || tid == 32)) {
+      // debug builds only: phase cycle counters of three threads overwrite the RHS output (needs H >= 27)
+      double *o = a.rhs_out + roff + (tid == 0 ? 0 : (tid == 32 ? 9 : 18));
+      for (int k = 0; k < 8; k++) o[k] = (double)yt_local[k];
+      o[8] = (double)(res.p1 + res.p2);
+    }
+#endif
     if (a.pos_out)  // positionOfVariable is the inverse permutation of variableAtPosition
       for (int k = tid; k < W + H; k += NT) a.pos_out[poff + t.var[k]] = k;
     if (kResident && a.var_out)
@@ -255,130 +300,6 @@ __global__ void __launch_bounds__(NW * 32, NW == 1 ? 12 : (NW == 2 ? 6 : (NW == 
     }
     __syncthreads();
   }
-}
-
-// K3 standalone: applyCuts (src/branchAndCut.ts:22-61) for a wave of nodes into HBM working copies
-// (row stride W, node stride Hcap*W) -- used in front of the grid kernel; K1/K2 fuse the same assembly.
-__global__ void k_assemble_nodes(long long n, int rootH, int W, int Hcap, const double *root, const int *root_pos,
-                                 const int *cut_off, const double *cut_sign, const int *cut_var, const double *cut_val,
-                                 double *work) {
-  const size_t root_cells = (size_t)rootH * W;
-  for (long long node = blockIdx.y; node < n; node += gridDim.y) {
-    double *dst = work + (size_t)node * Hcap * W;
-    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < root_cells; k += (size_t)gridDim.x * blockDim.x)
-      dst[k] = root[k];
-    const int cbeg = cut_off[node], ncuts = cut_off[node + 1] - cbeg;
-    for (int i = blockIdx.x; i < ncuts; i += gridDim.x) {
-      const double sign = cut_sign[cbeg + i], value = cut_val[cbeg + i];
-      const int p = root_pos[cut_var[cbeg + i]];
-      double *dr = dst + (size_t)(rootH + i) * W;
-      if (p < W) {
-        for (int c = threadIdx.x; c < W; c += blockDim.x) dr[c] = (c == 0) ? __dmul_rn(sign, value) : (c == p ? sign : 0.0);
-      } else {
-        const double *sr = root + (size_t)(p - W) * W;
-        for (int c = threadIdx.x; c < W; c += blockDim.x)
-          dr[c] = (c == 0) ? __dmul_rn(sign, __dsub_rn(value, sr[0])) : __dmul_rn(-sign, sr[c]);
-      }
-    }
-  }
-}
-
-// ---- K5: generators -------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ uint32_t prospector_hash(uint32_t x) {  // tests/helpers/util.ts:20-29
-  x ^= x >> 16;
-  x *= 0x21f0aaadu;
-  x ^= x >> 15;
-  x *= 0xd35a2d97u;
-  x ^= x >> 15;
-  return x;
-}
-
-// draw d (0-based) of newRand(seed0): state after d+1 increments (tests/helpers/util.ts:38-41)
-__host__ __device__ __forceinline__ double rand_draw(uint32_t seed0, uint32_t d) {
-  return (double)prospector_hash(seed0 + (d + 1u) * 0x9e3779b9u) / 4294967296.0;
-}
-
-// Dense synthetic LPs.  Draw order: c_1..c_n, then per row a_k1..a_kn, b_k.
-__global__ void k_generate_synthetic(long long first, long long n, int m, int nvars, int neg_rows, uint32_t salt,
-                                     double *out) {
-  const int W = nvars + 1, H = m + 1;
-  const size_t cells = (size_t)W * H;
-  const size_t total = (size_t)n * cells;
-  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
-    const long long i = (long long)(g / cells);
-    const int cell = (int)(g % cells);
-    const int r = cell / W, c = cell % W;
-    const uint32_t seed0 = prospector_hash((uint32_t)(first + i) ^ salt);
-    double v;
-    if (r == 0) {
-      v = (c == 0) ? 0.0 : rand_draw(seed0, (uint32_t)(c - 1));
-    } else {
-      const uint32_t base = (uint32_t)nvars + (uint32_t)(r - 1) * (uint32_t)(nvars + 1);
-      if (c == 0) {
-        const double u = rand_draw(seed0, base + (uint32_t)nvars);
-        v = (r <= neg_rows) ? -(0.5 + u) : (double)nvars * (0.25 + 0.5 * u);
-      } else {
-        v = rand_draw(seed0, base + (uint32_t)(c - 1));
-        if (r <= neg_rows) v = -v;
-      }
-    }
-    out[g] = v;
-  }
-}
-
-// RHS-perturbed replicas of one base tableau.
-__global__ void k_generate_replicas(long long first, long long n, int H, int W, const double *base, const int *group,
-                                    double eps, uint32_t salt, double *out) {
-  const size_t cells = (size_t)W * H;
-  const size_t total = (size_t)n * cells;
-  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
-    const long long i = (long long)(g / cells);
-    const int cell = (int)(g % cells);
-    const int r = cell / W, c = cell % W;
-    double v = base[cell];
-    if (c == 0 && group[r] >= 0) {
-      const uint32_t seed0 = prospector_hash((uint32_t)(first + i) ^ salt);
-      const double u = rand_draw(seed0, (uint32_t)group[r]);
-      v = __dmul_rn(v, __dadd_rn(1.0, __dmul_rn(eps, __dsub_rn(__dmul_rn(2.0, u), 1.0))));
-    }
-    out[g] = v;
-  }
-}
-
-// Non-zero count of a sample of one tableau (kernel-path policy: sparse batches go to the HBM/L2-resident kernel).
-__global__ void k_sample_density(const double *m, long long cells, long long step, int *out /* [2]: seen, nz */) {
-  int seen = 0, nz = 0;
-  for (long long k = (long long)threadIdx.x * step; k < cells; k += (long long)blockDim.x * step) {
-    seen++;
-    nz += m[k] != 0.0;
-  }
-  atomicAdd(out, seen);
-  atomicAdd(out + 1, nz);
-}
-
-__global__ void k_round_to_precision(long long n, const double *x, double precision, double *out) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = round_to_precision(x[i], precision);
-}
-
-// Shared-memory stream: every thread reads and rewrites 8-byte cells of a CTA-private buffer.
-// bytes = grid * iters * words * 16.
-__global__ void k_smem_stream(int words, int iters, double *sink) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double *buf = reinterpret_cast<double *>(smem_raw);
-  for (int k = threadIdx.x; k < words; k += blockDim.x) buf[k] = (double)k;
-  __syncthreads();
-  double acc = 0.0;
-  for (int it = 0; it < iters; it++) {
-#pragma unroll 4
-    for (int k = threadIdx.x; k < words; k += blockDim.x) {
-      const double x = buf[k];
-      buf[k] = x + 1.0;
-      acc += x;
-    }
-    __syncthreads();
-  }
-  if (acc == -1.0) sink[0] = acc;
 }
 
 }  // namespace yalps

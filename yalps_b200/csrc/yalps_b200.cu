@@ -21,7 +21,8 @@
 #include <unordered_map>
 #include <vector>
 
-#include "kernels.cuh"
+#include "kernel_table.h"
+#include "aux_kernels.cuh"
 #include "grid_kernel.cuh"
 #include "reg_kernel.cuh"
 
@@ -69,7 +70,7 @@ struct yalps_ctx {
   cudaStream_t streams[2]{};
   cudaEvent_t events[2]{};
   int64_t launches = 0;
-  int tune_path = 0, tune_threads = 0;
+  int tune_path = 0, tune_threads = 0, tune_rows = 0;
   int wave = 64;
   // pooled device buffers (index = purpose * 2 + pipeline slot)
   std::unordered_map<std::string, DevBuf> pool;
@@ -136,35 +137,40 @@ int pin_device_ptr(yalps_ctx *ctx, void *host, void **dev) {
 }
 
 // ---- kernel table -------------------------------------------------------------------------------------
-typedef void (*SimplexKernel)(const BatchArgs);
+// All k_simplex instantiations (kernel_table.h), gathered once.
+const std::vector<KernelEntry> &all_kernels() {
+  static const std::vector<KernelEntry> table = [] {
+    std::vector<KernelEntry> v;
+    int n = 0;
+    const KernelEntry *t;
+    t = kernel_table_base(&n);
+    v.insert(v.end(), t, t + n);
+    t = kernel_table_split_a(&n);
+    v.insert(v.end(), t, t + n);
+    t = kernel_table_split_b(&n);
+    v.insert(v.end(), t, t + n);
+    t = kernel_table_split_c(&n);
+    v.insert(v.end(), t, t + n);
+    return v;
+  }();
+  return table;
+}
 
-struct KernelEntry {
-  int nw, kc;
-  SimplexKernel resident, global;
-};
-
-#define KENTRY(NW, KC) {NW, KC, k_simplex<NW, KC, true>, k_simplex<NW, KC, false>}
-const KernelEntry kKernels[] = {
-    KENTRY(1, 1), KENTRY(1, 2),  KENTRY(1, 3),  KENTRY(1, 4),  KENTRY(2, 1),  KENTRY(2, 2),  KENTRY(2, 3),
-    KENTRY(2, 4), KENTRY(4, 1),  KENTRY(4, 2),  KENTRY(4, 4),  KENTRY(8, 1),  KENTRY(8, 2),  KENTRY(8, 4),
-    KENTRY(8, 8), KENTRY(16, 1), KENTRY(16, 2), KENTRY(16, 4), KENTRY(32, 1), KENTRY(32, 2), KENTRY(32, 4),
-    KENTRY(32, 8),
-};
-#undef KENTRY
-
-// Thread t keeps the pivot-row cells of vector-columns t, t+NT, ... in registers: NT*KC*VW >= W-1 is required.
-// Smallest NW >= nw_want whose widest KC covers the row, then the smallest covering KC.
-const KernelEntry *pick_kernel(int nw_want, int W, bool resident) {
+// Thread (row group, t) keeps the pivot-row cells of vector-columns t, t+NTC, ... in registers:
+// 32*NWC*KC*VW >= W-1 is required.  Among the kernels with `nwr` row groups: smallest NWC >= nwc_want whose
+// widest KC covers the row (else the largest NWC), then the smallest covering KC.
+const KernelEntry *pick_kernel(int nwc_want, int nwr, int W, bool resident) {
   const int vw = resident ? 2 : 1;
   const int wm1 = std::max(W - 1, 1);
   const KernelEntry *best = nullptr;
-  for (const auto &k : kKernels) {
+  for (const auto &k : all_kernels()) {
+    if (k.nwr != nwr) continue;
     if ((long long)k.nw * 32 * k.kc * vw < wm1) continue;
     if (!best) {
       best = &k;
       continue;
     }
-    const bool k_ok = k.nw >= nw_want, b_ok = best->nw >= nw_want;
+    const bool k_ok = k.nw >= nwc_want, b_ok = best->nw >= nwc_want;
     if (k_ok != b_ok) {
       if (k_ok) best = &k;
       continue;
@@ -250,10 +256,20 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
   }
   const int nw = ctx->tune_threads > 0 ? std::max(1, ctx->tune_threads / 32)
                                       : default_warps((long long)Hcap * Wcap, resident);
-  const KernelEntry *k = pick_kernel(nw, Wcap, resident);
+  // row groups: explicit tuning, else one (the throughput kernels)
+  int nwr = ctx->tune_rows > 0 ? ctx->tune_rows : 1;
+  const KernelEntry *k = nullptr;
+  if (nwr > 1) {
+    k = pick_kernel(std::max(1, nw / nwr), nwr, Wcap, resident);
+    if (k && SmemLayout(Hcap, Wcap, resident, k->nw * k->nwr, true).total > (size_t)ctx->smem_optin) k = nullptr;
+  }
+  if (!k) {
+    nwr = 1;
+    k = pick_kernel(nw, 1, Wcap, resident);
+  }
   if (k) {
-    Lr = SmemLayout(Hcap, Wcap, true, k->nw);
-    Lg = SmemLayout(Hcap, Wcap, false, k->nw);
+    Lr = SmemLayout(Hcap, Wcap, true, k->nw * k->nwr, k->nwr > 1);
+    Lg = SmemLayout(Hcap, Wcap, false, k->nw * k->nwr, k->nwr > 1);
   }
   if (k) {  // the attribute / occupancy queries cost microseconds: remember them per (kernel, shared memory size)
     const size_t smem_c = resident ? Lr.total : Lg.total;
@@ -279,7 +295,7 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
   const size_t smem = resident ? Lr.total : Lg.total;
   CU(ctx, raise_smem_limit(ctx->device, (const void *)fn, (int)smem));
   int occ = 0;
-  CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, k->nw * 32, smem));
+  CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, k->nw * k->nwr * 32, smem));
   if (occ < 1) return fail(ctx, YALPS_ERR_TOO_LARGE, "kernel does not fit on an SM (smem %zu)", smem);
   ctx->occ_cache[std::to_string((size_t)(void *)fn) + ":" + std::to_string(smem)] = occ;
   if (check_cycles) occ = std::min(occ, 4);  // bounds the history buffer
@@ -333,7 +349,7 @@ int launch_simplex(yalps_ctx *ctx, const LaunchPlan &plan, BatchArgs &args, cons
     return 0;
   }
   SimplexKernel fn = plan.resident ? plan.k->resident : plan.k->global;
-  fn<<<plan.grid, plan.k->nw * 32, plan.smem, stream>>>(args);
+  fn<<<plan.grid, plan.k->nw * plan.k->nwr * 32, plan.smem, stream>>>(args);
   CU(ctx, cudaGetLastError());
   ctx->launches++;
   return 0;
@@ -431,6 +447,14 @@ int yalps_set_tuning(yalps_ctx *ctx, int32_t path, int32_t threads_per_lp) {
   if (path < 0 || path > YALPS_PATH_REG) return fail(ctx, YALPS_ERR_ARGUMENT, "bad path %d", path);
   ctx->tune_path = path;
   ctx->tune_threads = threads_per_lp;
+  return 0;
+}
+
+int yalps_set_row_groups(yalps_ctx *ctx, int32_t row_groups) {
+  if (!ctx) return YALPS_ERR_ARGUMENT;
+  if (row_groups < 0 || row_groups > 16 || (row_groups & (row_groups - 1)))
+    return fail(ctx, YALPS_ERR_ARGUMENT, "row_groups must be 0 (automatic), 1, 2, 4, 8 or 16");
+  ctx->tune_rows = row_groups;
   return 0;
 }
 
@@ -996,6 +1020,28 @@ int yalps_round_to_precision(yalps_ctx *ctx, int64_t n, const double *x, double 
   ctx->launches++;
   CU(ctx, cudaMemcpyAsync(out, d_o, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
   CU(ctx, cudaStreamSynchronize(st));
+  return 0;
+}
+
+int yalps_probe_division(yalps_ctx *ctx, int64_t n, uint64_t seed, int32_t mode, uint64_t *mismatches,
+                         uint64_t *first_bad_bits) {
+  if (!ctx || !mismatches || n < 0 || mode < 0 || mode > 4) return YALPS_ERR_ARGUMENT;
+  CU(ctx, cudaSetDevice(ctx->device));
+  void *d;
+  if (int rc = dev_ensure(ctx, "probe_div", 32, &d)) return rc;
+  cudaStream_t st = ctx->streams[0];
+  CU(ctx, cudaMemsetAsync(d, 0, 32, st));
+  k_probe_division<<<ctx->prop.multiProcessorCount * 8, 256, 0, st>>>(n, seed, mode, (unsigned long long *)d);
+  CU(ctx, cudaGetLastError());
+  ctx->launches++;
+  unsigned long long h[4];
+  CU(ctx, cudaMemcpyAsync(h, d, 32, cudaMemcpyDeviceToHost, st));
+  CU(ctx, cudaStreamSynchronize(st));
+  *mismatches = h[0];
+  if (first_bad_bits) {
+    first_bad_bits[0] = h[2];
+    first_bad_bits[1] = h[3];
+  }
   return 0;
 }
 

@@ -75,8 +75,9 @@ class Engine:
         self._check(self._lib.yalps_device_info(self._ctx, *[C.byref(x) for x in v]))
         return {"sm_count": v[0].value, "smem_per_block_optin": v[1].value, "cc": (v[2].value, v[3].value)}
 
-    def set_tuning(self, path: int = PATH_AUTO, threads_per_lp: int = 0):
+    def set_tuning(self, path: int = PATH_AUTO, threads_per_lp: int = 0, row_groups: int = 0):
         self._check(self._lib.yalps_set_tuning(self._ctx, path, threads_per_lp))
+        self._check(self._lib.yalps_set_row_groups(self._ctx, row_groups))
 
     def set_wave(self, wave: int):
         self._check(self._lib.yalps_bnb_set_wave(self._ctx, int(wave)))
@@ -282,6 +283,13 @@ class Engine:
         out = np.empty_like(x)
         self._check(self._lib.yalps_round_to_precision(self._ctx, x.size, _ptr(x), float(precision), _ptr(out)))
         return out
+
+    def probe_division(self, n: int, seed: int, mode: int) -> tuple:
+        """(mismatches, (numerator bits, divisor bits) of the first one) of fastdiv.cuh vs __ddiv_rn."""
+        bad = C.c_uint64()
+        first = (C.c_uint64 * 2)()
+        self._check(self._lib.yalps_probe_division(self._ctx, n, seed, mode, C.byref(bad), first))
+        return int(bad.value), (int(first[0]), int(first[1]))
 
     def measure_smem_bandwidth(self) -> tuple:
         g, c = C.c_double(), C.c_double()
