@@ -10,7 +10,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libyalps_b200.so")
+# YALPS_B200_LIB: alternative build of the same library (A/B experiments, instrumented builds)
+LIB_PATH = os.environ.get("YALPS_B200_LIB") or os.path.join(_HERE, "libyalps_b200.so")
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)

@@ -28,6 +28,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "fastdiv.cuh"
+
 namespace yalps {
 
 constexpr double kTiny = 1e-16;  // sparsity threshold of src/simplex.ts:18,31
@@ -260,6 +262,17 @@ __device__ __forceinline__ void pivot_cta(const LpView &t, const Scratch &s, int
   const int ldA = t.ldA, ldb = t.ldb, H = t.H, Wm1 = t.W - 1;
   const int jc = col - 1;
   const double q = A[(size_t)row * ldA + jc];
+  // One divisor for every quotient of the pivot.  The shared-reciprocal form (fastdiv.cuh Recip) shortens the
+  // dependent chain and is what the latency kernels use (simplex_split.cuh); in this throughput kernel it measured
+  // 4 % slower than plain divisions (559 vs 583 M pivots/s on config 2), so it stays off here.
+#ifdef YALPS_K1_SHARED_RECIP
+  const Recip rq(q);
+#else
+  struct {
+    double d;
+    __device__ __forceinline__ double quot(double n) const { return __ddiv_rn(n, d); }
+  } rq{q};
+#endif
 
   // ---- normalise the pivot row into registers (:16-25); A and b are only read in this phase.
   // The pivot cell itself becomes 1/q (:25): same division code path with numerator 1.
@@ -280,7 +293,7 @@ __device__ __forceinline__ void pivot_cta(const LpView &t, const Scratch &s, int
           valid |= 1u << (k * VW + e);
           const double x = (j == jc) ? 1.0 : v.get(e);
           if (fabs(x) > kTiny) {
-            p[k][e] = __ddiv_rn(x, q);
+            p[k][e] = rq.quot(x);
             st |= 1u << (k * VW + e);  // the pivot column is rewritten too and fixed up after the update
           }
         } else if (VW == 2 && j0 < Wm1) {
@@ -300,7 +313,7 @@ __device__ __forceinline__ void pivot_cta(const LpView &t, const Scratch &s, int
     const double coef = A[(size_t)r * ldA + jc];
     const double num = (r == row) ? b[(size_t)row * ldb] : -coef;
     const bool nz = fabs(num) > kTiny;  // also false for NaN, as in the reference
-    const double quo = nz ? __ddiv_rn(num, q) : 0.0;
+    const double quo = nz ? rq.quot(num) : 0.0;
     if (r == row) {
       s.misc[0] = quo;
       s.misc[1] = nz ? 1.0 : 0.0;
@@ -412,7 +425,7 @@ __device__ __forceinline__ LpResult simplex_cta(const LpView &t, const Scratch &
             for (int e = 0; e < VW; e++) {
               const double coef = cf.get(e);
               if (j0 + e < Wm1 && coef < -precision) {
-                const double ratio = __ddiv_rn(-ob.get(e), coef);
+                const double ratio = div_rn(-ob.get(e), coef);
                 if (ratio > bv) {  // bv starts at -inf: -inf and NaN ratios never win, as in the reference
                   bv = ratio;
                   bi = j0 + e + 1;
@@ -463,7 +476,7 @@ __device__ __forceinline__ LpResult simplex_cta(const LpView &t, const Scratch &
       for (int r = 1 + tid; r < H; r += NT) {
         const double v = A[(size_t)r * ldA + (col - 1)];
         if (v > precision) {
-          const double ratio = __ddiv_rn(b[(size_t)r * ldb], v);
+          const double ratio = div_rn(b[(size_t)r * ldb], v);
           if (ratio < INF) {  // +inf and NaN never win (`ratio < minRatio` with minRatio = Infinity)
             const double key = (ratio <= precision) ? -INF : ratio;
             if (bi == kNone || key < bv) {

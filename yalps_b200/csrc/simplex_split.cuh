@@ -2,19 +2,26 @@
 // (src/simplex.ts:5-142 of the reference), for LPs that get a whole multi-warp CTA: single solve() calls,
 // branch-and-cut node waves, and batches whose tableaus leave room for only one or two CTAs per SM.
 //
-// A CTA is NWR row groups x NWC column warps.  Thread (rg, ctid) owns the vector-columns ctid, ctid+NTC, ...
-// (KC of them; every row group holds the same normalised pivot-row cells in registers) and updates only the
-// rows dealt to its row group.  What makes the pivot short:
+// A pivot on one CTA is a dependent chain (select column -> select row -> normalise -> update), and on this
+// machine a dependent FP64 op costs ~10 cycles, a division ~130, a warp reduction ~25 per REDUX, a CTA barrier
+// 30-90 (scripts/micro/latency.cu).  The kernel is organised to keep that chain short:
+//   * a CTA is NWR row groups x NWC column warps.  Thread (rg, ctid) owns the vector-columns ctid, ctid+NTC, ...
+//     (KC of them; every row group holds the same normalised pivot-row cells in registers) and updates only the
+//     rows dealt to its row group;
 //   * the rows the reference rewrites (|pivot-column coefficient| > 1e-16, src/simplex.ts:31) are compacted
 //     into a list while the pivot column is read: the update costs ceil(R / (NWR*RU)) straight-line blocks per
 //     thread instead of ceil(H / RU), which is what sparse Netlib-style tableaus need (R << H);
-//   * the list carries (coef, -coef/q) pairs, so the owner of the pivot column writes the final pivot-column
-//     cell during the update itself and the RHS cells are updated next to it: no fix-up pass, two CTA barriers
-//     per pivot plus one per selection;
-//   * every row loop covers H rows with all NT threads (one division per thread, not ceil(H/32)).
+//   * the list carries (coef, -coef/q) pairs and the row index, so the owner of the pivot column writes the final
+//     pivot-column cell right after its own rank-1 store, and the RHS cells are updated by the last row group
+//     next to the update: no fix-up pass, two CTA barriers per pivot plus one for the cross-warp selection;
+//   * all quotients by the pivot element (pivot row, pivot column, RHS) share one reciprocal refinement
+//     (fastdiv.cuh, bit-identical to IEEE division), and zero numerators skip nvcc's division slow path;
+//   * cheap scans (objective row, RHS column) are done redundantly by every warp when one warp covers them, so
+//     they need no barrier; only the ratio tests (one division per candidate) are split over the whole CTA.
 // Arithmetic, skip rules and tie-breaking are those of simplex_device.cuh: results are bit-identical.
 #pragma once
 
+#include "fastdiv.cuh"
 #include "simplex_device.cuh"
 
 namespace yalps {
@@ -38,33 +45,39 @@ struct SplitScratch {
 #endif
 };
 
-// RU active rows (indices ridx) for this thread's KC vector-columns: loads first, then arithmetic and stores.
-// jcbits marks the cell of the pivot column (owner thread only): it receives -coef/q (cnew) instead of the
-// rank-1 value (src/simplex.ts:36).
-template <int NTC, int KC, int VW, int RU, bool kPartial>
-__device__ __forceinline__ void update_rows_split(double *__restrict__ Ac, int ldA, const int (&ridx)[RU],
-                                                  const double (&coef)[RU], const double (&cnew)[RU],
-                                                  const double (&p)[KC][VW], unsigned st, unsigned full,
-                                                  unsigned jcbits) {
+// RU active rows for this thread's KC vector-columns: loads first, then arithmetic and stores.
+// kTail: some of the RU rows may be past the end of the list (n_in valid rows).
+template <int NTC, int KC, int VW, int RU, bool kPartial, bool kTail>
+__device__ __forceinline__ void update_block_split(double *__restrict__ Ac, int ldA, const int *list, const double *cc,
+                                                   int i, int n_in, const double (&p)[KC][VW], unsigned st,
+                                                   unsigned full, int jc_off) {
+  int ridx[RU];
+  double coef[RU], cnew[RU];
+#pragma unroll
+  for (int j = 0; j < RU; j++) {
+    const double2 c2 = *reinterpret_cast<const double2 *>(cc + 2 * (i + j));  // padded: always readable
+    ridx[j] = (!kTail || j < n_in) ? list[i + j] : 0;
+    coef[j] = c2.x;
+    cnew[j] = c2.y;
+  }
   Cells<VW> x[RU][KC];
 #pragma unroll
-  for (int i = 0; i < RU; i++)
+  for (int j = 0; j < RU; j++)
 #pragma unroll
     for (int k = 0; k < KC; k++) {
       const bool need = kPartial ? (((st >> (k * VW)) & ((1u << VW) - 1u)) != 0u) : (((full >> k) & 1u) != 0u);
-      if (coef[i] != 0.0 && need) x[i][k].load(Ac + (size_t)ridx[i] * ldA + (size_t)VW * NTC * k);
+      if ((!kTail || j < n_in) && need) x[j][k].load(Ac + (size_t)ridx[j] * ldA + (size_t)VW * NTC * k);
     }
 #pragma unroll
-  for (int i = 0; i < RU; i++)
+  for (int j = 0; j < RU; j++) {
+    const bool on = !kTail || j < n_in;
+    double *rowp = Ac + (size_t)ridx[j] * ldA;
 #pragma unroll
     for (int k = 0; k < KC; k++) {
-      double *dst = Ac + (size_t)ridx[i] * ldA + (size_t)VW * NTC * k;
-      const bool on = coef[i] != 0.0;
+      double *dst = rowp + (size_t)VW * NTC * k;
       if (VW == 2) {
-        double t0 = __dsub_rn(x[i][k].get(0), __dmul_rn(coef[i], p[k][0]));
-        double t1 = __dsub_rn(x[i][k].get(1), __dmul_rn(coef[i], p[k][VW - 1]));
-        if ((jcbits >> (k * VW)) & 1u) t0 = cnew[i];
-        if ((jcbits >> (k * VW + 1)) & 1u) t1 = cnew[i];
+        const double t0 = __dsub_rn(x[j][k].get(0), __dmul_rn(coef[j], p[k][0]));
+        const double t1 = __dsub_rn(x[j][k].get(1), __dmul_rn(coef[j], p[k][VW - 1]));
         if (on && ((full >> k) & 1u)) {
           *reinterpret_cast<double2 *>(dst) = make_double2(t0, t1);
         } else if (kPartial && on) {
@@ -72,29 +85,24 @@ __device__ __forceinline__ void update_rows_split(double *__restrict__ Ac, int l
           if ((st >> (k * VW + 1)) & 1u) dst[1] = t1;
         }
       } else {
-        double t0 = __dsub_rn(x[i][k].get(0), __dmul_rn(coef[i], p[k][0]));
-        if ((jcbits >> k) & 1u) t0 = cnew[i];
+        const double t0 = __dsub_rn(x[j][k].get(0), __dmul_rn(coef[j], p[k][0]));
         if (on && ((full >> k) & 1u)) dst[0] = t0;
       }
     }
+    // owner of the pivot column: the cell becomes -coef/q (src/simplex.ts:36), after this thread's own store
+    if (jc_off >= 0 && on) rowp[jc_off] = cnew[j];
+  }
 }
 
 template <int NTC, int KC, int VW, int RU, int NWR, bool kPartial>
 __device__ __forceinline__ void update_split(double *__restrict__ Ac, int ldA, int R, int rg, const int *list,
                                              const double *cc, const double (&p)[KC][VW], unsigned st, unsigned full,
-                                             unsigned jcbits) {
+                                             int jc_off) {
   for (int i = rg * RU; i < R; i += NWR * RU) {
-    int ridx[RU];
-    double coef[RU], cnew[RU];
-#pragma unroll
-    for (int j = 0; j < RU; j++) {
-      const bool in = i + j < R;
-      const double2 c2 = *reinterpret_cast<const double2 *>(cc + 2 * (i + j));  // padded: always readable
-      ridx[j] = in ? list[i + j] : 0;
-      coef[j] = in ? c2.x : 0.0;
-      cnew[j] = c2.y;
-    }
-    update_rows_split<NTC, KC, VW, RU, kPartial>(Ac, ldA, ridx, coef, cnew, p, st, full, jcbits);
+    if (i + RU <= R)
+      update_block_split<NTC, KC, VW, RU, kPartial, false>(Ac, ldA, list, cc, i, RU, p, st, full, jc_off);
+    else
+      update_block_split<NTC, KC, VW, RU, kPartial, true>(Ac, ldA, list, cc, i, R - i, p, st, full, jc_off);
   }
 }
 
@@ -109,40 +117,48 @@ __device__ __forceinline__ void pivot_split(const LpView &t, const SplitScratch 
   double *__restrict__ b = t.b;
   const int ldA = t.ldA, ldb = t.ldb, H = t.H, Wm1 = t.W - 1;
   const int jc = col - 1;
-  const double q = A[(size_t)row * ldA + jc];
 
-  // ---- normalise the pivot row into registers (:16-25), every row group for itself
-  double p[KC][VW];
-  unsigned st = 0, full = 0, valid = 0, partial = 0, jcbits = 0;
+  // ---- issue every load of this phase before the first division
+  const double q = A[(size_t)row * ldA + jc];
+  Cells<VW> v[KC];
   {
     const double *Arow = A + (size_t)row * ldA + VW * ctid;
 #pragma unroll
-    for (int k = 0; k < KC; k++) {
-      const int j0 = VW * (ctid + NTC * k);
-      Cells<VW> v;
-      if (j0 < Wm1) v.load(Arow + (size_t)VW * NTC * k);
+    for (int k = 0; k < KC; k++)
+      if (VW * (ctid + NTC * k) < Wm1) v[k].load(Arow + (size_t)VW * NTC * k);
+  }
+  double cell0 = 0.0;  // pivot-column cell of row `tid` (first pass of the column loop); RHS for the pivot row
+  if (tid < H) cell0 = (tid == row) ? b[(size_t)row * ldb] : A[(size_t)tid * ldA + jc];
+  const Recip rq(q);
+
+  // ---- normalise the pivot row into registers (:16-25), every row group for itself
+  double p[KC][VW];
+  unsigned st = 0, full = 0, valid = 0, partial = 0;
+  int jc_off = -1;  // owner thread of the pivot column: offset of that cell from this thread's column base
 #pragma unroll
-      for (int e = 0; e < VW; e++) {
-        p[k][e] = 0.0;
-        const int j = j0 + e;
-        if (j < Wm1) {
-          valid |= 1u << (k * VW + e);
-          if (j == jc) jcbits |= 1u << (k * VW + e);
-          const double x = (j == jc) ? 1.0 : v.get(e);
-          if (fabs(x) > kTiny) {
-            p[k][e] = __ddiv_rn(x, q);
-            st |= 1u << (k * VW + e);
-          }
-        } else if (VW == 2 && j0 < Wm1) {
-          st |= 1u << (k * VW + e);  // padding cell next to the last column: rewriting it is harmless
+  for (int k = 0; k < KC; k++) {
+    const int j0 = VW * (ctid + NTC * k);
+#pragma unroll
+    for (int e = 0; e < VW; e++) {
+      p[k][e] = 0.0;
+      const int j = j0 + e;
+      if (j < Wm1) {
+        valid |= 1u << (k * VW + e);
+        if (j == jc) jc_off = VW * NTC * k + e;
+        const double x = (j == jc) ? 1.0 : v[k].get(e);
+        if (fabs(x) > kTiny) {
+          p[k][e] = rq.quot(x);
+          st |= 1u << (k * VW + e);
         }
+      } else if (VW == 2 && j0 < Wm1) {
+        st |= 1u << (k * VW + e);  // padding cell next to the last column: rewriting it is harmless
       }
-      const unsigned m = (st >> (k * VW)) & ((1u << VW) - 1u);
-      if (m == (1u << VW) - 1u)
-        full |= 1u << k;
-      else if (m)
-        partial = 1u;
     }
+    const unsigned m = (st >> (k * VW)) & ((1u << VW) - 1u);
+    if (m == (1u << VW) - 1u)
+      full |= 1u << k;
+    else if (m)
+      partial = 1u;
   }
   YT_MARK(2);
   // ---- pivot column: -coef/q per row (:36), normalised RHS of the pivot row (:19 for c = 0), and the
@@ -150,12 +166,12 @@ __device__ __forceinline__ void pivot_split(const LpView &t, const SplitScratch 
   for (int r0 = 0; r0 < H; r0 += NT) {
     const int r = r0 + tid;
     bool act = false;
-    double coef = 0.0, quo = 0.0;
+    double cell = 0.0, quo = 0.0;
     if (r < H) {
-      coef = A[(size_t)r * ldA + jc];
-      const double num = (r == row) ? b[(size_t)row * ldb] : -coef;
+      cell = r0 == 0 ? cell0 : ((r == row) ? b[(size_t)row * ldb] : A[(size_t)r * ldA + jc]);
+      const double num = (r == row) ? cell : -cell;
       const bool nz = fabs(num) > kTiny;  // also false for NaN, as in the reference
-      quo = nz ? __ddiv_rn(num, q) : 0.0;
+      quo = nz ? rq.quot(num) : 0.0;
       if (r == row) {
         s.misc[0] = quo;
         s.misc[1] = nz ? 1.0 : 0.0;
@@ -171,7 +187,7 @@ __device__ __forceinline__ void pivot_split(const LpView &t, const SplitScratch 
       if (act) {
         const int k = base + __popc(m & ((1u << lane) - 1u));
         s.list[k] = r;
-        *reinterpret_cast<double2 *>(s.cc + 2 * k) = make_double2(coef, quo);
+        *reinterpret_cast<double2 *>(s.cc + 2 * k) = make_double2(cell, quo);
       }
     }
   }
@@ -181,28 +197,30 @@ __device__ __forceinline__ void pivot_split(const LpView &t, const SplitScratch 
     t.var[col] = leaving;
   }
   YT_MARK(3);
-  const bool any_partial = __syncthreads_or((int)partial) != 0;
+  __syncthreads();
   const int R = *s.cnt;
+  const bool any_partial = (VW == 2) && __any_sync(0xffffffffu, partial);  // per warp: warps need not agree
   YT_MARK(4);
 
-  // ---- RHS cells of the active rows (:34 for c = 0): independent of the coefficient block, no barrier needed
-  {
+  // ---- RHS cells of the active rows (:34 for c = 0) and of the pivot row, by the last row group: they are
+  // independent of the coefficient block, so no barrier separates them from the update
+  if (rg == NWR - 1) {
     const double p0 = s.misc[0];
     if (s.misc[1] != 0.0) {
-      for (int i = tid; i < R; i += NT) {
+      for (int i = ctid; i < R; i += NTC) {
         const int r = s.list[i];
         const double x = b[(size_t)r * ldb];
         b[(size_t)r * ldb] = __dsub_rn(x, __dmul_rn(s.cc[2 * i], p0));
       }
     }
-    if (tid == NT - 1) b[(size_t)row * ldb] = p0;
+    if (ctid == NTC - 1) b[(size_t)row * ldb] = p0;
   }
   YT_MARK(5);
   // ---- rank-1 update of the active rows, pivot-column cell included
   if (any_partial)
-    update_split<NTC, KC, VW, RU, NWR, true>(A + VW * ctid, ldA, R, rg, s.list, s.cc, p, st, full, jcbits);
+    update_split<NTC, KC, VW, RU, NWR, true>(A + VW * ctid, ldA, R, rg, s.list, s.cc, p, st, full, jc_off);
   else
-    update_split<NTC, KC, VW, RU, NWR, false>(A + VW * ctid, ldA, R, rg, s.list, s.cc, p, st, full, jcbits);
+    update_split<NTC, KC, VW, RU, NWR, false>(A + VW * ctid, ldA, R, rg, s.list, s.cc, p, st, full, jc_off);
   // pivot row (:19,22,25), by the last row group (it has the fewest update blocks)
   if (rg == NWR - 1) {
     double *Arow = A + (size_t)row * ldA + VW * ctid;
@@ -219,20 +237,24 @@ __device__ __forceinline__ void pivot_split(const LpView &t, const SplitScratch 
   YT_MARK(6);
   __syncthreads();
   YT_MARK(7);
-  if (tid == 0) *s.cnt = 0;  // next written after the barrier of the next selection
+  if (tid == 0) *s.cnt = 0;  // next written after the barrier of the next cross-warp selection
 }
 
 // src/simplex.ts:106-142 (phase1) falling through to 66-103 (phase2); the whole CTA executes this uniformly.
 template <int NWC, int KC, int NWR, int VW>
 __device__ __forceinline__ LpResult simplex_cta_split(const LpView &t, const SplitScratch &s, double precision,
                                                       double max_pivots, int check_cycles) {
-  constexpr int NW = NWC * NWR, NT = NW * 32;
+  constexpr int NTC = NWC * 32, NW = NWC * NWR, NT = NW * 32;
   static_assert(NW > 1, "the split kernel needs a cross-warp barrier between pivots");
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, ctid = tid % NTC;
   const double *__restrict__ A = t.A;
   const double *__restrict__ b = t.b;
   const int ldA = t.ldA, ldb = t.ldb, H = t.H, Wm1 = t.W - 1;
   const double INF = d_inf();
+  // `(double)iter < max_pivots` for integer iter == `iter < ceil(max_pivots)` (NaN / non-positive budgets: none)
+  const long long budget =
+      !(max_pivots > 0.0) ? 0LL : (max_pivots >= 9.0e18 ? 0x7fffffffffffffffLL : (long long)ceil(max_pivots));
+  const bool warp_rows = H <= 32 * 8;  // one warp scans the RHS column by itself
 
   LpResult res;
   res.status = ST_CYCLED;
@@ -242,20 +264,33 @@ __device__ __forceinline__ LpResult simplex_cta_split(const LpView &t, const Spl
   long long iter = 0;
 
   for (;;) {
-    if (!((double)iter < max_pivots)) break;  // per-phase budget exhausted -> "cycled" (:102,:141)
+    if (iter >= budget) break;  // per-phase budget exhausted -> "cycled" (:102,:141)
     int row, col;
     if (phase == 1) {
       // leaving row: first index of the most negative RHS below -precision (:111-119)
       double bv = INF;
       int bi = kNone;
-      for (int r = 1 + tid; r < H; r += NT) {
-        const double v = b[(size_t)r * ldb];
-        if (v < -precision && v < bv) {
-          bv = v;
-          bi = r;
+      if (warp_rows) {  // every warp scans all rows: no barrier
+#pragma unroll 4
+        for (int r = 1 + lane; r < H; r += 32) {
+          const double v = b[(size_t)r * ldb];
+          if (v < -precision && v < bv) {
+            bv = v;
+            bi = r;
+          }
         }
+        const unsigned long long key = bi == kNone ? no_key<false>() : order_key(bv);
+        row = warp_best<false>((unsigned)(key >> 32), (unsigned)key, bi).idx;
+      } else {
+        for (int r = 1 + tid; r < H; r += NT) {
+          const double v = b[(size_t)r * ldb];
+          if (v < -precision && v < bv) {
+            bv = v;
+            bi = r;
+          }
+        }
+        row = block_best<false, NW>(bi == kNone ? no_key<false>() : order_key(bv), bi, s.red, parity);
       }
-      row = block_best<false, NW>(bi == kNone ? no_key<false>() : order_key(bv), bi, s.red, parity);
       YT_MARK(0);
       if (row == kNone) {  // feasible: phase 2 with a fresh counter and history (:120, :67-69)
         phase = 2;
@@ -263,7 +298,8 @@ __device__ __forceinline__ LpResult simplex_cta_split(const LpView &t, const Spl
         hist_len = 0;
         continue;
       }
-      // entering column: first index of max -M[0,c]/M[row,c] over M[row,c] < -precision (:123-134)
+      // entering column: first index of max -M[0,c]/M[row,c] over M[row,c] < -precision (:123-134);
+      // one division per candidate, split over the whole CTA
       bv = -INF;
       bi = kNone;
       {
@@ -276,7 +312,7 @@ __device__ __forceinline__ LpResult simplex_cta_split(const LpView &t, const Spl
           for (int e = 0; e < VW; e++) {
             const double coef = cf.get(e);
             if (j0 + e < Wm1 && coef < -precision) {
-              const double ratio = __ddiv_rn(-ob.get(e), coef);
+              const double ratio = div_rn(-ob.get(e), coef);
               if (ratio > bv) {  // bv starts at -inf: -inf and NaN ratios never win, as in the reference
                 bv = ratio;
                 bi = j0 + e + 1;
@@ -292,22 +328,33 @@ __device__ __forceinline__ LpResult simplex_cta_split(const LpView &t, const Spl
         break;
       }
     } else {
-      // entering column: first index of the largest reduced cost above precision (:71-79)
+      // entering column: first index of the largest reduced cost above precision (:71-79); every row group scans
+      // its own copy of the columns (with one column warp that is every warp by itself: no barrier)
       double bv = -INF;
       int bi = kNone;
-      for (int j0 = VW * tid; j0 < Wm1; j0 += VW * NT) {
-        Cells<VW> ob;
-        ob.load(A + j0);
 #pragma unroll
-        for (int e = 0; e < VW; e++) {
-          const double v = ob.get(e);
-          if (j0 + e < Wm1 && v > precision && v > bv) {
-            bv = v;
-            bi = j0 + e + 1;
+      for (int k = 0; k < KC; k++) {
+        const int j0 = VW * (ctid + NTC * k);
+        if (j0 < Wm1) {
+          Cells<VW> ob;
+          ob.load(A + j0);
+#pragma unroll
+          for (int e = 0; e < VW; e++) {
+            const double v = ob.get(e);
+            if (j0 + e < Wm1 && v > precision && v > bv) {
+              bv = v;
+              bi = j0 + e + 1;
+            }
           }
         }
       }
-      col = block_best<true, NW>(bi == kNone ? no_key<true>() : order_key(bv), bi, s.red, parity);
+      {
+        const unsigned long long key = bi == kNone ? no_key<true>() : order_key(bv);
+        if (NWC == 1)
+          col = warp_best<true>((unsigned)(key >> 32), (unsigned)key, bi).idx;
+        else
+          col = block_best<true, NW>(key, bi, s.red, parity);
+      }
       YT_MARK(0);
       if (col == kNone) {
         res.status = ST_OPTIMAL;
@@ -321,7 +368,7 @@ __device__ __forceinline__ LpResult simplex_cta_split(const LpView &t, const Spl
       for (int r = 1 + tid; r < H; r += NT) {
         const double v = A[(size_t)r * ldA + (col - 1)];
         if (v > precision) {
-          const double ratio = __ddiv_rn(b[(size_t)r * ldb], v);
+          const double ratio = div_rn(b[(size_t)r * ldb], v);
           if (ratio < INF) {  // +inf and NaN never win (`ratio < minRatio` with minRatio = Infinity)
             const double key = (ratio <= precision) ? -INF : ratio;
             if (bi == kNone || key < bv) {

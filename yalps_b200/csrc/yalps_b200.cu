@@ -203,6 +203,7 @@ int default_warps(long long cells, bool resident) {
 
 struct LaunchPlan {
   bool reg = false;  // K1r: tableau in registers (small LPs)
+  bool small_for_grid = false;  // few LPs outside shared memory, yet small enough that one row-split CTA beats K4
   bool resident;
   const KernelEntry *k;
   size_t smem;
@@ -254,10 +255,35 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
     if (grid_ok) return 0;  // only the grid kernel (K4) can take it
     return fail(ctx, YALPS_ERR_TOO_LARGE, "tableau %dx%d: pivot row/column staging exceeds shared memory", Hcap, Wcap);
   }
-  const int nw = ctx->tune_threads > 0 ? std::max(1, ctx->tune_threads / 32)
-                                      : default_warps((long long)Hcap * Wcap, resident);
-  // row groups: explicit tuning, else one (the throughput kernels)
-  int nwr = ctx->tune_rows > 0 ? ctx->tune_rows : 1;
+  // CTA shape.  Explicit tuning wins; otherwise (scripts/single_lp_latency.py, scripts/sweep_config3.py on B200):
+  //  * latency mode (every LP can have an SM to itself): row-split CTAs, sized by the tableau;
+  //  * throughput mode: one row group and many CTAs per SM for tableaus in shared memory, a small row split for
+  //    the HBM/L2-resident kernel on mid-size tableaus.
+  const long long cells = (long long)Hcap * Wcap;
+  int want_threads = ctx->tune_threads, want_rows = ctx->tune_rows;
+  if (want_threads <= 0 && want_rows <= 0) {
+    if (n <= 2LL * ctx->prop.multiProcessorCount) {
+      if (!resident) {
+        want_threads = 512, want_rows = 4;
+      } else if (cells < 2500) {
+        want_threads = 128, want_rows = 4;
+      } else if (cells < 6000) {
+        want_threads = 256, want_rows = 8;
+      } else if (cells < 12000) {
+        want_threads = 256, want_rows = 4;
+      } else {
+        want_threads = 512, want_rows = 8;
+      }
+    } else if (!resident) {
+      if (cells >= 12000)
+        want_threads = 256, want_rows = 4;
+      else if (cells >= 5000)
+        want_threads = 128, want_rows = 2;
+    }
+  }
+  plan->small_for_grid = !resident && cells < 40000;
+  const int nw = want_threads > 0 ? std::max(1, want_threads / 32) : default_warps(cells, resident);
+  int nwr = want_rows > 0 ? want_rows : 1;
   const KernelEntry *k = nullptr;
   if (nwr > 1) {
     k = pick_kernel(std::max(1, nw / nwr), nwr, Wcap, resident);
@@ -314,7 +340,7 @@ bool use_grid_path(const yalps_ctx *ctx, long long n, const LaunchPlan &plan) {
   if (plan.reg) return false;
   if (ctx->tune_path == YALPS_PATH_GRID || plan.k == nullptr) return true;
   if (ctx->tune_path != YALPS_PATH_AUTO) return false;
-  return !plan.resident && n <= 16;
+  return !plan.resident && n <= 16 && !plan.small_for_grid;
 }
 
 int hist_capacity(const yalps_options *opt) {
