@@ -19,12 +19,12 @@ for _ in range(20): x.add_(1.0)
 torch.cuda.synchronize()
 for name in names:
     g = NL.get(name); H, W = g["height"], g["width"]
-    for n in (1, 148):
+    for n in ((1,) if os.environ.get('ONLY_ONE') else (1, 148)):
         d = torch.from_numpy(np.tile(np.asarray(g["matrix"], np.float64).reshape(-1), n)).cuda()
         work = torch.empty_like(d)
         st = torch.empty(n, dtype=torch.int32, device="cuda"); piv = torch.empty(n, 2, dtype=torch.int64, device="cuda")
-        for path, pn in ((E.PATH_SMEM, "K1"), (E.PATH_GMEM, "K2"), (E.PATH_GRID, "K4")):
-            for threads, rows in (((0, 0),) if path == E.PATH_GRID else
+        for path, pn in ((E.PATH_SMEM, "K1"), (E.PATH_GMEM, "K2"), (E.PATH_GRID, "K4"), (E.PATH_CLUSTER, "K3"), (E.PATH_AUTO, "auto")):
+            for threads, rows in (((0, 0),) if path in (E.PATH_GRID, E.PATH_CLUSTER, E.PATH_AUTO) else
                                   ((32, 1), (64, 1), (128, 1), (256, 1), (128, 2), (128, 4), (256, 2), (256, 4), (256, 8),
                                    (512, 4), (512, 8), (512, 16))):
                 if path == E.PATH_GRID and n > 1: continue

@@ -135,6 +135,70 @@ def test_row_split_netlib_sparse(engine, name):
         engine.set_tuning(E.PATH_AUTO, 0)
 
 
+CLUSTER_SHAPES = [(32, 64, 6), (5, 3, 2), (1, 1, 0), (40, 7, 10), (16, 100, 4), (90, 130, 30), (12, 700, 3), (150, 103, 40),
+                  (200, 260, 50), (330, 500, 60)]
+
+
+@pytest.mark.parametrize("m,nv,neg", CLUSTER_SHAPES)
+def test_cluster_kernel_bit_exact(engine, m, nv, neg):
+    """cluster_kernel.cuh: tableau distributed over a thread-block cluster, pivot row through DSMEM."""
+    n = 6 if m * nv > 50000 else 20
+    H, W = m + 1, nv + 1
+    mats = O.generate_synthetic(777 + m, n, m, nv, neg)
+    exp = oracle_batch(mats, H, W)
+    engine.set_tuning(E.PATH_CLUSTER, 0)
+    try:
+        got = engine.solve_batch(mats, H, W, want_matrices=True)
+    finally:
+        engine.set_tuning(E.PATH_AUTO, 0)
+    assert_batch_equal(got, exp, f"cluster {m}x{nv}")
+
+
+def test_cluster_kernel_options_special_values_and_cycles(engine):
+    H, W = 4, 5
+    t = np.zeros((4, H * W))
+    t[0].reshape(H, W)[:] = [[0.0, 3.0, 2.0, -0.0, 1.0], [4.0, 1.0, 1e-16, 1.0000000000000001e-16, -0.0],
+                             [5.0, 2e-16, 1.0, -1e-17, 3.0], [6.0, -0.0, 2.0, 1.0, 1e-15]]
+    t[1].reshape(H, W)[:] = [[0, 1, 1, 1, 1], [0, 1, 1, 1, 1], [0, 1, 1, 1, 1], [0, 1, 1, 1, 1]]
+    t[2].reshape(H, W)[:] = [[0, -1, -1, 2, 2], [-1, -1, -1, -1, -1], [-1, -1, -1, -1, -1], [3, 1, 1, 1, 1]]
+    t[3].reshape(H, W)[:] = 1.0
+    t[3].reshape(H, W)[1, 2] = math.nan
+    t[3].reshape(H, W)[2, 0] = math.inf
+    t[3].reshape(H, W)[0, 3] = 5.0
+    chv = np.array([[0, 10, -57, -9, -24], [0, 0.5, -5.5, -2.5, 9], [0, 0.5, -1.5, -0.5, 1], [1, 1, 0, 0, 0]], float)
+    m, nv = 32, 64
+    mats = O.generate_synthetic(300, 16, m, nv, 8)
+    engine.set_tuning(E.PATH_CLUSTER, 0)
+    try:
+        assert_batch_equal(engine.solve_batch(t, H, W, want_matrices=True), oracle_batch(t, H, W), "special")
+        for cc in (True, False):
+            c = chv.reshape(1, -1).copy()
+            assert_batch_equal(engine.solve_batch(c, 4, 5, E.make_options(check_cycles=cc), want_matrices=True),
+                               oracle_batch(c, 4, 5, check_cycles=cc), f"chvatal cc={cc}")
+        for mp in (0, 1, 7, 11.5, math.inf):
+            assert_batch_equal(engine.solve_batch(mats, m + 1, nv + 1, E.make_options(max_pivots=mp), want_matrices=True),
+                               oracle_batch(mats, m + 1, nv + 1, max_pivots=mp), f"maxPivots={mp}")
+        for prec in (1e-3, 0.0, 0.25):
+            assert_batch_equal(engine.solve_batch(mats, m + 1, nv + 1, E.make_options(precision=prec), want_matrices=True),
+                               oracle_batch(mats, m + 1, nv + 1, precision=prec), f"precision={prec}")
+    finally:
+        engine.set_tuning(E.PATH_AUTO, 0)
+
+
+@pytest.mark.parametrize("name", ["AFIRO", "SC105", "SC205", "ISRAEL", "AGG", "SCAGR7", "E226", "BEACONFD", "SHARE1B", "SCFXM1"])
+def test_cluster_kernel_netlib(engine, name):
+    g = load_netlib().get(name)
+    H, W = g["height"], g["width"]
+    mats = np.asarray(g["matrix"], np.float64).reshape(1, -1)
+    exp = oracle_batch(mats, H, W)
+    engine.set_tuning(E.PATH_CLUSTER, 0)
+    try:
+        got = engine.solve_batch(mats, H, W, want_matrices=True)
+    finally:
+        engine.set_tuning(E.PATH_AUTO, 0)
+    assert_batch_equal(got, exp, f"cluster {name}")
+
+
 def test_wide_tableau_multi_chunk(engine):
     """W > 32*KC forces several column chunks per row."""
     m, nv, n = 12, 700, 8

@@ -1,0 +1,501 @@
+// cluster_kernel.cuh -- K3: one LP per thread-block cluster, tableau resident in the cluster's shared memory.
+//
+// For tableaus that do not fit the 227 KB of one SM but fit the 1.8-3.6 MB of a cluster of 8-16 CTAs: Netlib-size
+// models solved one at a time, branch-and-cut roots, mid-size batches (BASELINE.json north_star (b)).  Same
+// algorithm, arithmetic and tie-breaking as simplex_split.cuh (src/simplex.ts:5-142), different placement:
+//   * rows 1..H-1 are dealt round-robin to the C CTAs of the cluster (row r lives in CTA (r-1) % C at local index
+//     (r-1) / C), in the padded layout [ A | pad | b | s ] of the resident kernels; pivot-column cells, ratio
+//     tests, RHS scans and the rank-1 update of a row are therefore local to its CTA;
+//   * every CTA keeps a private copy of the objective row (row 0) and applies the pivot to it with the same
+//     operands and operations as every other CTA, so the copies stay bit-identical and the entering-column scan
+//     of phase 2 needs no communication;
+//   * a row selection is a CTA-local arg-reduction, one 16-byte DSMEM store per peer (st.shared::cluster into the
+//     peer's exchange slots) and ONE cluster barrier per pivot.  DSMEM moves only ~20 B/clk per SM (measured: a
+//     first version in which every thread read the pivot row out of its owner's shared memory spent 4-16 k cycles
+//     per pivot there), so the pivot row itself travels through L2: before that barrier every CTA publishes the
+//     row of its own candidate (W cells, st.global.cg) to a per-cluster scratch buffer, after it every CTA stages
+//     the winner's row from L2 into its shared memory once (ld.global.cg) and all its row groups read it there;
+//   * the pivot row is normalised redundantly in registers by every thread that needs its cells (one shared
+//     reciprocal, fastdiv.cuh); the owner writes the normalised row back into its shared memory.
+// Per pivot: one cluster barrier and four CTA barriers, against two full grid barriers for K4.
+#pragma once
+
+#include <cooperative_groups.h>
+
+#include "kernels.cuh"
+
+namespace yalps {
+
+namespace cg = cooperative_groups;
+
+constexpr int kMaxCluster = 16;
+
+struct ClusterSmem {
+  size_t off_A, off_obj, off_prow, off_cc, off_list, off_cnt, off_misc, off_red, off_xch, off_var, total;
+  int ldA, Hloc;
+  __host__ __device__ ClusterSmem(int Hcap, int Wcap, int C) {
+    ldA = SmemLayout::ld_for(Wcap);
+    Hloc = (Hcap - 1 + C - 1) / C;
+    size_t o = 0;
+    off_A = o;
+    o += (size_t)Hloc * ldA * 8;
+    off_obj = o;
+    o += (size_t)ldA * 8;
+    off_prow = o;  // staged copy of the (raw) pivot row
+    o += (size_t)ldA * 8;
+    off_cc = o;
+    o += (size_t)(Hloc + 8) * 16;
+    off_list = o;
+    o += (size_t)((Hloc + 3) & ~3) * 4;
+    off_cnt = o;
+    o += 16;
+    off_misc = o;
+    o += 32;
+    off_red = o;
+    o += 192 * 4;
+    off_xch = o;
+    o += 2 * kMaxCluster * 16;
+    off_var = o;
+    o += (size_t)(Wcap + Hcap) * 4;
+    total = (o + 15) & ~(size_t)15;
+  }
+};
+
+// CTA-wide winner with its key (block_best of simplex_device.cuh returns only the index).
+template <bool kMax, int NW>
+__device__ __forceinline__ Best block_best_full(unsigned long long key, int idx, unsigned *red, int &parity) {
+  Best w = warp_best<kMax>((unsigned)(key >> 32), (unsigned)key, idx);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned *r = red + parity * 96;
+  parity ^= 1;
+  if (lane == 0) {
+    r[warp] = w.hi;
+    r[32 + warp] = w.lo;
+    r[64 + warp] = (unsigned)w.idx;
+  }
+  __syncthreads();
+  const unsigned long long nk = no_key<kMax>();
+  const unsigned hi = lane < NW ? r[lane] : (unsigned)(nk >> 32);
+  const unsigned lo = lane < NW ? r[32 + lane] : (unsigned)nk;
+  const int id = lane < NW ? (int)r[64 + lane] : kNone;
+  return warp_best<kMax>(hi, lo, id);
+}
+
+// Cluster-wide winning row.  Every CTA posts its local winner into slot [rank] of every CTA's exchange buffer and
+// publishes that candidate's row (padded layout, ldA cells) to scratch[xpar][rank]; after the barrier every CTA
+// stages the winner's row into prow_s.  Returns kNone (nothing staged) when no CTA had a candidate.
+template <bool kMax, int NW>
+__device__ __forceinline__ int cluster_select(cg::cluster_group &cluster, int C, int rank, unsigned long long key, int idx,
+                                              unsigned *red, int &parity, uint4 *xch, int &xpar, const double *A, int ldA,
+                                              double *scratch, double *prow_s) {
+  constexpr int NT = NW * 32;
+  const Best w = block_best_full<kMax, NW>(key, idx, red, parity);
+  uint4 *slots = xch + xpar * kMaxCluster;
+  double *pub = scratch + (size_t)xpar * C * ldA;
+  xpar ^= 1;
+  if (w.idx != kNone) {  // publish my candidate row (16-byte chunks; ldA is even and rows are 16-byte aligned)
+    const double2 *src = reinterpret_cast<const double2 *>(A + (size_t)((w.idx - 1) / C) * ldA);
+    double2 *dst = reinterpret_cast<double2 *>(pub + (size_t)rank * ldA);
+    for (int c = threadIdx.x; c < ldA / 2; c += NT) __stcg(dst + c, src[c]);
+  }
+  if ((int)threadIdx.x < C) {
+    uint4 *dst = cluster.map_shared_rank(slots + rank, threadIdx.x);
+    *dst = make_uint4(w.hi, w.lo, (unsigned)w.idx, 0u);
+  }
+  cluster.sync();
+  const int lane = threadIdx.x & 31;
+  const unsigned long long nk = no_key<kMax>();
+  uint4 e = make_uint4((unsigned)(nk >> 32), (unsigned)nk, (unsigned)kNone, 0u);
+  if (lane < C) e = slots[lane];
+  const int row = warp_best<kMax>(e.x, e.y, (int)e.z).idx;
+  if (row != kNone) {
+    const double2 *src = reinterpret_cast<const double2 *>(pub + (size_t)((row - 1) % C) * ldA);
+    double2 *dst = reinterpret_cast<double2 *>(prow_s);
+    for (int c = threadIdx.x; c < ldA / 2; c += NT) dst[c] = __ldcg(src + c);
+    __syncthreads();
+  }
+  return row;
+}
+
+template <int NWC, int KC, int NWR>
+__global__ void __launch_bounds__(NWC *NWR * 32, 1) k_simplex_cluster(const BatchArgs a) {
+  constexpr int NTC = NWC * 32, NW = NWC * NWR, NT = NW * 32, VW = 2;
+  constexpr int RU = KC >= 4 ? 1 : 4 / KC;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int tid = threadIdx.x, lane = tid & 31, ctid = tid % NTC, rg = tid / NTC;
+  const long long cid = blockIdx.x / C, ncl = gridDim.x / C;
+  const double INF = d_inf();
+
+  for (long long lp0 = cid; lp0 < a.n; lp0 += ncl) {
+    const long long lp = a.index ? a.index[lp0] : lp0;
+    int H, W;
+    size_t moff, roff, poff;
+    if (a.heights) {
+      H = a.heights[lp];
+      W = a.widths[lp];
+      moff = (size_t)a.mat_off[lp];
+      roff = (size_t)a.rhs_off[lp];
+      poff = (size_t)a.pos_off[lp];
+    } else {
+      H = a.H;
+      W = a.W;
+      moff = (size_t)lp * H * W;
+      roff = (size_t)lp * H;
+      poff = (size_t)lp * (W + H);
+    }
+    const ClusterSmem L(a.Hcap, a.Wcap, C);
+    double *__restrict__ A = reinterpret_cast<double *>(smem_raw + L.off_A);
+    double *__restrict__ obj = reinterpret_cast<double *>(smem_raw + L.off_obj);
+    double *prow_s = reinterpret_cast<double *>(smem_raw + L.off_prow);
+    double *cc = reinterpret_cast<double *>(smem_raw + L.off_cc);
+    int *list = reinterpret_cast<int *>(smem_raw + L.off_list);
+    int *cnt = reinterpret_cast<int *>(smem_raw + L.off_cnt);
+    unsigned *red = reinterpret_cast<unsigned *>(smem_raw + L.off_red);
+    uint4 *xch = reinterpret_cast<uint4 *>(smem_raw + L.off_xch);
+    int *var = reinterpret_cast<int *>(smem_raw + L.off_var);
+    const int ldA = SmemLayout::ld_for(W), Wm1 = W - 1;
+    const int bslot = ldA - 2;                                          // RHS cell of a row
+    const int nloc = (H - 1 > rank) ? (H - 1 - rank + C - 1) / C : 0;   // local rows: r = 1 + rank + l*C
+    int *hist = a.hist ? a.hist + (size_t)blockIdx.x * 2 * a.hist_cap : nullptr;
+    double *scratch = a.cl_scratch + (size_t)cid * 2 * C * L.ldA;  // [2][C][ldA] published candidate rows
+
+    // ---- load: local rows and the private objective-row copy, reference layout -> [ A | pad | b | s ]
+    {
+      const double *src = a.in + moff;
+      const int warp = tid >> 5;
+      for (int l = warp; l <= nloc; l += NW) {  // l == nloc: the objective row
+        const int r = l < nloc ? 1 + rank + l * C : 0;
+        double *drow = l < nloc ? A + (size_t)l * ldA : obj;
+        const double *g = src + (size_t)r * W;
+        if (lane == 0) cp_async8(drow + bslot, g);
+        for (int c = lane; c < Wm1; c += 32) cp_async8(drow + c, g + 1 + c);
+        for (int c = Wm1 + lane; c < bslot; c += 32) drow[c] = 0.0;  // padding cells
+      }
+      for (int k = tid; k < W + H; k += NT) var[k] = k;
+      if (tid == 0) *cnt = 0;
+      cp_async_wait_all();
+    }
+    __syncthreads();
+    cluster.sync();
+
+    LpResult res;
+    res.status = ST_CYCLED;
+    res.value = d_nan();
+    res.p1 = res.p2 = 0;
+    int phase = 1, parity = 0, xpar = 0, hist_len = 0;
+    long long iter = 0;
+    const double precision = a.precision;
+    const long long budget = !(a.max_pivots > 0.0) ? 0LL
+                                                    : (a.max_pivots >= 9.0e18 ? 0x7fffffffffffffffLL : (long long)ceil(a.max_pivots));
+
+#ifdef YALPS_TIMING
+    long long yt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, yt_last = clock64();
+#define CT_MARK(k) do { const long long now_ = clock64(); yt[k] += now_ - yt_last; yt_last = now_; } while (0)
+#else
+#define CT_MARK(k)
+#endif
+    for (;;) {
+      if (iter >= budget) break;  // per-phase budget exhausted -> "cycled" (:102,:141)
+      int row, col;
+      if (phase == 1) {
+        // leaving row: first index of the most negative RHS below -precision (:111-119)
+        double bv = INF;
+        int bi = kNone;
+        for (int l = tid; l < nloc; l += NT) {
+          const double v = A[(size_t)l * ldA + bslot];
+          if (v < -precision && v < bv) {
+            bv = v;
+            bi = 1 + rank + l * C;
+          }
+        }
+        row = cluster_select<false, NW>(cluster, C, rank, bi == kNone ? no_key<false>() : order_key(bv), bi, red, parity, xch, xpar,
+                                        A, ldA, scratch, prow_s);
+        CT_MARK(0);
+        if (row == kNone) {  // feasible: phase 2 with a fresh counter and history (:120, :67-69)
+          phase = 2;
+          iter = 0;
+          hist_len = 0;
+          continue;
+        }
+        // entering column: first index of max -M[0,c]/M[row,c] over M[row,c] < -precision (:123-134); every CTA
+        // scans all columns of the staged pivot row itself
+        bv = -INF;
+        bi = kNone;
+        {
+          const double *prow = prow_s;
+          for (int j0 = VW * tid; j0 < Wm1; j0 += VW * NT) {
+            const double2 cf = *reinterpret_cast<const double2 *>(prow + j0);
+            const double2 ob = *reinterpret_cast<const double2 *>(obj + j0);
+#pragma unroll
+            for (int e = 0; e < VW; e++) {
+              const double coef = e ? cf.y : cf.x;
+              if (j0 + e < Wm1 && coef < -precision) {
+                const double ratio = div_rn(-(e ? ob.y : ob.x), coef);
+                if (ratio > bv) {  // bv starts at -inf: -inf and NaN ratios never win, as in the reference
+                  bv = ratio;
+                  bi = j0 + e + 1;
+                }
+              }
+            }
+          }
+        }
+        col = block_best<true, NW>(bi == kNone ? no_key<true>() : order_key(bv), bi, red, parity);
+        CT_MARK(1);
+        if (col == kNone) {
+          res.status = ST_INFEASIBLE;
+          break;
+        }
+      } else {
+        // entering column: first index of the largest reduced cost above precision (:71-79), private objective copy
+        double bv = -INF;
+        int bi = kNone;
+#pragma unroll
+        for (int k = 0; k < KC; k++) {
+          const int j0 = VW * (ctid + NTC * k);
+          if (j0 < Wm1) {
+            const double2 ob = *reinterpret_cast<const double2 *>(obj + j0);
+#pragma unroll
+            for (int e = 0; e < VW; e++) {
+              const double v = e ? ob.y : ob.x;
+              if (j0 + e < Wm1 && v > precision && v > bv) {
+                bv = v;
+                bi = j0 + e + 1;
+              }
+            }
+          }
+        }
+        {
+          const unsigned long long key = bi == kNone ? no_key<true>() : order_key(bv);
+          if (NWC == 1)
+            col = warp_best<true>((unsigned)(key >> 32), (unsigned)key, bi).idx;
+          else
+            col = block_best<true, NW>(key, bi, red, parity);
+        }
+        CT_MARK(0);
+        if (col == kNone) {
+          res.status = ST_OPTIMAL;
+          res.value = round_to_precision(obj[bslot], precision);
+          break;
+        }
+        // leaving row: ratio test with the reference's early break (:83-95) == lowest r whose ratio is
+        // <= precision if any, else first index of the minimum ratio.  Ratios <= precision get key -inf.
+        bv = INF;
+        bi = kNone;
+        for (int l = tid; l < nloc; l += NT) {
+          const double v = A[(size_t)l * ldA + (col - 1)];
+          if (v > precision) {
+            const double ratio = div_rn(A[(size_t)l * ldA + bslot], v);
+            if (ratio < INF) {  // +inf and NaN never win (`ratio < minRatio` with minRatio = Infinity)
+              const double key = (ratio <= precision) ? -INF : ratio;
+              if (bi == kNone || key < bv) {
+                bv = key;
+                bi = 1 + rank + l * C;
+              }
+            }
+          }
+        }
+        row = cluster_select<false, NW>(cluster, C, rank, bi == kNone ? no_key<false>() : order_key(bv), bi, red, parity, xch, xpar,
+                                        A, ldA, scratch, prow_s);
+        CT_MARK(1);
+        if (row == kNone) {
+          res.status = ST_UNBOUNDED;
+          res.value = (double)col;
+          break;
+        }
+      }
+
+      if (a.check_cycles) {  // (:98, :137); every CTA keeps its own (identical) history
+        if (hist_len >= a.hist_cap) {
+          res.status = ST_ERR_HISTORY;
+          break;
+        }
+        if (tid == 0) {
+          hist[2 * hist_len] = var[W + row];
+          hist[2 * hist_len + 1] = var[col];
+        }
+        hist_len++;
+        __syncthreads();
+        if (history_has_cycle<NT>(hist, hist_len)) break;  // "cycled", NaN
+      }
+
+      // ================= pivot (src/simplex.ts:5-39) =================
+      {
+        const int jc = col - 1;
+        const int owner = (row - 1) % C, lrow = (row - 1) / C;
+        const double *prow = prow_s;
+        // every load of this phase first: pivot element, pivot row cells and its RHS (staged copy), local column cell
+        const double q = prow[jc];
+        const double braw = prow[bslot];
+        double2 v[KC];
+#pragma unroll
+        for (int k = 0; k < KC; k++)
+          if (VW * (ctid + NTC * k) < Wm1) v[k] = *reinterpret_cast<const double2 *>(prow + VW * (ctid + NTC * k));
+        const double coef0 = obj[jc];
+        double cell0 = 0.0;
+        if (tid < nloc) cell0 = A[(size_t)tid * ldA + jc];
+        const Recip rq(q);
+
+        double p[KC][VW];
+        unsigned st = 0, full = 0, valid = 0, partial = 0;
+        int jc_off = -1;
+#pragma unroll
+        for (int k = 0; k < KC; k++) {
+          const int j0 = VW * (ctid + NTC * k);
+#pragma unroll
+          for (int e = 0; e < VW; e++) {
+            p[k][e] = 0.0;
+            const int j = j0 + e;
+            if (j < Wm1) {
+              valid |= 1u << (k * VW + e);
+              if (j == jc) jc_off = VW * NTC * k + e;
+              const double x = (j == jc) ? 1.0 : (e ? v[k].y : v[k].x);
+              if (fabs(x) > kTiny) {
+                p[k][e] = rq.quot(x);
+                st |= 1u << (k * VW + e);
+              }
+            } else if (j0 < Wm1) {
+              st |= 1u << (k * VW + e);  // padding cell next to the last column: rewriting it is harmless
+            }
+          }
+          const unsigned m = (st >> (k * VW)) & 3u;
+          if (m == 3u)
+            full |= 1u << k;
+          else if (m)
+            partial = 1u;
+        }
+        const bool nz0 = fabs(braw) > kTiny;
+        const double p0 = nz0 ? rq.quot(braw) : 0.0;  // normalised RHS of the pivot row (:19 for c = 0)
+        CT_MARK(2);
+
+        // ---- local pivot-column cells: -coef/q (:36) and the compacted list of local rows to rewrite (:31)
+        for (int l0 = 0; l0 < nloc; l0 += NT) {
+          const int l = l0 + tid;
+          bool act = false;
+          double cell = 0.0, quo = 0.0;
+          if (l < nloc && !(owner == rank && l == lrow)) {
+            cell = l0 == 0 ? cell0 : A[(size_t)l * ldA + jc];
+            const double num = -cell;
+            act = fabs(num) > kTiny;  // also false for NaN, as in the reference
+            quo = act ? rq.quot(num) : 0.0;
+          }
+          const unsigned m = __ballot_sync(0xffffffffu, act);
+          if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(cnt, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (act) {
+              const int k = base + __popc(m & ((1u << lane) - 1u));
+              list[k] = l;
+              *reinterpret_cast<double2 *>(cc + 2 * k) = make_double2(cell, quo);
+            }
+          }
+        }
+        if (tid == 0) {  // basis bookkeeping (:7-12), every CTA for itself
+          const int leaving = var[W + row];
+          var[W + row] = var[col];
+          var[col] = leaving;
+        }
+        __syncthreads();
+        const int R = *cnt;
+        const bool any_partial = __any_sync(0xffffffffu, partial);
+        CT_MARK(3);
+
+        if (rg == NWR - 1) {
+          // RHS cells of the local active rows (:34 for c = 0)
+          if (nz0) {
+            for (int i = ctid; i < R; i += NTC) {
+              const int l = list[i];
+              const double x = A[(size_t)l * ldA + bslot];
+              A[(size_t)l * ldA + bslot] = __dsub_rn(x, __dmul_rn(cc[2 * i], p0));
+            }
+          }
+          // private objective row: the same update every CTA applies to its copy
+          if (fabs(coef0) > kTiny) {
+            const double cnew0 = rq.quot(-coef0);
+            double *orow = obj + VW * ctid;
+#pragma unroll
+            for (int k = 0; k < KC; k++) {
+              const unsigned m = (st >> (k * VW)) & 3u;
+              if (m) {
+                double *dst = orow + (size_t)VW * NTC * k;
+                const double2 x = *reinterpret_cast<const double2 *>(dst);
+                double t0 = __dsub_rn(x.x, __dmul_rn(coef0, p[k][0]));
+                double t1 = __dsub_rn(x.y, __dmul_rn(coef0, p[k][1]));
+                if (jc_off == VW * NTC * k) t0 = cnew0;
+                if (jc_off == VW * NTC * k + 1) t1 = cnew0;
+                if (m & 1u) dst[0] = t0;
+                if (m & 2u) dst[1] = t1;
+              }
+            }
+            if (ctid == NTC - 1 && nz0) obj[bslot] = __dsub_rn(obj[bslot], __dmul_rn(coef0, p0));
+          }
+        }
+        CT_MARK(4);
+        // ---- rank-1 update of the local active rows, pivot-column cell included
+        if (any_partial)
+          update_split<NTC, KC, VW, RU, NWR, true>(A + VW * ctid, ldA, R, rg, list, cc, p, st, full, jc_off);
+        else
+          update_split<NTC, KC, VW, RU, NWR, false>(A + VW * ctid, ldA, R, rg, list, cc, p, st, full, jc_off);
+        CT_MARK(5);
+        // ---- the owner writes the normalised pivot row back (:19,22,25); peers only ever read the published copy
+        if (owner == rank && rg == 0) {
+          double *Arow = A + (size_t)lrow * ldA + VW * ctid;
+#pragma unroll
+          for (int k = 0; k < KC; k++)
+            if ((valid >> (k * VW)) & 1u) *reinterpret_cast<double2 *>(Arow + (size_t)VW * NTC * k) = make_double2(p[k][0], p[k][1]);
+          if (ctid == 0) A[(size_t)lrow * ldA + bslot] = p0;
+        }
+        __syncthreads();
+        if (tid == 0) *cnt = 0;
+        CT_MARK(7);
+      }
+      if (phase == 1)
+        res.p1++;
+      else
+        res.p2++;
+      iter++;
+    }
+
+    // ---- outputs (every CTA its own rows; CTA 0 the scalars, the objective row and the basis)
+    cluster.sync();
+    if (rank == 0) {
+      if (tid == 0) {
+        if (a.status) a.status[lp] = res.status;
+        if (a.value) a.value[lp] = res.value;
+        if (a.pivots) {
+          a.pivots[2 * lp] = res.p1;
+          a.pivots[2 * lp + 1] = res.p2;
+        }
+        if (a.rhs_out) a.rhs_out[roff] = obj[bslot];
+      }
+      if (a.pos_out)
+        for (int k = tid; k < W + H; k += NT) a.pos_out[poff + var[k]] = k;
+      if (a.var_out)
+        for (int k = tid; k < W + H; k += NT) a.var_out[poff + k] = var[k];
+      if (a.mat_out)
+        for (int c = tid; c < W; c += NT) a.mat_out[moff + c] = (c == 0) ? obj[bslot] : obj[c - 1];
+    }
+    if (a.rhs_out)
+      for (int l = tid; l < nloc; l += NT) a.rhs_out[roff + 1 + rank + l * C] = A[(size_t)l * ldA + bslot];
+#ifdef YALPS_TIMING
+    __syncthreads();
+    if (a.rhs_out && rank == 0 && (tid == 0 || tid == NT - 1)) {  // debug builds only: overwrite the RHS output (H >= 18)
+      double *o = a.rhs_out + roff + (tid == 0 ? 0 : 9);
+      for (int k = 0; k < 8; k++) o[k] = (double)yt[k];
+      o[8] = (double)(res.p1 + res.p2);
+    }
+#endif
+    if (a.mat_out) {
+      for (int l = tid >> 5; l < nloc; l += NW) {
+        const double *sA = A + (size_t)l * ldA;
+        double *dr = a.mat_out + moff + (size_t)(1 + rank + l * C) * W;
+        for (int c = lane; c < W; c += 32) dr[c] = (c == 0) ? sA[bslot] : sA[c - 1];
+      }
+    }
+    cluster.sync();  // nobody may start overwriting its shared memory while a peer is still in this LP
+  }
+}
+
+}  // namespace yalps

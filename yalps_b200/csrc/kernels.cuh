@@ -43,6 +43,7 @@ struct BatchArgs {
   int *hist;        // gridDim.x * 2 * hist_cap
   int hist_cap;
   unsigned long long *counter;
+  double *cl_scratch;  // cluster kernel: per cluster 2 * C * ldA doubles (published candidate pivot rows)
 };
 
 // Shared-memory carve-up, identical on host and device.

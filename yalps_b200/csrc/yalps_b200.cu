@@ -23,6 +23,7 @@
 
 #include "kernel_table.h"
 #include "aux_kernels.cuh"
+#include "cluster_kernel.cuh"
 #include "grid_kernel.cuh"
 #include "reg_kernel.cuh"
 
@@ -215,18 +216,20 @@ struct LaunchPlan {
 // shared memory for the tableau and therefore runs many more LPs per SM (profiles/r01_sweep_paths.jsonl).
 int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycles, LaunchPlan *plan,
                 double density = -1.0, bool allow_reg = false) {
+  // a forced cluster path is resolved by maybe_cluster(); what it cannot take is planned as in automatic mode
+  const int tune_path = ctx->tune_path == YALPS_PATH_CLUSTER ? (int)YALPS_PATH_AUTO : ctx->tune_path;
   SmemLayout Lr(Hcap, Wcap, true, 32), Lg(Hcap, Wcap, false, 32);
   bool resident = Lr.total <= (size_t)ctx->smem_optin;
-  if (resident && ctx->tune_path == YALPS_PATH_AUTO && density >= 0.0 && density < 0.35 && n > 64) resident = false;
-  if (ctx->tune_path == YALPS_PATH_SMEM) {
+  if (resident && tune_path == YALPS_PATH_AUTO && density >= 0.0 && density < 0.35 && n > 64) resident = false;
+  if (tune_path == YALPS_PATH_SMEM) {
     if (!resident) return fail(ctx, YALPS_ERR_TOO_LARGE, "tableau %dx%d does not fit in shared memory", Hcap, Wcap);
-  } else if (ctx->tune_path == YALPS_PATH_GMEM) {
+  } else if (tune_path == YALPS_PATH_GMEM) {
     resident = false;
   }
-  const bool grid_ok = ctx->tune_path == YALPS_PATH_GRID || (ctx->tune_path == YALPS_PATH_AUTO && n <= 16);
+  const bool grid_ok = tune_path == YALPS_PATH_GRID || (tune_path == YALPS_PATH_AUTO && n <= 16);
   plan->reg = false;
   if (allow_reg && Hcap <= kRegMaxRows && Wcap <= kRegMaxCols && !check_cycles &&
-      ctx->tune_path == YALPS_PATH_REG) {  // explicit only: measured slower than K1 (see reg_kernel.cuh)
+      tune_path == YALPS_PATH_REG) {  // explicit only: measured slower than K1 (see reg_kernel.cuh)
     auto it = ctx->occ_cache.find("reg33");
     int occ = 0;
     if (it == ctx->occ_cache.end()) {
@@ -244,7 +247,7 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
       return 0;
     }
   }
-  if (ctx->tune_path == YALPS_PATH_REG)
+  if (tune_path == YALPS_PATH_REG)
     return fail(ctx, YALPS_ERR_TOO_LARGE, "tableau %dx%d does not fit the register-resident kernel (max %dx%d, no checkCycles)",
                 Hcap, Wcap, kRegMaxRows, kRegMaxCols);
   plan->resident = resident;
@@ -263,6 +266,10 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
   int want_threads = ctx->tune_threads, want_rows = ctx->tune_rows;
   if (want_threads <= 0 && want_rows <= 0) {
     if (n <= 2LL * ctx->prop.multiProcessorCount) {
+      // latency mode wants the row-split layout (compacted row list next to the tableau): a tableau that only fits
+      // shared memory without it is better off on the cluster / HBM-resident split kernels than on one-row-group K1
+      if (resident && tune_path == YALPS_PATH_AUTO && SmemLayout(Hcap, Wcap, true, 16, true).total > (size_t)ctx->smem_optin)
+        resident = false;
       if (!resident) {
         want_threads = 512, want_rows = 4;
       } else if (cells < 2500) {
@@ -339,7 +346,7 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
 bool use_grid_path(const yalps_ctx *ctx, long long n, const LaunchPlan &plan) {
   if (plan.reg) return false;
   if (ctx->tune_path == YALPS_PATH_GRID || plan.k == nullptr) return true;
-  if (ctx->tune_path != YALPS_PATH_AUTO) return false;
+  if (ctx->tune_path != YALPS_PATH_AUTO && ctx->tune_path != YALPS_PATH_CLUSTER) return false;
   return !plan.resident && n <= 16 && !plan.small_for_grid;
 }
 
@@ -379,6 +386,122 @@ int launch_simplex(yalps_ctx *ctx, const LaunchPlan &plan, BatchArgs &args, cons
   CU(ctx, cudaGetLastError());
   ctx->launches++;
   return 0;
+}
+
+// ---- K3: one LP per thread-block cluster (cluster_kernel.cuh) -------------------------------------------
+struct ClusterPlan {
+  const KernelEntry *k = nullptr;
+  int C = 0;          // CTAs per cluster
+  size_t smem = 0;
+  int clusters = 0;   // co-resident clusters
+};
+
+// Smallest cluster (2, 4, 8, 16 CTAs) whose shared memory holds the tableau, and the kernel covering its width.
+// plan->k stays null when the tableau does not fit or the device cannot co-schedule such a cluster.
+int plan_cluster(yalps_ctx *ctx, int Hcap, int Wcap, ClusterPlan *plan) {
+  plan->k = nullptr;
+  int count = 0;
+  const KernelEntry *tab = kernel_table_cluster(&count);
+  const KernelEntry *k = nullptr;
+  for (int i = 0; i < count && !k; i++)
+    if ((long long)tab[i].nw * 32 * tab[i].kc * 2 >= std::max(Wcap - 1, 1)) k = &tab[i];
+  if (!k) return 0;
+  for (int C = 2; C <= kMaxCluster; C *= 2) {
+    const ClusterSmem L(Hcap, Wcap, C);
+    if (L.total > (size_t)ctx->smem_optin) continue;
+    // more CTAs than the capacity needs when a CTA would otherwise own many rows (dense updates are row-parallel)
+    if (L.Hloc > 40 && C < kMaxCluster) continue;
+    const std::string key = "cl:" + std::to_string((size_t)(void *)k->resident) + ":" + std::to_string(C) + ":" + std::to_string(L.total);
+    int ncl = 0;
+    auto it = ctx->occ_cache.find(key);
+    if (it != ctx->occ_cache.end()) {
+      ncl = it->second;
+    } else {
+      CU(ctx, raise_smem_limit(ctx->device, (const void *)k->resident, (int)L.total));
+      if (C > 8) CU(ctx, cudaFuncSetAttribute((const void *)k->resident, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)C * 64);
+      cfg.blockDim = dim3((unsigned)(k->nw * k->nwr * 32));
+      cfg.dynamicSmemBytes = L.total;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = (unsigned)C;
+      attr[0].val.clusterDim.y = attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      if (cudaOccupancyMaxActiveClusters(&ncl, (const void *)k->resident, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        ncl = 0;
+      }
+      ctx->occ_cache[key] = ncl;
+    }
+    if (ncl < 1) continue;
+    CU(ctx, raise_smem_limit(ctx->device, (const void *)k->resident, (int)L.total));
+    plan->k = k;
+    plan->C = C;
+    plan->smem = L.total;
+    plan->clusters = ncl;
+    return 0;
+  }
+  return 0;
+}
+
+int launch_cluster(yalps_ctx *ctx, const ClusterPlan &plan, BatchArgs &args, const std::string &slot, cudaStream_t stream) {
+  const int ncl = (int)std::max<long long>(1, std::min<long long>(plan.clusters, args.n));
+  args.counter = nullptr;
+  args.hist = nullptr;
+  if (args.check_cycles) {
+    void *hist = nullptr;
+    if (int rc = dev_ensure(ctx, "hist_cl" + slot, (size_t)ncl * plan.C * 2 * args.hist_cap * sizeof(int), &hist)) return rc;
+    args.hist = (int *)hist;
+  }
+  {
+    void *scr = nullptr;
+    const size_t per_cluster = (size_t)2 * plan.C * SmemLayout::ld_for(args.Wcap) * sizeof(double);
+    if (int rc = dev_ensure(ctx, "cl_scratch" + slot, per_cluster * ncl, &scr)) return rc;
+    args.cl_scratch = (double *)scr;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(ncl * plan.C));
+  cfg.blockDim = dim3((unsigned)(plan.k->nw * plan.k->nwr * 32));
+  cfg.dynamicSmemBytes = plan.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)plan.C;
+  attr[0].val.clusterDim.y = attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CU(ctx, cudaLaunchKernelEx(&cfg, plan.k->resident, (const BatchArgs)args));
+  ctx->launches++;
+  return 0;
+}
+
+// Few LPs that do not fit one SM's shared memory: K3 when they fit a cluster's (tune_path AUTO or CLUSTER).
+bool want_cluster(const yalps_ctx *ctx, long long n, const LaunchPlan &plan, const ClusterPlan &cp) {
+  if (!cp.k) return false;
+  if (ctx->tune_path == YALPS_PATH_CLUSTER) return true;
+  if (ctx->tune_path != YALPS_PATH_AUTO || plan.reg) return false;
+  return !plan.resident && n <= 2LL * std::max(1, cp.clusters);
+}
+
+// 1 = launched on the cluster path, 0 = not applicable (caller goes on with its plan), < 0 = error.
+// plan == nullptr: before plan_launch, only the forced YALPS_PATH_CLUSTER is considered.
+int maybe_cluster(yalps_ctx *ctx, long long n, int Hcap, int Wcap, const LaunchPlan *plan, BatchArgs &a,
+                  const std::string &slot, cudaStream_t stream) {
+  const bool forced = ctx->tune_path == YALPS_PATH_CLUSTER;
+  if (!plan && !forced) return 0;
+  if (plan && (forced || ctx->tune_path != YALPS_PATH_AUTO || plan->resident || plan->reg)) return 0;
+  ClusterPlan cp;
+  if (int rc = plan_cluster(ctx, Hcap, Wcap, &cp)) return rc;
+  if (forced) {
+    if (!cp.k)
+      return fail(ctx, YALPS_ERR_TOO_LARGE, "tableau %dx%d does not fit the shared memory of a %d-CTA cluster", Hcap, Wcap, kMaxCluster);
+  } else if (!want_cluster(ctx, n, *plan, cp)) {
+    return 0;
+  }
+  if (int rc = launch_cluster(ctx, cp, a, slot, stream)) return rc;
+  return 1;
 }
 
 void fill_options(BatchArgs &a, const yalps_options *opt) {
@@ -470,7 +593,7 @@ int yalps_device_info(const yalps_ctx *ctx, int32_t *sm_count, int32_t *smem_per
 
 int yalps_set_tuning(yalps_ctx *ctx, int32_t path, int32_t threads_per_lp) {
   if (!ctx) return YALPS_ERR_ARGUMENT;
-  if (path < 0 || path > YALPS_PATH_REG) return fail(ctx, YALPS_ERR_ARGUMENT, "bad path %d", path);
+  if (path < 0 || path > YALPS_PATH_CLUSTER) return fail(ctx, YALPS_ERR_ARGUMENT, "bad path %d", path);
   ctx->tune_path = path;
   ctx->tune_threads = threads_per_lp;
   return 0;
@@ -589,8 +712,6 @@ int yalps_solve_batch_device(yalps_ctx *ctx, int64_t n, int32_t height, int32_t 
       density = it->second;
     }
   }
-  LaunchPlan plan;
-  if (int rc = plan_launch(ctx, n, height, width, opt->check_cycles != 0, &plan, density, true)) return rc;
   BatchArgs a{};
   a.n = n;
   a.mode = kModeBatch;
@@ -606,6 +727,10 @@ int yalps_solve_batch_device(yalps_ctx *ctx, int64_t n, int32_t height, int32_t 
   a.pos_out = d_pos_out;
   a.var_out = d_var_out;
   fill_options(a, opt);
+  if (int rc = maybe_cluster(ctx, n, height, width, nullptr, a, "dev", (cudaStream_t)stream)) return rc < 0 ? rc : 0;
+  LaunchPlan plan;
+  if (int rc = plan_launch(ctx, n, height, width, opt->check_cycles != 0, &plan, density, true)) return rc;
+  if (int rc = maybe_cluster(ctx, n, height, width, &plan, a, "dev", (cudaStream_t)stream)) return rc < 0 ? rc : 0;
   if (use_grid_path(ctx, n, plan)) {
     if (!d_work) return fail(ctx, YALPS_ERR_ARGUMENT, "d_work is required for the grid path");
     cudaStream_t st = (cudaStream_t)stream;
@@ -688,7 +813,7 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
     const size_t out_b = (size_t)n * 32 + rows_b + 2 * pv_b + 64 + (matrices_out ? in_b : 0);
     const size_t desc_b = ragged ? (size_t)n * 32 + 64 : 0;
     LaunchPlan plan;
-    if (in_b + out_b + desc_b <= ((size_t)768 << 10) && ctx->tune_path != YALPS_PATH_GRID &&
+    if (in_b + out_b + desc_b <= ((size_t)768 << 10) && ctx->tune_path != YALPS_PATH_GRID && ctx->tune_path != YALPS_PATH_CLUSTER &&
         plan_launch(ctx, n, Hcap, Wcap, opt->check_cycles != 0, &plan, -1.0, true) == 0 && (plan.k || plan.reg) && plan.resident) {
       auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
       size_t o = 0;
@@ -876,7 +1001,14 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
       a.pos_off = (const long long *)d_po;
     }
     fill_options(a, opt);
+    int on_cluster = 0;
     if (!ragged) {
+      if ((on_cluster = maybe_cluster(ctx, cn, chcap, cwcap, nullptr, a, s, st)) < 0) return on_cluster;
+      if (!on_cluster && (on_cluster = maybe_cluster(ctx, cn, chcap, cwcap, &plan, a, s, st)) < 0) return on_cluster;
+    }
+    if (on_cluster) {
+      // launched: one LP per thread-block cluster
+    } else if (!ragged) {
       if (use_grid_path(ctx, cn, plan)) {
         for (int64_t i = 0; i < cn; i++) {
           const long long mo = (long long)i * height * width;
@@ -925,7 +1057,17 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
         if ((rc = plan_launch(ctx, gn, caps[g].first, caps[g].second, opt->check_cycles != 0, &gp,
                               groups.size() == 1 ? density : -1.0, true)))
           return rc;
-        if (use_grid_path(ctx, gn, gp)) {
+        BatchArgs ca = a;
+        ca.n = gn;
+        ca.Hcap = caps[g].first;
+        ca.Wcap = caps[g].second;
+        ca.index = (const int *)d_index + at;
+        int g_cluster = maybe_cluster(ctx, gn, caps[g].first, caps[g].second, nullptr, ca, s, st);
+        if (g_cluster == 0) g_cluster = maybe_cluster(ctx, gn, caps[g].first, caps[g].second, &gp, ca, s, st);
+        if (g_cluster < 0) return g_cluster;
+        if (g_cluster) {
+          // launched on the cluster path
+        } else if (use_grid_path(ctx, gn, gp)) {
           for (int id : groups[g]) {
             const int hi = heights[begin + id], wi = widths[begin + id];
             const long long mo = moff[begin + id] - moff[begin], ro = roff[begin + id] - roff[begin],
