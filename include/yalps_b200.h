@@ -78,7 +78,7 @@ enum yalps_path {
   YALPS_PATH_SMEM = 1, /* K1: one tableau per CTA resident in shared memory */
   YALPS_PATH_GMEM = 2, /* K2: tableau in HBM/L2, CTA per LP, pivot row/column staged in shared memory */
   YALPS_PATH_GRID = 3, /* K4: one LP across the whole grid (cooperative launch) */
-  YALPS_PATH_CLUSTER = 5, /* K3: one LP per thread-block cluster, tableau distributed over the cluster's shared
+  YALPS_PATH_CLUSTER = 5, /* KC: one LP per thread-block cluster, tableau distributed over the cluster's shared
                              memory, pivot row read through DSMEM (csrc/cluster_kernel.cuh) */
   YALPS_PATH_REG = 4   /* K1r (experimental, never chosen automatically): one warp per LP, tableau in registers
                           (at most 33 x 65, no checkCycles); slower than K1, see csrc/reg_kernel.cuh */

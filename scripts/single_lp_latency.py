@@ -23,7 +23,7 @@ for name in names:
         d = torch.from_numpy(np.tile(np.asarray(g["matrix"], np.float64).reshape(-1), n)).cuda()
         work = torch.empty_like(d)
         st = torch.empty(n, dtype=torch.int32, device="cuda"); piv = torch.empty(n, 2, dtype=torch.int64, device="cuda")
-        for path, pn in ((E.PATH_SMEM, "K1"), (E.PATH_GMEM, "K2"), (E.PATH_GRID, "K4"), (E.PATH_CLUSTER, "K3"), (E.PATH_AUTO, "auto")):
+        for path, pn in ((E.PATH_SMEM, "K1"), (E.PATH_GMEM, "K2"), (E.PATH_GRID, "K4"), (E.PATH_CLUSTER, "KC"), (E.PATH_AUTO, "auto")):
             for threads, rows in (((0, 0),) if path in (E.PATH_GRID, E.PATH_CLUSTER, E.PATH_AUTO) else
                                   ((32, 1), (64, 1), (128, 1), (256, 1), (128, 2), (128, 4), (256, 2), (256, 4), (256, 8),
                                    (512, 4), (512, 8), (512, 16))):

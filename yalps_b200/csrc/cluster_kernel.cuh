@@ -1,4 +1,4 @@
-// cluster_kernel.cuh -- K3: one LP per thread-block cluster, tableau resident in the cluster's shared memory.
+// cluster_kernel.cuh -- KC: one LP per thread-block cluster, tableau resident in the cluster's shared memory.
 //
 // For tableaus that do not fit the 227 KB of one SM but fit the 1.8-3.6 MB of a cluster of 8-16 CTAs: Netlib-size
 // models solved one at a time, branch-and-cut roots, mid-size batches (BASELINE.json north_star (b)).  Same

@@ -1,4 +1,4 @@
-// K3: cluster-resident kernels (cluster_kernel.cuh), 256 threads per CTA (no register spills: the cluster barrier
+// KC: cluster-resident kernels (cluster_kernel.cuh), 256 threads per CTA (no register spills: the cluster barrier
 // invalidates L1, so every spill reload after it would be an L2 round trip).
 #include "cluster_kernel.cuh"
 #include "kernel_table.h"

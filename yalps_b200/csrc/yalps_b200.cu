@@ -388,7 +388,7 @@ int launch_simplex(yalps_ctx *ctx, const LaunchPlan &plan, BatchArgs &args, cons
   return 0;
 }
 
-// ---- K3: one LP per thread-block cluster (cluster_kernel.cuh) -------------------------------------------
+// ---- KC: one LP per thread-block cluster (cluster_kernel.cuh) -------------------------------------------
 struct ClusterPlan {
   const KernelEntry *k = nullptr;
   int C = 0;          // CTAs per cluster
@@ -477,7 +477,7 @@ int launch_cluster(yalps_ctx *ctx, const ClusterPlan &plan, BatchArgs &args, con
   return 0;
 }
 
-// Few LPs that do not fit one SM's shared memory: K3 when they fit a cluster's (tune_path AUTO or CLUSTER).
+// Few LPs that do not fit one SM's shared memory: KC when they fit a cluster's (tune_path AUTO or CLUSTER).
 bool want_cluster(const yalps_ctx *ctx, long long n, const LaunchPlan &plan, const ClusterPlan &cp) {
   if (!cp.k) return false;
   if (ctx->tune_path == YALPS_PATH_CLUSTER) return true;
