@@ -290,6 +290,27 @@ def test_ragged_batch(engine):
         assert same_bits(g["rhs"], e["rhs"][0]) and same_bits(g["matrix"], e["matrices"][0])
 
 
+def test_ragged_batch_on_the_cluster_kernel(engine):
+    """Ragged groups reach the cluster kernel through the LP index indirection."""
+    rng = np.random.default_rng(5)
+    tabs, shapes, exp = [], [], []
+    for i, (m, nv) in enumerate([(3, 4), (40, 70), (200, 260), (90, 130), (1, 1), (250, 300), (33, 9), (120, 400)]):
+        t = O.generate_synthetic(900 + i, 1, m, nv, min(m, 4))[0]
+        tabs.append(t)
+        shapes.append((m + 1, nv + 1))
+        exp.append(oracle_batch(t.reshape(1, -1), m + 1, nv + 1))
+    engine.set_tuning(E.PATH_CLUSTER, 0)
+    try:
+        got = engine.solve_ragged(tabs, shapes, want_matrices=True)
+    finally:
+        engine.set_tuning(E.PATH_AUTO, 0)
+    for g, e, s in zip(got, exp, shapes):
+        assert g["status"] == e["status"][0] and g["pivots"] == tuple(e["pivots"][0]), s
+        assert same_value(g["value"], e["value"][0])
+        assert np.array_equal(g["pos"], e["pos"][0]) and np.array_equal(g["var"], e["var"][0])
+        assert same_bits(g["rhs"], e["rhs"][0]) and same_bits(g["matrix"], e["matrices"][0]), s
+
+
 def test_round_to_precision_device(engine):
     rng = np.random.default_rng(1)
     xs = np.concatenate([rng.normal(size=4000) * 10.0 ** rng.integers(-10, 10, 4000),

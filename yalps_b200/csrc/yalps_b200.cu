@@ -282,10 +282,7 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
         want_threads = 512, want_rows = 8;
       }
     } else if (!resident) {
-      if (cells >= 12000)
-        want_threads = 256, want_rows = 4;
-      else if (cells >= 5000)
-        want_threads = 128, want_rows = 2;
+      if (cells >= 5000) want_threads = 128, want_rows = 2;
     }
   }
   plan->small_for_grid = !resident && cells < 40000;
