@@ -180,7 +180,8 @@ int yalps_bnb_solve_nodes(yalps_ctx *ctx, int64_t n, const int32_t *cut_offsets,
 int yalps_branch_and_cut(yalps_ctx *ctx, const int32_t *ints, int32_t nints, double sign, double init_result,
                          const yalps_options *opt, int32_t *status, double *result, int32_t *out_height,
                          double *rhs_out, int32_t *pos_out, int32_t *var_out, int64_t *stats);
-/* Wave width for the speculation (default 64). */
+/* Upper bound of the speculative look-ahead per wave (default 256; the driver adapts the actual width, starting at
+ * 16, to how much of each wave the replay consumes). */
 int yalps_bnb_set_wave(yalps_ctx *ctx, int32_t wave);
 
 /*

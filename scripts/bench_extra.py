@@ -138,10 +138,14 @@ if "config4" in what:  # MILP suite of benchmarks/json/read.ts
         sol = yalps_b200.solve(c["model"], c["options"], engine=eng, info=info)
         dt = time.perf_counter() - t0
         t0 = time.perf_counter()
+        yalps_b200.tableau_model(c["model"])
+        build = time.perf_counter() - t0
+        t0 = time.perf_counter()
         M.solve(c["model"], {**M.DEFAULT_OPTIONS, **c["options"]})
         cpu = time.perf_counter() - t0
         emit(workload=f"config4: {name} via solve() (tableau build on host + root LP + branch and cut waves)",
              status=sol["status"], result=sol["result"], expected=c["expected"]["result"], gpu_ms=dt * 1e3,
+             host_tableau_build_ms=build * 1e3,
              oracle_cpu_ms=cpu * 1e3, nodes=info["nodes"], node_pivots=info["node_pivots"], waves=info["waves"],
              device_nodes=info["device_nodes"], wave_us=info.get("wave_us"), bnb_us=info.get("bnb_us"), root_pivots=list(info["root_pivots"]),
              shape=[info["height"], info["width"]])

@@ -373,18 +373,29 @@ int yalps_branch_and_cut(yalps_ctx *ctx, const int32_t *ints, int32_t nints, dou
   std::vector<int32_t> w_var;
   BranchHeap peek;
   peek.arena = &arena;
+  int cur_wave = std::min(16, std::max(ctx->wave, 1)), last_wave_n = 0, consumed_since_wave = 0;
+  double avg_consumed = 8.0;
 
   auto run_wave = [&](int32_t needed) -> int {
     // the needed branch first, then the branches the heap would pop next (on a copy of the index heap)
+    // adaptive look-ahead: the number of waves is set by the depth of the search's dives, not by the wave size
+    // (Large Farm MIP: 135 waves for every size from 16 to 256), so speculation beyond what the replay consumes
+    // only costs host and device work.  Width = 1.5 x the running mean of the nodes consumed per wave.
+    if (last_wave_n > 0) {
+      avg_consumed = 0.75 * avg_consumed + 0.25 * (double)consumed_since_wave;
+      cur_wave = std::max(8, std::min(std::max(ctx->wave, 8), (int)(1.5 * avg_consumed) + 2));
+    }
+    consumed_since_wave = 0;
     auto wb = std::make_unique<WaveBuf>();
     wb->ids.push_back(needed);
     peek.a = heap.a;
-    while ((int)wb->ids.size() < ctx->wave && !peek.empty()) {
+    while ((int)wb->ids.size() < cur_wave && !peek.empty()) {
       const int32_t b = peek.pop();
       if (arena[b].eval > best_eval) break;  // would be pruned (:124)
       if (!cached(b)) wb->ids.push_back(b);
     }
     const int64_t n = (int64_t)wb->ids.size();
+    last_wave_n = (int)n;
     w_off.assign(1, 0);
     w_sign.clear();
     w_var.clear();
@@ -447,6 +458,7 @@ int yalps_branch_and_cut(yalps_ctx *ctx, const int32_t *ints, int32_t nints, dou
     const WaveBuf &wb = *waves[res_wave[br]];
     const int slot = res_slot[br];
     res_wave[br] = -1;  // consumed
+    consumed_since_wave++;
     const int32_t n_status = wb.status[slot];
     const double n_value = wb.value[slot];
     const int n_height = H + (int)arena[br].cuts.size();

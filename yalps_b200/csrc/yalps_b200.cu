@@ -72,7 +72,7 @@ struct yalps_ctx {
   cudaEvent_t events[2]{};
   int64_t launches = 0;
   int tune_path = 0, tune_threads = 0, tune_rows = 0;
-  int wave = 64;
+  int wave = 256;  // upper bound of the adaptive look-ahead of the branch-and-cut driver
   // pooled device buffers (index = purpose * 2 + pipeline slot)
   std::unordered_map<std::string, DevBuf> pool;
   std::unordered_map<std::string, DevBuf> pinned;
@@ -274,7 +274,7 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
         want_threads = 512, want_rows = 4;
       } else if (cells < 2500) {
         want_threads = 128, want_rows = 4;
-      } else if (cells < 6000) {
+      } else if (cells < 4000) {
         want_threads = 256, want_rows = 8;
       } else if (cells < 12000) {
         want_threads = 256, want_rows = 4;
