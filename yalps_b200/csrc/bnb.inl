@@ -149,6 +149,41 @@ int upload_root_host(yalps_ctx *ctx, int32_t height, int32_t width, const double
   return 0;
 }
 
+// Root tableau already on the device (the root LP was just solved there): device-to-device copy, no PCIe round trip
+// of the matrix.  rhs / pos / var are the host copies the driver needs anyway.
+int adopt_root_device(yalps_ctx *ctx, int32_t height, int32_t width, const double *d_matrix, const double *rhs,
+                      const int32_t *pos, const int32_t *var, int32_t max_extra_rows) {
+  Root &R = ctx->root;
+  const size_t cells = (size_t)height * width;
+  const size_t nv = (size_t)height + width;
+  auto ensure = [&](DevBuf &b, size_t bytes) -> int {
+    if (b.cap < bytes) {
+      if (b.p) CU(ctx, cudaFree(b.p));
+      b.p = nullptr;
+      b.cap = 0;
+      CU(ctx, cudaMalloc(&b.p, bytes));
+      b.cap = bytes;
+    }
+    return 0;
+  };
+  if (int rc = ensure(R.m, cells * 8)) return rc;
+  if (int rc = ensure(R.pos, nv * 4)) return rc;
+  if (int rc = ensure(R.var, nv * 4)) return rc;
+  cudaStream_t st = ctx->streams[0];
+  CU(ctx, cudaMemcpyAsync(R.m.p, d_matrix, cells * 8, cudaMemcpyDeviceToDevice, st));
+  CU(ctx, cudaMemcpyAsync(R.pos.p, pos, nv * 4, cudaMemcpyHostToDevice, st));
+  CU(ctx, cudaMemcpyAsync(R.var.p, var, nv * 4, cudaMemcpyHostToDevice, st));
+  CU(ctx, cudaStreamSynchronize(st));
+  R.H = height;
+  R.W = width;
+  R.max_extra = max_extra_rows;
+  R.h_rhs.assign(rhs, rhs + height);
+  R.h_pos.assign(pos, pos + nv);
+  R.h_var.assign(var, var + nv);
+  R.valid = true;
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -274,13 +309,40 @@ int yalps_bnb_solve_nodes(yalps_ctx *ctx, int64_t n, const int32_t *cut_offsets,
                                                    (const double *)d_val, (double *)d_work);
     CU(ctx, cudaGetLastError());
     ctx->launches++;
+    // the nodes of a wave are independent: give each of up to kGridLanes concurrent cooperative launches its share of
+    // the SMs (a K4 pivot on an L2-resident tableau is bound by its two grid barriers, which get cheaper with fewer
+    // CTAs, while the wave as a whole uses the whole GPU)
+    constexpr int kGridLanes = 6;
+    const int lanes = (int)std::min<int64_t>(n, kGridLanes);
+    while ((int)ctx->aux_streams.size() < lanes) {
+      cudaStream_t s2;
+      cudaEvent_t e2;
+      CU(ctx, cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+      CU(ctx, cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+      ctx->aux_streams.push_back(s2);
+      ctx->aux_events.push_back(e2);
+    }
+    if (!ctx->fork_event) CU(ctx, cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
+    const int share = lanes > 1 ? std::max(8, ctx->prop.multiProcessorCount / lanes) : 0;
+    if (lanes > 1) {
+      CU(ctx, cudaEventRecord(ctx->fork_event, st));
+      for (int l = 0; l < lanes; l++) CU(ctx, cudaStreamWaitEvent(ctx->aux_streams[l], ctx->fork_event, 0));
+    }
     for (int64_t j = 0; j < n; j++) {
       const int hj = R.H + (cut_offsets[j + 1] - cut_offsets[j]);
+      const int l = (int)(j % lanes);
+      cudaStream_t sj = lanes > 1 ? ctx->aux_streams[l] : st;
       if ((rc = launch_grid(ctx, hj, W, (double *)d_work + (size_t)j * Hcap * W, opt, (int *)d_status + j,
                             (double *)d_value + j, (long long *)d_piv + 2 * j, (double *)d_rhs + (size_t)j * Hcap,
-                            (int *)d_pos + (size_t)j * (W + Hcap), (int *)d_vr + (size_t)j * (W + Hcap), st,
-                            (const int *)R.var.p, W + R.H)))
+                            (int *)d_pos + (size_t)j * (W + Hcap), (int *)d_vr + (size_t)j * (W + Hcap), sj,
+                            (const int *)R.var.p, W + R.H, share, lanes > 1 ? "_l" + std::to_string(l) : "")))
         return rc;
+    }
+    if (lanes > 1) {
+      for (int l = 0; l < lanes; l++) {
+        CU(ctx, cudaEventRecord(ctx->aux_events[l], ctx->aux_streams[l]));
+        CU(ctx, cudaStreamWaitEvent(st, ctx->aux_events[l], 0));
+      }
     }
   } else if ((rc = launch_simplex(ctx, plan, a, "nd", st))) {
     return rc;
@@ -538,12 +600,19 @@ int yalps_solve(yalps_ctx *ctx, int32_t height, int32_t width, const double *mat
   int64_t piv[2] = {0, 0};
   const size_t cells = (size_t)height * width;
   const bool milp = nints > 0;
+  // A MILP root that is too big for the zero-copy small-call path stays on the device: branch and cut needs the whole
+  // final root tableau (applyCuts, src/branchAndCut.ts:28,38-42), and bringing it to the host only to upload it again
+  // costs two PCIe trips of the matrix (SURVEY 8b "bnb_adopt_root").
+  const bool keep_on_device = milp && cells * 8 > ((size_t)256 << 10);
   std::vector<double> final_m;
-  if (milp) final_m.resize(cells);
+  if (milp && !keep_on_device) final_m.resize(cells);
   // root LP (src/YALPS.ts:79)
-  if (int rc = yalps_solve_batch(ctx, 1, height, width, matrix, opt, &st, &val, piv, rhs_out, pos_out, var_out,
-                                 milp ? final_m.data() : nullptr))
-    return rc;
+  ctx->keep_final = keep_on_device;
+  ctx->kept_final = nullptr;
+  const int root_rc = yalps_solve_batch(ctx, 1, height, width, matrix, opt, &st, &val, piv, rhs_out, pos_out, var_out,
+                                        (milp && !keep_on_device) ? final_m.data() : nullptr);
+  ctx->keep_final = false;
+  if (root_rc) return root_rc;
   if (root_status) *root_status = st;
   if (root_value) *root_value = val;
   if (root_pivots) {
@@ -556,7 +625,14 @@ int yalps_solve(yalps_ctx *ctx, int32_t height, int32_t width, const double *mat
     *result = val;
     return 0;
   }
-  if (int rc = yalps_bnb_set_root(ctx, height, width, final_m.data(), pos_out, var_out, 2 * nints)) return rc;
+  if (keep_on_device) {
+    if (!ctx->kept_final) return fail(ctx, YALPS_ERR_CUDA, "root tableau was not kept on the device");
+    if (((long long)height + 2 * nints) * width >= (1LL << 31))
+      return fail(ctx, YALPS_ERR_TOO_LARGE, "(height+extra)*width must be < 2^31");
+    if (int rc = adopt_root_device(ctx, height, width, ctx->kept_final, rhs_out, pos_out, var_out, 2 * nints)) return rc;
+  } else if (int rc = yalps_bnb_set_root(ctx, height, width, final_m.data(), pos_out, var_out, 2 * nints)) {
+    return rc;
+  }
   return yalps_branch_and_cut(ctx, ints, nints, sign, val, opt, status, result, out_height, rhs_out, pos_out, var_out,
                               stats);
 }

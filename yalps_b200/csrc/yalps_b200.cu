@@ -72,6 +72,11 @@ struct yalps_ctx {
   cudaEvent_t events[2]{};
   int64_t launches = 0;
   int tune_path = 0, tune_threads = 0, tune_rows = 0;
+  std::vector<cudaStream_t> aux_streams;  // concurrent K4 launches of one node wave
+  std::vector<cudaEvent_t> aux_events;
+  cudaEvent_t fork_event = nullptr;
+  bool keep_final = false;         // solve_host (n == 1): leave the final tableau on the device, no D2H copy of it
+  double *kept_final = nullptr;    // ... and where it is (valid until the next batch call on this ctx)
   int wave = 256;  // upper bound of the adaptive look-ahead of the branch-and-cut driver
   // pooled device buffers (index = purpose * 2 + pipeline slot)
   std::unordered_map<std::string, DevBuf> pool;
@@ -573,6 +578,9 @@ void yalps_destroy(yalps_ctx *ctx) {
     if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
     if (ctx->events[i]) cudaEventDestroy(ctx->events[i]);
   }
+  for (cudaStream_t st : ctx->aux_streams) cudaStreamDestroy(st);
+  for (cudaEvent_t ev : ctx->aux_events) cudaEventDestroy(ev);
+  if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
   delete ctx;
 }
 
@@ -622,7 +630,8 @@ int yalps_host_free(yalps_ctx *ctx, void *ptr) {
 // K4: one LP over the whole grid.  d_M (H*W doubles, reference layout) is solved in place.
 static int launch_grid(yalps_ctx *ctx, int H, int W, double *d_M, const yalps_options *opt, int *d_status,
                        double *d_value, long long *d_pivots, double *d_rhs, int *d_pos, int *d_var,
-                       cudaStream_t stream, const int *d_init_var = nullptr, int init_n = 0) {
+                       cudaStream_t stream, const int *d_init_var = nullptr, int init_n = 0, int max_ctas = 0,
+                       const std::string &slot = "") {
   const GridSmem L(H, W);
   if (L.total > (size_t)ctx->smem_optin)
     return fail(ctx, YALPS_ERR_TOO_LARGE, "tableau %dx%d: pivot row/column staging exceeds shared memory", H, W);
@@ -640,6 +649,7 @@ static int launch_grid(yalps_ctx *ctx, int H, int W, double *d_M, const yalps_op
     grid = (int)std::min<long long>(grid, std::max(1LL, (items + 2 * kGridWarps - 1) / (2 * kGridWarps)));
   }
   if (const char *env = getenv("YALPS_GRID_CTAS")) grid = std::max(1, std::min(atoi(env), ctx->prop.multiProcessorCount * occ));
+  if (max_ctas > 0) grid = std::max(1, std::min(grid, max_ctas));  // several K4 launches sharing the GPU (node waves)
   GridArgs a{};
   a.M = d_M;
   a.H = H;
@@ -655,18 +665,18 @@ static int launch_grid(yalps_ctx *ctx, int H, int W, double *d_M, const yalps_op
   a.hist_cap = hist_capacity(opt);
   void *p = nullptr;
   if (!d_var) {
-    if (int rc = dev_ensure(ctx, "grid_var", (size_t)(W + H) * 4, &p)) return rc;
+    if (int rc = dev_ensure(ctx, "grid_var" + slot, (size_t)(W + H) * 4, &p)) return rc;
     d_var = (int *)p;
   }
   a.var = d_var;
   a.init_var = d_init_var;
   a.init_n = init_n;
-  if (int rc = dev_ensure(ctx, "grid_flags", 64, &p)) return rc;
+  if (int rc = dev_ensure(ctx, "grid_flags" + slot, 64, &p)) return rc;
   a.flags = (int *)p;
   a.barrier = (unsigned long long *)((char *)p + 32);
   CU(ctx, cudaMemsetAsync(p, 0, 64, stream));
   if (a.check_cycles) {
-    if (int rc = dev_ensure(ctx, "grid_hist", (size_t)2 * a.hist_cap * sizeof(int), &p)) return rc;
+    if (int rc = dev_ensure(ctx, "grid_hist" + slot, (size_t)2 * a.hist_cap * sizeof(int), &p)) return rc;
     a.hist = (int *)p;
   }
   void *params[] = {&a};
@@ -810,7 +820,7 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
     const size_t out_b = (size_t)n * 32 + rows_b + 2 * pv_b + 64 + (matrices_out ? in_b : 0);
     const size_t desc_b = ragged ? (size_t)n * 32 + 64 : 0;
     LaunchPlan plan;
-    if (in_b + out_b + desc_b <= ((size_t)768 << 10) && ctx->tune_path != YALPS_PATH_GRID && ctx->tune_path != YALPS_PATH_CLUSTER &&
+    if (!ctx->keep_final && in_b + out_b + desc_b <= ((size_t)768 << 10) && ctx->tune_path != YALPS_PATH_GRID && ctx->tune_path != YALPS_PATH_CLUSTER &&
         plan_launch(ctx, n, Hcap, Wcap, opt->check_cycles != 0, &plan, -1.0, true) == 0 && (plan.k || plan.reg) && plan.resident) {
       auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
       size_t o = 0;
@@ -936,7 +946,8 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
     if ((rc = dev_ensure(ctx, "pos" + s, cpv * 4, &d_pos))) return rc;
     if ((rc = dev_ensure(ctx, "var" + s, cpv * 4, &d_var))) return rc;
     void *d_out = nullptr;
-    if (matrices_out && (plan.resident || ragged))
+    const bool want_mat = matrices_out != nullptr || (ctx->keep_final && n == 1 && !ragged);
+    if (want_mat && (plan.resident || ragged))
       if ((rc = dev_ensure(ctx, "matout" + s, ccells * 8, &d_out))) return rc;
 
     const double *src = matrices + (ragged ? mat_offsets[begin] : cells_upto(begin));
@@ -965,7 +976,7 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
     a.Wcap = cwcap;
     a.in = (const double *)d_in;
     a.work = (double *)d_in;  // K2 works in place on the device copy
-    a.mat_out = matrices_out ? (plan.resident ? (double *)d_out : (double *)d_in) : nullptr;
+    a.mat_out = want_mat ? (plan.resident ? (double *)d_out : (double *)d_in) : nullptr;
     a.status = (int *)d_status;
     a.value = (double *)d_value;
     a.pivots = (long long *)d_piv;
@@ -1015,7 +1026,7 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
                                 st)))
             return rc;
         }
-        a.mat_out = matrices_out ? (double *)d_in : nullptr;
+        a.mat_out = want_mat ? (double *)d_in : nullptr;
       } else if ((rc = launch_simplex(ctx, plan, a, s, st))) {
         return rc;
       }
@@ -1095,6 +1106,7 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
     if (rhs_out) CU(ctx, cudaMemcpyAsync(rhs_out + rows_upto(begin), d_rhs, crows * 8, cudaMemcpyDeviceToHost, st));
     if (pos_out) CU(ctx, cudaMemcpyAsync(pos_out + pv_upto(begin), d_pos, cpv * 4, cudaMemcpyDeviceToHost, st));
     if (var_out) CU(ctx, cudaMemcpyAsync(var_out + pv_upto(begin), d_var, cpv * 4, cudaMemcpyDeviceToHost, st));
+    if (ctx->keep_final && n == 1 && !ragged) ctx->kept_final = a.mat_out;
     if (matrices_out) {
       if (ragged) {
         for (int64_t i = begin; i < end; i++)
