@@ -97,6 +97,33 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned allocation (first-touch puts
+    the staging buffers next to the GPU's PCIe root): with 8 ranks streaming 1.1 GB per step each, host tableaus that
+    cross the socket interconnect halve the end-to-end rate.  Best effort; returns a description for the JSON line."""
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(index)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if not out:
+            return None
+        bus = out[-12:] if len(out) >= 12 else out  # 00000000:1B:00.0 -> 0000:1b:00.0
+        base = f"/sys/bus/pci/devices/{bus}"
+        node = int(open(base + "/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed)}
+    except Exception:
+        return None
+
+
 def cpu_baseline(n_lp, m, nv, neg, first, threads, salt=0x5BD1E995):
     """Times the oracle (CPU restatement of the reference loop) on n_lp LPs of the workload."""
     import numpy as np
@@ -158,6 +185,8 @@ def run_native(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -266,6 +295,7 @@ def run_native(args):
                 traffic = ncu["dram_bytes_per_launch"]
         except (OSError, KeyError, ValueError):
             pass
+        os.sched_setaffinity(0, all_cpus)  # the CPU baseline uses every host core again
         cores = host_cores()
         cpu_n = min(n, 16384)
         cpu_v, cpu_lps, _, cpu_dt = cpu_baseline(cpu_n, m, nv, neg, 0, cores)
@@ -281,7 +311,8 @@ def run_native(args):
             "lps_per_s": n * world * args.steps / (elapsed_ms * 1e-3),
             "e2e": {"value": total_pivots_step / (e2e_ms * 1e-3), "unit": "pivots/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "lps_per_s": n * world / (e2e_ms * 1e-3),
-                    "api": "yalps_solve_batch (host pointers; pinned input and output buffers; chunked H2D/kernel/D2H pipeline)"},
+                    "api": "yalps_solve_batch (host pointers; pinned input and output buffers; chunked H2D/kernel/D2H pipeline)",
+                    "pcie_gbs": (h2d + d2h) * world / (e2e_ms * 1e-3) / 1e9, "numa_binding": numa},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "smem", "achieved": achieved, "peak": smem_gbs, "unit": "GB/s",
