@@ -536,6 +536,59 @@ def test_register_kernel_options_and_special_values(engine):
         engine.set_tuning(E.PATH_AUTO, 0)
 
 
+# ---------------------------------------------------------------------------------------------- K1t tensor-memory kernel
+@pytest.mark.parametrize("m,nv,neg", [(32, 64, 0), (32, 64, 8), (32, 64, 32), (1, 1, 0), (5, 3, 2), (7, 40, 3),
+                                      (32, 7, 10), (16, 33, 4), (31, 63, 9), (20, 64, 20), (32, 1, 1), (1, 64, 1),
+                                      (8, 64, 0), (9, 64, 5), (24, 48, 0)])
+def test_tensor_memory_kernel_bit_exact(engine, m, nv, neg):
+    """K1t: one warp per LP, tableau rows in tensor memory (at most 33 x 65); more LPs than resident warps so
+    that the queue, TMEM reuse across LPs and all four lane quarters are exercised."""
+    n = 4 * 148 * 4 + 37 if (m, nv) == (32, 64) else 200
+    mats = O.generate_synthetic(78000, n, m, nv, neg)
+    exp = oracle_batch(mats, m + 1, nv + 1)
+    engine.set_tuning(E.PATH_TMEM, 0)
+    try:
+        got = engine.solve_batch(mats, m + 1, nv + 1, want_matrices=True)
+    finally:
+        engine.set_tuning(E.PATH_AUTO, 0)
+    assert_batch_equal(got, exp, f"tmem {m}x{nv}")
+
+
+def test_tensor_memory_kernel_options_special_values_and_sparse(engine):
+    H, W = 4, 5
+    t = np.zeros((4, H * W))
+    t[0].reshape(H, W)[0, 1] = 1.0
+    t[0].reshape(H, W)[1:, 1] = -1.0
+    t[0].reshape(H, W)[1:, 0] = 1.0
+    t[1].reshape(H, W)[1, 0] = -1.0
+    t[1].reshape(H, W)[1, 1:] = 1.0
+    t[2].reshape(H, W)[:] = [[0.0, 3.0, 2.0, -0.0, 1.0], [4.0, 1.0, 1e-16, 1.0000000000000001e-16, -0.0],
+                             [5.0, 2e-16, 1.0, -1e-17, 3.0], [6.0, -0.0, 2.0, 1.0, 1e-15]]
+    t[3].reshape(H, W)[:] = [[0, -1, -1, 2, 2], [-1, -1, -1, -1, -1], [-1, -1, -1, -1, -1], [3, 1, 1, 1, 1]]
+    mats = O.generate_synthetic(5, 64, 32, 64, 8)
+    # sparse tableaus (zero coefficients: skipped rows, flushed pivot-row cells, signed zeros)
+    rng = np.random.default_rng(3)
+    sparse = O.generate_synthetic(9, 96, 32, 64, 6).reshape(96, 33, 65).copy()
+    mask = rng.random(sparse.shape) < 0.6
+    mask[:, :, 0] = False
+    sparse[mask] = 0.0
+    sparse[:, 1:, 1:][rng.random(sparse[:, 1:, 1:].shape) < 0.05] = -0.0
+    sparse = sparse.reshape(96, -1)
+    engine.set_tuning(E.PATH_TMEM, 0)
+    try:
+        assert_batch_equal(engine.solve_batch(t, H, W, want_matrices=True), oracle_batch(t, H, W), "tmem special")
+        assert_batch_equal(engine.solve_batch(sparse, 33, 65, want_matrices=True), oracle_batch(sparse, 33, 65), "tmem sparse")
+        for mp in (0, 1, 5, 11.5, math.inf):
+            for prec in (1e-8, 1e-3, 0.0):
+                exp = oracle_batch(mats, 33, 65, max_pivots=mp, precision=prec)
+                got = engine.solve_batch(mats, 33, 65, E.make_options(max_pivots=mp, precision=prec), want_matrices=True)
+                assert_batch_equal(got, exp, f"tmem maxPivots={mp} precision={prec}")
+        with pytest.raises(Exception):
+            engine.solve_batch(np.zeros(34 * 65), 34, 65)  # one row too many for the tensor-memory kernel
+    finally:
+        engine.set_tuning(E.PATH_AUTO, 0)
+
+
 def test_ragged_batch_mixed_sizes_are_grouped(engine):
     """A ragged batch with tiny, medium and beyond-shared-memory tableaus: each size class gets its own kernel
     configuration (K1 of several widths, K2/K4), results come back in the caller's order."""

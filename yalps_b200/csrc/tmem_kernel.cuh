@@ -1,0 +1,525 @@
+// tmem_kernel.cuh -- K1t: one small LP per warp with the tableau resident in TENSOR MEMORY.
+//
+// K1 (kernels.cuh) keeps a tableau in shared memory and is bound by the shared-memory data pipe: every cell goes
+// through it twice per pivot (128 B/clk/SM).  Blackwell's tensor memory (256 KB per SM, 128 lanes x 512 32-bit
+// columns) is normally the accumulator store of tcgen05.mma, but `tcgen05.ld/st.32x32b` make it a lane-private
+// scratchpad: lane i of warp w reads/writes TMEM lane 32*(w%4)+i.  scripts/micro/tmem_stream.cu measures 800 GB/s
+// per SM (read + write) for the ld - mul - sub - st pattern of the rank-1 update against 243 GB/s through shared
+// memory, so the simplex pivot (src/simplex.ts:5-39) of a tableau whose columns are OWNED by lanes never has to
+// touch shared memory for the tableau body:
+//
+//   * lane l owns the coefficient columns 2l+1, 2l+2 (two fp64 = four TMEM columns per row);
+//     rows 1..H-1 live in TMEM (row r at columns 4(r-1)..4(r-1)+3 of the warp's lane quarter);
+//   * row 0 (objective row) lives in registers (two cells per lane), the RHS column in registers (lane l owns row
+//     l+1), M[0,0] redundantly in every lane;
+//   * only the pivot column crosses lanes.  It goes through a 33-entry shared-memory buffer: its owner lane
+//     stores the cells, every lane reads back "its" row.  In phase 2 the NEXT entering column is known as soon as
+//     the objective row has been updated (registers, before the row pass), so the extraction is fused into the
+//     rank-1 pass (two predicated stores per row); phase 1 needs the updated leaving row first and extracts the
+//     column in a separate read-only pass.
+//   * the new pivot-column cells (-coef/q, lane-distributed after the division) return to their owner lane the
+//     same way: {coef, -coef/q} pairs are broadcast loads in the row pass.
+//
+// A CTA is four warps = the four lane quarters of a 128-column allocation; each warp solves its own LPs (no CTA
+// barrier in the loop) and four CTAs share an SM: 16 LPs per SM in flight.  Limits: H <= 33, W <= 65, no
+// checkCycles, no node mode.  Same selection rules, skip rules and rounding sequence as simplex_device.cuh, and
+// bit-identical results (tests/test_gpu_simplex.py).
+#pragma once
+
+#include "kernels.cuh"
+
+namespace yalps {
+
+constexpr int kTmemMaxRows = 33;   // rows 1..32 <-> lanes 0..31 for the RHS column, 32 rows x 4 columns of TMEM
+constexpr int kTmemMaxCols = 65;   // 64 coefficient columns = 32 lanes x 2
+constexpr int kTmemColumns = 128;  // TMEM columns per CTA (power of two >= 32)
+constexpr int kTmemWarps = 4;
+constexpr int kTmemCtasPerSm = 512 / kTmemColumns;
+
+// shared memory per warp
+struct TmemWarpSmem {
+  double2 cb[kTmemMaxRows + 7];  // [r] = {pivot-column coefficient or 0 (row left alone), new pivot-column cell}
+  double colx[kTmemMaxRows + 7];  // entering column M[r, col], r = 0..H-1
+  int var[kTmemMaxCols + kTmemMaxRows + 2];
+};
+
+// ---- tcgen05 wrappers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void tm_ld4(unsigned taddr, unsigned &a, unsigned &b, unsigned &c, unsigned &d) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(a), "=r"(b), "=r"(c), "=r"(d)
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tm_ld2(unsigned taddr, unsigned &a, unsigned &b) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(taddr));
+}
+__device__ __forceinline__ void tm_st4(unsigned taddr, unsigned a, unsigned b, unsigned c, unsigned d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// The loaded registers are operands of the wait so that no use of them can be scheduled in front of it.
+__device__ __forceinline__ void tm_wait_ld(unsigned (&v)[4]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3])::"memory");
+}
+template <int N>
+__device__ __forceinline__ void tm_wait_ld(unsigned (&v)[N][4]) {
+  static_assert(N <= 8, "at most 32 registers");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < N; i++) asm volatile("" : "+r"(v[i][0]), "+r"(v[i][1]), "+r"(v[i][2]), "+r"(v[i][3])::"memory");
+}
+template <int N>
+__device__ __forceinline__ void tm_wait_ld(unsigned (&v)[N][2]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < N; i++) asm volatile("" : "+r"(v[i][0]), "+r"(v[i][1])::"memory");
+}
+__device__ __forceinline__ void tm_store_row(unsigned taddr, double x0, double x1) {
+  tm_st4(taddr, (unsigned)__double2loint(x0), (unsigned)__double2hiint(x0), (unsigned)__double2loint(x1),
+         (unsigned)__double2hiint(x1));
+}
+
+// RU = 8 rows (32 TMEM columns) move with ONE tcgen05.ld / tcgen05.st.
+__device__ __forceinline__ void tm_ld32(unsigned taddr, unsigned (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tm_st32(unsigned taddr, const unsigned (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tm_wait_ld32(unsigned (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; i += 8)
+    asm volatile("" : "+r"(v[i]), "+r"(v[i + 1]), "+r"(v[i + 2]), "+r"(v[i + 3]), "+r"(v[i + 4]), "+r"(v[i + 5]),
+                      "+r"(v[i + 6]), "+r"(v[i + 7])::"memory");
+}
+
+// Per-pivot lane state of the rank-1 pass.
+struct TmemPivot {
+  double pn0, pn1;   // normalised pivot-row cells of my two columns (0.0 where the old cell was flushed)
+  bool st0, st1;     // the rank-1 pass rewrites my first / second cell
+  bool own0, own1;   // my first / second column is the pivot column: its cells become cb[r].y
+  bool ex0, ex1;     // my first / second column is the NEXT entering column: its updated cells go to colx[r]
+};
+
+// Eight rows r0..r0+7 of the rank-1 update.  cc[i] = {coef, cn}: coef == 0 leaves the row alone (:31); cn is the new
+// value of the row's pivot-column cell (the old one for rows that are left alone).
+// Fast form: every lane rewrites both cells of every row (dense pivot row, eight active rows), EC = which of my
+// two columns can be the pivot column.
+template <int EC>
+__device__ __forceinline__ void tmem_block_fast(unsigned t0, const double2 (&cc)[8], double *colx_r0, const TmemPivot &p) {
+  unsigned v[32];
+  tm_ld32(t0, v);
+  tm_wait_ld32(v);
+  const bool own = EC ? p.own1 : p.own0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    double x0 = __hiloint2double((int)v[4 * i + 1], (int)v[4 * i]), x1 = __hiloint2double((int)v[4 * i + 3], (int)v[4 * i + 2]);
+    x0 = __dsub_rn(x0, __dmul_rn(cc[i].x, p.pn0));
+    x1 = __dsub_rn(x1, __dmul_rn(cc[i].x, p.pn1));
+    if (EC == 0 && own) x0 = cc[i].y;
+    if (EC == 1 && own) x1 = cc[i].y;
+    if (p.ex0) colx_r0[i] = x0;
+    if (p.ex1) colx_r0[i] = x1;
+    v[4 * i] = (unsigned)__double2loint(x0);
+    v[4 * i + 1] = (unsigned)__double2hiint(x0);
+    v[4 * i + 2] = (unsigned)__double2loint(x1);
+    v[4 * i + 3] = (unsigned)__double2hiint(x1);
+  }
+  tm_st32(t0, v);
+}
+
+// General form: per-cell predicates, rows with coef == 0 untouched.
+__device__ __forceinline__ void tmem_block_general(unsigned t0, const double2 (&cc)[8], double *colx_r0, const TmemPivot &p) {
+  unsigned v[32];
+  tm_ld32(t0, v);
+  tm_wait_ld32(v);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    double x0 = __hiloint2double((int)v[4 * i + 1], (int)v[4 * i]), x1 = __hiloint2double((int)v[4 * i + 3], (int)v[4 * i + 2]);
+    if (cc[i].x != 0.0) {
+      if (p.st0) x0 = __dsub_rn(x0, __dmul_rn(cc[i].x, p.pn0));
+      if (p.st1) x1 = __dsub_rn(x1, __dmul_rn(cc[i].x, p.pn1));
+    }
+    if (p.own0) x0 = cc[i].y;
+    if (p.own1) x1 = cc[i].y;
+    if (p.ex0) colx_r0[i] = x0;
+    if (p.ex1) colx_r0[i] = x1;
+    v[4 * i] = (unsigned)__double2loint(x0);
+    v[4 * i + 1] = (unsigned)__double2hiint(x0);
+    v[4 * i + 2] = (unsigned)__double2loint(x1);
+    v[4 * i + 3] = (unsigned)__double2hiint(x1);
+  }
+  tm_st32(t0, v);
+}
+
+// Rank-1 update of the TMEM rows 1..H-1 in blocks of eight (rows past H-1 in the last block: cb = {0, 0}).
+// dense: every lane rewrites both of its cells; ec: which cell of the owner lane is the pivot column.
+__device__ __forceinline__ void tmem_update(unsigned trow1, int H, const double2 *cb, double *colx, const TmemPivot &p,
+                                            bool dense, int ec) {
+  for (int r0 = 1; r0 < H; r0 += 8) {
+    const unsigned t0 = trow1 + 4u * (unsigned)(r0 - 1);
+    double2 cc[8];
+    bool all_on = true;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      cc[i] = cb[r0 + i];
+      all_on &= cc[i].x != 0.0;
+    }
+    if (dense && all_on) {
+      if (ec == 0)
+        tmem_block_fast<0>(t0, cc, colx + r0, p);
+      else
+        tmem_block_fast<1>(t0, cc, colx + r0, p);
+    } else {
+      tmem_block_general(t0, cc, colx + r0, p);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tmem(const BatchArgs a) {
+  __shared__ __align__(16) TmemWarpSmem s_warp[kTmemWarps];
+  __shared__ unsigned s_tmem_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double precision = a.precision, INF = d_inf();
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(&s_tmem_base)),
+                 "n"(kTmemColumns)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // this warp's lane quarter; row r of the tableau starts at column 4(r-1)
+  const unsigned trow1 = s_tmem_base + ((unsigned)(warp & 3) * 32u << 16);
+
+  double2 *cb = s_warp[warp].cb;
+  double *colx = s_warp[warp].colx;
+  int *var = s_warp[warp].var;
+  const long long nwarps = (long long)gridDim.x * kTmemWarps;
+
+  for (long long static_lp = (long long)blockIdx.x * kTmemWarps + warp;; static_lp += nwarps) {
+    long long lp = static_lp;
+    if (a.counter) {
+      unsigned long long got = 0;
+      if (lane == 0) got = atomicAdd(a.counter, 1ULL);
+      lp = (long long)__shfl_sync(0xffffffffu, got, 0);
+    }
+    if (lp >= a.n) break;
+    if (a.index) lp = a.index[lp];
+    int H, W;
+    size_t moff, roff, poff;
+    if (a.heights) {
+      H = a.heights[lp];
+      W = a.widths[lp];
+      moff = (size_t)a.mat_off[lp];
+      roff = (size_t)a.rhs_off[lp];
+      poff = (size_t)a.pos_off[lp];
+    } else {
+      H = a.H;
+      W = a.W;
+      moff = (size_t)lp * H * W;
+      roff = (size_t)lp * H;
+      poff = (size_t)lp * (W + H);
+    }
+    const int Wm1 = W - 1;
+    const int j0 = 2 * lane;
+    const bool v0 = j0 < Wm1, v1 = j0 + 1 < Wm1;  // my two columns exist
+    const bool has_b = lane + 1 < H;               // I own the RHS cell of row lane+1
+
+    // ---- load: global -> registers -> TMEM (16 bytes per lane per row, 8 rows in flight)
+    const double *src = a.in + moff;
+    double o0 = v0 ? src[1 + j0] : 0.0, o1 = v1 ? src[2 + j0] : 0.0;
+    double bv = has_b ? src[(size_t)(lane + 1) * W] : 0.0;
+    double b0 = src[0];
+    for (int r0 = 1; r0 < H; r0 += 8) {
+      double x[8][2];
+      const double *rp = src + (size_t)r0 * W + 1 + j0;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        x[i][0] = (r0 + i < H && v0) ? rp[0] : 0.0;
+        x[i][1] = (r0 + i < H && v1) ? rp[1] : 0.0;
+        rp += W;
+      }
+      unsigned v[32];
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        v[4 * i] = (unsigned)__double2loint(x[i][0]);
+        v[4 * i + 1] = (unsigned)__double2hiint(x[i][0]);
+        v[4 * i + 2] = (unsigned)__double2loint(x[i][1]);
+        v[4 * i + 3] = (unsigned)__double2hiint(x[i][1]);
+      }
+      tm_st32(trow1 + 4u * (unsigned)(r0 - 1), v);
+    }
+    for (int k = lane; k < W + H; k += 32) var[k] = k;
+    // rows past H-1 in the last block of eight: garbage in, garbage out, never read (a non-zero coefficient keeps the
+    // block on the straight-line path)
+    for (int k = H + lane; k < kTmemMaxRows + 7; k += 32) cb[k] = make_double2(1.0, 0.0);
+    tm_wait_st();
+    __syncwarp();
+
+    int status = ST_CYCLED;
+    double value = d_nan();
+    long long p1 = 0, p2 = 0, iter = 0;
+    int phase = 1;
+    bool have_col = false;  // `col` (and colx) were prepared by the previous pivot
+    int col = kNone;
+
+    // entering column (phase 2): first index of the largest reduced cost above precision (:71-79)
+    auto select_entering = [&]() -> int {
+      double best = -INF;
+      int bi = kNone;
+      if (v0 && o0 > precision) {
+        best = o0;
+        bi = j0 + 1;
+      }
+      if (v1 && o1 > precision && o1 > best) {
+        best = o1;
+        bi = j0 + 2;
+      }
+      const unsigned long long key = bi == kNone ? no_key<true>() : order_key(best);
+      return warp_best<true>((unsigned)(key >> 32), (unsigned)key, bi).idx;
+    };
+    // read-only pass: column c of rows 0..H-1 -> colx
+    auto extract_column = [&](int c) {
+      const int l = (c - 1) >> 1, e = (c - 1) & 1;
+      if (lane == l) colx[0] = e ? o1 : o0;
+      for (int r0 = 1; r0 < H; r0 += 8) {
+        unsigned v[8][2];
+#pragma unroll
+        for (int i = 0; i < 8; i++) tm_ld2(trow1 + 4u * (unsigned)(r0 - 1 + i) + 2u * (unsigned)e, v[i][0], v[i][1]);
+        tm_wait_ld(v);
+        if (lane == l) {
+#pragma unroll
+          for (int i = 0; i < 8; i++) colx[r0 + i] = __hiloint2double((int)v[i][1], (int)v[i][0]);
+        }
+      }
+      __syncwarp();
+    };
+
+    for (;;) {
+      if (!((double)iter < a.max_pivots)) break;
+      int row;
+      double pr0 = 0.0, pr1 = 0.0;  // old pivot row cells of my two columns
+      double cmine = 0.0;           // pivot-column cell of my RHS row
+      if (phase == 1) {
+        // leaving row: first index of the most negative RHS below -precision (:111-119)
+        const bool cand = has_b && bv < -precision;
+        row = warp_best<false>(cand ? (unsigned)(order_key(bv) >> 32) : 0xffffffffu,
+                               cand ? (unsigned)order_key(bv) : 0xffffffffu, cand ? lane + 1 : kNone)
+                  .idx;
+        if (row == kNone) {  // feasible: phase 2 with a fresh counter (:120, :67-69)
+          phase = 2;
+          iter = 0;
+          have_col = false;
+          continue;
+        }
+        // entering column: first index of max -M[0,c]/M[row,c] over M[row,c] < -precision (:123-134)
+        {
+          unsigned v[4];
+          tm_ld4(trow1 + 4u * (unsigned)(row - 1), v[0], v[1], v[2], v[3]);
+          tm_wait_ld(v);
+          pr0 = __hiloint2double((int)v[1], (int)v[0]);
+          pr1 = __hiloint2double((int)v[3], (int)v[2]);
+        }
+        double best = -INF;
+        int bi = kNone;
+        if (v0 && pr0 < -precision) {
+          const double ratio = div_rn(-o0, pr0);
+          if (ratio > best) {
+            best = ratio;
+            bi = j0 + 1;
+          }
+        }
+        if (v1 && pr1 < -precision) {
+          const double ratio = div_rn(-o1, pr1);
+          if (ratio > best) {
+            best = ratio;
+            bi = j0 + 2;
+          }
+        }
+        const unsigned long long key = bi == kNone ? no_key<true>() : order_key(best);
+        col = warp_best<true>((unsigned)(key >> 32), (unsigned)key, bi).idx;
+        if (col == kNone) {
+          status = ST_INFEASIBLE;
+          break;
+        }
+        extract_column(col);
+        cmine = has_b ? colx[lane + 1] : 0.0;
+      } else {
+        if (!have_col) {
+          col = select_entering();
+          if (col != kNone) extract_column(col);
+        }
+        if (col == kNone) {
+          status = ST_OPTIMAL;
+          value = round_to_precision(b0, precision);
+          break;
+        }
+        cmine = has_b ? colx[lane + 1] : 0.0;
+        // leaving row: ratio test with the reference's early break (:83-95) == lowest r whose ratio is <= precision
+        // if any, else first index of the minimum ratio
+        bool cand = false;
+        double keyv = INF;
+        if (has_b && cmine > precision) {
+          const double ratio = div_rn(bv, cmine);
+          if (ratio < INF) {  // +inf and NaN never win
+            cand = true;
+            keyv = (ratio <= precision) ? -INF : ratio;
+          }
+        }
+        const unsigned long long key = cand ? order_key(keyv) : no_key<false>();
+        row = warp_best<false>((unsigned)(key >> 32), (unsigned)key, cand ? lane + 1 : kNone).idx;
+        if (row == kNone) {
+          status = ST_UNBOUNDED;
+          value = (double)col;
+          break;
+        }
+        unsigned v[4];
+        tm_ld4(trow1 + 4u * (unsigned)(row - 1), v[0], v[1], v[2], v[3]);
+        tm_wait_ld(v);
+        pr0 = __hiloint2double((int)v[1], (int)v[0]);
+        pr1 = __hiloint2double((int)v[3], (int)v[2]);
+      }
+
+      // ---- pivot(row, col) (:5-39)
+      const int jc = col - 1, lc = jc >> 1, ec = jc & 1;
+      const double q = colx[row];
+      const double c0raw = colx[0];
+#ifdef YALPS_TMEM_PLAIN_DIV
+      struct {
+        double d;
+        __device__ __forceinline__ double quot(double n) const { return __ddiv_rn(n, d); }
+      } rq{q};
+#else
+      const Recip rq(q);  // one reciprocal refinement for the four quotients of this lane
+#endif
+      // normalised pivot row cells of my columns; the pivot cell itself becomes 1/q
+      const double x0 = (j0 == jc) ? 1.0 : pr0, x1 = (j0 + 1 == jc) ? 1.0 : pr1;
+      const bool n0 = v0 && fabs(x0) > kTiny, n1 = v1 && fabs(x1) > kTiny;
+      const double pn0 = n0 ? rq.quot(x0) : 0.0, pn1 = n1 ? rq.quot(x1) : 0.0;
+      const bool own0 = lane == lc && ec == 0, own1 = lane == lc && ec == 1;
+      const bool st0 = n0 && !own0, st1 = n1 && !own1;  // cells the rank-1 pass rewrites
+      // rows 1..H-1: one lane each (the lane of the pivot row normalises the RHS cell instead)
+      const bool is_prow = has_b && lane + 1 == row;
+      const double num = is_prow ? bv : -cmine;
+      const bool nzq = has_b && fabs(num) > kTiny;  // false for NaN, as in the reference
+      const double quo = nzq ? rq.quot(num) : 0.0;
+      const double coef_mine = (nzq && !is_prow) ? cmine : 0.0;  // 0 = my row is skipped (:31) or is the pivot row
+      // the pivot row takes part in the row pass with a throw-away coefficient (it is rewritten afterwards)
+      if (has_b) cb[lane + 1] = make_double2(is_prow ? 1.0 : coef_mine, coef_mine != 0.0 ? quo : cmine);
+      // row 0 (objective row): every lane redundantly
+      const bool act0 = fabs(c0raw) > kTiny;
+      const double cn0 = act0 ? rq.quot(-c0raw) : 0.0;
+      const double p0 = __shfl_sync(0xffffffffu, quo, row - 1);        // normalised RHS of the pivot row
+      const bool nz0 = __shfl_sync(0xffffffffu, nzq ? 1 : 0, row - 1);  // ... was above 1e-16
+      if (lane == 0) {  // basis bookkeeping (:7-12)
+        const int leaving = var[W + row];
+        var[W + row] = var[col];
+        var[col] = leaving;
+      }
+      __syncwarp();  // cb complete; every lane has read q, c0raw and its colx cell
+
+      // objective row and RHS column in registers
+      if (act0) {
+        if (st0) o0 = __dsub_rn(o0, __dmul_rn(c0raw, pn0));
+        if (st1) o1 = __dsub_rn(o1, __dmul_rn(c0raw, pn1));
+        if (own0) o0 = cn0;
+        if (own1) o1 = cn0;
+        if (nz0) b0 = __dsub_rn(b0, __dmul_rn(c0raw, p0));
+      }
+      if (is_prow)
+        bv = quo;
+      else if (coef_mine != 0.0 && nz0)
+        bv = __dsub_rn(bv, __dmul_rn(coef_mine, p0));
+
+      // phase 2: the next entering column is already decided; its cells are collected during the row pass
+      int col_next = kNone;
+      bool ex0 = false, ex1 = false;
+      have_col = false;
+      if (phase == 2) {
+        col_next = select_entering();
+        have_col = col_next != col;  // (a re-entering pivot column takes the separate extraction pass)
+        if (col_next != kNone && have_col) {
+          const int ln = (col_next - 1) >> 1, en = (col_next - 1) & 1;
+          ex0 = lane == ln && en == 0;
+          ex1 = lane == ln && en == 1;
+          if (ex0) colx[0] = o0;
+          if (ex1) colx[0] = o1;
+        }
+      }
+
+      // rank-1 pass over the TMEM rows; a lane's padding cells (zeros, never read) count as rewritable
+      const bool dense = __all_sync(0xffffffffu, (st0 || own0 || !v0) && (st1 || own1 || !v1));
+      const TmemPivot pv{pn0, pn1, st0, st1, own0, own1, ex0, ex1};
+      tmem_update(trow1, H, cb, colx, pv, dense, ec);
+      tm_wait_st();  // the row pass stored a throw-away value in the pivot row: order the real one behind it
+      tm_store_row(trow1 + 4u * (unsigned)(row - 1), pn0, pn1);  // (:19,22,25)
+      if (ex0) colx[row] = pn0;
+      if (ex1) colx[row] = pn1;
+      tm_wait_st();
+      __syncwarp();
+      col = col_next;
+
+      if (phase == 1)
+        p1++;
+      else
+        p2++;
+      iter++;
+    }
+
+    // ---- outputs
+    if (lane == 0) {
+      if (a.status) a.status[lp] = status;
+      if (a.value) a.value[lp] = value;
+      if (a.pivots) {
+        a.pivots[2 * lp] = p1;
+        a.pivots[2 * lp + 1] = p2;
+      }
+      if (a.rhs_out) a.rhs_out[roff] = b0;
+    }
+    if (a.rhs_out && has_b) a.rhs_out[roff + lane + 1] = bv;
+    if (a.pos_out)
+      for (int k = lane; k < W + H; k += 32) a.pos_out[poff + var[k]] = k;
+    if (a.var_out)
+      for (int k = lane; k < W + H; k += 32) a.var_out[poff + k] = var[k];
+    if (a.mat_out) {
+      double *dst = a.mat_out + moff;
+      if (lane == 0) dst[0] = b0;
+      if (has_b) dst[(size_t)(lane + 1) * W] = bv;
+      if (v0) dst[1 + j0] = o0;
+      if (v1) dst[2 + j0] = o1;
+      for (int r = 1; r < H; r++) {
+        unsigned v[4];
+        tm_ld4(trow1 + 4u * (unsigned)(r - 1), v[0], v[1], v[2], v[3]);
+        tm_wait_ld(v);
+        if (v0) dst[(size_t)r * W + 1 + j0] = __hiloint2double((int)v[1], (int)v[0]);
+        if (v1) dst[(size_t)r * W + 2 + j0] = __hiloint2double((int)v[3], (int)v[2]);
+      }
+    }
+    __syncwarp();
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem_base), "n"(kTmemColumns) : "memory");
+}
+
+}  // namespace yalps

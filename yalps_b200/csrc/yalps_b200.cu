@@ -26,6 +26,7 @@
 #include "cluster_kernel.cuh"
 #include "grid_kernel.cuh"
 #include "reg_kernel.cuh"
+#include "tmem_launch.h"
 
 using namespace yalps;
 
@@ -209,6 +210,7 @@ int default_warps(long long cells, bool resident) {
 
 struct LaunchPlan {
   bool reg = false;  // K1r: tableau in registers (small LPs)
+  bool tmem = false;  // K1t: tableau in tensor memory, one LP per warp (tmem_kernel.cuh)
   bool small_for_grid = false;  // few LPs outside shared memory, yet small enough that one row-split CTA beats K4
   bool resident;
   const KernelEntry *k;
@@ -233,6 +235,20 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
   }
   const bool grid_ok = tune_path == YALPS_PATH_GRID || (tune_path == YALPS_PATH_AUTO && n <= 16);
   plan->reg = false;
+  plan->tmem = false;
+  if (allow_reg && tmem_kernel_fits(Hcap, Wcap) && !check_cycles && tune_path == YALPS_PATH_TMEM) {
+    plan->tmem = true;
+    plan->resident = true;
+    plan->k = nullptr;
+    plan->smem = tmem_kernel_dynamic_smem();
+    CU(ctx, raise_smem_limit(ctx->device, tmem_kernel_fn(), (int)plan->smem));
+    const long long ctas = (long long)tmem_kernel_ctas_per_sm() * ctx->prop.multiProcessorCount;
+    plan->grid = (int)std::max(1LL, std::min(ctas, (n + tmem_kernel_warps() - 1) / tmem_kernel_warps()));
+    return 0;
+  }
+  if (tune_path == YALPS_PATH_TMEM)
+    return fail(ctx, YALPS_ERR_TOO_LARGE, "tableau %dx%d does not fit the tensor-memory kernel (max %dx%d, no checkCycles, no node mode)",
+                Hcap, Wcap, 33, 65);
   if (allow_reg && Hcap <= kRegMaxRows && Wcap <= kRegMaxCols && !check_cycles &&
       tune_path == YALPS_PATH_REG) {  // explicit only: measured slower than K1 (see reg_kernel.cuh)
     auto it = ctx->occ_cache.find("reg33");
@@ -346,7 +362,7 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
 // K4 (whole grid per LP, LPs one after another) beats K2 (one CTA per LP) when the tableaus do not fit in
 // shared memory and there are too few of them to give every SM its own LP.
 bool use_grid_path(const yalps_ctx *ctx, long long n, const LaunchPlan &plan) {
-  if (plan.reg) return false;
+  if (plan.reg || plan.tmem) return false;
   if (ctx->tune_path == YALPS_PATH_GRID || plan.k == nullptr) return true;
   if (ctx->tune_path != YALPS_PATH_AUTO && ctx->tune_path != YALPS_PATH_CLUSTER) return false;
   return !plan.resident && n <= 16 && !plan.small_for_grid;
@@ -364,7 +380,8 @@ int hist_capacity(const yalps_options *opt) {
 int launch_simplex(yalps_ctx *ctx, const LaunchPlan &plan, BatchArgs &args, const std::string &slot,
                    cudaStream_t stream) {
   args.counter = nullptr;
-  if (args.n > plan.grid) {  // more LPs than CTAs: dynamic queue (pivot counts vary per LP)
+  const long long solvers = plan.tmem ? (long long)plan.grid * tmem_kernel_warps() : plan.grid;  // K1t: one LP per warp
+  if (args.n > solvers) {  // more LPs than CTAs: dynamic queue (pivot counts vary per LP)
     void *counter = nullptr;
     if (int rc = dev_ensure(ctx, "counter" + slot, 8, &counter)) return rc;
     CU(ctx, cudaMemsetAsync(counter, 0, 8, stream));
@@ -376,6 +393,11 @@ int launch_simplex(yalps_ctx *ctx, const LaunchPlan &plan, BatchArgs &args, cons
     args.hist = (int *)hist;
   } else {
     args.hist = nullptr;
+  }
+  if (plan.tmem) {
+    CU(ctx, launch_simplex_tmem(args, plan.grid, stream));
+    ctx->launches++;
+    return 0;
   }
   if (plan.reg) {
     k_simplex_reg<kRegMaxRows><<<plan.grid, 32, 0, stream>>>(args);
@@ -483,7 +505,7 @@ int launch_cluster(yalps_ctx *ctx, const ClusterPlan &plan, BatchArgs &args, con
 bool want_cluster(const yalps_ctx *ctx, long long n, const LaunchPlan &plan, const ClusterPlan &cp) {
   if (!cp.k) return false;
   if (ctx->tune_path == YALPS_PATH_CLUSTER) return true;
-  if (ctx->tune_path != YALPS_PATH_AUTO || plan.reg) return false;
+  if (ctx->tune_path != YALPS_PATH_AUTO || plan.reg || plan.tmem) return false;
   return !plan.resident && n <= 2LL * std::max(1, cp.clusters);
 }
 
@@ -493,7 +515,7 @@ int maybe_cluster(yalps_ctx *ctx, long long n, int Hcap, int Wcap, const LaunchP
                   const std::string &slot, cudaStream_t stream) {
   const bool forced = ctx->tune_path == YALPS_PATH_CLUSTER;
   if (!plan && !forced) return 0;
-  if (plan && (forced || ctx->tune_path != YALPS_PATH_AUTO || plan->resident || plan->reg)) return 0;
+  if (plan && (forced || ctx->tune_path != YALPS_PATH_AUTO || plan->resident || plan->reg || plan->tmem)) return 0;
   ClusterPlan cp;
   if (int rc = plan_cluster(ctx, Hcap, Wcap, &cp)) return rc;
   if (forced) {
@@ -598,7 +620,7 @@ int yalps_device_info(const yalps_ctx *ctx, int32_t *sm_count, int32_t *smem_per
 
 int yalps_set_tuning(yalps_ctx *ctx, int32_t path, int32_t threads_per_lp) {
   if (!ctx) return YALPS_ERR_ARGUMENT;
-  if (path < 0 || path > YALPS_PATH_CLUSTER) return fail(ctx, YALPS_ERR_ARGUMENT, "bad path %d", path);
+  if (path < 0 || path > YALPS_PATH_TMEM) return fail(ctx, YALPS_ERR_ARGUMENT, "bad path %d", path);
   ctx->tune_path = path;
   ctx->tune_threads = threads_per_lp;
   return 0;
@@ -821,7 +843,7 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
     const size_t desc_b = ragged ? (size_t)n * 32 + 64 : 0;
     LaunchPlan plan;
     if (!ctx->keep_final && in_b + out_b + desc_b <= ((size_t)768 << 10) && ctx->tune_path != YALPS_PATH_GRID && ctx->tune_path != YALPS_PATH_CLUSTER &&
-        plan_launch(ctx, n, Hcap, Wcap, opt->check_cycles != 0, &plan, -1.0, true) == 0 && (plan.k || plan.reg) && plan.resident) {
+        plan_launch(ctx, n, Hcap, Wcap, opt->check_cycles != 0, &plan, -1.0, true) == 0 && (plan.k || plan.reg || plan.tmem) && plan.resident) {
       auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
       size_t o = 0;
       const size_t o_in = o; o += up16(in_b);
