@@ -8,8 +8,9 @@ import yalps_b200
 from yalps_b200 import engine as E
 eng = yalps_b200.Engine(0)
 stream = torch.cuda.current_stream().cuda_stream
-shapes = [(32, 64, 65536), (32, 64, 262144), (24, 48, 65536), (16, 32, 65536), (32, 32, 65536), (8, 64, 65536)]
-if len(sys.argv) > 1: shapes = shapes[: int(sys.argv[1])]
+shapes = [(32, 64, 65536), (32, 64, 262144), (24, 48, 65536), (16, 32, 65536), (32, 32, 65536), (8, 64, 65536), (8, 16, 65536), (16, 64, 65536),
+          (32, 16, 65536), (24, 64, 65536), (32, 48, 65536)]
+if len(sys.argv) > 1: shapes = shapes[int(sys.argv[2]) if len(sys.argv) > 2 else 0: int(sys.argv[1])]
 for (m, nv, n) in shapes:
     H, W = m + 1, nv + 1
     d = torch.empty(n * H * W, dtype=torch.float64, device="cuda")

@@ -8,17 +8,18 @@
 // memory, so the simplex pivot (src/simplex.ts:5-39) of a tableau whose columns are OWNED by lanes never has to
 // touch shared memory for the tableau body:
 //
-//   * lane l owns the coefficient columns 2l+1, 2l+2 (two fp64 = four TMEM columns per row);
-//     rows 1..H-1 live in TMEM (row r at columns 4(r-1)..4(r-1)+3 of the warp's lane quarter);
+//   * lane l owns the coefficient columns 2l+1, 2l+2 (two fp64 = four 32-bit TMEM columns per row).  Rows 1..H-1
+//     live in TMEM in blocks of eight rows = 32 TMEM columns, element-major inside a block:
+//         row r, k = r-1:  my first cell  at columns 32*(k/8)      + 2*(k%8), +1
+//                          my second cell at columns 32*(k/8) + 16 + 2*(k%8), +1
+//     so that ONE tcgen05.ld/st.x32 moves a block for the rank-1 update and ONE tcgen05.ld.x16 reads one tableau
+//     column of eight rows (the entering column, below);
 //   * row 0 (objective row) lives in registers (two cells per lane), the RHS column in registers (lane l owns row
 //     l+1), M[0,0] redundantly in every lane;
-//   * only the pivot column crosses lanes.  It goes through a 33-entry shared-memory buffer: its owner lane
-//     stores the cells, every lane reads back "its" row.  In phase 2 the NEXT entering column is known as soon as
-//     the objective row has been updated (registers, before the row pass), so the extraction is fused into the
-//     rank-1 pass (two predicated stores per row); phase 1 needs the updated leaving row first and extracts the
-//     column in a separate read-only pass.
-//   * the new pivot-column cells (-coef/q, lane-distributed after the division) return to their owner lane the
-//     same way: {coef, -coef/q} pairs are broadcast loads in the row pass.
+//   * only the pivot column crosses lanes, through shared memory: after the entering column is chosen its owner
+//     lane reads its cells of all rows (four tcgen05.ld.x16) and stores them (colx), every lane reads back "its"
+//     row; the new pivot-column cells (-coef/q, lane-distributed after the division) return to their owner lane
+//     as {coef, -coef/q} broadcast loads in the row pass.
 //
 // A CTA is four warps = the four lane quarters of a 128-column allocation; each warp solves its own LPs (no CTA
 // barrier in the loop) and four CTAs share an SM: 16 LPs per SM in flight.  Limits: H <= 33, W <= 65, no
@@ -39,47 +40,30 @@ constexpr int kTmemCtasPerSm = 512 / kTmemColumns;
 // shared memory per warp
 struct TmemWarpSmem {
   double2 cb[kTmemMaxRows + 7];  // [r] = {pivot-column coefficient or 0 (row left alone), new pivot-column cell}
-  double colx[kTmemMaxRows + 7];  // entering column M[r, col], r = 0..H-1
+  double colx_store[kTmemMaxRows + 9];  // colx = colx_store + 1: entering column M[r, col]; &colx[1] is 16-byte aligned
   int var[kTmemMaxCols + kTmemMaxRows + 2];
 };
 
 // ---- tcgen05 wrappers ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void tm_ld4(unsigned taddr, unsigned &a, unsigned &b, unsigned &c, unsigned &d) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(a), "=r"(b), "=r"(c), "=r"(d)
-               : "r"(taddr));
-}
+// (the consumers of a tcgen05.ld go through tm_wait_ld*, which takes the registers as operands so that no use of
+// them can be scheduled in front of the wait)
 __device__ __forceinline__ void tm_ld2(unsigned taddr, unsigned &a, unsigned &b) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(taddr));
 }
-__device__ __forceinline__ void tm_st4(unsigned taddr, unsigned a, unsigned b, unsigned c, unsigned d) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d)
-               : "memory");
+__device__ __forceinline__ void tm_st2(unsigned taddr, unsigned a, unsigned b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
 }
 __device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// The loaded registers are operands of the wait so that no use of them can be scheduled in front of it.
-__device__ __forceinline__ void tm_wait_ld(unsigned (&v)[4]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3])::"memory");
+__device__ __forceinline__ void tm_wait_ld4(unsigned &a, unsigned &b, unsigned &c, unsigned &d) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(a), "+r"(b), "+r"(c), "+r"(d)::"memory");
 }
-template <int N>
-__device__ __forceinline__ void tm_wait_ld(unsigned (&v)[N][4]) {
-  static_assert(N <= 8, "at most 32 registers");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < N; i++) asm volatile("" : "+r"(v[i][0]), "+r"(v[i][1]), "+r"(v[i][2]), "+r"(v[i][3])::"memory");
+__device__ __forceinline__ void tm_ld16(unsigned taddr, unsigned *v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
 }
-template <int N>
-__device__ __forceinline__ void tm_wait_ld(unsigned (&v)[N][2]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < N; i++) asm volatile("" : "+r"(v[i][0]), "+r"(v[i][1])::"memory");
-}
-__device__ __forceinline__ void tm_store_row(unsigned taddr, double x0, double x1) {
-  tm_st4(taddr, (unsigned)__double2loint(x0), (unsigned)__double2hiint(x0), (unsigned)__double2loint(x1),
-         (unsigned)__double2hiint(x1));
-}
-
-// RU = 8 rows (32 TMEM columns) move with ONE tcgen05.ld / tcgen05.st.
 __device__ __forceinline__ void tm_ld32(unsigned taddr, unsigned (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
@@ -100,12 +84,32 @@ __device__ __forceinline__ void tm_st32(unsigned taddr, const unsigned (&v)[32])
       "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
 }
-__device__ __forceinline__ void tm_wait_ld32(unsigned (&v)[32]) {
+template <int N>
+__device__ __forceinline__ void tm_wait_ld(unsigned (&v)[N]) {
+  static_assert(N % 8 == 0, "whole groups of eight registers");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-  for (int i = 0; i < 32; i += 8)
+  for (int i = 0; i < N; i += 8)
     asm volatile("" : "+r"(v[i]), "+r"(v[i + 1]), "+r"(v[i + 2]), "+r"(v[i + 3]), "+r"(v[i + 4]), "+r"(v[i + 5]),
                       "+r"(v[i + 6]), "+r"(v[i + 7])::"memory");
+}
+
+// first TMEM column (relative to the warp's base) of cell e (0/1) of row r >= 1
+__device__ __forceinline__ unsigned tm_cell(int r, int e) {
+  const unsigned k = (unsigned)(r - 1);
+  return 32u * (k >> 3) + 16u * (unsigned)e + 2u * (k & 7u);
+}
+__device__ __forceinline__ void tm_load_row(unsigned tbase, int r, double &x0, double &x1) {
+  unsigned a, b, c, d;
+  tm_ld2(tbase + tm_cell(r, 0), a, b);
+  tm_ld2(tbase + tm_cell(r, 1), c, d);
+  tm_wait_ld4(a, b, c, d);
+  x0 = __hiloint2double((int)b, (int)a);
+  x1 = __hiloint2double((int)d, (int)c);
+}
+__device__ __forceinline__ void tm_store_row(unsigned tbase, int r, double x0, double x1) {
+  tm_st2(tbase + tm_cell(r, 0), (unsigned)__double2loint(x0), (unsigned)__double2hiint(x0));
+  tm_st2(tbase + tm_cell(r, 1), (unsigned)__double2loint(x1), (unsigned)__double2hiint(x1));
 }
 
 // Per-pivot lane state of the rank-1 pass.
@@ -113,82 +117,59 @@ struct TmemPivot {
   double pn0, pn1;   // normalised pivot-row cells of my two columns (0.0 where the old cell was flushed)
   bool st0, st1;     // the rank-1 pass rewrites my first / second cell
   bool own0, own1;   // my first / second column is the pivot column: its cells become cb[r].y
-  bool ex0, ex1;     // my first / second column is the NEXT entering column: its updated cells go to colx[r]
 };
 
-// Eight rows r0..r0+7 of the rank-1 update.  cc[i] = {coef, cn}: coef == 0 leaves the row alone (:31); cn is the new
-// value of the row's pivot-column cell (the old one for rows that are left alone).
+// Eight rows r0..r0+7 (one TMEM block) of the rank-1 update.  cc[i] = {coef, cn}: coef == 0 leaves the row alone
+// (:31); cn is the new value of the row's pivot-column cell (the old one for rows that are left alone).
 // Fast form: every lane rewrites both cells of every row (dense pivot row, eight active rows), EC = which of my
 // two columns can be the pivot column.
 template <int EC>
-__device__ __forceinline__ void tmem_block_fast(unsigned t0, const double2 (&cc)[8], double *colx_r0, const TmemPivot &p) {
+__device__ __forceinline__ void tmem_block_fast(unsigned tblk, const double2 *cbr, const TmemPivot &p) {
   unsigned v[32];
-  tm_ld32(t0, v);
-  tm_wait_ld32(v);
+  tm_ld32(tblk, v);
+  double2 cc[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) cc[i] = cbr[i];
+  tm_wait_ld(v);
   const bool own = EC ? p.own1 : p.own0;
 #pragma unroll
   for (int i = 0; i < 8; i++) {
-    double x0 = __hiloint2double((int)v[4 * i + 1], (int)v[4 * i]), x1 = __hiloint2double((int)v[4 * i + 3], (int)v[4 * i + 2]);
+    double x0 = __hiloint2double((int)v[2 * i + 1], (int)v[2 * i]), x1 = __hiloint2double((int)v[16 + 2 * i + 1], (int)v[16 + 2 * i]);
     x0 = __dsub_rn(x0, __dmul_rn(cc[i].x, p.pn0));
     x1 = __dsub_rn(x1, __dmul_rn(cc[i].x, p.pn1));
     if (EC == 0 && own) x0 = cc[i].y;
     if (EC == 1 && own) x1 = cc[i].y;
-    if (p.ex0) colx_r0[i] = x0;
-    if (p.ex1) colx_r0[i] = x1;
-    v[4 * i] = (unsigned)__double2loint(x0);
-    v[4 * i + 1] = (unsigned)__double2hiint(x0);
-    v[4 * i + 2] = (unsigned)__double2loint(x1);
-    v[4 * i + 3] = (unsigned)__double2hiint(x1);
+    v[2 * i] = (unsigned)__double2loint(x0);
+    v[2 * i + 1] = (unsigned)__double2hiint(x0);
+    v[16 + 2 * i] = (unsigned)__double2loint(x1);
+    v[16 + 2 * i + 1] = (unsigned)__double2hiint(x1);
   }
-  tm_st32(t0, v);
+  tm_st32(tblk, v);
 }
 
 // General form: per-cell predicates, rows with coef == 0 untouched.
-__device__ __forceinline__ void tmem_block_general(unsigned t0, const double2 (&cc)[8], double *colx_r0, const TmemPivot &p) {
+__device__ __forceinline__ void tmem_block_general(unsigned tblk, const double2 *cbr, const TmemPivot &p) {
   unsigned v[32];
-  tm_ld32(t0, v);
-  tm_wait_ld32(v);
+  tm_ld32(tblk, v);
+  double2 cc[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) cc[i] = cbr[i];
+  tm_wait_ld(v);
 #pragma unroll
   for (int i = 0; i < 8; i++) {
-    double x0 = __hiloint2double((int)v[4 * i + 1], (int)v[4 * i]), x1 = __hiloint2double((int)v[4 * i + 3], (int)v[4 * i + 2]);
+    double x0 = __hiloint2double((int)v[2 * i + 1], (int)v[2 * i]), x1 = __hiloint2double((int)v[16 + 2 * i + 1], (int)v[16 + 2 * i]);
     if (cc[i].x != 0.0) {
       if (p.st0) x0 = __dsub_rn(x0, __dmul_rn(cc[i].x, p.pn0));
       if (p.st1) x1 = __dsub_rn(x1, __dmul_rn(cc[i].x, p.pn1));
     }
     if (p.own0) x0 = cc[i].y;
     if (p.own1) x1 = cc[i].y;
-    if (p.ex0) colx_r0[i] = x0;
-    if (p.ex1) colx_r0[i] = x1;
-    v[4 * i] = (unsigned)__double2loint(x0);
-    v[4 * i + 1] = (unsigned)__double2hiint(x0);
-    v[4 * i + 2] = (unsigned)__double2loint(x1);
-    v[4 * i + 3] = (unsigned)__double2hiint(x1);
+    v[2 * i] = (unsigned)__double2loint(x0);
+    v[2 * i + 1] = (unsigned)__double2hiint(x0);
+    v[16 + 2 * i] = (unsigned)__double2loint(x1);
+    v[16 + 2 * i + 1] = (unsigned)__double2hiint(x1);
   }
-  tm_st32(t0, v);
-}
-
-// Rank-1 update of the TMEM rows 1..H-1 in blocks of eight (rows past H-1 in the last block: cb = {0, 0}).
-// dense: every lane rewrites both of its cells; ec: which cell of the owner lane is the pivot column.
-__device__ __forceinline__ void tmem_update(unsigned trow1, int H, const double2 *cb, double *colx, const TmemPivot &p,
-                                            bool dense, int ec) {
-  for (int r0 = 1; r0 < H; r0 += 8) {
-    const unsigned t0 = trow1 + 4u * (unsigned)(r0 - 1);
-    double2 cc[8];
-    bool all_on = true;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      cc[i] = cb[r0 + i];
-      all_on &= cc[i].x != 0.0;
-    }
-    if (dense && all_on) {
-      if (ec == 0)
-        tmem_block_fast<0>(t0, cc, colx + r0, p);
-      else
-        tmem_block_fast<1>(t0, cc, colx + r0, p);
-    } else {
-      tmem_block_general(t0, cc, colx + r0, p);
-    }
-  }
+  tm_st32(tblk, v);
 }
 
 __global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tmem(const BatchArgs a) {
@@ -207,13 +188,15 @@ __global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tme
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  // this warp's lane quarter; row r of the tableau starts at column 4(r-1)
-  const unsigned trow1 = s_tmem_base + ((unsigned)(warp & 3) * 32u << 16);
+  const unsigned tbase = s_tmem_base + ((unsigned)(warp & 3) * 32u << 16);  // this warp's lane quarter
 
   double2 *cb = s_warp[warp].cb;
-  double *colx = s_warp[warp].colx;
+  double *colx = s_warp[warp].colx_store + 1;
   int *var = s_warp[warp].var;
   const long long nwarps = (long long)gridDim.x * kTmemWarps;
+  // per-phase pivot budget as an integer: (double)iter < maxPivots  <=>  iter < ceil(maxPivots)  (:69,:109)
+  long long budget = 0;
+  if (a.max_pivots > 0.0) budget = a.max_pivots >= 9.0e18 ? 0x7fffffffffffffffLL : (long long)ceil(a.max_pivots);
 
   for (long long static_lp = (long long)blockIdx.x * kTmemWarps + warp;; static_lp += nwarps) {
     long long lp = static_lp;
@@ -243,13 +226,15 @@ __global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tme
     const int j0 = 2 * lane;
     const bool v0 = j0 < Wm1, v1 = j0 + 1 < Wm1;  // my two columns exist
     const bool has_b = lane + 1 < H;               // I own the RHS cell of row lane+1
+    const int nblocks = (H - 1 + 7) >> 3;          // TMEM blocks of eight rows
 
     // ---- load: global -> registers -> TMEM (16 bytes per lane per row, 8 rows in flight)
     const double *src = a.in + moff;
     double o0 = v0 ? src[1 + j0] : 0.0, o1 = v1 ? src[2 + j0] : 0.0;
     double bv = has_b ? src[(size_t)(lane + 1) * W] : 0.0;
     double b0 = src[0];
-    for (int r0 = 1; r0 < H; r0 += 8) {
+    for (int blk = 0; blk < nblocks; blk++) {
+      const int r0 = 1 + 8 * blk;
       double x[8][2];
       const double *rp = src + (size_t)r0 * W + 1 + j0;
 #pragma unroll
@@ -261,64 +246,48 @@ __global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tme
       unsigned v[32];
 #pragma unroll
       for (int i = 0; i < 8; i++) {
-        v[4 * i] = (unsigned)__double2loint(x[i][0]);
-        v[4 * i + 1] = (unsigned)__double2hiint(x[i][0]);
-        v[4 * i + 2] = (unsigned)__double2loint(x[i][1]);
-        v[4 * i + 3] = (unsigned)__double2hiint(x[i][1]);
+        v[2 * i] = (unsigned)__double2loint(x[i][0]);
+        v[2 * i + 1] = (unsigned)__double2hiint(x[i][0]);
+        v[16 + 2 * i] = (unsigned)__double2loint(x[i][1]);
+        v[16 + 2 * i + 1] = (unsigned)__double2hiint(x[i][1]);
       }
-      tm_st32(trow1 + 4u * (unsigned)(r0 - 1), v);
+      tm_st32(tbase + 32u * (unsigned)blk, v);
     }
     for (int k = lane; k < W + H; k += 32) var[k] = k;
-    // rows past H-1 in the last block of eight: garbage in, garbage out, never read (a non-zero coefficient keeps the
-    // block on the straight-line path)
+    // rows past H-1 in the last block of eight: zeros in TMEM, never read; a non-zero coefficient keeps the block on
+    // the straight-line path
     for (int k = H + lane; k < kTmemMaxRows + 7; k += 32) cb[k] = make_double2(1.0, 0.0);
     tm_wait_st();
     __syncwarp();
 
     int status = ST_CYCLED;
     double value = d_nan();
-    long long p1 = 0, p2 = 0, iter = 0;
+    long long p1 = 0, iter = 0;
     int phase = 1;
-    bool have_col = false;  // `col` (and colx) were prepared by the previous pivot
-    int col = kNone;
 
-    // entering column (phase 2): first index of the largest reduced cost above precision (:71-79)
-    auto select_entering = [&]() -> int {
-      double best = -INF;
-      int bi = kNone;
-      if (v0 && o0 > precision) {
-        best = o0;
-        bi = j0 + 1;
-      }
-      if (v1 && o1 > precision && o1 > best) {
-        best = o1;
-        bi = j0 + 2;
-      }
-      const unsigned long long key = bi == kNone ? no_key<true>() : order_key(best);
-      return warp_best<true>((unsigned)(key >> 32), (unsigned)key, bi).idx;
-    };
-    // read-only pass: column c of rows 0..H-1 -> colx
+    // read-only pass: cells of column c in rows 0..H-1 -> colx (its owner lane reads them, one tcgen05.ld per block)
     auto extract_column = [&](int c) {
       const int l = (c - 1) >> 1, e = (c - 1) & 1;
       if (lane == l) colx[0] = e ? o1 : o0;
-      for (int r0 = 1; r0 < H; r0 += 8) {
-        unsigned v[8][2];
-#pragma unroll
-        for (int i = 0; i < 8; i++) tm_ld2(trow1 + 4u * (unsigned)(r0 - 1 + i) + 2u * (unsigned)e, v[i][0], v[i][1]);
-        tm_wait_ld(v);
+      for (int blk = 0; blk < nblocks; blk += 2) {
+        unsigned u[32];
+        tm_ld16(tbase + 32u * (unsigned)blk + 16u * (unsigned)e, u);
+        tm_ld16(tbase + 32u * (unsigned)(blk + 1) + 16u * (unsigned)e, u + 16);  // (may be a block past H-1: never read)
+        tm_wait_ld(u);
         if (lane == l) {
+          uint4 *dst = reinterpret_cast<uint4 *>(colx + 1 + 8 * blk);
 #pragma unroll
-          for (int i = 0; i < 8; i++) colx[r0 + i] = __hiloint2double((int)v[i][1], (int)v[i][0]);
+          for (int i = 0; i < 8; i++) dst[i] = make_uint4(u[4 * i], u[4 * i + 1], u[4 * i + 2], u[4 * i + 3]);
         }
       }
       __syncwarp();
     };
 
     for (;;) {
-      if (!((double)iter < a.max_pivots)) break;
-      int row;
-      double pr0 = 0.0, pr1 = 0.0;  // old pivot row cells of my two columns
-      double cmine = 0.0;           // pivot-column cell of my RHS row
+      if (iter >= budget) break;  // per-phase budget exhausted -> "cycled" (:102,:141)
+      int row, col;
+      double pr0, pr1;  // old pivot row cells of my two columns
+      double cmine;     // pivot-column cell of my RHS row
       if (phase == 1) {
         // leaving row: first index of the most negative RHS below -precision (:111-119)
         const bool cand = has_b && bv < -precision;
@@ -327,18 +296,12 @@ __global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tme
                   .idx;
         if (row == kNone) {  // feasible: phase 2 with a fresh counter (:120, :67-69)
           phase = 2;
+          p1 = iter;
           iter = 0;
-          have_col = false;
           continue;
         }
         // entering column: first index of max -M[0,c]/M[row,c] over M[row,c] < -precision (:123-134)
-        {
-          unsigned v[4];
-          tm_ld4(trow1 + 4u * (unsigned)(row - 1), v[0], v[1], v[2], v[3]);
-          tm_wait_ld(v);
-          pr0 = __hiloint2double((int)v[1], (int)v[0]);
-          pr1 = __hiloint2double((int)v[3], (int)v[2]);
-        }
+        tm_load_row(tbase, row, pr0, pr1);
         double best = -INF;
         int bi = kNone;
         if (v0 && pr0 < -precision) {
@@ -364,15 +327,27 @@ __global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tme
         extract_column(col);
         cmine = has_b ? colx[lane + 1] : 0.0;
       } else {
-        if (!have_col) {
-          col = select_entering();
-          if (col != kNone) extract_column(col);
+        // entering column: first index of the largest reduced cost above precision (:71-79)
+        {
+          double best = -INF;
+          int bi = kNone;
+          if (v0 && o0 > precision) {
+            best = o0;
+            bi = j0 + 1;
+          }
+          if (v1 && o1 > precision && o1 > best) {
+            best = o1;
+            bi = j0 + 2;
+          }
+          const unsigned long long key = bi == kNone ? no_key<true>() : order_key(best);
+          col = warp_best<true>((unsigned)(key >> 32), (unsigned)key, bi).idx;
         }
         if (col == kNone) {
           status = ST_OPTIMAL;
           value = round_to_precision(b0, precision);
           break;
         }
+        extract_column(col);
         cmine = has_b ? colx[lane + 1] : 0.0;
         // leaving row: ratio test with the reference's early break (:83-95) == lowest r whose ratio is <= precision
         // if any, else first index of the minimum ratio
@@ -392,11 +367,7 @@ __global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tme
           value = (double)col;
           break;
         }
-        unsigned v[4];
-        tm_ld4(trow1 + 4u * (unsigned)(row - 1), v[0], v[1], v[2], v[3]);
-        tm_wait_ld(v);
-        pr0 = __hiloint2double((int)v[1], (int)v[0]);
-        pr1 = __hiloint2double((int)v[3], (int)v[2]);
+        tm_load_row(tbase, row, pr0, pr1);
       }
 
       // ---- pivot(row, col) (:5-39)
@@ -412,19 +383,21 @@ __global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tme
       const Recip rq(q);  // one reciprocal refinement for the four quotients of this lane
 #endif
       // normalised pivot row cells of my columns; the pivot cell itself becomes 1/q
-      const double x0 = (j0 == jc) ? 1.0 : pr0, x1 = (j0 + 1 == jc) ? 1.0 : pr1;
+      const bool own0 = lane == lc && ec == 0, own1 = lane == lc && ec == 1;
+      const double x0 = own0 ? 1.0 : pr0, x1 = own1 ? 1.0 : pr1;
       const bool n0 = v0 && fabs(x0) > kTiny, n1 = v1 && fabs(x1) > kTiny;
       const double pn0 = n0 ? rq.quot(x0) : 0.0, pn1 = n1 ? rq.quot(x1) : 0.0;
-      const bool own0 = lane == lc && ec == 0, own1 = lane == lc && ec == 1;
       const bool st0 = n0 && !own0, st1 = n1 && !own1;  // cells the rank-1 pass rewrites
       // rows 1..H-1: one lane each (the lane of the pivot row normalises the RHS cell instead)
-      const bool is_prow = has_b && lane + 1 == row;
+      const bool is_prow = lane + 1 == row;
       const double num = is_prow ? bv : -cmine;
       const bool nzq = has_b && fabs(num) > kTiny;  // false for NaN, as in the reference
       const double quo = nzq ? rq.quot(num) : 0.0;
       const double coef_mine = (nzq && !is_prow) ? cmine : 0.0;  // 0 = my row is skipped (:31) or is the pivot row
       // the pivot row takes part in the row pass with a throw-away coefficient (it is rewritten afterwards)
-      if (has_b) cb[lane + 1] = make_double2(is_prow ? 1.0 : coef_mine, coef_mine != 0.0 ? quo : cmine);
+      const double cbx = is_prow ? 1.0 : coef_mine;
+      if (has_b) cb[lane + 1] = make_double2(cbx, coef_mine != 0.0 ? quo : cmine);
+      const unsigned on_mask = __ballot_sync(0xffffffffu, !has_b || cbx != 0.0);  // bit l: row l+1 takes the fast form
       // row 0 (objective row): every lane redundantly
       const bool act0 = fabs(c0raw) > kTiny;
       const double cn0 = act0 ? rq.quot(-c0raw) : 0.0;
@@ -450,40 +423,34 @@ __global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tme
       else if (coef_mine != 0.0 && nz0)
         bv = __dsub_rn(bv, __dmul_rn(coef_mine, p0));
 
-      // phase 2: the next entering column is already decided; its cells are collected during the row pass
-      int col_next = kNone;
-      bool ex0 = false, ex1 = false;
-      have_col = false;
-      if (phase == 2) {
-        col_next = select_entering();
-        have_col = col_next != col;  // (a re-entering pivot column takes the separate extraction pass)
-        if (col_next != kNone && have_col) {
-          const int ln = (col_next - 1) >> 1, en = (col_next - 1) & 1;
-          ex0 = lane == ln && en == 0;
-          ex1 = lane == ln && en == 1;
-          if (ex0) colx[0] = o0;
-          if (ex1) colx[0] = o1;
+      // rank-1 pass over the TMEM blocks; a lane's padding cells (zeros, never read) count as rewritable
+      {
+        const bool dense = __all_sync(0xffffffffu, (st0 || own0 || !v0) && (st1 || own1 || !v1));
+        const TmemPivot pv{pn0, pn1, st0, st1, own0, own1};
+        unsigned m = dense ? on_mask : 0u;
+        for (int blk = 0; blk < nblocks; blk++, m >>= 8) {
+          const unsigned tblk = tbase + 32u * (unsigned)blk;
+          const double2 *cbr = cb + 1 + 8 * blk;
+          if ((m & 0xffu) == 0xffu) {
+            if (ec == 0)
+              tmem_block_fast<0>(tblk, cbr, pv);
+            else
+              tmem_block_fast<1>(tblk, cbr, pv);
+          } else {
+            tmem_block_general(tblk, cbr, pv);
+          }
         }
       }
-
-      // rank-1 pass over the TMEM rows; a lane's padding cells (zeros, never read) count as rewritable
-      const bool dense = __all_sync(0xffffffffu, (st0 || own0 || !v0) && (st1 || own1 || !v1));
-      const TmemPivot pv{pn0, pn1, st0, st1, own0, own1, ex0, ex1};
-      tmem_update(trow1, H, cb, colx, pv, dense, ec);
       tm_wait_st();  // the row pass stored a throw-away value in the pivot row: order the real one behind it
-      tm_store_row(trow1 + 4u * (unsigned)(row - 1), pn0, pn1);  // (:19,22,25)
-      if (ex0) colx[row] = pn0;
-      if (ex1) colx[row] = pn1;
+      tm_store_row(tbase, row, pn0, pn1);  // (:19,22,25)
       tm_wait_st();
-      __syncwarp();
-      col = col_next;
-
-      if (phase == 1)
-        p1++;
-      else
-        p2++;
       iter++;
     }
+    long long p2 = 0;
+    if (phase == 1)
+      p1 = iter;
+    else
+      p2 = iter;
 
     // ---- outputs
     if (lane == 0) {
@@ -507,11 +474,10 @@ __global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tme
       if (v0) dst[1 + j0] = o0;
       if (v1) dst[2 + j0] = o1;
       for (int r = 1; r < H; r++) {
-        unsigned v[4];
-        tm_ld4(trow1 + 4u * (unsigned)(r - 1), v[0], v[1], v[2], v[3]);
-        tm_wait_ld(v);
-        if (v0) dst[(size_t)r * W + 1 + j0] = __hiloint2double((int)v[1], (int)v[0]);
-        if (v1) dst[(size_t)r * W + 2 + j0] = __hiloint2double((int)v[3], (int)v[2]);
+        double y0, y1;
+        tm_load_row(tbase, r, y0, y1);
+        if (v0) dst[(size_t)r * W + 1 + j0] = y0;
+        if (v1) dst[(size_t)r * W + 2 + j0] = y1;
       }
     }
     __syncwarp();
