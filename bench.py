@@ -13,7 +13,9 @@ collective: LPs are independent); the time is the max over ranks, the value the 
 `e2e`       pivots/s through the host C-ABI call (yalps_solve_batch) from pinned host buffers, H2D of the
             tableaus and D2H of status/value/pivots/RHS/basis inside the timed region
 `roofline`  SURVEY 8(d): algorithmic bytes = 16*H*W per pivot, against the shared-memory stream bandwidth
-            measured live (K1 keeps the tableau in shared memory) -- the HBM view is reported alongside
+            measured live (north_star's denominator; K1 keeps the tableau in shared memory).  The automatic
+            path for this workload is K1t, which keeps the tableau in TENSOR memory: its own stream bandwidth
+            (tcgen05.ld/st, measured live too) and the HBM view are reported alongside
 `cpu_baseline` the CPU restatement of the reference loop (oracle/, C -O2 -ffp-contract=off; Node is not
             available) on the box's host cores, bounded sample of the same workload
 
@@ -281,6 +283,7 @@ def run_native(args):
         bytes_per_pivot = 16 * H * W  # SURVEY 8(d), dense tableau
         achieved = pivots_per_step * bytes_per_pivot / (kernel_ms * 1e-3) / 1e9
         smem_gbs, _ = eng.measure_smem_bandwidth()
+        tmem_gbs, _ = eng.measure_tmem_bandwidth()
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -290,7 +293,7 @@ def run_native(args):
         hbm_alg = n * (cells * 8 + 4 + 8 + 16 + H * 8 + 2 * (W + H) * 4) / (kernel_ms * 1e-3) / 1e9
         traffic = None
         try:  # dram bytes per launch of this kernel from the committed ncu --set full capture (profiles/)
-            ncu = json.load(open(os.path.join(ROOT, "profiles", "r01h_k1_ncu_summary.json")))
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "r01j_k1t_ncu_summary.json")))
             if args.workload == "config2":
                 traffic = ncu["dram_bytes_per_launch"]
         except (OSError, KeyError, ValueError):
@@ -317,11 +320,17 @@ def run_native(args):
             "clocks": clocks,
             "roofline": {"bound": "smem", "achieved": achieved, "peak": smem_gbs, "unit": "GB/s",
                          "frac": achieved / smem_gbs, "traffic": traffic,
-                         "traffic_note": "dram__bytes_read+write per launch (ncu --set full, profiles/r01h_k1_ncu_summary.json); "
-                                         "the tableau is read from HBM once, every pivot runs out of shared memory",
+                         "traffic_note": "dram__bytes_read+write per launch (ncu --set full, profiles/r01j_k1t_ncu_summary.json); "
+                                         "the tableau is read from HBM once, every pivot runs out of tensor memory",
                          "peak_source": "measured live: ld/st.shared.f64 stream on all SMs (yalps_measure_smem_bandwidth)",
                          "bytes_per_unit": bytes_per_pivot, "units_per_launch": pivots_per_step,
-                         "kernel_ms": kernel_ms, "kernel": "k_simplex<NW,KC,resident>",
+                         "kernel_ms": kernel_ms,
+                         "kernel": "k_simplex_tmem (K1t)" if args.path in (0, 6) and args.threads == 0 else "k_simplex<NW,KC,resident>",
+                         "tmem": {"achieved": achieved, "peak": tmem_gbs, "frac": achieved / tmem_gbs,
+                                  "peak_source": "measured live: tcgen05.ld/st.32x32b.x32 read-modify-write stream, 16 warps/SM "
+                                                 "(yalps_measure_tmem_bandwidth)",
+                                  "note": "K1t keeps the tableau rows in tensor memory; the shared-memory stream stays the "
+                                          "headline denominator because BASELINE.json's target is quoted on it"},
                          "hbm": {"achieved": hbm_alg, "peak": hbm_peak, "frac": hbm_alg / hbm_peak,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                                  "note": "tableau read once + results written once per LP"}},
@@ -346,7 +355,7 @@ def main():
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="config2")
     ap.add_argument("--threads", type=int, default=0, help="threads per LP (0 = auto)")
-    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 smem, 2 gmem")
+    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 smem (K1), 2 gmem (K2), 6 tmem (K1t)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

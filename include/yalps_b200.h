@@ -208,6 +208,9 @@ int yalps_probe_division(yalps_ctx *ctx, int64_t n, uint64_t seed, int32_t mode,
 /* Shared-memory stream microbenchmark: bytes moved per second by ld/st.shared.f64 on all SMs
  * (the measured denominator of the K1 roofline).  Returns GB/s in *gbs. */
 int yalps_measure_smem_bandwidth(yalps_ctx *ctx, double *gbs, double *sm_clock_mhz);
+/* Tensor-memory stream microbenchmark: bytes read + written per second by tcgen05.ld/st.32x32b.x32 with the
+ * multiply-subtract of the rank-1 update in between, 16 warps per SM (what bounds K1t's row pass). */
+int yalps_measure_tmem_bandwidth(yalps_ctx *ctx, double *gbs, double *sm_clock_mhz);
 
 #ifdef __cplusplus
 }

@@ -67,3 +67,29 @@ def test_launch_counter_and_device_info(engine):
     assert engine.launch_count == before + 1
     info = engine.device_info()
     assert info["cc"][0] >= 10 and info["sm_count"] >= 100 and info["smem_per_block_optin"] >= 200 * 1024
+
+
+def test_scratchpad_stream_measurements(engine):
+    """The roofline denominators bench.py measures live: the shared-memory stream and the tensor-memory stream
+    (tcgen05.ld/st as a lane-private scratchpad moves more bytes per clock than the shared-memory data pipe)."""
+    smem, mhz = engine.measure_smem_bandwidth()
+    tmem, _ = engine.measure_tmem_bandwidth()
+    assert mhz > 500 and 10e3 < smem < 60e3   # GB/s: 128 B/clk/SM x 148 SMs ~ 37 TB/s at 1965 MHz
+    assert tmem > smem
+
+
+def test_automatic_path_matches_forced_paths_on_a_dense_batch(engine):
+    """n > 2 x SMs dense LPs that fit tensor memory take K1t automatically; K1, K1t and auto agree bit for bit."""
+    mats = O.generate_synthetic(4242, 700, 32, 64, 4)
+    outs = []
+    for path in (E.PATH_SMEM, E.PATH_TMEM, E.PATH_AUTO):
+        engine.set_tuning(path, 0)
+        try:
+            outs.append(engine.solve_batch(mats, 33, 65, want_matrices=True))
+        finally:
+            engine.set_tuning(E.PATH_AUTO, 0)
+    for o in outs[1:]:
+        for k in ("status", "pivots", "pos", "var"):
+            assert np.array_equal(outs[0][k], o[k]), k
+        for k in ("value", "rhs", "matrices"):
+            assert np.array_equal(outs[0][k].view(np.uint64), o[k].view(np.uint64)), k

@@ -72,6 +72,7 @@ SIGNATURES = {
                               _ip, _vp, _vp, _vp, _ip, _dp, _vp, _vp]),
     "yalps_round_to_precision": (C.c_int, [_vp, C.c_int64, _vp, C.c_double, _vp]),
     "yalps_measure_smem_bandwidth": (C.c_int, [_vp, _dp, _dp]),
+    "yalps_measure_tmem_bandwidth": (C.c_int, [_vp, _dp, _dp]),
 }
 
 _lib = None

@@ -427,18 +427,14 @@ __global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tme
       {
         const bool dense = __all_sync(0xffffffffu, (st0 || own0 || !v0) && (st1 || own1 || !v1));
         const TmemPivot pv{pn0, pn1, st0, st1, own0, own1};
-        unsigned m = dense ? on_mask : 0u;
-        for (int blk = 0; blk < nblocks; blk++, m >>= 8) {
-          const unsigned tblk = tbase + 32u * (unsigned)blk;
-          const double2 *cbr = cb + 1 + 8 * blk;
-          if ((m & 0xffu) == 0xffu) {
-            if (ec == 0)
-              tmem_block_fast<0>(tblk, cbr, pv);
-            else
-              tmem_block_fast<1>(tblk, cbr, pv);
+        if (dense && on_mask == 0xffffffffu) {  // the common case of a dense LP: every block takes the fast form
+          if (ec == 0) {
+            for (int blk = 0; blk < nblocks; blk++) tmem_block_fast<0>(tbase + 32u * (unsigned)blk, cb + 1 + 8 * blk, pv);
           } else {
-            tmem_block_general(tblk, cbr, pv);
+            for (int blk = 0; blk < nblocks; blk++) tmem_block_fast<1>(tbase + 32u * (unsigned)blk, cb + 1 + 8 * blk, pv);
           }
+        } else {
+          for (int blk = 0; blk < nblocks; blk++) tmem_block_general(tbase + 32u * (unsigned)blk, cb + 1 + 8 * blk, pv);
         }
       }
       tm_wait_st();  // the row pass stored a throw-away value in the pivot row: order the real one behind it

@@ -1287,6 +1287,40 @@ int yalps_measure_smem_bandwidth(yalps_ctx *ctx, double *gbs, double *sm_clock_m
   return 0;
 }
 
+int yalps_measure_tmem_bandwidth(yalps_ctx *ctx, double *gbs, double *sm_clock_mhz) {
+  if (!ctx || !gbs) return YALPS_ERR_ARGUMENT;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, raise_smem_limit(ctx->device, tmem_stream_fn(), (int)tmem_kernel_dynamic_smem()));
+  void *sink;
+  if (int rc = dev_ensure(ctx, "sink", 64, &sink)) return rc;
+  const int grid = ctx->prop.multiProcessorCount * tmem_kernel_ctas_per_sm();
+  cudaStream_t st = ctx->streams[0];
+  cudaEvent_t e0, e1;
+  CU(ctx, cudaEventCreate(&e0));
+  CU(ctx, cudaEventCreate(&e1));
+  float best = 1e30f;
+  double bytes = 0.0;
+  for (int rep = 0; rep < 5; rep++) {
+    CU(ctx, cudaEventRecord(e0, st));
+    CU(ctx, launch_tmem_stream(grid, 4000, (double *)sink, st, &bytes));
+    CU(ctx, cudaEventRecord(e1, st));
+    CU(ctx, cudaEventSynchronize(e1));
+    ctx->launches++;
+    float ms = 0;
+    CU(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0) best = std::min(best, ms);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *gbs = bytes / (best * 1e-3) / 1e9;
+  if (sm_clock_mhz) {
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+    *sm_clock_mhz = khz / 1000.0;
+  }
+  return 0;
+}
+
 }  // extern "C"
 
 #include "bnb.inl"

@@ -291,6 +291,11 @@ class Engine:
         self._check(self._lib.yalps_probe_division(self._ctx, n, seed, mode, C.byref(bad), first))
         return int(bad.value), (int(first[0]), int(first[1]))
 
+    def measure_tmem_bandwidth(self) -> tuple:
+        g, c = C.c_double(), C.c_double()
+        self._check(self._lib.yalps_measure_tmem_bandwidth(self._ctx, C.byref(g), C.byref(c)))
+        return g.value, c.value
+
     def measure_smem_bandwidth(self) -> tuple:
         g, c = C.c_double(), C.c_double()
         self._check(self._lib.yalps_measure_smem_bandwidth(self._ctx, C.byref(g), C.byref(c)))
