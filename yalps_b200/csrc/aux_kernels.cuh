@@ -145,8 +145,18 @@ __global__ void k_probe_division(long long n, unsigned long long seed, int mode,
     const Recip rc(y);
     const double q1 = rc.quot(x), q2 = rc.quot(y), q3 = div_rn(1.0, y);
     const double r1 = __ddiv_rn(x, y), r2 = __ddiv_rn(y, y), r3 = __ddiv_rn(1.0, y);
+    // the branch-free batch form (K1t): accepted quotients must already be exact, rejected ones go out of line
+    RecipBatch rb(y);
+    double b1 = rb.quot(x), b2 = rb.quot(y), b3 = rb.quot(1.0);
+    (void)rb.quot(__longlong_as_double((long long)(a ^ b)), false);  // an unused quotient must not change the verdict
+    if (!rb.ok) {
+      b1 = div_rn_slow(x, y);
+      b2 = div_rn_slow(y, y);
+      b3 = div_rn_slow(1.0, y);
+    }
     if (__double_as_longlong(q1) != __double_as_longlong(r1) || __double_as_longlong(q2) != __double_as_longlong(r2) ||
-        __double_as_longlong(q3) != __double_as_longlong(r3)) {
+        __double_as_longlong(q3) != __double_as_longlong(r3) || __double_as_longlong(b1) != __double_as_longlong(r1) ||
+        __double_as_longlong(b2) != __double_as_longlong(r2) || __double_as_longlong(b3) != __double_as_longlong(r3)) {
       bad++;
       if (atomicAdd(out + 1, 1ULL) == 0) {
         out[2] = (unsigned long long)__double_as_longlong(x);

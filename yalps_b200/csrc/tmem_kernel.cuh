@@ -269,6 +269,7 @@ __global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tme
     auto extract_column = [&](int c) {
       const int l = (c - 1) >> 1, e = (c - 1) & 1;
       if (lane == l) colx[0] = e ? o1 : o0;
+      tm_wait_st();  // the pivot-row store of the previous pivot
       for (int blk = 0; blk < nblocks; blk += 2) {
         unsigned u[32];
         tm_ld16(tbase + 32u * (unsigned)blk + 16u * (unsigned)e, u);
@@ -301,20 +302,24 @@ __global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tme
           continue;
         }
         // entering column: first index of max -M[0,c]/M[row,c] over M[row,c] < -precision (:123-134)
+        tm_wait_st();  // the pivot-row store of the previous pivot
         tm_load_row(tbase, row, pr0, pr1);
         double best = -INF;
         int bi = kNone;
-        if (v0 && pr0 < -precision) {
-          const double ratio = div_rn(-o0, pr0);
-          if (ratio > best) {
-            best = ratio;
+        {
+          const bool c0 = v0 && pr0 < -precision, c1 = v1 && pr1 < -precision;
+          RecipBatch d0(pr0, c0), d1(pr1, c1);
+          double ratio0 = d0.quot(-o0, c0), ratio1 = d1.quot(-o1, c1);
+          if (!(d0.ok && d1.ok)) {  // rare: exact division out of line
+            ratio0 = div_rn_slow(-o0, pr0);
+            ratio1 = div_rn_slow(-o1, pr1);
+          }
+          if (c0 && ratio0 > best) {  // best starts at -inf: -inf and NaN ratios never win, as in the reference
+            best = ratio0;
             bi = j0 + 1;
           }
-        }
-        if (v1 && pr1 < -precision) {
-          const double ratio = div_rn(-o1, pr1);
-          if (ratio > best) {
-            best = ratio;
+          if (c1 && ratio1 > best) {
+            best = ratio1;
             bi = j0 + 2;
           }
         }
@@ -351,14 +356,14 @@ __global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tme
         cmine = has_b ? colx[lane + 1] : 0.0;
         // leaving row: ratio test with the reference's early break (:83-95) == lowest r whose ratio is <= precision
         // if any, else first index of the minimum ratio
-        bool cand = false;
+        bool cand = has_b && cmine > precision;
         double keyv = INF;
-        if (has_b && cmine > precision) {
-          const double ratio = div_rn(bv, cmine);
-          if (ratio < INF) {  // +inf and NaN never win
-            cand = true;
-            keyv = (ratio <= precision) ? -INF : ratio;
-          }
+        {
+          RecipBatch dr(cmine, cand);
+          double ratio = dr.quot(bv, cand);
+          if (!dr.ok) ratio = div_rn_slow(bv, cmine);  // rare (e.g. a zero RHS): exact division out of line
+          cand = cand && ratio < INF;                  // +inf and NaN never win
+          if (cand) keyv = (ratio <= precision) ? -INF : ratio;
         }
         const unsigned long long key = cand ? order_key(keyv) : no_key<false>();
         row = warp_best<false>((unsigned)(key >> 32), (unsigned)key, cand ? lane + 1 : kNone).idx;
@@ -374,33 +379,33 @@ __global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tme
       const int jc = col - 1, lc = jc >> 1, ec = jc & 1;
       const double q = colx[row];
       const double c0raw = colx[0];
-#ifdef YALPS_TMEM_PLAIN_DIV
-      struct {
-        double d;
-        __device__ __forceinline__ double quot(double n) const { return __ddiv_rn(n, d); }
-      } rq{q};
-#else
-      const Recip rq(q);  // one reciprocal refinement for the four quotients of this lane
-#endif
+      RecipBatch rq(q);  // one reciprocal refinement and one acceptance branch for the four quotients of this lane
       // normalised pivot row cells of my columns; the pivot cell itself becomes 1/q
       const bool own0 = lane == lc && ec == 0, own1 = lane == lc && ec == 1;
       const double x0 = own0 ? 1.0 : pr0, x1 = own1 ? 1.0 : pr1;
       const bool n0 = v0 && fabs(x0) > kTiny, n1 = v1 && fabs(x1) > kTiny;
-      const double pn0 = n0 ? rq.quot(x0) : 0.0, pn1 = n1 ? rq.quot(x1) : 0.0;
-      const bool st0 = n0 && !own0, st1 = n1 && !own1;  // cells the rank-1 pass rewrites
       // rows 1..H-1: one lane each (the lane of the pivot row normalises the RHS cell instead)
       const bool is_prow = lane + 1 == row;
       const double num = is_prow ? bv : -cmine;
       const bool nzq = has_b && fabs(num) > kTiny;  // false for NaN, as in the reference
-      const double quo = nzq ? rq.quot(num) : 0.0;
+      const bool act0 = fabs(c0raw) > kTiny;       // row 0 (objective row): every lane redundantly
+      double pn0 = rq.quot(x0, n0), pn1 = rq.quot(x1, n1), quo = rq.quot(num, nzq), cn0 = rq.quot(-c0raw, act0);
+      if (!rq.ok) {  // rare: exact divisions out of line
+        pn0 = div_rn_slow(x0, q);
+        pn1 = div_rn_slow(x1, q);
+        quo = div_rn_slow(num, q);
+        cn0 = div_rn_slow(-c0raw, q);
+      }
+      pn0 = n0 ? pn0 : 0.0;
+      pn1 = n1 ? pn1 : 0.0;
+      quo = nzq ? quo : 0.0;
+      cn0 = act0 ? cn0 : 0.0;
+      const bool st0 = n0 && !own0, st1 = n1 && !own1;  // cells the rank-1 pass rewrites
       const double coef_mine = (nzq && !is_prow) ? cmine : 0.0;  // 0 = my row is skipped (:31) or is the pivot row
       // the pivot row takes part in the row pass with a throw-away coefficient (it is rewritten afterwards)
       const double cbx = is_prow ? 1.0 : coef_mine;
       if (has_b) cb[lane + 1] = make_double2(cbx, coef_mine != 0.0 ? quo : cmine);
       const unsigned on_mask = __ballot_sync(0xffffffffu, !has_b || cbx != 0.0);  // bit l: row l+1 takes the fast form
-      // row 0 (objective row): every lane redundantly
-      const bool act0 = fabs(c0raw) > kTiny;
-      const double cn0 = act0 ? rq.quot(-c0raw) : 0.0;
       const double p0 = __shfl_sync(0xffffffffu, quo, row - 1);        // normalised RHS of the pivot row
       const bool nz0 = __shfl_sync(0xffffffffu, nzq ? 1 : 0, row - 1);  // ... was above 1e-16
       if (lane == 0) {  // basis bookkeeping (:7-12)
@@ -438,8 +443,7 @@ __global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tme
         }
       }
       tm_wait_st();  // the row pass stored a throw-away value in the pivot row: order the real one behind it
-      tm_store_row(tbase, row, pn0, pn1);  // (:19,22,25)
-      tm_wait_st();
+      tm_store_row(tbase, row, pn0, pn1);  // (:19,22,25); waited for in front of the next TMEM read
       iter++;
     }
     long long p2 = 0;
@@ -463,6 +467,7 @@ __global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tme
       for (int k = lane; k < W + H; k += 32) a.pos_out[poff + var[k]] = k;
     if (a.var_out)
       for (int k = lane; k < W + H; k += 32) a.var_out[poff + k] = var[k];
+    tm_wait_st();
     if (a.mat_out) {
       double *dst = a.mat_out + moff;
       if (lane == 0) dst[0] = b0;
