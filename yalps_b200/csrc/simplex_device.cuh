@@ -262,18 +262,10 @@ __device__ __forceinline__ void pivot_cta(const LpView &t, const Scratch &s, int
   const int ldA = t.ldA, ldb = t.ldb, H = t.H, Wm1 = t.W - 1;
   const int jc = col - 1;
   const double q = A[(size_t)row * ldA + jc];
-  // One divisor for every quotient of the pivot.  The shared-reciprocal form (fastdiv.cuh Recip) shortens the
-  // dependent chain and is what the latency kernels use (simplex_split.cuh); in this throughput kernel it measured
-  // 4 % slower than plain divisions (559 vs 583 M pivots/s on config 2), so it stays off here.
-#ifdef YALPS_K1_SHARED_RECIP
-  const Recip rq(q);
-#else
-  struct {
-    double d;
-    __device__ __forceinline__ double quot(double n) const { return __ddiv_rn(n, d); }
-  } rq{q};
-#endif
-
+  // One divisor for every quotient of the pivot: branch-free quotients, one acceptance test per batch and the exact
+  // division out of line for the operands the fast sequence rejects (fastdiv.cuh RecipBatch).  The per-quotient
+  // test-and-branch forms (__ddiv_rn, Recip::quot) cost 10-14 % in the throughput kernels.
+  RecipBatch rq(q);
   // ---- normalise the pivot row into registers (:16-25); A and b are only read in this phase.
   // The pivot cell itself becomes 1/q (:25): same division code path with numerator 1.
   double p[KC][VW];
@@ -292,8 +284,10 @@ __device__ __forceinline__ void pivot_cta(const LpView &t, const Scratch &s, int
         if (j < Wm1) {
           valid |= 1u << (k * VW + e);
           const double x = (j == jc) ? 1.0 : v.get(e);
-          if (fabs(x) > kTiny) {
-            p[k][e] = rq.quot(x);
+          const bool nzx = fabs(x) > kTiny;
+          const double quo = rq.quot(x, nzx);
+          if (nzx) {
+            p[k][e] = quo;
             st |= 1u << (k * VW + e);  // the pivot column is rewritten too and fixed up after the update
           }
         } else if (VW == 2 && j0 < Wm1) {
@@ -307,13 +301,32 @@ __device__ __forceinline__ void pivot_cta(const LpView &t, const Scratch &s, int
         partial = 1u;
     }
   }
+  if (!rq.ok) {  // rare: some quotient of this thread needs the exact division (the pivot row is still unchanged)
+    const double *Arow = A + (size_t)row * ldA + VW * tid;
+#pragma unroll
+    for (int k = 0; k < KC; k++)
+#pragma unroll
+      for (int e = 0; e < VW; e++) {
+        const int j = VW * (tid + NT * k) + e;
+        if (j < Wm1) {
+          const double x = (j == jc) ? 1.0 : Arow[(size_t)VW * NT * k + e];
+          if (fabs(x) > kTiny) p[k][e] = div_rn_slow(x, q);
+        }
+      }
+    rq.reset();
+  }
   const bool any_partial = (VW == 2) && (NW == 1 ? __any_sync(0xffffffffu, partial) : __syncthreads_or((int)partial));
   // old pivot column, -coef/q, and the RHS cell of the pivot row (:19 for c = 0, :28-36): one division each
   for (int r = tid; r < H; r += NT) {
     const double coef = A[(size_t)r * ldA + jc];
     const double num = (r == row) ? b[(size_t)row * ldb] : -coef;
     const bool nz = fabs(num) > kTiny;  // also false for NaN, as in the reference
-    const double quo = nz ? rq.quot(num) : 0.0;
+    double quo = rq.quot(num, nz);
+    if (!rq.ok) {
+      quo = div_rn_slow(num, q);
+      rq.reset();
+    }
+    quo = nz ? quo : 0.0;
     if (r == row) {
       s.misc[0] = quo;
       s.misc[1] = nz ? 1.0 : 0.0;
