@@ -169,13 +169,15 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "pivots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit_line(line)
     return 0
 
 
 def workload_name(name, n, m, nv, neg):
     return (f"{name}: {n} synthetic dense LPs {m}x{nv} fp64 per GPU (tableau {m + 1}x{nv + 1}, "
-            f"{'feasible start' if not neg else str(neg) + ' infeasible rows'}), one tableau per CTA in shared memory")
+            f"{'feasible start' if not neg else str(neg) + ' infeasible rows'}), BASELINE.json configs[1]; tableaus stay on chip "
+            f"for the whole solve (automatic kernel: one LP per warp in tensor memory, K1t; --path 1: one LP per CTA in "
+            f"shared memory, K1)")
 
 
 def run_native(args):
@@ -340,11 +342,27 @@ def run_native(args):
                              "lps_per_s": cpu_lps,
                              "note": "C restatement of src/simplex.ts (oracle/), not Node/V8"},
         }
-        print(json.dumps(line))
+        emit_line(line)
     eng.close()
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+def emit_line(line):
+    """The JSON line goes to the REAL stdout; everything else a library prints there (NCCL's version banner) was
+    sent to stderr by quiet_stdout()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
+def quiet_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
 
 def main():
@@ -357,6 +375,7 @@ def main():
     ap.add_argument("--threads", type=int, default=0, help="threads per LP (0 = auto)")
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 smem (K1), 2 gmem (K2), 6 tmem (K1t)")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_native(args)
