@@ -650,3 +650,32 @@ def test_host_pipeline_with_several_chunks(engine):
     got = engine.solve_batch(mats, m + 1, nv + 1)
     got["matrices"] = None
     assert_batch_equal(got, exp, "chunked host pipeline")
+
+
+def test_config2_full_size_tensor_memory_against_shared_memory_kernel(engine):
+    """BASELINE config 2 at full size (65,536 LPs 33x65 generated on the device): K1t and K1 must agree on every
+    output bit of every LP -- status, value, pivot counts per phase, RHS column, both basis arrays."""
+    import torch
+    m, nv, n = 32, 64, 65536
+    H, W = m + 1, nv + 1
+    d = torch.empty(n * H * W, dtype=torch.float64, device="cuda")
+    engine.generate_synthetic_device(0, n, m, nv, d.data_ptr(), neg_rows=3)
+    outs = []
+    for path in (E.PATH_SMEM, E.PATH_TMEM):
+        st = torch.empty(n, dtype=torch.int32, device="cuda")
+        val = torch.empty(n, dtype=torch.float64, device="cuda")
+        piv = torch.empty(n, 2, dtype=torch.int64, device="cuda")
+        rhs = torch.empty(n * H, dtype=torch.float64, device="cuda")
+        pos = torch.empty(n * (W + H), dtype=torch.int32, device="cuda")
+        var = torch.empty(n * (W + H), dtype=torch.int32, device="cuda")
+        engine.set_tuning(path, 0)
+        try:
+            engine.solve_batch_device(n, H, W, d.data_ptr(), d_status=st.data_ptr(), d_value=val.data_ptr(),
+                                      d_pivots=piv.data_ptr(), d_rhs=rhs.data_ptr(), d_pos=pos.data_ptr(), d_var=var.data_ptr())
+            torch.cuda.synchronize()
+        finally:
+            engine.set_tuning(E.PATH_AUTO, 0)
+        outs.append((st, val.view(torch.int64), piv, rhs.view(torch.int64), pos, var))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert int(outs[0][2].sum()) > 10 * n  # real work: more than ten pivots per LP on average
