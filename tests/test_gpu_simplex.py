@@ -679,3 +679,26 @@ def test_config2_full_size_tensor_memory_against_shared_memory_kernel(engine):
     for a, b in zip(*outs):
         assert torch.equal(a, b)
     assert int(outs[0][2].sum()) > 10 * n  # real work: more than ten pivots per LP on average
+
+
+def test_tensor_memory_kernel_on_a_ragged_batch(engine):
+    """K1t through yalps_solve_ragged: LPs of many different shapes (all within 33 x 65) share launches, every warp
+    reads its LP's own height / width / offsets, TMEM rows left over from a taller previous LP must not leak."""
+    rng = np.random.default_rng(5)
+    tabs, shapes, exp = [], [], []
+    for i in range(420):
+        m, nv = int(rng.integers(1, 33)), int(rng.integers(1, 65))
+        t = O.generate_synthetic(9000 + i, 1, m, nv, int(rng.integers(0, m + 1)))[0]
+        tabs.append(t)
+        shapes.append((m + 1, nv + 1))
+        exp.append(oracle_batch(t.reshape(1, -1), m + 1, nv + 1))
+    engine.set_tuning(E.PATH_TMEM, 0)
+    try:
+        got = engine.solve_ragged(tabs, shapes, want_matrices=True)
+    finally:
+        engine.set_tuning(E.PATH_AUTO, 0)
+    for g, e, s in zip(got, exp, shapes):
+        assert g["status"] == e["status"][0] and g["pivots"] == tuple(e["pivots"][0]), s
+        assert same_value(g["value"], e["value"][0])
+        assert np.array_equal(g["pos"], e["pos"][0]) and np.array_equal(g["var"], e["var"][0])
+        assert same_bits(g["rhs"], e["rhs"][0]) and same_bits(g["matrix"], e["matrices"][0]), s
