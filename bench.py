@@ -149,12 +149,16 @@ def run_reference(args):
     for _ in range(args.warmup):
         cpu_baseline(min(sample, 2048), m, nv, neg, 0, cores)
     tot_piv, tot_t, tot_lp = 0, 0.0, 0
+    rates = []  # per-step samples, as benchmarks/benchmark.ts:64-79 reports mean and standard deviation
     for s in range(args.steps):
         _, _, piv, dt = cpu_baseline(sample, m, nv, neg, (s * sample) % n, cores)
         tot_piv += piv
         tot_t += dt
         tot_lp += sample
+        rates.append(piv / dt)
     value = tot_piv / tot_t
+    mean = sum(rates) / len(rates)
+    sigma = (sum((r - mean) ** 2 for r in rates) / max(1, len(rates) - 1)) ** 0.5
     one_thread = cpu_baseline(2048, m, nv, neg, 0, 1)[0]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pivots/s", "n_gpus": args.gpus,
@@ -162,6 +166,7 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.workload, n, m, nv, neg), "l2": "inputs larger than L2"},
         "lps_per_s": tot_lp / tot_t,
+        "samples": {"n": len(rates), "mean": mean, "stddev": sigma, "unit": "pivots/s"},
         "cpu_baseline": {"value": value, "unit": "pivots/s", "cores": cores, "kind": "port",
                          "sample": f"{sample} LPs of the workload per step, {cores} threads; single thread: "
                                    f"{one_thread:.4g} pivots/s",
