@@ -300,7 +300,7 @@ def run_native(args):
         hbm_alg = n * (cells * 8 + 4 + 8 + 16 + H * 8 + 2 * (W + H) * 4) / (kernel_ms * 1e-3) / 1e9
         traffic = None
         try:  # dram bytes per launch of this kernel from the committed ncu --set full capture (profiles/)
-            ncu = json.load(open(os.path.join(ROOT, "profiles", "r01j_k1t_ncu_summary.json")))
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "r01k_k1t_ncu_summary.json")))
             if args.workload == "config2":
                 traffic = ncu["dram_bytes_per_launch"]
         except (OSError, KeyError, ValueError):
@@ -327,7 +327,7 @@ def run_native(args):
             "clocks": clocks,
             "roofline": {"bound": "smem", "achieved": achieved, "peak": smem_gbs, "unit": "GB/s",
                          "frac": achieved / smem_gbs, "traffic": traffic,
-                         "traffic_note": "dram__bytes_read+write per launch (ncu --set full, profiles/r01j_k1t_ncu_summary.json); "
+                         "traffic_note": "dram__bytes_read+write per launch (ncu --set full, profiles/r01k_k1t_ncu_summary.json); "
                                          "the tableau is read from HBM once, every pivot runs out of tensor memory",
                          "peak_source": "measured live: ld/st.shared.f64 stream on all SMs (yalps_measure_smem_bandwidth)",
                          "bytes_per_unit": bytes_per_pivot, "units_per_launch": pivots_per_step,
