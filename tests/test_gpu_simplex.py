@@ -702,3 +702,23 @@ def test_tensor_memory_kernel_on_a_ragged_batch(engine):
         assert same_value(g["value"], e["value"][0])
         assert np.array_equal(g["pos"], e["pos"][0]) and np.array_equal(g["var"], e["var"][0])
         assert same_bits(g["rhs"], e["rhs"][0]) and same_bits(g["matrix"], e["matrices"][0]), s
+
+
+def test_ragged_batch_with_many_small_lps_on_the_automatic_path(engine):
+    """solve_many-style input: 900 LPs of two shapes in one ragged call.  Each size class has more than two LPs per SM,
+    so the automatic policy puts the classes on the tensor-memory kernel (index-mapped launch-local LP ids)."""
+    tabs, shapes, exp = [], [], []
+    for i in range(900):
+        m, nv = ((8, 16), (32, 64))[i % 2]
+        t = O.generate_synthetic(20000 + i, 1, m, nv, i % 5)[0]
+        tabs.append(t)
+        shapes.append((m + 1, nv + 1))
+        exp.append(oracle_batch(t.reshape(1, -1), m + 1, nv + 1))
+    before = engine.launch_count
+    got = engine.solve_ragged(tabs, shapes, want_matrices=True)
+    assert engine.launch_count - before <= 4
+    for g, e, s in zip(got, exp, shapes):
+        assert g["status"] == e["status"][0] and g["pivots"] == tuple(e["pivots"][0]), s
+        assert same_value(g["value"], e["value"][0])
+        assert np.array_equal(g["pos"], e["pos"][0]) and np.array_equal(g["var"], e["var"][0])
+        assert same_bits(g["rhs"], e["rhs"][0]) and same_bits(g["matrix"], e["matrices"][0]), s
