@@ -237,7 +237,7 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
   plan->reg = false;
   plan->tmem = false;
   // K1t (tensor-memory resident, one LP per warp): every dense batch that fits it, in throughput mode -- measured
-  // 1.22-1.46x K1 on all shapes from 9x17 to 33x65 (scripts/tmem_vs_smem.py).  Sparse batches stay on K2 (density
+  // 1.47-1.68x K1 on all shapes from 9x17 to 33x65 (scripts/tmem_vs_smem.py).  Sparse batches stay on K2 (density
   // probe above), few LPs on the row-split latency kernels.
   const bool tmem_auto = tune_path == YALPS_PATH_AUTO && resident && ctx->tune_threads <= 0 && ctx->tune_rows <= 0 &&
                          n > 2LL * ctx->prop.multiProcessorCount;
