@@ -198,7 +198,8 @@ __global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tme
   long long budget = 0;
   if (a.max_pivots > 0.0) budget = a.max_pivots >= 9.0e18 ? 0x7fffffffffffffffLL : (long long)ceil(a.max_pivots);
 
-  for (long long static_lp = (long long)blockIdx.x * kTmemWarps + warp;; static_lp += nwarps) {
+  // static assignment (few LPs): LP i -> CTA i % grid, warp i / grid, so that a small batch spreads over the SMs
+  for (long long static_lp = (long long)warp * gridDim.x + blockIdx.x;; static_lp += nwarps) {
     long long lp = static_lp;
     if (a.counter) {
       unsigned long long got = 0;

@@ -236,11 +236,12 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
   const bool grid_ok = tune_path == YALPS_PATH_GRID || (tune_path == YALPS_PATH_AUTO && n <= 16);
   plan->reg = false;
   plan->tmem = false;
-  // K1t (tensor-memory resident, one LP per warp): every dense batch that fits it, in throughput mode -- measured
-  // 1.47-1.68x K1 on all shapes from 9x17 to 33x65 (scripts/tmem_vs_smem.py).  Sparse batches stay on K2 (density
-  // probe above), few LPs on the row-split latency kernels.
-  const bool tmem_auto = tune_path == YALPS_PATH_AUTO && resident && ctx->tune_threads <= 0 && ctx->tune_rows <= 0 &&
-                         n > 2LL * ctx->prop.multiProcessorCount;
+  // K1t (tensor-memory resident, one LP per warp, no CTA barrier in the pivot loop): every batch whose tableaus fit
+  // it, whatever its size and density.  Measured against the previous choices on B200: 1.47-1.68x K1 on big dense
+  // batches of every shape from 9x17 to 33x65 (scripts/tmem_vs_smem.py); 1.5-2.3x K2 on big batches with 70-90 % zeros
+  // (scripts/tmem_sparse_batches.py); 8-33 % faster than the row-split latency kernels for 1..296 LPs, dense or sparse
+  // (scripts/tmem_small_batches.py).
+  const bool tmem_auto = tune_path == YALPS_PATH_AUTO && ctx->tune_threads <= 0 && ctx->tune_rows <= 0;
   if (allow_reg && tmem_kernel_fits(Hcap, Wcap) && !check_cycles && (tune_path == YALPS_PATH_TMEM || tmem_auto)) {
     plan->tmem = true;
     plan->resident = true;
@@ -248,7 +249,7 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
     plan->smem = tmem_kernel_dynamic_smem();
     CU(ctx, raise_smem_limit(ctx->device, tmem_kernel_fn(), (int)plan->smem));
     const long long ctas = (long long)tmem_kernel_ctas_per_sm() * ctx->prop.multiProcessorCount;
-    plan->grid = (int)std::max(1LL, std::min(ctas, (n + tmem_kernel_warps() - 1) / tmem_kernel_warps()));
+    plan->grid = (int)std::max(1LL, std::min(ctas, n));  // few LPs: one per CTA (the kernel deals LP i to CTA i % grid)
     return 0;
   }
   if (tune_path == YALPS_PATH_TMEM)
