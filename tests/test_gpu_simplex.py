@@ -539,11 +539,14 @@ def test_register_kernel_options_and_special_values(engine):
 # ---------------------------------------------------------------------------------------------- K1t tensor-memory kernel
 @pytest.mark.parametrize("m,nv,neg", [(32, 64, 0), (32, 64, 8), (32, 64, 32), (1, 1, 0), (5, 3, 2), (7, 40, 3),
                                       (32, 7, 10), (16, 33, 4), (31, 63, 9), (20, 64, 20), (32, 1, 1), (1, 64, 1),
-                                      (8, 64, 0), (9, 64, 5), (24, 48, 0)])
+                                      (8, 64, 0), (9, 64, 5), (24, 48, 0),
+                                      # the 256-column shape (34..65 rows, two RHS cells per lane)
+                                      (64, 64, 0), (64, 64, 20), (64, 64, 64), (33, 64, 5), (35, 32, 8), (40, 10, 3),
+                                      (64, 1, 1), (50, 33, 7), (57, 64, 30)])
 def test_tensor_memory_kernel_bit_exact(engine, m, nv, neg):
-    """K1t: one warp per LP, tableau rows in tensor memory (at most 33 x 65); more LPs than resident warps so
+    """K1t: one warp per LP, tableau rows in tensor memory (at most 65 x 65); more LPs than resident warps so
     that the queue, TMEM reuse across LPs and all four lane quarters are exercised."""
-    n = 4 * 148 * 4 + 37 if (m, nv) == (32, 64) else 200
+    n = 4 * 148 * 4 + 37 if (m, nv) in ((32, 64), (64, 64)) else 200
     mats = O.generate_synthetic(78000, n, m, nv, neg)
     exp = oracle_batch(mats, m + 1, nv + 1)
     engine.set_tuning(E.PATH_TMEM, 0)
@@ -584,7 +587,7 @@ def test_tensor_memory_kernel_options_special_values_and_sparse(engine):
                 got = engine.solve_batch(mats, 33, 65, E.make_options(max_pivots=mp, precision=prec), want_matrices=True)
                 assert_batch_equal(got, exp, f"tmem maxPivots={mp} precision={prec}")
         with pytest.raises(Exception):
-            engine.solve_batch(np.zeros(34 * 65), 34, 65)  # one row too many for the tensor-memory kernel
+            engine.solve_batch(np.zeros(66 * 65), 66, 65)  # one row too many for the tensor-memory kernel
     finally:
         engine.set_tuning(E.PATH_AUTO, 0)
 
@@ -687,7 +690,7 @@ def test_tensor_memory_kernel_on_a_ragged_batch(engine):
     rng = np.random.default_rng(5)
     tabs, shapes, exp = [], [], []
     for i in range(420):
-        m, nv = int(rng.integers(1, 33)), int(rng.integers(1, 65))
+        m, nv = int(rng.integers(1, 65)), int(rng.integers(1, 65))  # both TMEM shapes (up to 33 / up to 65 rows)
         t = O.generate_synthetic(9000 + i, 1, m, nv, int(rng.integers(0, m + 1)))[0]
         tabs.append(t)
         shapes.append((m + 1, nv + 1))

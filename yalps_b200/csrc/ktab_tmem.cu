@@ -6,13 +6,17 @@ namespace yalps {
 
 bool tmem_kernel_fits(int Hcap, int Wcap) { return Hcap >= 1 && Wcap >= 1 && Hcap <= kTmemMaxRows && Wcap <= kTmemMaxCols; }
 int tmem_kernel_warps() { return kTmemWarps; }
-int tmem_kernel_ctas_per_sm() { return kTmemCtasPerSm; }
+// shape by tableau height: HR = 1 (up to 33 rows, 16 LPs per SM) or HR = 2 (up to 65 rows, 8 LPs per SM)
+static bool tall(int Hcap) { return Hcap > TmemShape<1>::kMaxRows; }
+bool tmem_kernel_is_tall(int Hcap) { return tall(Hcap); }
+int tmem_kernel_ctas_per_sm(int Hcap) { return tall(Hcap) ? TmemShape<2>::kCtasPerSm : TmemShape<1>::kCtasPerSm; }
 
-// A CTA beyond 512 / kTmemColumns per SM would block in tcgen05.alloc until a resident (persistent) CTA exits:
-// a dynamic shared-memory request that only fits kTmemCtasPerSm times keeps such CTAs from becoming resident.
-size_t tmem_kernel_dynamic_smem() { return (size_t)(227 * 1024) / (kTmemCtasPerSm + 1) + 1024; }
+// A CTA beyond 512 / kColumns per SM would block in tcgen05.alloc until a resident (persistent) CTA exits:
+// a dynamic shared-memory request that only fits kCtasPerSm times keeps such CTAs from becoming resident.
+size_t tmem_kernel_dynamic_smem(int Hcap) { return (size_t)(227 * 1024) / (tmem_kernel_ctas_per_sm(Hcap) + 1) + 1024; }
+size_t tmem_stream_dynamic_smem() { return tmem_kernel_dynamic_smem(1); }
 
-const void *tmem_kernel_fn() { return (const void *)k_simplex_tmem; }
+const void *tmem_kernel_fn(int Hcap) { return tall(Hcap) ? (const void *)k_simplex_tmem<2> : (const void *)k_simplex_tmem<1>; }
 
 // Tensor-memory stream: every lane reads and rewrites its eight-row blocks (tcgen05.ld/st.32x32b.x32) with the
 // multiply-subtract of the rank-1 update in between.  bytes = grid * 128 lanes * iters * 128 columns * 4 B * 2.
@@ -64,15 +68,19 @@ __global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_tmem_stream
 }
 
 const void *tmem_stream_fn() { return (const void *)k_tmem_stream; }
+int tmem_stream_ctas_per_sm() { return kTmemCtasPerSm; }
 
 cudaError_t launch_tmem_stream(int grid, int iters, double *sink, cudaStream_t stream, double *bytes) {
-  k_tmem_stream<<<grid, kTmemWarps * 32, tmem_kernel_dynamic_smem(), stream>>>(iters, 0.5, sink);
+  k_tmem_stream<<<grid, kTmemWarps * 32, tmem_stream_dynamic_smem(), stream>>>(iters, 0.5, sink);
   *bytes = (double)grid * kTmemWarps * 32 * iters * kTmemColumns * 4.0 * 2.0;
   return cudaGetLastError();
 }
 
 cudaError_t launch_simplex_tmem(const BatchArgs &args, int grid, cudaStream_t stream) {
-  k_simplex_tmem<<<grid, kTmemWarps * 32, tmem_kernel_dynamic_smem(), stream>>>(args);
+  if (tall(args.Hcap))
+    k_simplex_tmem<2><<<grid, kTmemWarps * 32, tmem_kernel_dynamic_smem(args.Hcap), stream>>>(args);
+  else
+    k_simplex_tmem<1><<<grid, kTmemWarps * 32, tmem_kernel_dynamic_smem(args.Hcap), stream>>>(args);
   return cudaGetLastError();
 }
 

@@ -31,17 +31,28 @@
 
 namespace yalps {
 
-constexpr int kTmemMaxRows = 33;   // rows 1..32 <-> lanes 0..31 for the RHS column, 32 rows x 4 columns of TMEM
+// Template parameter HR = RHS cells per lane: HR = 1 holds tableaus of up to 33 rows (128 TMEM columns per CTA, four
+// CTAs = 16 LPs per SM), HR = 2 up to 65 rows (256 columns per CTA, two CTAs = 8 LPs per SM; lane l owns the RHS
+// cells of rows l+1 and l+33).
 constexpr int kTmemMaxCols = 65;   // 64 coefficient columns = 32 lanes x 2
-constexpr int kTmemColumns = 128;  // TMEM columns per CTA (power of two >= 32)
 constexpr int kTmemWarps = 4;
-constexpr int kTmemCtasPerSm = 512 / kTmemColumns;
+template <int HR>
+struct TmemShape {
+  static constexpr int kMaxRows = 32 * HR + 1;   // rows 1..32*HR <-> (lane, slot) for the RHS column
+  static constexpr int kColumns = 128 * HR;      // TMEM columns per CTA (power of two): 4 columns per row
+  static constexpr int kCtasPerSm = 512 / kColumns;
+  static_assert(HR == 1 || HR == 2, "supported shapes");
+};
+constexpr int kTmemMaxRows = TmemShape<2>::kMaxRows;  // tallest tableau of any shape
+constexpr int kTmemColumns = TmemShape<1>::kColumns;  // (k_tmem_stream uses the HR = 1 shape)
+constexpr int kTmemCtasPerSm = TmemShape<1>::kCtasPerSm;
 
 // shared memory per warp
+template <int HR>
 struct TmemWarpSmem {
-  double2 cb[kTmemMaxRows + 7];  // [r] = {pivot-column coefficient or 0 (row left alone), new pivot-column cell}
-  double colx_store[kTmemMaxRows + 9];  // colx = colx_store + 1: entering column M[r, col]; &colx[1] is 16-byte aligned
-  int var[kTmemMaxCols + kTmemMaxRows + 2];
+  double2 cb[TmemShape<HR>::kMaxRows + 7];  // [r] = {pivot-column coefficient or 0 (row left alone), new pivot-column cell}
+  double colx_store[TmemShape<HR>::kMaxRows + 9];  // colx = colx_store + 1: entering column M[r, col]; &colx[1] is 16-byte aligned
+  int var[kTmemMaxCols + TmemShape<HR>::kMaxRows + 2];
 };
 
 // ---- tcgen05 wrappers ---------------------------------------------------------------------------------------
@@ -172,8 +183,10 @@ __device__ __forceinline__ void tmem_block_general(unsigned tblk, const double2 
   tm_st32(tblk, v);
 }
 
-__global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tmem(const BatchArgs a) {
-  __shared__ __align__(16) TmemWarpSmem s_warp[kTmemWarps];
+template <int HR>
+__global__ void __launch_bounds__(kTmemWarps * 32, TmemShape<HR>::kCtasPerSm) k_simplex_tmem(const BatchArgs a) {
+  using S = TmemShape<HR>;
+  __shared__ __align__(16) TmemWarpSmem<HR> s_warp[kTmemWarps];
   __shared__ unsigned s_tmem_base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const double precision = a.precision, INF = d_inf();
@@ -181,7 +194,7 @@ __global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tme
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      (unsigned)__cvta_generic_to_shared(&s_tmem_base)),
-                 "n"(kTmemColumns)
+                 "n"(S::kColumns)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -226,13 +239,17 @@ __global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tme
     const int Wm1 = W - 1;
     const int j0 = 2 * lane;
     const bool v0 = j0 < Wm1, v1 = j0 + 1 < Wm1;  // my two columns exist
-    const bool has_b = lane + 1 < H;               // I own the RHS cell of row lane+1
+    bool has_b[HR];                                // I own the RHS cell of row lane+1+32h
+#pragma unroll
+    for (int h = 0; h < HR; h++) has_b[h] = lane + 1 + 32 * h < H;
     const int nblocks = (H - 1 + 7) >> 3;          // TMEM blocks of eight rows
 
     // ---- load: global -> registers -> TMEM (16 bytes per lane per row, 8 rows in flight)
     const double *src = a.in + moff;
     double o0 = v0 ? src[1 + j0] : 0.0, o1 = v1 ? src[2 + j0] : 0.0;
-    double bv = has_b ? src[(size_t)(lane + 1) * W] : 0.0;
+    double bv[HR];
+#pragma unroll
+    for (int h = 0; h < HR; h++) bv[h] = has_b[h] ? src[(size_t)(lane + 1 + 32 * h) * W] : 0.0;
     double b0 = src[0];
     for (int blk = 0; blk < nblocks; blk++) {
       const int r0 = 1 + 8 * blk;
@@ -257,7 +274,7 @@ __global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tme
     for (int k = lane; k < W + H; k += 32) var[k] = k;
     // rows past H-1 in the last block of eight: zeros in TMEM, never read; a non-zero coefficient keeps the block on
     // the straight-line path
-    for (int k = H + lane; k < kTmemMaxRows + 7; k += 32) cb[k] = make_double2(1.0, 0.0);
+    for (int k = H + lane; k < S::kMaxRows + 7; k += 32) cb[k] = make_double2(1.0, 0.0);
     tm_wait_st();
     __syncwarp();
 
@@ -288,14 +305,22 @@ __global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tme
     for (;;) {
       if (iter >= budget) break;  // per-phase budget exhausted -> "cycled" (:102,:141)
       int row, col;
-      double pr0, pr1;  // old pivot row cells of my two columns
-      double cmine;     // pivot-column cell of my RHS row
+      double pr0, pr1;   // old pivot row cells of my two columns
+      double cmine[HR];  // pivot-column cells of my RHS rows
       if (phase == 1) {
         // leaving row: first index of the most negative RHS below -precision (:111-119)
-        const bool cand = has_b && bv < -precision;
-        row = warp_best<false>(cand ? (unsigned)(order_key(bv) >> 32) : 0xffffffffu,
-                               cand ? (unsigned)order_key(bv) : 0xffffffffu, cand ? lane + 1 : kNone)
-                  .idx;
+        {
+          double best = INF;
+          int bi = kNone;
+#pragma unroll
+          for (int h = 0; h < HR; h++)
+            if (has_b[h] && bv[h] < -precision && bv[h] < best) {  // ascending rows: strict < keeps the first
+              best = bv[h];
+              bi = lane + 1 + 32 * h;
+            }
+          const unsigned long long key = bi == kNone ? no_key<false>() : order_key(best);
+          row = warp_best<false>((unsigned)(key >> 32), (unsigned)key, bi).idx;
+        }
         if (row == kNone) {  // feasible: phase 2 with a fresh counter (:120, :67-69)
           phase = 2;
           p1 = iter;
@@ -331,7 +356,8 @@ __global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tme
           break;
         }
         extract_column(col);
-        cmine = has_b ? colx[lane + 1] : 0.0;
+#pragma unroll
+        for (int h = 0; h < HR; h++) cmine[h] = has_b[h] ? colx[lane + 1 + 32 * h] : 0.0;
       } else {
         // entering column: first index of the largest reduced cost above precision (:71-79)
         {
@@ -354,20 +380,29 @@ __global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tme
           break;
         }
         extract_column(col);
-        cmine = has_b ? colx[lane + 1] : 0.0;
+#pragma unroll
+        for (int h = 0; h < HR; h++) cmine[h] = has_b[h] ? colx[lane + 1 + 32 * h] : 0.0;
         // leaving row: ratio test with the reference's early break (:83-95) == lowest r whose ratio is <= precision
         // if any, else first index of the minimum ratio
-        bool cand = has_b && cmine > precision;
-        double keyv = INF;
         {
-          RecipBatch dr(cmine, cand);
-          double ratio = dr.quot(bv, cand);
-          if (!dr.ok) ratio = div_rn_slow(bv, cmine);  // rare (e.g. a zero RHS): exact division out of line
-          cand = cand && ratio < INF;                  // +inf and NaN never win
-          if (cand) keyv = (ratio <= precision) ? -INF : ratio;
+          double keyv = INF;
+          int bi = kNone;
+#pragma unroll
+          for (int h = 0; h < HR; h++) {
+            bool cand = has_b[h] && cmine[h] > precision;
+            RecipBatch dr(cmine[h], cand);
+            double ratio = dr.quot(bv[h], cand);
+            if (!dr.ok) ratio = div_rn_slow(bv[h], cmine[h]);  // rare (e.g. a zero RHS): exact division out of line
+            cand = cand && ratio < INF;                        // +inf and NaN never win
+            const double k = (ratio <= precision) ? -INF : ratio;
+            if (cand && (bi == kNone || k < keyv)) {  // ascending rows: strict < keeps the first
+              keyv = k;
+              bi = lane + 1 + 32 * h;
+            }
+          }
+          const unsigned long long key = bi == kNone ? no_key<false>() : order_key(keyv);
+          row = warp_best<false>((unsigned)(key >> 32), (unsigned)key, bi).idx;
         }
-        const unsigned long long key = cand ? order_key(keyv) : no_key<false>();
-        row = warp_best<false>((unsigned)(key >> 32), (unsigned)key, cand ? lane + 1 : kNone).idx;
         if (row == kNone) {
           status = ST_UNBOUNDED;
           value = (double)col;
@@ -385,30 +420,47 @@ __global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tme
       const bool own0 = lane == lc && ec == 0, own1 = lane == lc && ec == 1;
       const double x0 = own0 ? 1.0 : pr0, x1 = own1 ? 1.0 : pr1;
       const bool n0 = v0 && fabs(x0) > kTiny, n1 = v1 && fabs(x1) > kTiny;
-      // rows 1..H-1: one lane each (the lane of the pivot row normalises the RHS cell instead)
-      const bool is_prow = lane + 1 == row;
-      const double num = is_prow ? bv : -cmine;
-      const bool nzq = has_b && fabs(num) > kTiny;  // false for NaN, as in the reference
+      // rows 1..H-1: one (lane, slot) each (the owner of the pivot row normalises the RHS cell instead)
+      bool is_prow[HR], nzq[HR];
+      double num[HR], quo[HR];
+#pragma unroll
+      for (int h = 0; h < HR; h++) {
+        is_prow[h] = lane + 1 + 32 * h == row;
+        num[h] = is_prow[h] ? bv[h] : -cmine[h];
+        nzq[h] = has_b[h] && fabs(num[h]) > kTiny;  // false for NaN, as in the reference
+      }
       const bool act0 = fabs(c0raw) > kTiny;       // row 0 (objective row): every lane redundantly
-      double pn0 = rq.quot(x0, n0), pn1 = rq.quot(x1, n1), quo = rq.quot(num, nzq), cn0 = rq.quot(-c0raw, act0);
+      double pn0 = rq.quot(x0, n0), pn1 = rq.quot(x1, n1);
+#pragma unroll
+      for (int h = 0; h < HR; h++) quo[h] = rq.quot(num[h], nzq[h]);
+      double cn0 = rq.quot(-c0raw, act0);
       if (!rq.ok) {  // rare: exact divisions out of line
         pn0 = div_rn_slow(x0, q);
         pn1 = div_rn_slow(x1, q);
-        quo = div_rn_slow(num, q);
+#pragma unroll
+        for (int h = 0; h < HR; h++) quo[h] = div_rn_slow(num[h], q);
         cn0 = div_rn_slow(-c0raw, q);
       }
       pn0 = n0 ? pn0 : 0.0;
       pn1 = n1 ? pn1 : 0.0;
-      quo = nzq ? quo : 0.0;
       cn0 = act0 ? cn0 : 0.0;
       const bool st0 = n0 && !own0, st1 = n1 && !own1;  // cells the rank-1 pass rewrites
-      const double coef_mine = (nzq && !is_prow) ? cmine : 0.0;  // 0 = my row is skipped (:31) or is the pivot row
-      // the pivot row takes part in the row pass with a throw-away coefficient (it is rewritten afterwards)
-      const double cbx = is_prow ? 1.0 : coef_mine;
-      if (has_b) cb[lane + 1] = make_double2(cbx, coef_mine != 0.0 ? quo : cmine);
-      const unsigned on_mask = __ballot_sync(0xffffffffu, !has_b || cbx != 0.0);  // bit l: row l+1 takes the fast form
-      const double p0 = __shfl_sync(0xffffffffu, quo, row - 1);        // normalised RHS of the pivot row
-      const bool nz0 = __shfl_sync(0xffffffffu, nzq ? 1 : 0, row - 1);  // ... was above 1e-16
+      double coef_mine[HR];
+      bool rows_on = true;  // my rows take the fast form of the row pass
+#pragma unroll
+      for (int h = 0; h < HR; h++) {
+        quo[h] = nzq[h] ? quo[h] : 0.0;
+        coef_mine[h] = (nzq[h] && !is_prow[h]) ? cmine[h] : 0.0;  // 0 = my row is skipped (:31) or is the pivot row
+        // the pivot row takes part in the row pass with a throw-away coefficient (it is rewritten afterwards)
+        const double cbx = is_prow[h] ? 1.0 : coef_mine[h];
+        if (has_b[h]) cb[lane + 1 + 32 * h] = make_double2(cbx, coef_mine[h] != 0.0 ? quo[h] : cmine[h]);
+        rows_on = rows_on && (!has_b[h] || cbx != 0.0);
+      }
+      const unsigned on_mask = __ballot_sync(0xffffffffu, rows_on);  // all ones: every row takes the fast form
+      // normalised RHS of the pivot row and whether it was above 1e-16, from its owner: lane (row-1)%32, slot (row-1)/32
+      const bool pslot = HR > 1 && row > 32;
+      const double p0 = __shfl_sync(0xffffffffu, pslot ? quo[HR - 1] : quo[0], (row - 1) & 31);
+      const bool nz0 = __shfl_sync(0xffffffffu, (pslot ? nzq[HR - 1] : nzq[0]) ? 1 : 0, (row - 1) & 31);
       if (lane == 0) {  // basis bookkeeping (:7-12)
         const int leaving = var[W + row];
         var[W + row] = var[col];
@@ -424,10 +476,13 @@ __global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tme
         if (own1) o1 = cn0;
         if (nz0) b0 = __dsub_rn(b0, __dmul_rn(c0raw, p0));
       }
-      if (is_prow)
-        bv = quo;
-      else if (coef_mine != 0.0 && nz0)
-        bv = __dsub_rn(bv, __dmul_rn(coef_mine, p0));
+#pragma unroll
+      for (int h = 0; h < HR; h++) {
+        if (is_prow[h])
+          bv[h] = quo[h];
+        else if (coef_mine[h] != 0.0 && nz0)
+          bv[h] = __dsub_rn(bv[h], __dmul_rn(coef_mine[h], p0));
+      }
 
       // rank-1 pass over the TMEM blocks; a lane's padding cells (zeros, never read) count as rewritable
       {
@@ -463,7 +518,9 @@ __global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tme
       }
       if (a.rhs_out) a.rhs_out[roff] = b0;
     }
-    if (a.rhs_out && has_b) a.rhs_out[roff + lane + 1] = bv;
+#pragma unroll
+    for (int h = 0; h < HR; h++)
+      if (a.rhs_out && has_b[h]) a.rhs_out[roff + lane + 1 + 32 * h] = bv[h];
     if (a.pos_out)
       for (int k = lane; k < W + H; k += 32) a.pos_out[poff + var[k]] = k;
     if (a.var_out)
@@ -472,7 +529,9 @@ __global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tme
     if (a.mat_out) {
       double *dst = a.mat_out + moff;
       if (lane == 0) dst[0] = b0;
-      if (has_b) dst[(size_t)(lane + 1) * W] = bv;
+#pragma unroll
+      for (int h = 0; h < HR; h++)
+        if (has_b[h]) dst[(size_t)(lane + 1 + 32 * h) * W] = bv[h];
       if (v0) dst[1 + j0] = o0;
       if (v1) dst[2 + j0] = o1;
       for (int r = 1; r < H; r++) {
@@ -487,7 +546,7 @@ __global__ void __launch_bounds__(kTmemWarps * 32, kTmemCtasPerSm) k_simplex_tme
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem_base), "n"(kTmemColumns) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem_base), "n"(S::kColumns) : "memory");
 }
 
 }  // namespace yalps

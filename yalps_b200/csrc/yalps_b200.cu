@@ -241,20 +241,22 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
   // batches of every shape from 9x17 to 33x65 (scripts/tmem_vs_smem.py); 1.5-2.3x K2 on big batches with 70-90 % zeros
   // (scripts/tmem_sparse_batches.py); 8-33 % faster than the row-split latency kernels for 1..296 LPs, dense or sparse
   // (scripts/tmem_small_batches.py).
-  const bool tmem_auto = tune_path == YALPS_PATH_AUTO && ctx->tune_threads <= 0 && ctx->tune_rows <= 0;
+  // Tableaus of 34..65 rows take the 256-column shape (8 LPs per SM): automatic in latency mode only.
+  const bool tmem_auto = tune_path == YALPS_PATH_AUTO && ctx->tune_threads <= 0 && ctx->tune_rows <= 0 &&
+                         (!tmem_kernel_is_tall(Hcap) || n <= 2LL * ctx->prop.multiProcessorCount);
   if (allow_reg && tmem_kernel_fits(Hcap, Wcap) && !check_cycles && (tune_path == YALPS_PATH_TMEM || tmem_auto)) {
     plan->tmem = true;
     plan->resident = true;
     plan->k = nullptr;
-    plan->smem = tmem_kernel_dynamic_smem();
-    CU(ctx, raise_smem_limit(ctx->device, tmem_kernel_fn(), (int)plan->smem));
-    const long long ctas = (long long)tmem_kernel_ctas_per_sm() * ctx->prop.multiProcessorCount;
+    plan->smem = tmem_kernel_dynamic_smem(Hcap);
+    CU(ctx, raise_smem_limit(ctx->device, tmem_kernel_fn(Hcap), (int)plan->smem));
+    const long long ctas = (long long)tmem_kernel_ctas_per_sm(Hcap) * ctx->prop.multiProcessorCount;
     plan->grid = (int)std::max(1LL, std::min(ctas, n));  // few LPs: one per CTA (the kernel deals LP i to CTA i % grid)
     return 0;
   }
   if (tune_path == YALPS_PATH_TMEM)
     return fail(ctx, YALPS_ERR_TOO_LARGE, "tableau %dx%d does not fit the tensor-memory kernel (max %dx%d, no checkCycles, no node mode)",
-                Hcap, Wcap, 33, 65);
+                Hcap, Wcap, 65, 65);
   if (allow_reg && Hcap <= kRegMaxRows && Wcap <= kRegMaxCols && !check_cycles &&
       tune_path == YALPS_PATH_REG) {  // explicit only: measured slower than K1 (see reg_kernel.cuh)
     auto it = ctx->occ_cache.find("reg33");
@@ -1291,10 +1293,10 @@ int yalps_measure_smem_bandwidth(yalps_ctx *ctx, double *gbs, double *sm_clock_m
 int yalps_measure_tmem_bandwidth(yalps_ctx *ctx, double *gbs, double *sm_clock_mhz) {
   if (!ctx || !gbs) return YALPS_ERR_ARGUMENT;
   CU(ctx, cudaSetDevice(ctx->device));
-  CU(ctx, raise_smem_limit(ctx->device, tmem_stream_fn(), (int)tmem_kernel_dynamic_smem()));
+  CU(ctx, raise_smem_limit(ctx->device, tmem_stream_fn(), (int)tmem_stream_dynamic_smem()));
   void *sink;
   if (int rc = dev_ensure(ctx, "sink", 64, &sink)) return rc;
-  const int grid = ctx->prop.multiProcessorCount * tmem_kernel_ctas_per_sm();
+  const int grid = ctx->prop.multiProcessorCount * tmem_stream_ctas_per_sm();
   cudaStream_t st = ctx->streams[0];
   cudaEvent_t e0, e1;
   CU(ctx, cudaEventCreate(&e0));
