@@ -241,9 +241,13 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
   // batches of every shape from 9x17 to 33x65 (scripts/tmem_vs_smem.py); 1.5-2.3x K2 on big batches with 70-90 % zeros
   // (scripts/tmem_sparse_batches.py); 8-33 % faster than the row-split latency kernels for 1..296 LPs, dense or sparse
   // (scripts/tmem_small_batches.py).
-  // Tableaus of 34..65 rows take the 256-column shape (8 LPs per SM): automatic in latency mode only.
+  // Tableaus of 34..65 rows take the 256-column shape (8 LPs per SM, scripts/tmem_tall_crossover.py): 1.4-1.85x K1 on
+  // big batches, dense or sparse; 10-20 % faster than K1s for 1..296 DENSE LPs, but 26-40 % slower on sparse Netlib
+  // models (AFIRO, KLEIN1: the row-split kernels compact the few active rows, one warp walks all blocks) -- so in
+  // latency mode the tall shape needs a density probe that says "dense".
+  const bool latency_mode = n <= 2LL * ctx->prop.multiProcessorCount;
   const bool tmem_auto = tune_path == YALPS_PATH_AUTO && ctx->tune_threads <= 0 && ctx->tune_rows <= 0 &&
-                         (!tmem_kernel_is_tall(Hcap) || n <= 2LL * ctx->prop.multiProcessorCount);
+                         (!tmem_kernel_is_tall(Hcap) || (latency_mode ? density >= 0.5 : resident));
   if (allow_reg && tmem_kernel_fits(Hcap, Wcap) && !check_cycles && (tune_path == YALPS_PATH_TMEM || tmem_auto)) {
     plan->tmem = true;
     plan->resident = true;
