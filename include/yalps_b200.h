@@ -81,7 +81,7 @@ enum yalps_path {
   YALPS_PATH_CLUSTER = 5, /* KC: one LP per thread-block cluster, tableau distributed over the cluster's shared
                              memory, pivot row read through DSMEM (csrc/cluster_kernel.cuh) */
   YALPS_PATH_TMEM = 6, /* K1t: one LP per warp, tableau resident in tensor memory (tcgen05.ld/st as a lane-private
-                          scratchpad; at most 33 x 65, no checkCycles), csrc/tmem_kernel.cuh */
+                          scratchpad; at most 65 x 65, no checkCycles), csrc/tmem_kernel.cuh */
   YALPS_PATH_REG = 4   /* K1r (experimental, never chosen automatically): one warp per LP, tableau in registers
                           (at most 33 x 65, no checkCycles); slower than K1, see csrc/reg_kernel.cuh */
 };

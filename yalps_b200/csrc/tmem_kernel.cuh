@@ -22,7 +22,8 @@
 //     as {coef, -coef/q} broadcast loads in the row pass.
 //
 // A CTA is four warps = the four lane quarters of a 128-column allocation; each warp solves its own LPs (no CTA
-// barrier in the loop) and four CTAs share an SM: 16 LPs per SM in flight.  Limits: H <= 33, W <= 65, no
+// barrier in the loop) and four CTAs share an SM: 16 LPs per SM in flight (tableaus of 34..65 rows: 256-column
+// allocations, two RHS cells per lane, 8 LPs per SM -- template parameter HR).  Limits: H <= 65, W <= 65, no
 // checkCycles, no node mode.  Same selection rules, skip rules and rounding sequence as simplex_device.cuh, and
 // bit-identical results (tests/test_gpu_simplex.py).
 #pragma once
