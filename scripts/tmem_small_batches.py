@@ -34,18 +34,20 @@ import numpy as np
 sys.path.insert(0, os.path.join(ROOT))
 from oracle import lib as O
 rng = np.random.default_rng(3)
-for (m, nv) in ((32, 64), (16, 32)):
+for (m, nv, zeros) in ((32, 64, 0.6), (16, 32, 0.6), (32, 64, 0.9), (32, 32, 0.9), (16, 32, 0.9)):
     H, W = m + 1, nv + 1
     for n in (1, 32, 148, 296):
-        t = O.generate_synthetic(9, n, m, nv, 0).reshape(n, H, W).copy()
-        mask = rng.random(t.shape) < 0.6
+        t = O.generate_synthetic(9, n, m, nv, 4).reshape(n, H, W).copy()
+        mask = rng.random(t.shape) < zeros
         mask[:, :, 0] = False
         t[mask] = 0.0
         d = torch.from_numpy(t.reshape(-1)).cuda()
         st = torch.empty(n, dtype=torch.int32, device="cuda"); piv = torch.empty(n, 2, dtype=torch.int64, device="cuda")
-        row = {"shape": [H, W], "n": n, "sparse": 0.6}
-        for path, name in ((E.PATH_AUTO, "auto"), (E.PATH_TMEM, "K1t")):
-            eng.set_tuning(path, 0)
+        row = {"shape": [H, W], "n": n, "sparse": zeros}
+        cells = H * W
+        cfg = (128, 4) if cells < 2500 else (256, 8) if cells < 4000 else (256, 4)
+        for args, name in (((E.PATH_SMEM,) + cfg, "K1s"), ((E.PATH_TMEM, 0, 0), "K1t")):
+            eng.set_tuning(*args)
             run = lambda: eng.solve_batch_device(n, H, W, d.data_ptr(), d_status=st.data_ptr(), d_pivots=piv.data_ptr(), stream=stream)
             for _ in range(3): run()
             torch.cuda.synchronize()

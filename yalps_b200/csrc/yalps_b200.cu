@@ -246,8 +246,11 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
   // models (AFIRO, KLEIN1: the row-split kernels compact the few active rows, one warp walks all blocks) -- so in
   // latency mode the tall shape needs a density probe that says "dense".
   const bool latency_mode = n <= 2LL * ctx->prop.multiProcessorCount;
+  // The short shape loses to K1s only on very sparse tableaus of more than 17 rows in latency mode (90 % zeros,
+  // 33 rows: 23 vs 19 us for one LP; scripts/tmem_small_batches.py).
+  const bool short_ok = !(latency_mode && density >= 0.0 && density < 0.25 && Hcap > 17);
   const bool tmem_auto = tune_path == YALPS_PATH_AUTO && ctx->tune_threads <= 0 && ctx->tune_rows <= 0 &&
-                         (!tmem_kernel_is_tall(Hcap) || (latency_mode ? density >= 0.5 : resident));
+                         (tmem_kernel_is_tall(Hcap) ? (latency_mode ? density >= 0.5 : resident) : short_ok);
   if (allow_reg && tmem_kernel_fits(Hcap, Wcap) && !check_cycles && (tune_path == YALPS_PATH_TMEM || tmem_auto)) {
     plan->tmem = true;
     plan->resident = true;
@@ -854,8 +857,18 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
     const size_t out_b = (size_t)n * 32 + rows_b + 2 * pv_b + 64 + (matrices_out ? in_b : 0);
     const size_t desc_b = ragged ? (size_t)n * 32 + 64 : 0;
     LaunchPlan plan;
+    // density of (a sample of) the first tableau: the latency-mode policy distinguishes dense from very sparse LPs
+    double small_density = -1.0;
+    if (n > 0 && in_b + out_b + desc_b <= ((size_t)768 << 10)) {
+      const double *m0 = matrices + (ragged ? mat_offsets[0] : 0);
+      const long long c0 = ragged ? (long long)heights[0] * widths[0] : (long long)height * width;
+      const long long step = std::max(1LL, c0 / 4096);
+      long long seen = 0, nz = 0;
+      for (long long k = 0; k < c0; k += step, seen++) nz += m0[k] != 0.0;
+      small_density = seen ? (double)nz / (double)seen : 1.0;
+    }
     if (!ctx->keep_final && in_b + out_b + desc_b <= ((size_t)768 << 10) && ctx->tune_path != YALPS_PATH_GRID && ctx->tune_path != YALPS_PATH_CLUSTER &&
-        plan_launch(ctx, n, Hcap, Wcap, opt->check_cycles != 0, &plan, -1.0, true) == 0 && (plan.k || plan.reg || plan.tmem) && plan.resident) {
+        plan_launch(ctx, n, Hcap, Wcap, opt->check_cycles != 0, &plan, small_density, true) == 0 && (plan.k || plan.reg || plan.tmem) && plan.resident) {
       auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
       size_t o = 0;
       const size_t o_in = o; o += up16(in_b);
