@@ -184,6 +184,47 @@ __device__ __forceinline__ void tmem_block_general(unsigned tblk, const double2 
   tm_st32(tblk, v);
 }
 
+// Sparse pivot column: only the rows with a non-zero coefficient are touched (bit l of `mask` <-> row first_row + l),
+// four rows per TMEM round trip -- the one-warp counterpart of the row-split kernels' active-row compaction.
+__device__ __forceinline__ void tmem_rows_sparse(unsigned tbase, unsigned mask, int first_row, const double2 *cb,
+                                                 const TmemPivot &p) {
+  while (mask) {
+    int r[4];
+    unsigned v[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      r[i] = -1;
+      if (mask) {
+        r[i] = first_row + __ffs((int)mask) - 1;
+        mask &= mask - 1;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) v[i][k] = 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      if (r[i] >= 0) {  // (warp-uniform)
+        tm_ld2(tbase + tm_cell(r[i], 0), v[i][0], v[i][1]);
+        tm_ld2(tbase + tm_cell(r[i], 1), v[i][2], v[i][3]);
+      }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 4; i++) asm volatile("" : "+r"(v[i][0]), "+r"(v[i][1]), "+r"(v[i][2]), "+r"(v[i][3])::"memory");
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      if (r[i] >= 0) {
+        const double2 cc = cb[r[i]];
+        double x0 = __hiloint2double((int)v[i][1], (int)v[i][0]), x1 = __hiloint2double((int)v[i][3], (int)v[i][2]);
+        if (p.st0) x0 = __dsub_rn(x0, __dmul_rn(cc.x, p.pn0));
+        if (p.st1) x1 = __dsub_rn(x1, __dmul_rn(cc.x, p.pn1));
+        if (p.own0) x0 = cc.y;
+        if (p.own1) x1 = cc.y;
+        tm_st2(tbase + tm_cell(r[i], 0), (unsigned)__double2loint(x0), (unsigned)__double2hiint(x0));
+        tm_st2(tbase + tm_cell(r[i], 1), (unsigned)__double2loint(x1), (unsigned)__double2hiint(x1));
+      }
+  }
+}
+
 template <int HR>
 __global__ void __launch_bounds__(kTmemWarps * 32, TmemShape<HR>::kCtasPerSm) k_simplex_tmem(const BatchArgs a) {
   using S = TmemShape<HR>;
@@ -496,7 +537,19 @@ __global__ void __launch_bounds__(kTmemWarps * 32, TmemShape<HR>::kCtasPerSm) k_
             for (int blk = 0; blk < nblocks; blk++) tmem_block_fast<1>(tbase + 32u * (unsigned)blk, cb + 1 + 8 * blk, pv);
           }
         } else {
-          for (int blk = 0; blk < nblocks; blk++) tmem_block_general(tbase + 32u * (unsigned)blk, cb + 1 + 8 * blk, pv);
+          unsigned act[HR];  // rows the update rewrites (:31): not skipped, not the pivot row
+          int nact = 0;
+#pragma unroll
+          for (int h = 0; h < HR; h++) {
+            act[h] = __ballot_sync(0xffffffffu, coef_mine[h] != 0.0);
+            nact += __popc(act[h]);
+          }
+          if (4 * nact <= H - 1) {  // sparse pivot column: touch the active rows only
+#pragma unroll
+            for (int h = 0; h < HR; h++) tmem_rows_sparse(tbase, act[h], 1 + 32 * h, cb, pv);
+          } else {
+            for (int blk = 0; blk < nblocks; blk++) tmem_block_general(tbase + 32u * (unsigned)blk, cb + 1 + 8 * blk, pv);
+          }
         }
       }
       tm_wait_st();  // the row pass stored a throw-away value in the pivot row: order the real one behind it

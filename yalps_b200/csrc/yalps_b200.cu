@@ -246,11 +246,10 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
   // models (AFIRO, KLEIN1: the row-split kernels compact the few active rows, one warp walks all blocks) -- so in
   // latency mode the tall shape needs a density probe that says "dense".
   const bool latency_mode = n <= 2LL * ctx->prop.multiProcessorCount;
-  // The short shape loses to K1s only on very sparse tableaus of more than 17 rows in latency mode (90 % zeros,
-  // 33 rows: 23 vs 19 us for one LP; scripts/tmem_small_batches.py).
-  const bool short_ok = !(latency_mode && density >= 0.0 && density < 0.25 && Hcap > 17);
+  // The short shape wins or ties everywhere, very sparse tableaus included (its sparse row pass touches only the
+  // active rows: 90 % zeros, 33x65, one LP: 18.8 vs 18.9 us for K1s; scripts/tmem_small_batches.py).
   const bool tmem_auto = tune_path == YALPS_PATH_AUTO && ctx->tune_threads <= 0 && ctx->tune_rows <= 0 &&
-                         (tmem_kernel_is_tall(Hcap) ? (latency_mode ? density >= 0.5 : resident) : short_ok);
+                         (!tmem_kernel_is_tall(Hcap) || (latency_mode ? density >= 0.5 : resident));
   if (allow_reg && tmem_kernel_fits(Hcap, Wcap) && !check_cycles && (tune_path == YALPS_PATH_TMEM || tmem_auto)) {
     plan->tmem = true;
     plan->resident = true;
