@@ -159,7 +159,9 @@ __device__ __forceinline__ void tmem_block_fast(unsigned tblk, const double2 *cb
   tm_st32(tblk, v);
 }
 
-// General form: per-cell predicates, rows with coef == 0 untouched.
+// General form: per-cell predicates, rows with coef == 0 untouched.  Flat predicates (row active AND cell rewritten)
+// instead of a branch per row: the block stays one straight-line sequence.
+template <int EC>
 __device__ __forceinline__ void tmem_block_general(unsigned tblk, const double2 *cbr, const TmemPivot &p) {
   unsigned v[32];
   tm_ld32(tblk, v);
@@ -167,15 +169,17 @@ __device__ __forceinline__ void tmem_block_general(unsigned tblk, const double2 
 #pragma unroll
   for (int i = 0; i < 8; i++) cc[i] = cbr[i];
   tm_wait_ld(v);
+  const bool own = EC ? p.own1 : p.own0;
 #pragma unroll
   for (int i = 0; i < 8; i++) {
     double x0 = __hiloint2double((int)v[2 * i + 1], (int)v[2 * i]), x1 = __hiloint2double((int)v[16 + 2 * i + 1], (int)v[16 + 2 * i]);
-    if (cc[i].x != 0.0) {
-      if (p.st0) x0 = __dsub_rn(x0, __dmul_rn(cc[i].x, p.pn0));
-      if (p.st1) x1 = __dsub_rn(x1, __dmul_rn(cc[i].x, p.pn1));
-    }
-    if (p.own0) x0 = cc[i].y;
-    if (p.own1) x1 = cc[i].y;
+    const bool on = cc[i].x != 0.0;
+    const bool a0 = on && p.st0, a1 = on && p.st1;
+    const double t0 = __dsub_rn(x0, __dmul_rn(cc[i].x, p.pn0)), t1 = __dsub_rn(x1, __dmul_rn(cc[i].x, p.pn1));
+    x0 = a0 ? t0 : x0;  // (selects, not branches: the arithmetic of an untouched cell is computed and dropped)
+    x1 = a1 ? t1 : x1;
+    if (EC == 0 && own) x0 = cc[i].y;
+    if (EC == 1 && own) x1 = cc[i].y;
     v[2 * i] = (unsigned)__double2loint(x0);
     v[2 * i + 1] = (unsigned)__double2hiint(x0);
     v[16 + 2 * i] = (unsigned)__double2loint(x1);
@@ -548,7 +552,11 @@ __global__ void __launch_bounds__(kTmemWarps * 32, TmemShape<HR>::kCtasPerSm) k_
 #pragma unroll
             for (int h = 0; h < HR; h++) tmem_rows_sparse(tbase, act[h], 1 + 32 * h, cb, pv);
           } else {
-            for (int blk = 0; blk < nblocks; blk++) tmem_block_general(tbase + 32u * (unsigned)blk, cb + 1 + 8 * blk, pv);
+            if (ec == 0) {
+              for (int blk = 0; blk < nblocks; blk++) tmem_block_general<0>(tbase + 32u * (unsigned)blk, cb + 1 + 8 * blk, pv);
+            } else {
+              for (int blk = 0; blk < nblocks; blk++) tmem_block_general<1>(tbase + 32u * (unsigned)blk, cb + 1 + 8 * blk, pv);
+            }
           }
         }
       }
