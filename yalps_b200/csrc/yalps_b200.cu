@@ -227,7 +227,11 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
   const int tune_path = ctx->tune_path == YALPS_PATH_CLUSTER ? (int)YALPS_PATH_AUTO : ctx->tune_path;
   SmemLayout Lr(Hcap, Wcap, true, 32), Lg(Hcap, Wcap, false, 32);
   bool resident = Lr.total <= (size_t)ctx->smem_optin;
-  if (resident && tune_path == YALPS_PATH_AUTO && density >= 0.0 && density < 0.35 && n > 64) resident = false;
+  // (throughput mode only: with at most two LPs per SM the shared-memory row-split kernels are 3x faster than K2 on
+  // sparse Netlib models -- AFIRO, 148 LPs: 46 vs 155 us)
+  if (resident && tune_path == YALPS_PATH_AUTO && density >= 0.0 && density < 0.35 &&
+      n > std::max(64LL, 2LL * ctx->prop.multiProcessorCount))
+    resident = false;
   if (tune_path == YALPS_PATH_SMEM) {
     if (!resident) return fail(ctx, YALPS_ERR_TOO_LARGE, "tableau %dx%d does not fit in shared memory", Hcap, Wcap);
   } else if (tune_path == YALPS_PATH_GMEM) {
