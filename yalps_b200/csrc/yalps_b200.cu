@@ -253,7 +253,12 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
   // The short shape wins or ties everywhere, very sparse tableaus included (its sparse row pass touches only the
   // active rows: 90 % zeros, 33x65, one LP: 18.8 vs 18.9 us for K1s; scripts/tmem_small_batches.py).
   const bool tmem_auto = tune_path == YALPS_PATH_AUTO && ctx->tune_threads <= 0 && ctx->tune_rows <= 0 &&
-                         (!tmem_kernel_is_tall(Hcap) || (latency_mode ? density >= 0.5 : resident));
+                         (!tmem_kernel_is_tall(Hcap) ||
+                          (latency_mode ? density >= 0.5
+                                        // throughput mode (scripts/policy_mid_batches.py): KLEIN1 55x55 (density 0.24) 2.2-2.6x
+                                        // the HBM-resident K2; very sparse AFIRO 36x33 (0.1) only while one wave of
+                                        // 8 LPs per SM covers the batch, beyond that K2 is 20-30 % faster
+                                        : (density < 0.0 || density >= 0.15 || n <= 8LL * ctx->prop.multiProcessorCount)));
   if (allow_reg && tmem_kernel_fits(Hcap, Wcap) && !check_cycles && (tune_path == YALPS_PATH_TMEM || tmem_auto)) {
     plan->tmem = true;
     plan->resident = true;
