@@ -1,0 +1,125 @@
+"""MPS BOUNDS support: yalps_b200.mps.apply_bounds turns column bounds into a model solve() can take
+(shifted / negated / split columns plus `x' <= u - l` rows) and maps the solution back.  The reference cannot run
+such models (benchmarks/netlib/read.ts:50 filters them out), so the expectations are the published Netlib optima and
+an independent LP solver (scipy / HiGHS); the oracle solves the transformed models on the CPU."""
+import gzip
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import model as OM
+from yalps_b200 import mps as P
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def bounded_fixture():
+    with gzip.open(os.path.join(HERE, "golden", "netlib_bounded.json.gz"), "rt") as f:
+        return json.load(f)
+
+
+def random_bounded_model(rng, m, n):
+    names = [f"x{j}" for j in range(n)]
+    A = rng.integers(-3, 6, size=(m, n)).astype(float)
+    A[rng.random((m, n)) < 0.4] = 0.0
+    c = rng.integers(-5, 6, size=n).astype(float)
+    kinds = rng.integers(0, 6, size=n)
+    bounds, lo, hi = {}, np.zeros(n), np.full(n, np.inf)
+    for j, k in enumerate(kinds):
+        if k == 1:
+            lo[j], hi[j] = 0.0, float(rng.integers(1, 8))
+        elif k == 2:
+            lo[j], hi[j] = float(rng.integers(-6, 0)), float(rng.integers(1, 6))
+        elif k == 3:
+            lo[j], hi[j] = -np.inf, float(rng.integers(-3, 4))
+        elif k == 4:
+            lo[j], hi[j] = -np.inf, np.inf
+        elif k == 5:
+            lo[j] = hi[j] = float(rng.integers(-2, 3))
+        if k:
+            bounds[names[j]] = [lo[j], hi[j]]
+    x0 = np.where(np.isfinite(lo), lo, np.where(np.isfinite(hi), hi, 0.0)) + rng.random(n) * np.where(np.isfinite(hi - lo), hi - lo, 2.0) * 0.5
+    x0 = np.clip(x0, lo, hi)
+    b = A @ x0 + rng.integers(0, 4, size=m)  # feasible by construction (x0)
+    box = 50.0  # keeps every LP bounded: sum |x| cannot run away along a free direction
+    variables = [(names[j], [("obj", c[j])] + [(f"r{i}", A[i, j]) for i in range(m) if A[i, j] != 0.0]) for j in range(n)]
+    constraints = [(f"r{i}", {"max": float(b[i])}) for i in range(m)]
+    for j in range(n):  # explicit box so that HiGHS and the tableau simplex agree on boundedness
+        if not np.isfinite(lo[j]):
+            lo[j] = -box
+        if not np.isfinite(hi[j]):
+            hi[j] = box
+        bounds[names[j]] = [float(lo[j]), float(hi[j])]
+    model = {"name": "rand", "direction": "minimize", "objective": "obj", "constraints": constraints, "variables": variables,
+             "integers": set(), "binaries": set(), "bounds": bounds}
+    return model, A, b, c, lo, hi
+
+
+def test_transformation_against_highs_on_random_bounded_lps():
+    linprog = pytest.importorskip("scipy.optimize").linprog
+    rng = np.random.default_rng(7)
+    checked = 0
+    for _ in range(40):
+        m, n = int(rng.integers(2, 7)), int(rng.integers(2, 8))
+        model, A, b, c, lo, hi = random_bounded_model(rng, m, n)
+        ref = linprog(c, A_ub=A, b_ub=b, bounds=list(zip(lo, hi)), method="highs")
+        tm, recover = P.apply_bounds(model)
+        assert "bounds" not in tm
+        sol = recover(OM.solve(tm))
+        if ref.status == 0:
+            assert sol["status"] == "optimal"
+            assert abs(sol["result"] - ref.fun) <= 1e-6 * max(1.0, abs(ref.fun))
+            x = dict(sol["variables"])
+            xs = np.array([x.get(f"x{j}", 0.0) for j in range(n)])
+            assert (xs >= lo - 1e-7).all() and (xs <= hi + 1e-7).all() and (A @ xs <= b + 1e-6).all()
+            assert abs(c @ xs - sol["result"]) <= 1e-6 * max(1.0, abs(ref.fun))
+            checked += 1
+        elif ref.status == 2:
+            assert sol["status"] == "infeasible"
+    assert checked >= 25
+
+
+def test_each_bound_kind_by_hand():
+    base = {"name": "t", "direction": "maximize", "objective": "o", "integers": set(), "binaries": set(),
+            "constraints": [("c", {"max": 10.0})]}
+    # x in [2, 5], y free, z in (-inf, 3], w fixed at 4:   max x + y + z + w  s.t.  x + y + z + w <= 10
+    model = dict(base, variables=[("x", [("o", 1.0), ("c", 1.0)]), ("y", [("o", 1.0), ("c", 1.0)]),
+                                  ("z", [("o", 1.0), ("c", 1.0)]), ("w", [("o", 1.0), ("c", 1.0)])],
+                 bounds={"x": [2.0, 5.0], "y": [-math.inf, math.inf], "z": [-math.inf, 3.0], "w": [4.0, 4.0]})
+    tm, recover = P.apply_bounds(model)
+    keys = [k for k, _ in tm["variables"]]
+    assert keys == ["x", "y", "y__neg", "z"]                      # w became a constant, y was split
+    cons = dict(tm["constraints"])
+    assert cons["c"] == {"max": 10.0 - 2.0 - 3.0 - 4.0} and cons["x__ub"] == {"max": 3.0}
+    assert dict(dict(tm["variables"])["z"])["c"] == -1.0           # z = 3 - z'
+    sol = recover(OM.solve(tm))
+    assert sol["status"] == "optimal" and sol["result"] == 10.0
+    x = dict(sol["variables"])
+    assert x["w"] == 4.0 and 2.0 <= x["x"] <= 5.0 and x.get("z", 0.0) <= 3.0
+    with pytest.raises(ValueError):
+        P.apply_bounds(dict(model, bounds={"x": [3.0, 1.0]}))
+
+
+def test_bounded_netlib_models_reach_the_published_optimum_on_the_oracle():
+    for case in bounded_fixture():
+        tm, recover = P.apply_bounds(P.netlib_model(case["mps"]))
+        sol = recover(OM.solve(tm, {"maxPivots": 8192}))
+        assert sol["status"] == "optimal", case["name"]
+        assert abs(sol["result"] - case["published"]) <= 1e-5 * abs(case["published"]), case["name"]  # tests/additional/netlib.ts tolerance
+        assert sol["result"] == case["oracle_result"]
+
+
+@pytest.mark.gpu
+def test_bounded_netlib_models_through_the_product_path(engine):
+    """The same models through yalps_b200.solve (GPU kernels): published optimum within 1e-5 and the oracle's result
+    bit for bit."""
+    import yalps_b200
+    for case in bounded_fixture():
+        tm, recover = P.apply_bounds(P.netlib_model(case["mps"]))
+        sol = recover(yalps_b200.solve(tm, {"maxPivots": 8192}, engine=engine))
+        assert sol["status"] == "optimal", case["name"]
+        assert abs(sol["result"] - case["published"]) <= 1e-5 * abs(case["published"]), case["name"]
+        assert sol["result"] == case["oracle_result"], case["name"]

@@ -205,3 +205,84 @@ def netlib_model(text: str) -> dict:
     return {"name": mps["name"], "direction": "minimize", "objective": mps["objective"], "constraints": constraints,
             "variables": [(k, list(v.items())) for k, v in mps["variables"].items()], "integers": mps["integers"],
             "binaries": mps["binaries"], "bounds": mps["bounds"]}
+
+
+def apply_bounds(model: dict) -> tuple:
+    """Column bounds (the MPS BOUNDS section) expressed in a model solve() can take.
+
+    The reference's variables are implicitly >= 0 and its Netlib harness drops every model with a BOUNDS section
+    (benchmarks/netlib/read.ts:50); this is the host-side transformation SURVEY 8(f)-4 asks for.  For a column x
+    with bounds [l, u] (default [0, inf), benchmarks/mps.ts:254-258):
+
+      l finite   x = l + x'            x' >= 0; every constraint bound and the objective shift by coef * l;
+                                       u finite adds the row  x' <= u - l  (a fixed column, l == u, becomes a constant)
+      l = -inf   x = u - x' (u finite) x' >= 0, coefficients negated, shifts by coef * u
+                 x = x+ - x-  (free)   two non-negative columns
+
+    Returns (model without "bounds", recover) where recover(solution) maps a Solution of the transformed model back
+    to the original variables and objective value.  `model` is a netlib_model()-style dict (pair lists).
+    """
+    bounds = model.get("bounds") or {}
+    shift = {}       # constraint key -> sum of coef * offset (moved to the right-hand side)
+    obj_const = 0.0
+    variables, extra_rows, back = [], [], {}
+    for name, coefs in model["variables"]:
+        lo, hi = bounds.get(name, (0.0, math.inf))
+        coefs = list(coefs)
+        if lo > hi:
+            raise ValueError(f"column {name}: lower bound {lo} above upper bound {hi}")
+        if math.isfinite(lo):
+            offset, sign = lo, 1.0
+        elif math.isfinite(hi):
+            offset, sign = hi, -1.0
+        else:  # free column: x = x+ - x-
+            variables.append((name, coefs))
+            variables.append((name + "__neg", [(k, -c) for k, c in coefs]))
+            back[name] = ("free", name, name + "__neg")
+            continue
+        if offset != 0.0:
+            for k, c in coefs:
+                if k == model["objective"]:
+                    obj_const += c * offset
+                shift[k] = shift.get(k, 0.0) + c * offset
+        if sign < 0:
+            coefs = [(k, -c) for k, c in coefs]
+        width = hi - lo if sign > 0 else math.inf  # range left for x'
+        if width == 0.0:
+            back[name] = ("const", offset)
+            continue  # fixed column: only its constant contribution remains
+        if math.isfinite(width):
+            row = name + "__ub"
+            coefs.append((row, 1.0))
+            extra_rows.append((row, {"max": width}))
+        variables.append((name, coefs))
+        back[name] = ("affine", offset, sign)
+    constraints = []
+    for key, con in model["constraints"]:
+        s = shift.get(key, 0.0)
+        constraints.append((key, {f: v - s for f, v in con.items()} if s != 0.0 else dict(con)))
+    out = {k: v for k, v in model.items() if k != "bounds"}
+    out["constraints"] = constraints + extra_rows
+    out["variables"] = variables
+
+    def recover(solution: dict) -> dict:
+        sol = dict(solution)
+        if solution["status"] not in ("optimal", "timedout") or solution["result"] != solution["result"]:
+            return sol
+        vals = dict(solution["variables"])
+        orig = []
+        for name, _ in model["variables"]:
+            kind = back[name]
+            if kind[0] == "const":
+                x = kind[1]
+            elif kind[0] == "free":
+                x = vals.get(kind[1], 0.0) - vals.get(kind[2], 0.0)
+            else:
+                x = kind[1] + kind[2] * vals.get(name, 0.0)
+            if x != 0.0:
+                orig.append([name, x])
+        sol["variables"] = orig
+        sol["result"] = solution["result"] + obj_const
+        return sol
+
+    return out, recover
