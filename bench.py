@@ -145,7 +145,7 @@ def run_reference(args):
         return 0
     n, m, nv, neg = WORKLOADS[args.workload]
     cores = host_cores()
-    sample = min(n, 16384)
+    sample = n  # every step is the whole batch of the native arm's step (same config, same sample as its cpu_baseline)
     for _ in range(args.warmup):
         cpu_baseline(min(sample, 2048), m, nv, neg, 0, cores)
     tot_piv, tot_t, tot_lp = 0, 0.0, 0
@@ -168,7 +168,7 @@ def run_reference(args):
         "lps_per_s": tot_lp / tot_t,
         "samples": {"n": len(rates), "mean": mean, "stddev": sigma, "unit": "pivots/s"},
         "cpu_baseline": {"value": value, "unit": "pivots/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} LPs of the workload per step, {cores} threads; single thread: "
+                         "sample": f"all {sample} LPs of one step per step, {cores} threads; single thread: "
                                    f"{one_thread:.4g} pivots/s",
                          "note": "C restatement of src/simplex.ts (oracle/), not Node/V8: no JS engine in this image"},
         "e2e": {"value": value, "unit": "pivots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -79,11 +79,12 @@ enum yalps_path {
   YALPS_PATH_GMEM = 2, /* K2: tableau in HBM/L2, CTA per LP, pivot row/column staged in shared memory */
   YALPS_PATH_GRID = 3, /* K4: one LP across the whole grid (cooperative launch) */
   YALPS_PATH_CLUSTER = 5, /* KC: one LP per thread-block cluster, tableau distributed over the cluster's shared
-                             memory, pivot row read through DSMEM (csrc/cluster_kernel.cuh) */
+                             memory; candidate pivot rows are published to an L2-resident scratch and the winner's row
+                             is staged from there, DSMEM carries only the 16-byte selection records
+                             (csrc/cluster_kernel.cuh) */
   YALPS_PATH_TMEM = 6, /* K1t: one LP per warp, tableau resident in tensor memory (tcgen05.ld/st as a lane-private
                           scratchpad; at most 65 x 65, no checkCycles), csrc/tmem_kernel.cuh */
-  YALPS_PATH_REG = 4   /* K1r (experimental, never chosen automatically): one warp per LP, tableau in registers
-                          (at most 33 x 65, no checkCycles); slower than K1, see csrc/reg_kernel.cuh */
+  /* 4 is retired (a register-resident experiment that never beat K1) and rejected by yalps_set_tuning */
 };
 
 /* ---- context ------------------------------------------------------------ */

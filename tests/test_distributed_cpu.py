@@ -98,3 +98,45 @@ def test_sharded_branch_and_cut_world2(case_name):
         assert same_bits(np.asarray(lp_value), ref_lp["value"])
         assert inc == 5.0
     assert outs[0][1:] == outs[1][1:]  # both ranks hold identical results
+
+
+def _timeout_worker(rank, world, port, queue):
+    """A finite timeout with ranks whose node evaluation takes different wall time: without a collective stop decision
+    the fast rank would leave the loop while the slow one enters the next wave's all_gather."""
+    import time
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        case = next(c for c in load_cases() if c["name"] == "Fancy Stock Cutting Problem")
+        opt = {**M.DEFAULT_OPTIONS, **case["options"], "timeout": 60.0}
+        tm = M.tableau_model(case["model"])
+        t = tm.tableau
+        st, value, _ = O.simplex(t.matrix, t.width, t.height, t.pos, t.var, opt["precision"], opt["maxPivots"], False)
+        rhs = t.matrix.reshape(t.height, t.width)[:, 0].copy()
+        inner = oracle_eval_nodes(t, opt)
+
+        def slow_eval(cut_lists):
+            time.sleep(0.015 * (1 + rank))  # rank 1 is twice as slow: the ranks' clocks cross the deadline in different iterations
+            return inner(cut_lists)
+
+        res = D.branch_and_cut_sharded(slow_eval, rhs, t.pos, t.var, t.width, t.height, tm.integers, tm.sign, value,
+                                       opt, wave=4, allreduce_every=2)
+        queue.put((rank, res["status"], repr(res["result"]), res["stats"]["nodes"], res["stats"]["waves"]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_branch_and_cut_finite_timeout_is_collective():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=_timeout_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert outs[0][1:] == outs[1][1:], outs     # same status, result, node and wave counts on both ranks
+    assert outs[0][1] == "timedout", outs        # 129 nodes at >= 15 ms per wave of 4 cannot finish in 60 ms

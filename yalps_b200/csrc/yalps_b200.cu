@@ -25,7 +25,6 @@
 #include "aux_kernels.cuh"
 #include "cluster_kernel.cuh"
 #include "grid_kernel.cuh"
-#include "reg_kernel.cuh"
 #include "tmem_launch.h"
 
 using namespace yalps;
@@ -209,7 +208,6 @@ int default_warps(long long cells, bool resident) {
 }
 
 struct LaunchPlan {
-  bool reg = false;  // K1r: tableau in registers (small LPs)
   bool tmem = false;  // K1t: tableau in tensor memory, one LP per warp (tmem_kernel.cuh)
   bool small_for_grid = false;  // few LPs outside shared memory, yet small enough that one row-split CTA beats K4
   bool resident;
@@ -222,7 +220,7 @@ struct LaunchPlan {
 // the rank-1 update, their pivots are latency-bound, and the HBM/L2-resident kernel wins because it needs no
 // shared memory for the tableau and therefore runs many more LPs per SM (profiles/r01_sweep_paths.jsonl).
 int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycles, LaunchPlan *plan,
-                double density = -1.0, bool allow_reg = false) {
+                double density = -1.0, bool allow_tmem = false) {
   // a forced cluster path is resolved by maybe_cluster(); what it cannot take is planned as in automatic mode
   const int tune_path = ctx->tune_path == YALPS_PATH_CLUSTER ? (int)YALPS_PATH_AUTO : ctx->tune_path;
   SmemLayout Lr(Hcap, Wcap, true, 32), Lg(Hcap, Wcap, false, 32);
@@ -238,7 +236,6 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
     resident = false;
   }
   const bool grid_ok = tune_path == YALPS_PATH_GRID || (tune_path == YALPS_PATH_AUTO && n <= 16);
-  plan->reg = false;
   plan->tmem = false;
   // K1t (tensor-memory resident, one LP per warp, no CTA barrier in the pivot loop): every batch whose tableaus fit
   // it, whatever its size and density.  Measured against the previous choices on B200: 1.47-1.68x K1 on big dense
@@ -259,7 +256,7 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
                                         // the HBM-resident K2; very sparse AFIRO 36x33 (0.1) only while one wave of
                                         // 8 LPs per SM covers the batch, beyond that K2 is 20-30 % faster
                                         : (density < 0.0 || density >= 0.15 || n <= 8LL * ctx->prop.multiProcessorCount)));
-  if (allow_reg && tmem_kernel_fits(Hcap, Wcap) && !check_cycles && (tune_path == YALPS_PATH_TMEM || tmem_auto)) {
+  if (allow_tmem && tmem_kernel_fits(Hcap, Wcap) && !check_cycles && (tune_path == YALPS_PATH_TMEM || tmem_auto)) {
     plan->tmem = true;
     plan->resident = true;
     plan->k = nullptr;
@@ -272,28 +269,6 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
   if (tune_path == YALPS_PATH_TMEM)
     return fail(ctx, YALPS_ERR_TOO_LARGE, "tableau %dx%d does not fit the tensor-memory kernel (max %dx%d, no checkCycles, no node mode)",
                 Hcap, Wcap, 65, 65);
-  if (allow_reg && Hcap <= kRegMaxRows && Wcap <= kRegMaxCols && !check_cycles &&
-      tune_path == YALPS_PATH_REG) {  // explicit only: measured slower than K1 (see reg_kernel.cuh)
-    auto it = ctx->occ_cache.find("reg33");
-    int occ = 0;
-    if (it == ctx->occ_cache.end()) {
-      CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_simplex_reg<kRegMaxRows>, 32, 0));
-      ctx->occ_cache["reg33"] = occ;
-    } else {
-      occ = it->second;
-    }
-    if (occ >= 1) {
-      plan->reg = true;
-      plan->resident = true;
-      plan->k = nullptr;
-      plan->smem = 0;
-      plan->grid = (int)std::max(1LL, std::min((long long)occ * ctx->prop.multiProcessorCount, n));
-      return 0;
-    }
-  }
-  if (tune_path == YALPS_PATH_REG)
-    return fail(ctx, YALPS_ERR_TOO_LARGE, "tableau %dx%d does not fit the register-resident kernel (max %dx%d, no checkCycles)",
-                Hcap, Wcap, kRegMaxRows, kRegMaxCols);
   plan->resident = resident;
   plan->k = nullptr;
   plan->smem = 0;
@@ -385,7 +360,7 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
 // K4 (whole grid per LP, LPs one after another) beats K2 (one CTA per LP) when the tableaus do not fit in
 // shared memory and there are too few of them to give every SM its own LP.
 bool use_grid_path(const yalps_ctx *ctx, long long n, const LaunchPlan &plan) {
-  if (plan.reg || plan.tmem) return false;
+  if (plan.tmem) return false;
   if (ctx->tune_path == YALPS_PATH_GRID || plan.k == nullptr) return true;
   if (ctx->tune_path != YALPS_PATH_AUTO && ctx->tune_path != YALPS_PATH_CLUSTER) return false;
   return !plan.resident && n <= 16 && !plan.small_for_grid;
@@ -419,12 +394,6 @@ int launch_simplex(yalps_ctx *ctx, const LaunchPlan &plan, BatchArgs &args, cons
   }
   if (plan.tmem) {
     CU(ctx, launch_simplex_tmem(args, plan.grid, stream));
-    ctx->launches++;
-    return 0;
-  }
-  if (plan.reg) {
-    k_simplex_reg<kRegMaxRows><<<plan.grid, 32, 0, stream>>>(args);
-    CU(ctx, cudaGetLastError());
     ctx->launches++;
     return 0;
   }
@@ -528,7 +497,7 @@ int launch_cluster(yalps_ctx *ctx, const ClusterPlan &plan, BatchArgs &args, con
 bool want_cluster(const yalps_ctx *ctx, long long n, const LaunchPlan &plan, const ClusterPlan &cp) {
   if (!cp.k) return false;
   if (ctx->tune_path == YALPS_PATH_CLUSTER) return true;
-  if (ctx->tune_path != YALPS_PATH_AUTO || plan.reg || plan.tmem) return false;
+  if (ctx->tune_path != YALPS_PATH_AUTO || plan.tmem) return false;
   return !plan.resident && n <= 2LL * std::max(1, cp.clusters);
 }
 
@@ -538,7 +507,7 @@ int maybe_cluster(yalps_ctx *ctx, long long n, int Hcap, int Wcap, const LaunchP
                   const std::string &slot, cudaStream_t stream) {
   const bool forced = ctx->tune_path == YALPS_PATH_CLUSTER;
   if (!plan && !forced) return 0;
-  if (plan && (forced || ctx->tune_path != YALPS_PATH_AUTO || plan->resident || plan->reg || plan->tmem)) return 0;
+  if (plan && (forced || ctx->tune_path != YALPS_PATH_AUTO || plan->resident || plan->tmem)) return 0;
   ClusterPlan cp;
   if (int rc = plan_cluster(ctx, Hcap, Wcap, &cp)) return rc;
   if (forced) {
@@ -643,7 +612,7 @@ int yalps_device_info(const yalps_ctx *ctx, int32_t *sm_count, int32_t *smem_per
 
 int yalps_set_tuning(yalps_ctx *ctx, int32_t path, int32_t threads_per_lp) {
   if (!ctx) return YALPS_ERR_ARGUMENT;
-  if (path < 0 || path > YALPS_PATH_TMEM) return fail(ctx, YALPS_ERR_ARGUMENT, "bad path %d", path);
+  if (path < 0 || path > YALPS_PATH_TMEM || path == 4) return fail(ctx, YALPS_ERR_ARGUMENT, "bad path %d", path);
   ctx->tune_path = path;
   ctx->tune_threads = threads_per_lp;
   return 0;
@@ -876,7 +845,7 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
       small_density = seen ? (double)nz / (double)seen : 1.0;
     }
     if (!ctx->keep_final && in_b + out_b + desc_b <= ((size_t)768 << 10) && ctx->tune_path != YALPS_PATH_GRID && ctx->tune_path != YALPS_PATH_CLUSTER &&
-        plan_launch(ctx, n, Hcap, Wcap, opt->check_cycles != 0, &plan, small_density, true) == 0 && (plan.k || plan.reg || plan.tmem) && plan.resident) {
+        plan_launch(ctx, n, Hcap, Wcap, opt->check_cycles != 0, &plan, small_density, true) == 0 && (plan.k || plan.tmem) && plan.resident) {
       auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
       size_t o = 0;
       const size_t o_in = o; o += up16(in_b);

@@ -44,6 +44,17 @@ def allreduce_min(value: float, device=None) -> float:
     return float(t.item())
 
 
+def allreduce_flag(flag: bool, device=None) -> bool:
+    """Collective OR of a stop flag: every rank gets True as soon as one rank raises it."""
+    dist = _dist()
+    if dist is None or dist.get_world_size() == 1:
+        return bool(flag)
+    import torch
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device or "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return bool(int(t.item()))
+
+
 def gather_arrays(local: np.ndarray, counts: Sequence[int], device=None) -> np.ndarray:
     """all_gather of per-rank row blocks with known row counts -> concatenated array on every rank."""
     dist = _dist()
@@ -120,6 +131,12 @@ def branch_and_cut_sharded(eval_nodes: Callable[[list], list], root_rhs, root_po
     eval_nodes(list_of_cut_lists) -> list of {"status", "value", "pivots", "rhs", "pos", "var"} evaluated on
     THIS rank's GPU (e.g. Engine.bnb_solve_nodes against the replicated root).  Every rank calls this function
     with the same arguments and returns the same result.
+
+    `timeout` (src/branchAndCut.ts:115-116,162) is a wall-clock test, and the ranks' clocks differ: a rank that
+    decided on its own could leave the loop while the others enter the next wave's collectives.  With more than one
+    rank the decision is therefore collective: the clock is read where all ranks arrive in lockstep -- once before
+    the loop and at every wave boundary -- and OR-reduced; between waves the (sticky) agreed flag is used.  With one
+    rank, or with the default `timeout = inf` (no clock test needed at all), the loop is the reference's.
     """
     dist = _dist()
     world = dist.get_world_size() if dist else 1
@@ -141,7 +158,12 @@ def branch_and_cut_sharded(eval_nodes: Callable[[list], list], root_rhs, root_po
     cache: dict = {}
     threshold = init_result * (1.0 - sign * options["tolerance"])
     stop_time = options["timeout"] + math.floor(time.time() * 1000.0)
-    timedout = math.floor(time.time() * 1000.0) >= stop_time
+    collective_clock = world > 1 and math.isfinite(options["timeout"])
+
+    def clock_says_stop() -> bool:
+        return math.floor(time.time() * 1000.0) >= stop_time
+
+    timedout = allreduce_flag(clock_says_stop(), device) if collective_clock else clock_says_stop()
     found, best_eval, best = False, math.inf, None
     it = 0
 
@@ -191,6 +213,10 @@ def branch_and_cut_sharded(eval_nodes: Callable[[list], list], root_rhs, root_po
         if br.eval > best_eval:
             break
         if br.id not in cache:
+            if collective_clock and allreduce_flag(clock_says_stop(), device):
+                heapq.heappush(heap, br)  # same heap contents on every rank: the status rule below sees it non-empty
+                timedout = True
+                break
             run_wave(br)
             if allreduce_every and stats["waves"] % allreduce_every == 0:
                 agreed = allreduce_min(best_eval, device)
@@ -217,7 +243,8 @@ def branch_and_cut_sharded(eval_nodes: Callable[[list], list], root_rhs, root_po
                 heapq.heappush(heap, _Branch(node["value"], upper, next_id))
                 heapq.heappush(heap, _Branch(node["value"], lower, next_id + 1))
                 next_id += 2
-        timedout = math.floor(time.time() * 1000.0) >= stop_time
+        if not collective_clock:
+            timedout = clock_says_stop()
         it += 1
 
     unfinished = (timedout or it >= options["maxIterations"]) and bool(heap) and best_eval >= threshold

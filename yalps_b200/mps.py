@@ -40,9 +40,9 @@ def model_from_mps(text: str, direction: Optional[str] = None) -> dict:
     if start is None:
         raise MpsError("Line 1: No NAME section was found")
     model = {"name": _fields(lines[start])[2], "direction": direction, "objective": None, "constraints": {},
-             "variables": {}, "bounds": {}, "integers": set(), "binaries": set()}
+             "variables": {}, "bounds": {}, "column_bounds": {}, "integers": set(), "binaries": set()}
     row_type: dict = {}
-    state = {"section": None, "int": False, "col": None, "lineno": start + 1}
+    state = {"section": None, "int": False, "col": None, "lineno": start + 1, "bound_lower_seen": set()}
 
     def fail(msg):
         raise MpsError(f"Line {state['lineno'] + 1}: {msg}")
@@ -158,6 +158,30 @@ def model_from_mps(text: str, direction: Optional[str] = None) -> dict:
             b[0] = lo
         if not math.isnan(hi):
             b[1] = hi
+        # `bounds` above is the reference reader's table, quirk included: every BOUNDS line rewrites BOTH sides
+        # (benchmarks/mps.ts:254-258,287-288), so `LO x 1` + `UP x 4` ends as [0, 4] or [1, inf) depending on the line
+        # order.  The reference never reads it (benchmarks/netlib/read.ts:50 drops such models); apply_bounds() does,
+        # so the usual MPS meaning -- one side per line -- is kept separately in `column_bounds`.
+        cb = model["column_bounds"].setdefault(col, [0.0, INF])
+        seen = state["bound_lower_seen"]
+        if typ in ("LO", "LI"):
+            cb[0] = v
+            seen.add(col)
+        elif typ in ("UP", "UI"):
+            cb[1] = v
+            if v < 0.0 and col not in seen:  # the common convention: a negative upper bound without a lower one
+                cb[0] = -INF
+        elif typ == "FX":
+            cb[0] = cb[1] = v
+            seen.add(col)
+        elif typ == "FR":
+            cb[0], cb[1] = -INF, INF
+            seen.add(col)
+        elif typ == "MI":
+            cb[0] = -INF
+            seen.add(col)
+        elif typ == "PL":
+            cb[1] = INF
 
     handlers = {"ROWS": on_rows, "COLUMNS": on_columns, "RHS": on_rhs, "RANGES": on_ranges, "BOUNDS": on_bounds}
     order = {"ROWS": ("COLUMNS",), "COLUMNS": ("RHS",), "RHS": ("RANGES", "BOUNDS", "ENDATA"),
@@ -204,7 +228,7 @@ def netlib_model(text: str) -> dict:
             constraints.append((key, {"max": hi}))
     return {"name": mps["name"], "direction": "minimize", "objective": mps["objective"], "constraints": constraints,
             "variables": [(k, list(v.items())) for k, v in mps["variables"].items()], "integers": mps["integers"],
-            "binaries": mps["binaries"], "bounds": mps["bounds"]}
+            "binaries": mps["binaries"], "bounds": mps["bounds"], "column_bounds": mps["column_bounds"]}
 
 
 def apply_bounds(model: dict) -> tuple:
@@ -222,13 +246,25 @@ def apply_bounds(model: dict) -> tuple:
     Returns (model without "bounds", recover) where recover(solution) maps a Solution of the transformed model back
     to the original variables and objective value.  `model` is a netlib_model()-style dict (pair lists).
     """
-    bounds = model.get("bounds") or {}
+    # `column_bounds` (one side per BOUNDS line) when the model came from model_from_mps(); a hand-made model may give
+    # the same table under "bounds"
+    bounds = model.get("column_bounds") if model.get("column_bounds") is not None else (model.get("bounds") or {})
+    integers = set(model.get("integers") or ())
+    binaries = set(model.get("binaries") or ())
+    new_integers = set(integers)
     shift = {}       # constraint key -> sum of coef * offset (moved to the right-hand side)
     obj_const = 0.0
     variables, extra_rows, back = [], [], {}
     for name, coefs in model["variables"]:
         lo, hi = bounds.get(name, (0.0, math.inf))
         coefs = list(coefs)
+        if name in integers and name not in binaries:
+            # an integer column only takes integer values: tightening its bounds to integers changes nothing and
+            # keeps the shifted column x' = x - l integral
+            lo = float(math.ceil(lo)) if math.isfinite(lo) else lo
+            hi = float(math.floor(hi)) if math.isfinite(hi) else hi
+        elif name in binaries and (lo, hi) != (0.0, math.inf):
+            raise ValueError(f"column {name}: a binary column cannot carry other bounds")
         if lo > hi:
             raise ValueError(f"column {name}: lower bound {lo} above upper bound {hi}")
         if math.isfinite(lo):
@@ -239,6 +275,8 @@ def apply_bounds(model: dict) -> tuple:
             variables.append((name, coefs))
             variables.append((name + "__neg", [(k, -c) for k, c in coefs]))
             back[name] = ("free", name, name + "__neg")
+            if name in integers:  # x integer <=> both parts can be taken integer
+                new_integers.add(name + "__neg")
             continue
         if offset != 0.0:
             for k, c in coefs:
@@ -261,9 +299,10 @@ def apply_bounds(model: dict) -> tuple:
     for key, con in model["constraints"]:
         s = shift.get(key, 0.0)
         constraints.append((key, {f: v - s for f, v in con.items()} if s != 0.0 else dict(con)))
-    out = {k: v for k, v in model.items() if k != "bounds"}
+    out = {k: v for k, v in model.items() if k not in ("bounds", "column_bounds")}
     out["constraints"] = constraints + extra_rows
     out["variables"] = variables
+    out["integers"] = new_integers - {n for n, kind in back.items() if kind[0] == "const"}
 
     def recover(solution: dict) -> dict:
         sol = dict(solution)
