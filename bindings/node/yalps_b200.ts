@@ -1,31 +1,97 @@
-// bindings/node/yalps_b200.ts -- drop-in `simplex` / `solveMany` for YALPS on top of the N-API addon.
-// NOT COMPILED HERE (no Node/tsc in the build image).  In the YALPS tree this file replaces the import
-//     import { simplex } from "./simplex.js"          (src/YALPS.ts:4, src/branchAndCut.ts:3)
-// and leaves tableauModel / solution / types untouched.
+// bindings/node/yalps_b200.ts -- drop-in `simplex` and the new `solveMany` for YALPS on top of the N-API addon.
+// NOT COMPILED HERE (no Node/tsc in the build image; tests/test_bindings.py only checks that it calls what addon.c
+// exports).  In the YALPS tree this file sits in src/ and replaces one import in BOTH callers of the seam:
+//     import { simplex } from "./simplex.js"   ->   import { simplex } from "./yalps_b200.js"
+//         src/YALPS.ts:4          (root LP: identity basis)
+//         src/branchAndCut.ts:3   (node LPs: applyCuts' output carries the ROOT's permutation, :46-52)
+// tableauModel, applyCuts, mostFractionalVar, solution and all types stay untouched.
 import { createRequire } from "node:module"
 import type { Model, Options, Solution, SolutionStatus } from "./types.js"
 import { Tableau, tableauModel, TableauModel } from "./tableau.js"
+import { defaultOptions, solution } from "./YALPS.js" // `solution` (src/YALPS.ts:8) needs an `export`
 
 const native = createRequire(import.meta.url)("../build/Release/yalps_b200.node")
-const ctx = native.create(0) // throws without a CUDA device: there is no CPU fallback
 const STATUS: SolutionStatus[] = ["optimal", "infeasible", "unbounded", "timedout", "cycled"]
+
+// Created on first use; both throw without a CUDA device: there is no CPU fallback.
+let ctx: unknown
+let multi: unknown
+const getCtx = () => (ctx ??= native.create(0))
+const getMulti = (devices?: number[]) => (multi ??= native.createMulti(Int32Array.from(devices ?? [0])))
 
 const packOptions = (o: Required<Options>) =>
   Float64Array.of(o.precision, o.maxPivots, o.tolerance, o.timeout, o.maxIterations, o.checkCycles ? 1 : 0)
 
-// Same contract as src/simplex.ts:144: mutates the tableau's RHS column and permutation arrays in place.
+// Same contract as src/simplex.ts:144: the WHOLE tableau is mutated in place -- every cell of `matrix` (applyCuts
+// builds the cut rows of the node LPs from the final root rows, src/branchAndCut.ts:38-42), `positionOfVariable` and
+// `variableAtPosition` -- and the incoming permutation arrays are honoured (yalps_solve_batch_basis).
+// `matrix` / the permutations may be subarray views (src/branchAndCut.ts:54-60): N-API hands over the view's own
+// start address and length.
 export const simplex = (tableau: Tableau, options: Required<Options>): [SolutionStatus, number] => {
   const { width, height, matrix, positionOfVariable, variableAtPosition } = tableau
-  const status = new Int32Array(1), value = new Float64Array(1), pivots = new BigInt64Array(2)
-  const rhs = new Float64Array(height)
-  const rc = native.solveBatch(ctx, 1, height, width, matrix, packOptions(options), status, value, pivots, rhs,
-                               positionOfVariable, variableAtPosition)
-  if (rc !== 0) throw new Error(native.lastError(ctx))
-  for (let r = 0; r < height; r++) matrix[r * width] = rhs[r] // solution() reads only column 0 (src/YALPS.ts:18-19)
-  return [STATUS[status[0]], value[0]]
+  const out = new Float64Array(2)
+  const rc = native.simplex(getCtx(), height, width, matrix, positionOfVariable, variableAtPosition,
+                            packOptions(options), out)
+  if (rc !== 0) throw new Error(native.lastError(getCtx()))
+  return [STATUS[out[0]], out[1]]
 }
 
-// New: many models, one device batch for all root LPs (uniform shapes shown; ragged via yalps_solve_ragged).
-export const solveMany = <V, C>(models: Model<V, C>[], options?: Options): TableauModel<V, C>[] => {
-  return models.map(m => tableauModel(m)) // then pack matrices and call native.solveBatch once, see INTEGRATION.md
+// New API: many models, ONE native call.  All root LPs run as one ragged device batch (sharded over `devices` when
+// several GPUs are given); models with integer variables whose root is optimal and fractional then run branch and
+// cut on the device side of the ABI, many searches concurrently (yalps_multi_solve_many).  Each result equals
+// solve(model, options).
+export const solveMany = <VarKey = string, ConKey = string>(
+  models: readonly Model<VarKey, ConKey>[],
+  options?: Options,
+  devices?: number[],
+): Solution<VarKey>[] => {
+  const opt = { ...defaultOptions, ...options } as Required<Options>
+  const tabmods: TableauModel<VarKey, ConKey>[] = models.map(m => tableauModel(m))
+  const n = tabmods.length
+  if (n === 0) return []
+
+  const heights = new Int32Array(n), widths = new Int32Array(n), signs = new Float64Array(n)
+  const offsets = new BigInt64Array(n), intsOffsets = new BigInt64Array(n + 1)
+  let cells = 0, nints = 0, rows = 0, perms = 0
+  tabmods.forEach(({ tableau: t, integers, sign }, i) => {
+    heights[i] = t.height
+    widths[i] = t.width
+    signs[i] = sign
+    offsets[i] = BigInt(cells)
+    intsOffsets[i] = BigInt(nints)
+    cells += t.height * t.width
+    nints += integers.length
+    rows += t.height + 2 * integers.length // branch and cut appends up to 2*|integers| cut rows (src/branchAndCut.ts:108)
+    perms += t.width + t.height + 2 * integers.length
+  })
+  intsOffsets[n] = BigInt(nints)
+  const matrices = new Float64Array(cells), ints = new Int32Array(Math.max(nints, 1))
+  tabmods.forEach(({ tableau: t, integers }, i) => {
+    matrices.set(t.matrix, Number(offsets[i]))
+    ints.set(integers, Number(intsOffsets[i]))
+  })
+
+  const status = new Int32Array(n), result = new Float64Array(n), outHeight = new Int32Array(n)
+  const rhs = new Float64Array(rows), pos = new Int32Array(perms), vars = new Int32Array(perms)
+  const m = getMulti(devices)
+  const rc = native.solveMany(m, heights, widths, offsets, matrices, intsOffsets, ints, signs, packOptions(opt),
+                              status, result, outHeight, rhs, pos, vars)
+  if (rc !== 0) throw new Error(native.lastError(m))
+
+  // solution() reads column 0 and the two permutation arrays of the final (best) tableau and nothing else
+  // (src/YALPS.ts:16-19,32): rebuild exactly that view per model.
+  let r0 = 0, p0 = 0
+  return tabmods.map((tabmod, i) => {
+    const width = widths[i], height = outHeight[i], k = tabmod.integers.length
+    const matrix = new Float64Array(height * width)
+    for (let r = 0; r < height; r++) matrix[r * width] = rhs[r0 + r]
+    const final: Tableau = {
+      matrix, width, height,
+      positionOfVariable: pos.subarray(p0, p0 + width + height),
+      variableAtPosition: vars.subarray(p0, p0 + width + height),
+    }
+    r0 += heights[i] + 2 * k
+    p0 += widths[i] + heights[i] + 2 * k
+    return solution({ ...tabmod, tableau: final }, STATUS[status[i]], result[i], opt)
+  })
 }

@@ -121,6 +121,34 @@ int yalps_solve_batch(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
                       const yalps_options *opt, int32_t *status, double *value, int64_t *pivots, double *rhs_out,
                       int32_t *pos_out, int32_t *var_out, double *matrices_out);
 
+/*
+ * simplex(tableau, options) on tableaus that carry their own basis bookkeeping: pos_in / var_in
+ * (int32[n*(width+height)], mutually inverse permutations) are the positionOfVariable / variableAtPosition
+ * the tableaus arrive with.  This is the drop-in for the SECOND caller of the seam, src/branchAndCut.ts:127,
+ * where simplex runs on applyCuts' output whose permutation is the root's final one (:46-52), not the identity.
+ * Every output may alias the corresponding input (matrices_out == matrices etc.) for the reference's in-place
+ * contract.  pos_in == var_in == NULL is yalps_solve_batch.
+ */
+int yalps_solve_batch_basis(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, const double *matrices,
+                            const int32_t *pos_in, const int32_t *var_in, const yalps_options *opt, int32_t *status,
+                            double *value, int64_t *pivots, double *rhs_out, int32_t *pos_out, int32_t *var_out,
+                            double *matrices_out);
+int yalps_solve_ragged_basis(yalps_ctx *ctx, int64_t n, const int32_t *heights, const int32_t *widths,
+                             const int64_t *mat_offsets, const double *matrices, const int32_t *pos_in,
+                             const int32_t *var_in, const yalps_options *opt, int32_t *status, double *value,
+                             int64_t *pivots, double *rhs_out, int32_t *pos_out, int32_t *var_out,
+                             double *matrices_out);
+
+/*
+ * n replicas of ONE base tableau that differ only in column 0 (BASELINE config 3: perturbed right-hand sides):
+ * the caller ships base (height*width doubles) once and rhs (n*height doubles, replica-major; rhs[i*height + 0] is
+ * replica i's M[0,0]) -- 8*height bytes per LP over PCIe instead of 8*height*width.  The working copies are
+ * assembled on the device.  Outputs as yalps_solve_batch.
+ */
+int yalps_solve_replicas(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, const double *base,
+                         const double *rhs, const yalps_options *opt, int32_t *status, double *value, int64_t *pivots,
+                         double *rhs_out, int32_t *pos_out, int32_t *var_out);
+
 /* Ragged batch: LP i is heights[i] x widths[i] at matrices[mat_offsets[i]];
  * rhs_out is packed by cumulative heights, pos_out/var_out by cumulative (width+height). */
 int yalps_solve_ragged(yalps_ctx *ctx, int64_t n, const int32_t *heights, const int32_t *widths,
@@ -197,6 +225,65 @@ int yalps_solve(yalps_ctx *ctx, int32_t height, int32_t width, const double *mat
                 int32_t nints, double sign, const yalps_options *opt, int32_t *status, double *result,
                 int32_t *out_height, double *rhs_out, int32_t *pos_out, int32_t *var_out, int32_t *root_status,
                 double *root_value, int64_t *root_pivots, int64_t *stats);
+
+/* ---- one process, several GPUs ------------------------------------------------------------
+ * The reference is single-process and synchronous (src/YALPS.ts:73-92); a Node addon cannot use torchrun.  A
+ * yalps_multi owns one ctx (plus worker ctxs for concurrent branch-and-cut searches) per entry of `devices` and one
+ * host thread per ctx.  Independent LPs shard as contiguous ranges, LP i -> rank floor(i*ndev/n), with no collective
+ * on the data path; results land in the caller's arrays exactly as from the single-GPU entry points.  An entry may
+ * repeat a device (several logical ranks on one GPU: how a 1-GPU box exercises the multi-rank code).
+ */
+typedef struct yalps_multi yalps_multi;
+int yalps_create_multi(const int32_t *devices, int32_t ndev, yalps_multi **out);
+void yalps_destroy_multi(yalps_multi *m);
+const char *yalps_multi_last_error(const yalps_multi *m); /* m may be NULL: error of the last failed create */
+int32_t yalps_multi_size(const yalps_multi *m);
+yalps_ctx *yalps_multi_ctx(yalps_multi *m, int32_t rank); /* rank's ctx (tuning, launch counts); owned by m */
+int64_t yalps_multi_launch_count(const yalps_multi *m);   /* kernels launched by all ctxs of m */
+int yalps_multi_solve_batch(yalps_multi *m, int64_t n, int32_t height, int32_t width, const double *matrices,
+                            const int32_t *pos_in, const int32_t *var_in, const yalps_options *opt, int32_t *status,
+                            double *value, int64_t *pivots, double *rhs_out, int32_t *pos_out, int32_t *var_out,
+                            double *matrices_out);
+int yalps_multi_solve_ragged(yalps_multi *m, int64_t n, const int32_t *heights, const int32_t *widths,
+                             const int64_t *mat_offsets, const double *matrices, const yalps_options *opt,
+                             int32_t *status, double *value, int64_t *pivots, double *rhs_out, int32_t *pos_out,
+                             int32_t *var_out, double *matrices_out);
+int yalps_multi_solve_replicas(yalps_multi *m, int64_t n, int32_t height, int32_t width, const double *base,
+                               const double *rhs, const yalps_options *opt, int32_t *status, double *value,
+                               int64_t *pivots, double *rhs_out, int32_t *pos_out, int32_t *var_out);
+/*
+ * incumbent_allreduce (north_star): min-allreduce of one fp64 per rank -- the incumbent objective of a
+ * branch-and-bound search, lower is better internally (src/branchAndCut.ts:124,130).  local[ndev] in, agreed[ndev]
+ * out (all equal).  Ranks that share a GPU are reduced by one kernel; the distinct GPUs go through
+ * ncclAllReduce(ncclMin) on communicators from ncclCommInitAll (libnccl.so.2 is opened on first use; without it the
+ * call fails with YALPS_ERR_CUDA -- there is no host-side substitute).
+ */
+int yalps_incumbent_allreduce(yalps_multi *m, const double *local, double *agreed);
+/*
+ * solve()'s numeric part (yalps_solve) with the branch-and-bound frontier sharded over the ranks (north_star,
+ * BASELINE config 4): root LP on rank 0, final root tableau replicated on every rank, the nodes of each speculative
+ * wave dealt over the ranks as contiguous ranges when a wave is worth splitting (nodes too big for one SM's shared
+ * memory, or many small ones), the incumbent min-allreduced every `allreduce_every` waves; the replay stays the
+ * reference's sequential loop, so nodes, pivots and the result are those of yalps_solve.  stats[8] as
+ * yalps_branch_and_cut, plus stats[8] = waves that were sharded, stats[9] = allreduces (stats has 10 entries).
+ */
+int yalps_multi_solve(yalps_multi *m, int32_t height, int32_t width, const double *matrix, const int32_t *ints,
+                      int32_t nints, double sign, const yalps_options *opt, int32_t allreduce_every, int32_t *status,
+                      double *result, int32_t *out_height, double *rhs_out, int32_t *pos_out, int32_t *var_out,
+                      int32_t *root_status, double *root_value, int64_t *root_pivots, int64_t *stats);
+/*
+ * solveMany(models, options): n_models tableaus (ragged, as yalps_solve_ragged) with their integer-variable lists
+ * ints[ints_offsets[i] .. ints_offsets[i+1]) and signs[i].  All root LPs run as one ragged batch sharded over the
+ * ranks; the models whose root is optimal and fractional then run branch and cut, MANY SEARCHES IN PARALLEL (each
+ * search is a chain of latency-bound waves): they are dealt to ndev * searches_per_device worker contexts.
+ * Outputs per model i: status, result, out_height; rhs_out packed by cumulative (heights[i] + 2*nints_i),
+ * pos_out/var_out by cumulative (widths[i] + heights[i] + 2*nints_i).  Results equal yalps_solve per model.
+ */
+int yalps_multi_solve_many(yalps_multi *m, int64_t n_models, const int32_t *heights, const int32_t *widths,
+                           const int64_t *mat_offsets, const double *matrices, const int64_t *ints_offsets,
+                           const int32_t *ints, const double *signs, const yalps_options *opt,
+                           int32_t searches_per_device, int32_t *status, double *result, int32_t *out_height,
+                           double *rhs_out, int32_t *pos_out, int32_t *var_out);
 
 /* roundToPrecision (src/util.ts:1-4) evaluated on the device for n values (parity probe). */
 int yalps_round_to_precision(yalps_ctx *ctx, int64_t n, const double *x, double precision, double *out);

@@ -6,13 +6,13 @@ kernels, C ABI in include/yalps_b200.h); importing this package without the buil
 it without a CUDA device, raises.
 """
 from .constraint import equal_to, equalTo, greater_eq, greaterEq, in_range, inRange, less_eq, lessEq
-from .engine import Engine, STATUS_NAMES, make_options
+from .engine import Engine, MultiEngine, STATUS_NAMES, make_options
 from .solver import default_options, defaultOptions, get_engine, solve, solve_many, solveMany
 from .mps import apply_bounds, model_from_mps, netlib_model
 from .tableau import Tableau, TableauModel, tableau_model
 
 __all__ = [
     "solve", "solve_many", "solveMany", "default_options", "defaultOptions", "less_eq", "greater_eq", "equal_to",
-    "in_range", "lessEq", "greaterEq", "equalTo", "inRange", "Engine", "make_options", "STATUS_NAMES",
+    "in_range", "lessEq", "greaterEq", "equalTo", "inRange", "Engine", "MultiEngine", "make_options", "STATUS_NAMES",
     "tableau_model", "Tableau", "TableauModel", "get_engine", "model_from_mps", "netlib_model", "apply_bounds",
 ]

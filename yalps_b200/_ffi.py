@@ -56,6 +56,29 @@ SIGNATURES = {
                                     _vp, _vp, _vp]),
     "yalps_solve_ragged": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, C.POINTER(Options), _vp, _vp, _vp, _vp, _vp,
                                      _vp, _vp]),
+    "yalps_solve_batch_basis": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, _vp, C.POINTER(Options), _vp, _vp,
+                                          _vp, _vp, _vp, _vp, _vp]),
+    "yalps_solve_ragged_basis": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(Options), _vp, _vp, _vp,
+                                           _vp, _vp, _vp, _vp]),
+    "yalps_solve_replicas": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, C.POINTER(Options), _vp, _vp, _vp,
+                                       _vp, _vp, _vp]),
+    "yalps_create_multi": (C.c_int, [_ip, C.c_int32, C.POINTER(_vp)]),
+    "yalps_destroy_multi": (None, [_vp]),
+    "yalps_multi_last_error": (C.c_char_p, [_vp]),
+    "yalps_multi_size": (C.c_int32, [_vp]),
+    "yalps_multi_ctx": (_vp, [_vp, C.c_int32]),
+    "yalps_multi_launch_count": (C.c_int64, [_vp]),
+    "yalps_multi_solve_batch": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, _vp, C.POINTER(Options), _vp, _vp,
+                                          _vp, _vp, _vp, _vp, _vp]),
+    "yalps_multi_solve_ragged": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, C.POINTER(Options), _vp, _vp, _vp, _vp, _vp,
+                                           _vp, _vp]),
+    "yalps_multi_solve_replicas": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, C.POINTER(Options), _vp, _vp,
+                                             _vp, _vp, _vp, _vp]),
+    "yalps_incumbent_allreduce": (C.c_int, [_vp, _dp, _dp]),
+    "yalps_multi_solve": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, _vp, C.c_int32, C.c_double, C.POINTER(Options),
+                                    C.c_int32, _ip, _dp, _ip, _vp, _vp, _vp, _ip, _dp, _vp, _vp]),
+    "yalps_multi_solve_many": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(Options), C.c_int32,
+                                         _vp, _vp, _vp, _vp, _vp, _vp]),
     "yalps_solve_batch_device": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, C.POINTER(Options), _vp,
                                            _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "yalps_generate_synthetic_device": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32,

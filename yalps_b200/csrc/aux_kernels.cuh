@@ -95,6 +95,32 @@ __global__ void k_generate_replicas(long long first, long long n, int H, int W, 
   }
 }
 
+// Replicas of one base tableau that differ only in the RHS column (yalps_solve_replicas): the caller ships the base
+// once and n*H right-hand sides; the working copies are assembled here, in HBM, at copy bandwidth.
+__global__ void k_expand_replicas(long long n, int H, int W, const double *base, const double *rhs, double *out) {
+  const size_t cells = (size_t)W * H;
+  const size_t total = (size_t)n * cells;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = g / cells;
+    const int cell = (int)(g - i * cells);
+    const int r = cell / W, c = cell - r * W;
+    out[g] = c == 0 ? rhs[i * (size_t)H + r] : base[cell];
+  }
+}
+
+// Incumbent min-allreduce, the part inside one GPU: the logical ranks that share this GPU are reduced by ONE kernel
+// over all their slots (never by launches that wait for one another); slot[k] then goes through ncclAllReduce(min)
+// across the distinct GPUs and is broadcast back to the rank slots.
+__global__ void k_incumbent_reduce(double *slots, int k) {
+  double m = slots[0];
+  for (int i = 1; i < k; i++) m = slots[i] < m ? slots[i] : m;
+  slots[k] = m;
+}
+__global__ void k_incumbent_broadcast(double *slots, int k) {
+  const double m = slots[k];
+  for (int i = 0; i < k; i++) slots[i] = m;
+}
+
 // Non-zero count of a sample of one tableau (kernel-path policy: sparse batches go to the HBM/L2-resident kernel).
 __global__ void k_sample_density(const double *m, long long cells, long long step, int *out /* [2]: seen, nz */) {
   int seen = 0, nz = 0;

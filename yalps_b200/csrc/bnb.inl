@@ -184,6 +184,11 @@ int adopt_root_device(yalps_ctx *ctx, int32_t height, int32_t width, const doubl
   return 0;
 }
 
+int bnb_solve_nodes_impl(yalps_ctx *ctx, int64_t n, const int32_t *cut_offsets, const double *cut_sign,
+                         const int32_t *cut_var, const double *cut_value, const yalps_options *opt, int32_t *status,
+                         double *value, int64_t *pivots, double *rhs_out, int32_t *pos_out, int32_t *var_out,
+                         double *matrices_out, int min_maxcuts);
+
 }  // namespace
 
 extern "C" {
@@ -209,6 +214,20 @@ int yalps_bnb_solve_nodes(yalps_ctx *ctx, int64_t n, const int32_t *cut_offsets,
                           const int32_t *cut_var, const double *cut_value, const yalps_options *opt, int32_t *status,
                           double *value, int64_t *pivots, double *rhs_out, int32_t *pos_out, int32_t *var_out,
                           double *matrices_out) {
+  return bnb_solve_nodes_impl(ctx, n, cut_offsets, cut_sign, cut_var, cut_value, opt, status, value, pivots, rhs_out,
+                              pos_out, var_out, matrices_out, 0);
+}
+
+}  // extern "C"
+
+namespace {
+
+// min_maxcuts: lower bound of the output stride (height + max cuts) -- a wave sharded over several GPUs must come
+// back with ONE stride although every shard only sees its own nodes.
+int bnb_solve_nodes_impl(yalps_ctx *ctx, int64_t n, const int32_t *cut_offsets, const double *cut_sign,
+                         const int32_t *cut_var, const double *cut_value, const yalps_options *opt, int32_t *status,
+                         double *value, int64_t *pivots, double *rhs_out, int32_t *pos_out, int32_t *var_out,
+                         double *matrices_out, int min_maxcuts) {
   if (!ctx) return YALPS_ERR_ARGUMENT;
   Root &R = ctx->root;
   if (!R.valid) return fail(ctx, YALPS_ERR_ARGUMENT, "no root tableau: call yalps_bnb_set_root first");
@@ -216,7 +235,7 @@ int yalps_bnb_solve_nodes(yalps_ctx *ctx, int64_t n, const int32_t *cut_offsets,
   if (n == 0) return 0;
   CU(ctx, cudaSetDevice(ctx->device));
   const int W = R.W;
-  int maxcuts = 0;
+  int maxcuts = std::max(0, min_maxcuts);
   for (int64_t j = 0; j < n; j++) {
     const int k = cut_offsets[j + 1] - cut_offsets[j];
     if (k < 0) return fail(ctx, YALPS_ERR_ARGUMENT, "cut_offsets must be non-decreasing");
@@ -360,9 +379,38 @@ int yalps_bnb_solve_nodes(yalps_ctx *ctx, int64_t n, const int32_t *cut_offsets,
   return check_device_status(ctx, status, n);
 }
 
+// Evaluates the n node LPs of one wave (cut lists in CSR form, offsets starting at 0) into arrays strided by
+// height + maxcuts.  The default evaluator runs them on the ctx's GPU; the multi-GPU driver deals them over its ranks.
+using WaveEval = std::function<int(int64_t n, const int32_t *off, const double *sign, const int32_t *var,
+                                   const double *val, int maxcuts, int32_t *status, double *value, int64_t *piv,
+                                   double *rhs, int32_t *pos, int32_t *var_out)>;
+// Called after every wave with the incumbent (inf while none): the multi-GPU driver runs its min-allreduce here.
+using WaveHook = std::function<int(int64_t wave_index, double best_eval)>;
+
+int branch_and_cut_impl(yalps_ctx *ctx, const WaveEval *wave_eval, const WaveHook *wave_hook, const int32_t *ints,
+                        int32_t nints, double sign, double init_result, const yalps_options *opt, int32_t *status,
+                        double *result, int32_t *out_height, double *rhs_out, int32_t *pos_out, int32_t *var_out,
+                        int64_t *stats);
+
+}  // namespace
+
+extern "C" {
+
 int yalps_branch_and_cut(yalps_ctx *ctx, const int32_t *ints, int32_t nints, double sign, double init_result,
                          const yalps_options *opt, int32_t *status, double *result, int32_t *out_height,
                          double *rhs_out, int32_t *pos_out, int32_t *var_out, int64_t *stats) {
+  return branch_and_cut_impl(ctx, nullptr, nullptr, ints, nints, sign, init_result, opt, status, result, out_height,
+                             rhs_out, pos_out, var_out, stats);
+}
+
+}  // extern "C"
+
+namespace {
+
+int branch_and_cut_impl(yalps_ctx *ctx, const WaveEval *wave_eval, const WaveHook *wave_hook, const int32_t *ints,
+                        int32_t nints, double sign, double init_result, const yalps_options *opt, int32_t *status,
+                        double *result, int32_t *out_height, double *rhs_out, int32_t *pos_out, int32_t *var_out,
+                        int64_t *stats) {
   if (!ctx) return YALPS_ERR_ARGUMENT;
   Root &R = ctx->root;
   if (!R.valid) return fail(ctx, YALPS_ERR_ARGUMENT, "no root tableau: call yalps_bnb_set_root first");
@@ -481,10 +529,17 @@ int yalps_branch_and_cut(yalps_ctx *ctx, const int32_t *ints, int32_t nints, dou
     wb->pos.resize((size_t)n * (W + wb->Hcap));
     wb->var.resize((size_t)n * (W + wb->Hcap));
     const auto t0 = std::chrono::steady_clock::now();
-    if (int rc = yalps_bnb_solve_nodes(ctx, n, w_off.data(), w_sign.data(), w_var.data(), w_val.data(), opt,
-                                       wb->status.data(), wb->value.data(), wb->piv.data(), wb->rhs.data(),
-                                       wb->pos.data(), wb->var.data(), nullptr))
+    if (wave_eval) {
+      if (int rc = (*wave_eval)(n, w_off.data(), w_sign.data(), w_var.data(), w_val.data(), maxcuts, wb->status.data(),
+                                wb->value.data(), wb->piv.data(), wb->rhs.data(), wb->pos.data(), wb->var.data()))
+        return rc;
+    } else if (int rc = bnb_solve_nodes_impl(ctx, n, w_off.data(), w_sign.data(), w_var.data(), w_val.data(), opt,
+                                             wb->status.data(), wb->value.data(), wb->piv.data(), wb->rhs.data(),
+                                             wb->pos.data(), wb->var.data(), nullptr, 0)) {
       return rc;
+    }
+    if (wave_hook)
+      if (int rc = (*wave_hook)(st_waves, best_eval)) return rc;
     st_wave_us += std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
     st_waves++;
     st_devnodes += n;
@@ -585,6 +640,10 @@ int yalps_branch_and_cut(yalps_ctx *ctx, const int32_t *ints, int32_t nints, dou
   write_stats();
   return 0;
 }
+
+}  // namespace
+
+extern "C" {
 
 int yalps_solve(yalps_ctx *ctx, int32_t height, int32_t width, const double *matrix, const int32_t *ints,
                 int32_t nints, double sign, const yalps_options *opt, int32_t *status, double *result,

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_simplex_cluster(const Batc
         for (int c = lane; c < Wm1; c += 32) cp_async8(drow + c, g + 1 + c);
         for (int c = Wm1 + lane; c < bslot; c += 32) drow[c] = 0.0;  // padding cells
       }
-      for (int k = tid; k < W + H; k += NT) var[k] = k;
+      for (int k = tid; k < W + H; k += NT) var[k] = a.var_in ? a.var_in[poff + k] : k;
       if (tid == 0) *cnt = 0;
       cp_async_wait_all();
     }

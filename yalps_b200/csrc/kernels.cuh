@@ -30,6 +30,7 @@ struct BatchArgs {
   long long *pivots;
   double *rhs_out;
   int *pos_out, *var_out;
+  const int *var_in;  // optional initial variableAtPosition, packed like var_out (null: the identity, src/tableau.ts:95-98)
   // node mode
   const double *root;
   const int *root_pos, *root_var;
@@ -250,6 +251,8 @@ __global__ void __launch_bounds__(NWC *NWR * 32, min_ctas_per_sm(NWC, NWR)) k_si
       }
       const int nroot = W + rootH;
       for (int k = tid; k < W + H; k += NT) t.var[k] = k < nroot ? a.root_var[k] : k;
+    } else if (a.var_in) {  // caller-supplied basis (src/branchAndCut.ts:127 calls simplex on applyCuts' permutation)
+      for (int k = tid; k < W + H; k += NT) t.var[k] = a.var_in[poff + k];
     } else {
       for (int k = tid; k < W + H; k += NT) t.var[k] = k;
     }

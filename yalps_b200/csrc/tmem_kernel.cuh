@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(kTmemWarps * 32, TmemShape<HR>::kCtasPerSm) k_
       }
       tm_st32(tbase + 32u * (unsigned)blk, v);
     }
-    for (int k = lane; k < W + H; k += 32) var[k] = k;
+    for (int k = lane; k < W + H; k += 32) var[k] = a.var_in ? a.var_in[poff + k] : k;
     // rows past H-1 in the last block of eight: zeros in TMEM, never read; a non-zero coefficient keeps the block on
     // the straight-line path
     for (int k = H + lane; k < S::kMaxRows + 7; k += 32) cb[k] = make_double2(1.0, 0.0);

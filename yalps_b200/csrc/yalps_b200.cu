@@ -7,6 +7,9 @@
 
 #include <cuda_runtime.h>
 
+#include <dlfcn.h>
+#include <nccl.h>  // types and prototypes only: libnccl.so.2 is opened at run time (multi.inl)
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -14,10 +17,13 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <condition_variable>
+#include <functional>
 #include <limits>
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -700,10 +706,12 @@ static int launch_grid(yalps_ctx *ctx, int H, int W, double *d_M, const yalps_op
 }
 
 // ---------------------------------------------------------------------------------------------------------
-int yalps_solve_batch_device(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, const double *d_matrices,
-                             double *d_work, const yalps_options *opt, int32_t *d_status, double *d_value,
-                             int64_t *d_pivots, double *d_rhs_out, int32_t *d_pos_out, int32_t *d_var_out,
-                             double *d_matrices_out, void *stream) {
+// `slot` names the pooled scratch (LP queue counter, cycle history, cluster scratch) of this launch: calls that may be in
+// flight at the same time on different streams of one ctx must use different slots.
+static int solve_batch_device_impl(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, const double *d_matrices,
+                                   double *d_work, const yalps_options *opt, int32_t *d_status, double *d_value,
+                                   int64_t *d_pivots, double *d_rhs_out, int32_t *d_pos_out, int32_t *d_var_out,
+                                   double *d_matrices_out, void *stream, const std::string &slot) {
   if (!ctx) return YALPS_ERR_ARGUMENT;
   if (n < 0 || height < 1 || width < 1 || !opt || (n > 0 && !d_matrices))
     return fail(ctx, YALPS_ERR_ARGUMENT, "bad arguments (n=%lld, %dx%d)", (long long)n, height, width);
@@ -748,10 +756,10 @@ int yalps_solve_batch_device(yalps_ctx *ctx, int64_t n, int32_t height, int32_t 
   a.pos_out = d_pos_out;
   a.var_out = d_var_out;
   fill_options(a, opt);
-  if (int rc = maybe_cluster(ctx, n, height, width, nullptr, a, "dev", (cudaStream_t)stream)) return rc < 0 ? rc : 0;
+  if (int rc = maybe_cluster(ctx, n, height, width, nullptr, a, slot, (cudaStream_t)stream)) return rc < 0 ? rc : 0;
   LaunchPlan plan;
   if (int rc = plan_launch(ctx, n, height, width, opt->check_cycles != 0, &plan, density, true)) return rc;
-  if (int rc = maybe_cluster(ctx, n, height, width, &plan, a, "dev", (cudaStream_t)stream)) return rc < 0 ? rc : 0;
+  if (int rc = maybe_cluster(ctx, n, height, width, &plan, a, slot, (cudaStream_t)stream)) return rc < 0 ? rc : 0;
   if (use_grid_path(ctx, n, plan)) {
     if (!d_work) return fail(ctx, YALPS_ERR_ARGUMENT, "d_work is required for the grid path");
     cudaStream_t st = (cudaStream_t)stream;
@@ -763,7 +771,7 @@ int yalps_solve_batch_device(yalps_ctx *ctx, int64_t n, int32_t height, int32_t 
                                d_value ? d_value + i : nullptr, d_pivots ? (long long *)d_pivots + 2 * i : nullptr,
                                d_rhs_out ? d_rhs_out + i * height : nullptr,
                                d_pos_out ? d_pos_out + i * (width + height) : nullptr,
-                               d_var_out ? d_var_out + i * (width + height) : nullptr, st))
+                               d_var_out ? d_var_out + i * (width + height) : nullptr, st, nullptr, 0, 0, slot))
         return rc;
     }
     if (d_matrices_out && d_matrices_out != d_work)
@@ -774,21 +782,32 @@ int yalps_solve_batch_device(yalps_ctx *ctx, int64_t n, int32_t height, int32_t 
     if (!d_work) return fail(ctx, YALPS_ERR_ARGUMENT, "d_work is required for the HBM-resident path");
     if (!d_pos_out || !d_var_out) {
       void *p = nullptr;
-      if (int rc = dev_ensure(ctx, "posvar_scratch", (size_t)n * (width + height) * 2 * sizeof(int), &p)) return rc;
+      if (int rc = dev_ensure(ctx, "posvar_scratch" + slot, (size_t)n * (width + height) * 2 * sizeof(int), &p)) return rc;
       if (!a.pos_out) a.pos_out = (int *)p;
       if (!a.var_out) a.var_out = (int *)p + (size_t)n * (width + height);
     }
   }
-  return launch_simplex(ctx, plan, a, "dev", (cudaStream_t)stream);
+  return launch_simplex(ctx, plan, a, slot, (cudaStream_t)stream);
+}
+
+int yalps_solve_batch_device(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, const double *d_matrices,
+                             double *d_work, const yalps_options *opt, int32_t *d_status, double *d_value,
+                             int64_t *d_pivots, double *d_rhs_out, int32_t *d_pos_out, int32_t *d_var_out,
+                             double *d_matrices_out, void *stream) {
+  return solve_batch_device_impl(ctx, n, height, width, d_matrices, d_work, opt, d_status, d_value, d_pivots, d_rhs_out,
+                                 d_pos_out, d_var_out, d_matrices_out, stream, "dev");
 }
 
 // Shared host-side pipeline for uniform and ragged batches.
 static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, const int32_t *heights,
                       const int32_t *widths, const int64_t *mat_offsets, const double *matrices,
                       const yalps_options *opt, int32_t *status, double *value, int64_t *pivots, double *rhs_out,
-                      int32_t *pos_out, int32_t *var_out, double *matrices_out) {
+                      int32_t *pos_out, int32_t *var_out, double *matrices_out, const int32_t *pos_in = nullptr,
+                      const int32_t *var_in = nullptr) {
   if (!ctx) return YALPS_ERR_ARGUMENT;
   if (n < 0 || !opt || (n > 0 && !matrices)) return fail(ctx, YALPS_ERR_ARGUMENT, "bad arguments");
+  if ((pos_in == nullptr) != (var_in == nullptr))
+    return fail(ctx, YALPS_ERR_ARGUMENT, "pos_in and var_in must be given together (or both null for the identity)");
   if (n == 0) return 0;
   CU(ctx, cudaSetDevice(ctx->device));
   const bool ragged = heights != nullptr;
@@ -827,12 +846,27 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
   auto rows_upto = [&](int64_t i) -> long long { return ragged ? roff[i] : (long long)i * height; };
   auto pv_upto = [&](int64_t i) -> long long { return ragged ? poff[i] : (long long)i * (height + width); };
 
+  // caller-supplied basis: the two arrays must be inverse permutations of 0..W+H-1 (src/tableau.ts:9-15); the kernels
+  // carry variableAtPosition and rebuild positionOfVariable on output, so an inconsistent pair would silently
+  // change meaning instead of behaving like the reference
+  if (var_in) {
+    for (int64_t i = 0; i < n; i++) {
+      const long long o = pv_upto(i), len = pv_upto(i + 1) - o;
+      for (long long k = 0; k < len; k++) {
+        const int32_t v = var_in[o + k];
+        if (v < 0 || v >= len || pos_in[o + v] != (int32_t)k)
+          return fail(ctx, YALPS_ERR_ARGUMENT, "LP %lld: pos_in/var_in are not inverse permutations at position %lld",
+                      (long long)i, k);
+      }
+    }
+  }
+
   // ---- small calls (a single LP, a handful of models): latency-bound.  Stage through one mapped pinned buffer,
   // let the kernel read the tableaus and write the results zero-copy: launch + synchronise, no memcpy calls.
   {
     const size_t in_b = (size_t)cells_upto(n) * 8, rows_b = (size_t)rows_upto(n) * 8, pv_b = (size_t)pv_upto(n) * 4;
     const size_t out_b = (size_t)n * 32 + rows_b + 2 * pv_b + 64 + (matrices_out ? in_b : 0);
-    const size_t desc_b = ragged ? (size_t)n * 32 + 64 : 0;
+    const size_t desc_b = (ragged ? (size_t)n * 32 + 64 : 0) + (var_in ? pv_b + 16 : 0);
     LaunchPlan plan;
     // density of (a sample of) the first tableau: the latency-mode policy distinguishes dense from very sparse LPs
     double small_density = -1.0;
@@ -854,6 +888,7 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
       const size_t o_mo = o; o += ragged ? up16((size_t)n * 8) : 0;
       const size_t o_ro = o; o += ragged ? up16((size_t)n * 8) : 0;
       const size_t o_po = o; o += ragged ? up16((size_t)n * 8) : 0;
+      const size_t o_vin = o; o += var_in ? up16(pv_b) : 0;
       const size_t o_st = o; o += up16((size_t)n * 4);
       const size_t o_val = o; o += up16((size_t)n * 8);
       const size_t o_piv = o; o += up16((size_t)n * 16);
@@ -877,6 +912,7 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
       } else {
         std::memcpy(h + o_in, matrices, in_b);
       }
+      if (var_in) std::memcpy(h + o_vin, var_in, pv_b);
       BatchArgs a{};
       a.n = n;
       a.mode = kModeBatch;
@@ -893,6 +929,7 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
       a.rhs_out = (double *)(d + o_rhs);
       a.pos_out = (int *)(d + o_pos);
       a.var_out = (int *)(d + o_var);
+      a.var_in = var_in ? (const int *)(d + o_vin) : nullptr;
       if (ragged) {
         a.heights = (const int *)(d + o_h);
         a.widths = (const int *)(d + o_w);
@@ -969,6 +1006,11 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
     if ((rc = dev_ensure(ctx, "rhs" + s, crows * 8, &d_rhs))) return rc;
     if ((rc = dev_ensure(ctx, "pos" + s, cpv * 4, &d_pos))) return rc;
     if ((rc = dev_ensure(ctx, "var" + s, cpv * 4, &d_var))) return rc;
+    void *d_vin = nullptr;
+    if (var_in) {
+      if ((rc = dev_ensure(ctx, "varin" + s, cpv * 4, &d_vin))) return rc;
+      CU(ctx, cudaMemcpyAsync(d_vin, var_in + pv_upto(begin), cpv * 4, cudaMemcpyHostToDevice, st));
+    }
     void *d_out = nullptr;
     const bool want_mat = matrices_out != nullptr || (ctx->keep_final && n == 1 && !ragged);
     if (want_mat && (plan.resident || ragged))
@@ -1007,6 +1049,7 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
     a.rhs_out = (double *)d_rhs;
     a.pos_out = (int *)d_pos;
     a.var_out = (int *)d_var;
+    a.var_in = (const int *)d_vin;
     if (ragged) {
       void *d_h, *d_w, *d_mo, *d_ro, *d_po;
       std::vector<long long> lm(cn), lr(cn), lpv(cn);
@@ -1047,7 +1090,8 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
           if ((rc = launch_grid(ctx, height, width, (double *)d_in + mo, opt, (int *)d_status + i, (double *)d_value + i,
                                 (long long *)d_piv + 2 * i, (double *)d_rhs + (size_t)i * height,
                                 (int *)d_pos + (size_t)i * (width + height), (int *)d_var + (size_t)i * (width + height),
-                                st)))
+                                st, d_vin ? (const int *)d_vin + (size_t)i * (width + height) : nullptr,
+                                d_vin ? width + height : 0)))
             return rc;
         }
         a.mat_out = want_mat ? (double *)d_in : nullptr;
@@ -1106,7 +1150,7 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
                             po = poff[begin + id] - poff[begin];
             if ((rc = launch_grid(ctx, hi, wi, (double *)d_in + mo, opt, (int *)d_status + id, (double *)d_value + id,
                                   (long long *)d_piv + 2 * id, (double *)d_rhs + ro, (int *)d_pos + po, (int *)d_var + po,
-                                  st)))
+                                  st, d_vin ? (const int *)d_vin + po : nullptr, d_vin ? wi + hi : 0)))
               return rc;
             if (matrices_out)
               CU(ctx, cudaMemcpyAsync((double *)d_out + mo, (double *)d_in + mo, (size_t)hi * wi * 8,
@@ -1164,6 +1208,82 @@ int yalps_solve_ragged(yalps_ctx *ctx, int64_t n, const int32_t *heights, const 
   if (!heights) return fail(ctx, YALPS_ERR_ARGUMENT, "heights is null");
   return solve_host(ctx, n, 0, 0, heights, widths, mat_offsets, matrices, opt, status, value, pivots, rhs_out,
                     pos_out, var_out, matrices_out);
+}
+
+int yalps_solve_batch_basis(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, const double *matrices,
+                            const int32_t *pos_in, const int32_t *var_in, const yalps_options *opt, int32_t *status,
+                            double *value, int64_t *pivots, double *rhs_out, int32_t *pos_out, int32_t *var_out,
+                            double *matrices_out) {
+  return solve_host(ctx, n, height, width, nullptr, nullptr, nullptr, matrices, opt, status, value, pivots, rhs_out,
+                    pos_out, var_out, matrices_out, pos_in, var_in);
+}
+
+int yalps_solve_ragged_basis(yalps_ctx *ctx, int64_t n, const int32_t *heights, const int32_t *widths,
+                             const int64_t *mat_offsets, const double *matrices, const int32_t *pos_in,
+                             const int32_t *var_in, const yalps_options *opt, int32_t *status, double *value,
+                             int64_t *pivots, double *rhs_out, int32_t *pos_out, int32_t *var_out,
+                             double *matrices_out) {
+  if (!heights) return fail(ctx, YALPS_ERR_ARGUMENT, "heights is null");
+  return solve_host(ctx, n, 0, 0, heights, widths, mat_offsets, matrices, opt, status, value, pivots, rhs_out,
+                    pos_out, var_out, matrices_out, pos_in, var_in);
+}
+
+int yalps_solve_replicas(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, const double *base,
+                         const double *rhs, const yalps_options *opt, int32_t *status, double *value, int64_t *pivots,
+                         double *rhs_out, int32_t *pos_out, int32_t *var_out) {
+  if (!ctx) return YALPS_ERR_ARGUMENT;
+  if (n < 0 || height < 1 || width < 1 || !opt || (n > 0 && (!base || !rhs)))
+    return fail(ctx, YALPS_ERR_ARGUMENT, "bad arguments (n=%lld, %dx%d)", (long long)n, height, width);
+  if ((long long)height * width >= (1LL << 31)) return fail(ctx, YALPS_ERR_TOO_LARGE, "height*width must be < 2^31");
+  if (n == 0) return 0;
+  CU(ctx, cudaSetDevice(ctx->device));
+  const size_t cells = (size_t)height * width, pv = (size_t)height + width;
+  void *d_base;
+  int rc;
+  if ((rc = dev_ensure(ctx, "rep_base", cells * 8, &d_base))) return rc;
+  CU(ctx, cudaMemcpy(d_base, base, cells * 8, cudaMemcpyHostToDevice));
+  // two pipeline slots of at most ~1.5 GiB of working copies each: the H2D of chunk k+1's right-hand sides and the
+  // D2H of chunk k-1's results overlap the solve of chunk k
+  const int64_t per_chunk = std::max<int64_t>(1, std::min<int64_t>((n + 1) / 2 > 4096 ? (n + 7) / 8 : n,
+                                                                  (int64_t)(((size_t)1536 << 20) / (cells * 8))));
+  bool used[2] = {false, false};
+  int slot = 0;
+  for (int64_t begin = 0; begin < n; begin += per_chunk, slot ^= 1) {
+    const int64_t cn = std::min(per_chunk, n - begin);
+    const std::string s = "rp" + std::to_string(slot);
+    cudaStream_t st = ctx->streams[slot];
+    if (used[slot]) CU(ctx, cudaEventSynchronize(ctx->events[slot]));
+    void *d_rin, *d_work, *d_status, *d_value, *d_piv, *d_rhs, *d_pos, *d_var;
+    if ((rc = dev_ensure(ctx, "rin" + s, (size_t)cn * height * 8, &d_rin))) return rc;
+    if ((rc = dev_ensure(ctx, "work" + s, (size_t)cn * cells * 8, &d_work))) return rc;
+    if ((rc = dev_ensure(ctx, "status" + s, (size_t)cn * 4, &d_status))) return rc;
+    if ((rc = dev_ensure(ctx, "value" + s, (size_t)cn * 8, &d_value))) return rc;
+    if ((rc = dev_ensure(ctx, "pivots" + s, (size_t)cn * 16, &d_piv))) return rc;
+    if ((rc = dev_ensure(ctx, "rhs" + s, (size_t)cn * height * 8, &d_rhs))) return rc;
+    if ((rc = dev_ensure(ctx, "pos" + s, (size_t)cn * pv * 4, &d_pos))) return rc;
+    if ((rc = dev_ensure(ctx, "var" + s, (size_t)cn * pv * 4, &d_var))) return rc;
+    CU(ctx, cudaMemcpyAsync(d_rin, rhs + (size_t)begin * height, (size_t)cn * height * 8, cudaMemcpyHostToDevice, st));
+    const size_t total = (size_t)cn * cells;
+    const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)ctx->prop.multiProcessorCount * 16);
+    k_expand_replicas<<<grid, 256, 0, st>>>(cn, height, width, (const double *)d_base, (const double *)d_rin, (double *)d_work);
+    CU(ctx, cudaGetLastError());
+    ctx->launches++;
+    if ((rc = solve_batch_device_impl(ctx, cn, height, width, (const double *)d_work, (double *)d_work, opt,
+                                      (int32_t *)d_status, (double *)d_value, (int64_t *)d_piv, (double *)d_rhs,
+                                      (int32_t *)d_pos, (int32_t *)d_var, nullptr, st, s)))
+      return rc;
+    if (status) CU(ctx, cudaMemcpyAsync(status + begin, d_status, (size_t)cn * 4, cudaMemcpyDeviceToHost, st));
+    if (value) CU(ctx, cudaMemcpyAsync(value + begin, d_value, (size_t)cn * 8, cudaMemcpyDeviceToHost, st));
+    if (pivots) CU(ctx, cudaMemcpyAsync(pivots + 2 * begin, d_piv, (size_t)cn * 16, cudaMemcpyDeviceToHost, st));
+    if (rhs_out) CU(ctx, cudaMemcpyAsync(rhs_out + (size_t)begin * height, d_rhs, (size_t)cn * height * 8, cudaMemcpyDeviceToHost, st));
+    if (pos_out) CU(ctx, cudaMemcpyAsync(pos_out + (size_t)begin * pv, d_pos, (size_t)cn * pv * 4, cudaMemcpyDeviceToHost, st));
+    if (var_out) CU(ctx, cudaMemcpyAsync(var_out + (size_t)begin * pv, d_var, (size_t)cn * pv * 4, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaEventRecord(ctx->events[slot], st));
+    used[slot] = true;
+  }
+  for (int i = 0; i < 2; i++)
+    if (used[i]) CU(ctx, cudaStreamSynchronize(ctx->streams[i]));
+  return check_device_status(ctx, status, n);
 }
 
 int yalps_generate_synthetic_device(yalps_ctx *ctx, int64_t first, int64_t n, int32_t m, int32_t nvars,
@@ -1321,3 +1441,4 @@ int yalps_measure_tmem_bandwidth(yalps_ctx *ctx, double *gbs, double *sm_clock_m
 }  // extern "C"
 
 #include "bnb.inl"
+#include "multi.inl"

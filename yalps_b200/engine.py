@@ -111,9 +111,12 @@ class Engine:
         }
 
     def solve_batch(self, matrices: np.ndarray, height: int, width: int, options: Optional[Options] = None,
-                    want_matrices: bool = False, want_basis: bool = True, out: Optional[dict] = None) -> dict:
+                    want_matrices: bool = False, want_basis: bool = True, out: Optional[dict] = None,
+                    pos_in: Optional[np.ndarray] = None, var_in: Optional[np.ndarray] = None) -> dict:
         """n same-shape tableaus, `matrices` float64 of n*height*width values (not modified).
-        `out` may be a dict from batch_outputs() to reuse (pinned) result buffers."""
+        `out` may be a dict from batch_outputs() to reuse (pinned) result buffers.
+        pos_in / var_in (int32, n*(width+height)): the basis bookkeeping the tableaus arrive with (the node LPs of
+        src/branchAndCut.ts:127); None = the identity of a fresh tableau (src/tableau.ts:95-98)."""
         opt = options or make_options()
         m = np.ascontiguousarray(matrices, dtype=np.float64).reshape(-1)
         cells = height * width
@@ -124,9 +127,56 @@ class Engine:
             out = self.batch_outputs(n, height, width, want_matrices, want_basis)
         elif out["status"].shape[0] != n:
             raise ValueError("out was allocated for a different batch size")
-        self._check(self._lib.yalps_solve_batch(self._ctx, n, height, width, _ptr(m), C.byref(opt), _ptr(out["status"]),
-                                                _ptr(out["value"]), _ptr(out["pivots"]), _ptr(out["rhs"]),
-                                                _ptr(out["pos"]), _ptr(out["var"]), _ptr(out["matrices"])))
+        if pos_in is None and var_in is None:
+            self._check(self._lib.yalps_solve_batch(self._ctx, n, height, width, _ptr(m), C.byref(opt),
+                                                    _ptr(out["status"]), _ptr(out["value"]), _ptr(out["pivots"]),
+                                                    _ptr(out["rhs"]), _ptr(out["pos"]), _ptr(out["var"]),
+                                                    _ptr(out["matrices"])))
+            return out
+        p = None if pos_in is None else np.ascontiguousarray(pos_in, np.int32).reshape(-1)
+        v = None if var_in is None else np.ascontiguousarray(var_in, np.int32).reshape(-1)
+        for arr in (p, v):
+            if arr is not None and arr.size != n * (width + height):
+                raise ValueError("pos_in / var_in need n*(width+height) entries")
+        self._check(self._lib.yalps_solve_batch_basis(self._ctx, n, height, width, _ptr(m), _ptr(p), _ptr(v), C.byref(opt),
+                                                      _ptr(out["status"]), _ptr(out["value"]), _ptr(out["pivots"]),
+                                                      _ptr(out["rhs"]), _ptr(out["pos"]), _ptr(out["var"]),
+                                                      _ptr(out["matrices"])))
+        return out
+
+    def simplex(self, tableau, options: Optional[Options] = None) -> tuple:
+        """simplex(tableau, options) -> (status, number), src/simplex.ts:144, with the reference's in-place contract:
+        `tableau` is a yalps_b200.Tableau (.matrix float64 height*width, .width, .height, .position_of_variable,
+        .variable_at_position) and all three arrays are overwritten with the final state."""
+        opt = options or make_options()
+        m = tableau.matrix
+        if not (isinstance(m, np.ndarray) and m.dtype == np.float64 and m.flags.c_contiguous):
+            raise ValueError("tableau.matrix must be a contiguous float64 array (it is modified in place)")
+        h, w = int(tableau.height), int(tableau.width)
+        pos = np.ascontiguousarray(tableau.position_of_variable, np.int32)
+        var = np.ascontiguousarray(tableau.variable_at_position, np.int32)
+        status, value = np.empty(1, np.int32), np.empty(1, np.float64)
+        self._check(self._lib.yalps_solve_batch_basis(self._ctx, 1, h, w, _ptr(m), _ptr(pos), _ptr(var), C.byref(opt),
+                                                      _ptr(status), _ptr(value), None, None, _ptr(pos), _ptr(var),
+                                                      _ptr(m)))
+        tableau.position_of_variable[:] = pos
+        tableau.variable_at_position[:] = var
+        return STATUS_NAMES[int(status[0])], float(value[0])
+
+    def solve_replicas(self, base: np.ndarray, rhs: np.ndarray, height: int, width: int,
+                       options: Optional[Options] = None, want_basis: bool = True, out: Optional[dict] = None) -> dict:
+        """n replicas of `base` (height*width) that differ only in column 0: rhs is float64 (n, height)."""
+        opt = options or make_options()
+        b = np.ascontiguousarray(base, np.float64).reshape(-1)
+        r = np.ascontiguousarray(rhs, np.float64).reshape(-1)
+        if b.size != height * width or r.size % height:
+            raise ValueError("base must hold height*width values and rhs n*height")
+        n = r.size // height
+        if out is None:
+            out = self.batch_outputs(n, height, width, False, want_basis)
+        self._check(self._lib.yalps_solve_replicas(self._ctx, n, height, width, _ptr(b), _ptr(r), C.byref(opt),
+                                                   _ptr(out["status"]), _ptr(out["value"]), _ptr(out["pivots"]),
+                                                   _ptr(out["rhs"]), _ptr(out["pos"]), _ptr(out["var"])))
         return out
 
     def solve_ragged(self, tableaus: Sequence[np.ndarray], shapes: Sequence[tuple], options: Optional[Options] = None,
@@ -300,3 +350,182 @@ class Engine:
         g, c = C.c_double(), C.c_double()
         self._check(self._lib.yalps_measure_smem_bandwidth(self._ctx, C.byref(g), C.byref(c)))
         return g.value, c.value
+
+
+class MultiEngine:
+    """yalps_multi: one process driving several GPUs (include/yalps_b200.h, csrc/multi.inl).  `devices` may repeat a
+    GPU (several logical ranks on one device)."""
+
+    def __init__(self, devices: Sequence[int]):
+        self._lib = _ffi.load()
+        self._m = C.c_void_p()
+        dev = np.ascontiguousarray(devices, np.int32)
+        rc = self._lib.yalps_create_multi(dev.ctypes.data_as(C.POINTER(C.c_int32)), int(dev.size), C.byref(self._m))
+        if rc != 0:
+            msg = self._lib.yalps_multi_last_error(None)
+            raise YalpsError(rc, msg.decode() if msg else "yalps_create_multi failed")
+        self.devices = [int(d) for d in dev]
+
+    def close(self):
+        if getattr(self, "_m", None) and self._m.value:
+            self._lib.yalps_destroy_multi(self._m)
+            self._m = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != 0:
+            msg = self._lib.yalps_multi_last_error(self._m)
+            raise YalpsError(rc, msg.decode() if msg else "")
+
+    @property
+    def size(self) -> int:
+        return int(self._lib.yalps_multi_size(self._m))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.yalps_multi_launch_count(self._m))
+
+    def set_tuning(self, path: int = PATH_AUTO, threads_per_lp: int = 0, row_groups: int = 0):
+        for r in range(self.size):
+            ctx = C.c_void_p(self._lib.yalps_multi_ctx(self._m, r))
+            if self._lib.yalps_set_tuning(ctx, path, threads_per_lp) or self._lib.yalps_set_row_groups(ctx, row_groups):
+                raise YalpsError(-2, (self._lib.yalps_last_error(ctx) or b"").decode())
+
+    @staticmethod
+    def _outputs(n, height, width, want_matrices):
+        return {"status": np.empty(n, np.int32), "value": np.empty(n, np.float64), "pivots": np.empty((n, 2), np.int64),
+                "rhs": np.empty((n, height), np.float64), "pos": np.empty((n, width + height), np.int32),
+                "var": np.empty((n, width + height), np.int32),
+                "matrices": np.empty((n, height * width), np.float64) if want_matrices else None}
+
+    def solve_batch(self, matrices: np.ndarray, height: int, width: int, options: Optional[Options] = None,
+                    want_matrices: bool = False, pos_in=None, var_in=None, out: Optional[dict] = None) -> dict:
+        opt = options or make_options()
+        m = np.ascontiguousarray(matrices, np.float64).reshape(-1)
+        n = m.size // (height * width)
+        out = out or self._outputs(n, height, width, want_matrices)
+        p = None if pos_in is None else np.ascontiguousarray(pos_in, np.int32).reshape(-1)
+        v = None if var_in is None else np.ascontiguousarray(var_in, np.int32).reshape(-1)
+        self._check(self._lib.yalps_multi_solve_batch(self._m, n, height, width, _ptr(m), _ptr(p), _ptr(v), C.byref(opt),
+                                                      _ptr(out["status"]), _ptr(out["value"]), _ptr(out["pivots"]),
+                                                      _ptr(out["rhs"]), _ptr(out["pos"]), _ptr(out["var"]),
+                                                      _ptr(out["matrices"])))
+        return out
+
+    def solve_replicas(self, base: np.ndarray, rhs: np.ndarray, height: int, width: int,
+                       options: Optional[Options] = None, out: Optional[dict] = None) -> dict:
+        opt = options or make_options()
+        b = np.ascontiguousarray(base, np.float64).reshape(-1)
+        r = np.ascontiguousarray(rhs, np.float64).reshape(-1)
+        n = r.size // height
+        out = out or self._outputs(n, height, width, False)
+        self._check(self._lib.yalps_multi_solve_replicas(self._m, n, height, width, _ptr(b), _ptr(r), C.byref(opt),
+                                                         _ptr(out["status"]), _ptr(out["value"]), _ptr(out["pivots"]),
+                                                         _ptr(out["rhs"]), _ptr(out["pos"]), _ptr(out["var"])))
+        return out
+
+    def solve_ragged(self, tableaus: Sequence[np.ndarray], shapes: Sequence[tuple], options: Optional[Options] = None,
+                     want_matrices: bool = False) -> list:
+        opt = options or make_options()
+        n = len(tableaus)
+        if n == 0:
+            return []
+        heights = np.asarray([s[0] for s in shapes], np.int32)
+        widths = np.asarray([s[1] for s in shapes], np.int32)
+        offs = np.zeros(n + 1, np.int64)
+        np.cumsum(heights.astype(np.int64) * widths, out=offs[1:])
+        packed = np.concatenate([np.asarray(t, np.float64).reshape(-1) for t in tableaus])
+        roffs = np.zeros(n + 1, np.int64)
+        np.cumsum(heights, out=roffs[1:])
+        poffs = np.zeros(n + 1, np.int64)
+        np.cumsum(heights.astype(np.int64) + widths, out=poffs[1:])
+        status, value, pivots = np.empty(n, np.int32), np.empty(n, np.float64), np.empty((n, 2), np.int64)
+        rhs, pos, var = np.empty(int(roffs[-1])), np.empty(int(poffs[-1]), np.int32), np.empty(int(poffs[-1]), np.int32)
+        mats = np.empty(int(offs[-1]), np.float64) if want_matrices else None
+        self._check(self._lib.yalps_multi_solve_ragged(self._m, n, _ptr(heights), _ptr(widths), _ptr(offs[:-1].copy()),
+                                                       _ptr(packed), C.byref(opt), _ptr(status), _ptr(value),
+                                                       _ptr(pivots), _ptr(rhs), _ptr(pos), _ptr(var), _ptr(mats)))
+        return [{"status": int(status[i]), "value": float(value[i]), "pivots": (int(pivots[i, 0]), int(pivots[i, 1])),
+                 "rhs": rhs[roffs[i]:roffs[i + 1]], "pos": pos[poffs[i]:poffs[i + 1]], "var": var[poffs[i]:poffs[i + 1]],
+                 "matrix": mats[offs[i]:offs[i + 1]] if want_matrices else None} for i in range(n)]
+
+    def incumbent_allreduce(self, local: Sequence[float]) -> np.ndarray:
+        """Min-allreduce of one fp64 per rank (NCCL across the distinct GPUs)."""
+        loc = np.ascontiguousarray(local, np.float64)
+        if loc.size != self.size:
+            raise ValueError("one value per rank")
+        out = np.empty_like(loc)
+        self._check(self._lib.yalps_incumbent_allreduce(self._m, loc.ctypes.data_as(C.POINTER(C.c_double)),
+                                                        out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def solve_tableau(self, matrix: np.ndarray, height: int, width: int, integers: Sequence[int], sign: float,
+                      options: Optional[Options] = None, allreduce_every: int = 4) -> dict:
+        """Engine.solve_tableau with the branch-and-bound frontier sharded over the ranks."""
+        opt = options or make_options()
+        m = np.ascontiguousarray(matrix, np.float64).reshape(-1)
+        ints = np.ascontiguousarray(integers, np.int32)
+        cap = height + 2 * ints.size
+        rhs, pos, var = np.empty(cap, np.float64), np.empty(width + cap, np.int32), np.empty(width + cap, np.int32)
+        status, out_h, root_status = C.c_int32(), C.c_int32(), C.c_int32()
+        result, root_value = C.c_double(), C.c_double()
+        root_piv, stats = np.zeros(2, np.int64), np.zeros(10, np.int64)
+        self._check(self._lib.yalps_multi_solve(self._m, height, width, _ptr(m), _ptr(ints) if ints.size else None,
+                                                int(ints.size), float(sign), C.byref(opt), int(allreduce_every),
+                                                C.byref(status), C.byref(result), C.byref(out_h), _ptr(rhs), _ptr(pos),
+                                                _ptr(var), C.byref(root_status), C.byref(root_value), _ptr(root_piv),
+                                                _ptr(stats)))
+        h = out_h.value
+        return {"status": status.value, "result": result.value, "height": h, "rhs": rhs[:h], "pos": pos[:width + h],
+                "var": var[:width + h], "root_status": root_status.value, "root_value": root_value.value,
+                "root_pivots": (int(root_piv[0]), int(root_piv[1])),
+                "stats": {"nodes": int(stats[0]), "node_pivots": int(stats[1]), "max_cuts": int(stats[2]),
+                          "max_heap": int(stats[3]), "waves": int(stats[4]), "device_nodes": int(stats[5]),
+                          "wave_us": int(stats[6]), "bnb_us": int(stats[7]), "sharded_waves": int(stats[8]),
+                          "allreduces": int(stats[9])}}
+
+    def solve_many_tableaus(self, tabmods: Sequence, options: Optional[Options] = None,
+                            searches_per_device: int = 4) -> list:
+        """yalps_multi_solve_many over TableauModel-like objects (.tableau.matrix/.height/.width, .integers, .sign)."""
+        opt = options or make_options()
+        n = len(tabmods)
+        if n == 0:
+            return []
+        heights = np.asarray([tm.tableau.height for tm in tabmods], np.int32)
+        widths = np.asarray([tm.tableau.width for tm in tabmods], np.int32)
+        nints = np.asarray([len(tm.integers) for tm in tabmods], np.int64)
+        offs = np.zeros(n + 1, np.int64)
+        np.cumsum(heights.astype(np.int64) * widths, out=offs[1:])
+        packed = np.concatenate([np.asarray(tm.tableau.matrix, np.float64).reshape(-1) for tm in tabmods])
+        ioffs = np.zeros(n + 1, np.int64)
+        np.cumsum(nints, out=ioffs[1:])
+        ints = np.asarray([v for tm in tabmods for v in tm.integers], np.int32) if ioffs[-1] else np.zeros(1, np.int32)
+        signs = np.asarray([tm.sign for tm in tabmods], np.float64)
+        roffs = np.zeros(n + 1, np.int64)
+        np.cumsum(heights + 2 * nints, out=roffs[1:])
+        poffs = np.zeros(n + 1, np.int64)
+        np.cumsum(heights.astype(np.int64) + widths + 2 * nints, out=poffs[1:])
+        status, result, out_h = np.empty(n, np.int32), np.empty(n, np.float64), np.empty(n, np.int32)
+        rhs, pos, var = np.empty(int(roffs[-1])), np.empty(int(poffs[-1]), np.int32), np.empty(int(poffs[-1]), np.int32)
+        self._check(self._lib.yalps_multi_solve_many(self._m, n, _ptr(heights), _ptr(widths), _ptr(offs[:-1].copy()),
+                                                     _ptr(packed), _ptr(ioffs), _ptr(ints), _ptr(signs), C.byref(opt),
+                                                     int(searches_per_device), _ptr(status), _ptr(result), _ptr(out_h),
+                                                     _ptr(rhs), _ptr(pos), _ptr(var)))
+        res = []
+        for i in range(n):
+            h, w = int(out_h[i]), int(widths[i])
+            res.append({"status": int(status[i]), "result": float(result[i]), "height": h,
+                        "rhs": rhs[roffs[i]:roffs[i] + h], "pos": pos[poffs[i]:poffs[i] + w + h],
+                        "var": var[poffs[i]:poffs[i] + w + h]})
+        return res

@@ -16,7 +16,7 @@ from typing import Optional, Sequence
 
 import numpy as np
 
-from .engine import Engine, STATUS_NAMES, make_options
+from .engine import Engine, MultiEngine, STATUS_NAMES, make_options
 from .tableau import TableauModel, tableau_model
 
 # src/YALPS.ts:52-60
@@ -94,6 +94,7 @@ def solve(model: dict, options: Optional[dict] = None, *, engine: Optional[Engin
     opt = {**_DEFAULTS, **(options or {})}
     eng = engine or get_engine()
     t = tabmod.tableau
+    # a MultiEngine shards the branch-and-bound frontier over its GPUs (same search, same result)
     r = eng.solve_tableau(t.matrix, t.height, t.width, tabmod.integers, tabmod.sign, _c_options(opt))
     if info is not None:
         info.update(r["stats"], root_status=STATUS_NAMES[r["root_status"]], root_value=r["root_value"],
@@ -127,6 +128,10 @@ def solve_many(models: Sequence[dict], options: Optional[dict] = None, *, engine
     tabmods = [tableau_model(m) for m in models]
     if not tabmods:
         return []
+    if isinstance(eng, MultiEngine):  # one C-ABI call: roots sharded over the GPUs, searches dealt to worker contexts
+        res = eng.solve_many_tableaus(tabmods, copt, searches_per_device=milp_workers)
+        return [_solution(tm, STATUS_NAMES[r["status"]], r["result"], r["rhs"], r["pos"], r["var"], opt)
+                for tm, r in zip(tabmods, res)]
     roots = eng.solve_ragged([tm.tableau.matrix for tm in tabmods],
                              [(tm.tableau.height, tm.tableau.width) for tm in tabmods], copt,
                              want_matrices=any(tm.integers for tm in tabmods))
