@@ -12,10 +12,12 @@ collective: LPs are independent); the time is the max over ranks, the value the 
 `value`     pivots/s with the tableaus already resident in HBM (device entry point of the C ABI)
 `e2e`       pivots/s through the host C-ABI call (yalps_solve_batch) from pinned host buffers, H2D of the
             tableaus and D2H of status/value/pivots/RHS/basis inside the timed region
-`roofline`  SURVEY 8(d): algorithmic bytes = 16*H*W per pivot, against the shared-memory stream bandwidth
+`roofline`  SURVEY 8(d): algorithmic bytes = 16*W*(1+R) + 8*(2(H-1)+2(W-1)) per pivot with R, the rows a pivot
+            rewrites, COUNTED ON THE DEVICE in a measuring pass, against the shared-memory stream bandwidth
             measured live (north_star's denominator; K1 keeps the tableau in shared memory).  The automatic
             path for this workload is K1t, which keeps the tableau in TENSOR memory: its own stream bandwidth
             (tcgen05.ld/st, measured live too) and the HBM view are reported alongside
+`secondary` (N=1 only) BASELINE.json configs 3, 4 and 5 with the same fields per workload (bench_workloads.py)
 `cpu_baseline` the CPU restatement of the reference loop (oracle/, C -O2 -ffp-contract=off; Node is not
             available) on the box's host cores, bounded sample of the same workload
 
@@ -238,6 +240,13 @@ def run_native(args):
     torch.cuda.synchronize()
     pivots_per_step = int(d_piv.sum().item())
     statuses = torch.bincount(d_status.to(torch.int64), minlength=5).tolist()
+    # measuring pass: rows rewritten by the rank-1 updates (R of SURVEY 8d), counted by the kernel itself
+    d_rows = torch.zeros(1, dtype=torch.int64, device=dev)
+    eng.set_row_counter(d_rows.data_ptr(), per_lp=False)
+    step()
+    torch.cuda.synchronize()
+    eng.set_row_counter(0)
+    rows_per_step = int(d_rows.item())
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -272,23 +281,28 @@ def run_native(args):
         out = eng.solve_batch(h_in, H, W, opt, out=h_out)
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+    # the bare copy of the same bytes on every rank at once: what the box's PCIe / host-memory fabric allows
+    barrier()
+    h2d_s = eng.measure_h2d_seconds(h_in, reps=3, nstreams=2)
     clocks = sampler.stop() if rank == 0 else None  # sampled over the device-timed and the end-to-end regions
     h2d = n * cells * 8
     d2h = n * (4 + 8 + 16 + H * 8 + 2 * (W + H) * 4)
 
     # ---- max over ranks, sum of work
-    t = torch.tensor([elapsed_ms, e2e_s * 1e3, kernel_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([elapsed_ms, e2e_s * 1e3, kernel_ms, h2d_s * 1e3], dtype=torch.float64, device=dev)
     work = torch.tensor([float(pivots_per_step)], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(work, op=dist.ReduceOp.SUM)
-    elapsed_ms, e2e_ms, kernel_ms_max = (float(x) for x in t.tolist())
+    elapsed_ms, e2e_ms, kernel_ms_max, h2d_ms = (float(x) for x in t.tolist())
     total_pivots_step = float(work.item())
 
     if rank == 0:
         value = total_pivots_step * args.steps / (elapsed_ms * 1e-3)
-        bytes_per_pivot = 16 * H * W  # SURVEY 8(d), dense tableau
-        achieved = pivots_per_step * bytes_per_pivot / (kernel_ms * 1e-3) / 1e9
+        import bench_workloads as BW
+        alg_bytes = BW.pivot_bytes(H, W, pivots_per_step, rows_per_step)  # SURVEY 8(d) with the counted R
+        bytes_per_pivot = alg_bytes / pivots_per_step
+        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
         smem_gbs, _ = eng.measure_smem_bandwidth()
         tmem_gbs, _ = eng.measure_tmem_bandwidth()
         peaks = {}
@@ -326,7 +340,11 @@ def run_native(args):
             "e2e": {"value": total_pivots_step / (e2e_ms * 1e-3), "unit": "pivots/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "lps_per_s": n * world / (e2e_ms * 1e-3),
                     "api": "yalps_solve_batch (host pointers; pinned input and output buffers; chunked H2D/kernel/D2H pipeline)",
-                    "pcie_gbs": (h2d + d2h) * world / (e2e_ms * 1e-3) / 1e9, "numa_binding": numa},
+                    "pcie_gbs": (h2d + d2h) * world / (e2e_ms * 1e-3) / 1e9, "numa_binding": numa,
+                    "h2d_ceiling_gbs": h2d * world / (h2d_ms * 1e-3) / 1e9,
+                    "h2d_ceiling_note": "bare cudaMemcpyAsync of the same pinned tableaus on all ranks at once (two streams per "
+                                        "GPU, max over ranks): the end-to-end step cannot beat h2d_bytes / this rate",
+                    "ms_floor_from_ceiling": h2d_ms},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "smem", "achieved": achieved, "peak": smem_gbs, "unit": "GB/s",
@@ -335,6 +353,9 @@ def run_native(args):
                                          "the tableau is read from HBM once, every pivot runs out of tensor memory",
                          "peak_source": "measured live: ld/st.shared.f64 stream on all SMs (yalps_measure_smem_bandwidth)",
                          "bytes_per_unit": bytes_per_pivot, "units_per_launch": pivots_per_step,
+                         "bytes_formula": "16*W*(pivots + rows_rewritten) + pivots*8*(2(H-1)+2(W-1)), SURVEY 8(d)",
+                         "rows_rewritten": rows_per_step, "mean_rows_per_pivot": rows_per_step / pivots_per_step,
+                         "rows_dense": H - 1,
                          "kernel_ms": kernel_ms,
                          "kernel": "k_simplex_tmem (K1t)" if args.path in (0, 6) and args.threads == 0 else "k_simplex<NW,KC,resident>",
                          "tmem": {"achieved": achieved, "peak": tmem_gbs, "frac": achieved / tmem_gbs,
@@ -351,6 +372,8 @@ def run_native(args):
                              "lps_per_s": cpu_lps,
                              "note": "C restatement of src/simplex.ts (oracle/), not Node/V8"},
         }
+        if world == 1 and args.workload == "config2" and not args.no_secondary:
+            line["secondary"] = BW.run_all(torch, eng, hbm_peak, cores)
         emit_line(line)
     eng.close()
     if dist is not None:
@@ -383,6 +406,7 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="config2")
     ap.add_argument("--threads", type=int, default=0, help="threads per LP (0 = auto)")
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 smem (K1), 2 gmem (K2), 6 tmem (K1t)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the configs 3/4/5 block of the N=1 line")
     args = ap.parse_args()
     quiet_stdout()
     if args.impl == "reference":

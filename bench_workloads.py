@@ -1,0 +1,281 @@
+"""Secondary workloads of bench.py: BASELINE.json configs 3, 4 and 5 (config 2 is the headline, config 1 the parity
+anchor).  Every entry of the `secondary` array carries ms, pivots/s, LPs/s and a roofline whose bytes follow
+SURVEY 8(d) exactly:
+
+    bytes(pivot) = 16*W*(1+R) + 8*(2(H-1) + 2(W-1)),   R = rows the rank-1 update rewrites (|coef| > 1e-16)
+
+with R COUNTED ON THE DEVICE (yalps_set_row_counter: the kernels add the R of every pivot to a 64-bit counter) in a
+measuring pass over the same inputs; the timed passes run without the counter.  `traffic` is the DRAM traffic of the
+same kernel from the committed ncu --set full summaries under profiles/ (null where none was captured).
+
+Inputs come from tests/golden/ (the Netlib base tableaus and the reference's MILP test cases, generated from the
+reference by tests/golden/make_golden.py); nothing here reads /root/reference.
+"""
+import gzip
+import json
+import math
+import os
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def netlib_base(name):
+    z = np.load(os.path.join(GOLDEN, "netlib.npz"))
+    h, w = (int(x) for x in z[f"{name}/shape"])
+    m = np.zeros(h * w, np.float64)
+    m[z[f"{name}/nz_idx"]] = z[f"{name}/nz_val"]
+    m[z[f"{name}/neg_zero_idx"]] = -0.0
+    return {"height": h, "width": w, "matrix": m, "row_groups": z[f"{name}/row_groups"],
+            "pivots": tuple(int(x) for x in z[f"{name}/pivots"]), "status": int(z[f"{name}/status"][0])}
+
+
+def milp_case(name):
+    with gzip.open(os.path.join(GOLDEN, "cases.json.gz"), "rt", encoding="utf-8") as f:
+        cases = json.load(f)
+    c = next(x for x in cases if x["name"] == name)
+    m = c["model"]
+    m["constraints"] = [(k, v) for k, v in m["constraints"]]
+    m["variables"] = [(k, [(ck, cv) for ck, cv in v]) for k, v in m["variables"]]
+    for key in ("integers", "binaries", "direction", "objective"):
+        if m.get(key) is None:
+            m.pop(key, None)
+    return c
+
+
+def pivot_bytes(H, W, pivots, rows):
+    """SURVEY 8(d) summed over `pivots` pivots that rewrote `rows` rows in total."""
+    return 16.0 * W * (pivots + rows) + pivots * 8.0 * (2 * (H - 1) + 2 * (W - 1))
+
+
+def ncu_traffic(name):
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", name)))["dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
+def _events(torch, fn, reps, warm=1):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for e0, e1 in evs:
+        e0.record()
+        fn()
+        e1.record()
+    torch.cuda.synchronize()
+    return sum(e0.elapsed_time(e1) for e0, e1 in evs) / reps
+
+
+def _counter(torch, eng, fn):
+    """One pass of fn() with the device row counter set: total rows rewritten."""
+    c = torch.zeros(1, dtype=torch.int64, device="cuda")
+    eng.set_row_counter(c.data_ptr(), per_lp=False)
+    try:
+        fn()
+        torch.cuda.synchronize()
+    finally:
+        eng.set_row_counter(0)
+    return int(c.item())
+
+
+def config3(torch, eng, name, n, hbm_peak, cpu_cores):
+    """n RHS-perturbed replicas of a Netlib model, HBM-resident working copies (the automatic policy picks the kernel).
+    The timed step = copy of the pristine replicas into the working buffer is EXCLUDED (device-to-device copy timed
+    separately and subtracted is not needed: the kernel solves from `d` into `work` itself)."""
+    from yalps_b200.engine import make_options
+    from oracle import lib as O
+    g = netlib_base(name)
+    H, W = g["height"], g["width"]
+    cells = H * W
+    opt = make_options()
+    stream = torch.cuda.current_stream().cuda_stream
+    d = torch.empty(n * cells, dtype=torch.float64, device="cuda")
+    eng.generate_replicas_device(0, n, g["matrix"], H, W, g["row_groups"], d.data_ptr(), stream=stream)
+    work = torch.empty_like(d)
+    st = torch.empty(n, dtype=torch.int32, device="cuda")
+    val = torch.empty(n, dtype=torch.float64, device="cuda")
+    piv = torch.empty(n, 2, dtype=torch.int64, device="cuda")
+    rhs = torch.empty(n, H, dtype=torch.float64, device="cuda")
+    pos = torch.empty(n, W + H, dtype=torch.int32, device="cuda")
+    var = torch.empty(n, W + H, dtype=torch.int32, device="cuda")
+
+    def step():
+        eng.solve_batch_device(n, H, W, d.data_ptr(), opt, d_work=work.data_ptr(), d_status=st.data_ptr(),
+                               d_value=val.data_ptr(), d_pivots=piv.data_ptr(), d_rhs=rhs.data_ptr(),
+                               d_pos=pos.data_ptr(), d_var=var.data_ptr(), stream=stream)
+
+    launches0 = eng.launch_count
+    step()
+    torch.cuda.synchronize()
+    launches = eng.launch_count - launches0
+    rows = _counter(torch, eng, step)
+    ms = _events(torch, step, reps=3, warm=1)
+    pivots = int(piv.sum().item())
+    optimal = int((st == 0).sum().item())
+    alg = pivot_bytes(H, W, pivots, rows)
+    achieved = alg / (ms * 1e-3) / 1e9
+
+    # end to end through the data-reducing replica entry: base once + n*H right-hand sides from pinned host memory
+    h_rhs = eng.pinned_empty((n, H), np.float64)
+    h_rhs[:] = d.view(n, H, W)[:, :, 0].cpu().numpy()
+    out = eng.batch_outputs(n, H, W, pinned=True)
+    eng.solve_replicas(g["matrix"], h_rhs, H, W, opt, out=out)  # warm-up (allocates the device pool)
+    assert int(out["pivots"].sum()) == pivots and int((out["status"] == 0).sum()) == optimal
+    t0 = time.perf_counter()
+    reps = 2
+    for _ in range(reps):
+        eng.solve_replicas(g["matrix"], h_rhs, H, W, opt, out=out)
+    e2e_s = (time.perf_counter() - t0) / reps
+
+    # CPU port on a bounded sample, all cores
+    cn = min(n, 64 * cpu_cores)
+    sample = d.view(n, cells)[:cn].cpu().numpy().copy()
+    t0 = time.perf_counter()
+    ref = O.simplex_batch(sample, W, H, nthreads=cpu_cores, want_pos=False)
+    cpu_dt = time.perf_counter() - t0
+    same = bool(np.array_equal(ref["pivots"], piv[:cn].cpu().numpy()) and
+                np.array_equal(ref["rhs"].view(np.uint64), rhs[:cn].cpu().numpy().view(np.uint64)))
+    return {
+        "workload": f"config3_{name.lower()}: {n} RHS-perturbed (eps 1e-2) replicas of Netlib {name}, tableau {H}x{W}, "
+                    f"working copies in HBM ({n * cells * 8 / 1e9:.1f} GB, larger than L2), BASELINE.json configs[2]",
+        "ms": ms, "pivots_per_s": pivots / ms * 1e3, "lps_per_s": n / ms * 1e3, "pivots": pivots, "optimal": optimal,
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": ncu_traffic(f"r02_k2s_{name.lower()}_ncu_summary.json"),
+                     "bytes_formula": "16*W*(pivots + rows_rewritten) + pivots*8*(2(H-1)+2(W-1)), SURVEY 8(d)",
+                     "rows_rewritten": rows, "mean_rows_per_pivot": rows / max(pivots, 1), "rows_dense": H - 1,
+                     "note": "R counted on the device; the kernel is bound by the per-pivot dependent chain of one CTA "
+                             "per LP (latency), not by HBM: the working set of the resident CTAs lives in L2"},
+        "e2e": {"api": "yalps_solve_replicas (base tableau once + n*H right-hand sides from pinned host memory; "
+                       "status/value/pivots/RHS/basis back)", "ms": e2e_s * 1e3, "lps_per_s": n / e2e_s,
+                "pivots_per_s": pivots / e2e_s, "h2d_bytes_per_step": cells * 8 + n * H * 8,
+                "d2h_bytes_per_step": n * (4 + 8 + 16 + H * 8 + 2 * (W + H) * 4)},
+        "cpu_baseline": {"value": int(ref["pivots"].sum()) / cpu_dt, "unit": "pivots/s", "lps_per_s": cn / cpu_dt,
+                         "cores": cpu_cores, "kind": "port", "sample": f"the first {cn} replicas, {cpu_dt:.2f} s",
+                         "bit_identical_to_gpu": same},
+    }
+
+
+def config4(torch, eng, hbm_peak):
+    """The MILP suite of benchmarks/json/read.ts through solve(): host tableau build + root LP + branch and cut."""
+    import yalps_b200
+    from oracle import model as M
+    out = []
+    for name in ("Large Farm MIP", "Monster 2", "Vendor Selection", "Monster Problem"):
+        c = milp_case(name)
+        info = {}
+        yalps_b200.solve(c["model"], c["options"], engine=eng, info=info)  # warm-up
+        rows = _counter(torch, eng, lambda: yalps_b200.solve(c["model"], c["options"], engine=eng))
+        launches0 = eng.launch_count
+        reps = 3
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            sol = yalps_b200.solve(c["model"], c["options"], engine=eng, info=info)
+        dt = (time.perf_counter() - t0) / reps
+        launches = (eng.launch_count - launches0) // reps
+        t0 = time.perf_counter()
+        ref = M.solve(c["model"], {**M.DEFAULT_OPTIONS, **c["options"]})
+        cpu = time.perf_counter() - t0
+        H, W = info["height"], info["width"]
+        piv = sum(info["root_pivots"]) + info["node_pivots"]
+        alg = pivot_bytes(H, W, piv, rows)  # node tableaus have a few more rows than the root: a lower bound
+        same = sol["status"] == ref["status"] and (sol["result"] == ref["result"] or
+                                                   (math.isnan(sol["result"]) and math.isnan(ref["result"])))
+        out.append({
+            "workload": f"config4_{name.lower().replace(' ', '_')}: {name} via solve() (tableau {H}x{W}, "
+                        f"{len(c['model'].get('integers') or [])} integer variables), BASELINE.json configs[3]",
+            "ms": dt * 1e3, "pivots_per_s": piv / dt, "lps_per_s": (1 + info["device_nodes"]) / dt,
+            "nodes": info["nodes"], "node_pivots": info["node_pivots"], "root_pivots": list(info["root_pivots"]),
+            "waves": info["waves"], "device_nodes": info["device_nodes"], "nodes_per_s": info["nodes"] / dt,
+            "status": sol["status"], "result": sol["result"], "expected": c["expected"]["result"],
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": alg / dt / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": alg / dt / 1e9 / hbm_peak, "traffic": None, "rows_rewritten": rows,
+                         "note": "latency-bound by construction: a search is a chain of dependent waves of a few "
+                                 "node LPs (SURVEY 8d); wall time includes the host tableau build and the replay"},
+            "cpu_baseline": {"ms": cpu * 1e3, "cores": 1, "kind": "port", "sample": "the same solve(), once",
+                             "same_status_and_result": bool(same)},
+        })
+    return out
+
+
+def config5(torch, eng, hbm_peak):
+    """One large dense LP on the whole GPU (K4): the 4097x8193 synthetic tableau (268.5 MB > L2) for a capped number of
+    pivots, and Netlib 25FV47 (1338x1572, L2-resident) to the end."""
+    from yalps_b200.engine import make_options
+    from oracle import lib as O
+    out = []
+    stream = torch.cuda.current_stream().cuda_stream
+    cases = [("synthetic 4096x8192", None, 4096, 8192, 48.0), ("Netlib 25FV47", "25FV47", 0, 0, math.inf)]
+    for label, netlib, m, nv, cap in cases:
+        if netlib:
+            g = netlib_base(netlib)
+            H, W = g["height"], g["width"]
+            d = torch.from_numpy(g["matrix"]).cuda()
+        else:
+            H, W = m + 1, nv + 1
+            d = torch.empty(H * W, dtype=torch.float64, device="cuda")
+            eng.generate_synthetic_device(0, 1, m, nv, d.data_ptr(), stream=stream)
+        work = torch.empty_like(d)
+        st = torch.empty(1, dtype=torch.int32, device="cuda")
+        piv = torch.empty(1, 2, dtype=torch.int64, device="cuda")
+        opt = make_options(max_pivots=cap)
+        copy_ms = _events(torch, lambda: work.copy_(d), reps=3)
+
+        def step():
+            work.copy_(d)
+            eng.solve_batch_device(1, H, W, work.data_ptr(), opt, d_work=work.data_ptr(), d_status=st.data_ptr(),
+                                   d_pivots=piv.data_ptr(), stream=stream)
+
+        launches0 = eng.launch_count
+        step()
+        torch.cuda.synchronize()
+        launches = eng.launch_count - launches0
+        rows = _counter(torch, eng, step)
+        ms = _events(torch, step, reps=2, warm=0) - copy_ms
+        p = int(piv.sum().item())
+        alg = pivot_bytes(H, W, p, rows)
+        entry = {
+            "workload": f"config5: one LP on the whole GPU, {label} (tableau {H}x{W}, {H * W * 8 / 1e6:.1f} MB, "
+                        f"{'larger than' if H * W * 8 > 126e6 else 'resident in'} L2), BASELINE.json configs[4]"
+                        + (f"; first {int(cap)} pivots per phase" if math.isfinite(cap) else "; full solve"),
+            "ms": ms, "pivots": p, "pivots_per_s": p / ms * 1e3, "lps_per_s": 1e3 / ms, "us_per_pivot": ms * 1e3 / max(p, 1),
+            "status": int(st.item()), "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak,
+                         "traffic": ncu_traffic("r02_k4_ncu_summary.json") if not netlib else None,
+                         "rows_rewritten": rows, "mean_rows_per_pivot": rows / max(p, 1), "rows_dense": H - 1,
+                         "note": None if not netlib else "L2-resident and sparse: bound by the grid barriers of a pivot, "
+                                                         "not by bandwidth"},
+        }
+        if netlib:  # the reference's own outcome on this model: infeasible after 3110 phase-1 pivots
+            entry["matches_oracle_golden"] = bool(int(st.item()) == g["status"] and
+                                                  tuple(int(x) for x in piv[0].tolist()) == g["pivots"])
+        else:
+            k = 6  # CPU port: the first k pivots of the same tableau, one thread (a pivot is a sequential rank-1 update)
+            host = d.cpu().numpy().copy()
+            posv = np.arange(W + H, dtype=np.int32)
+            varv = posv.copy()
+            t0 = time.perf_counter()
+            O.simplex(host, W, H, posv, varv, max_pivots=k)
+            cpu_dt = time.perf_counter() - t0
+            entry["cpu_baseline"] = {"value": k / cpu_dt, "unit": "pivots/s", "cores": 1, "kind": "port",
+                                     "sample": f"the first {k} pivots of the same tableau, {cpu_dt:.2f} s"}
+        out.append(entry)
+        del d, work
+    return out
+
+
+def run_all(torch, eng, hbm_peak, cpu_cores):
+    out = []
+    for name, n in (("SC105", 32768), ("ADLITTLE", 65536)):
+        out.append(config3(torch, eng, name, n, hbm_peak, cpu_cores))
+        torch.cuda.empty_cache()
+    out.extend(config4(torch, eng, hbm_peak))
+    out.extend(config5(torch, eng, hbm_peak))
+    return out

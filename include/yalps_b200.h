@@ -101,6 +101,16 @@ int yalps_set_row_groups(yalps_ctx *ctx, int32_t row_groups);
 /* Number of kernels launched by this ctx since creation (bench.py's gpu_launches). */
 int64_t yalps_launch_count(const yalps_ctx *ctx);
 
+/*
+ * Roofline diagnostics: algorithmic bytes of a pivot are 16*W*(1+R) + 8*(2(H-1)+2(W-1)) with R = the rows
+ * the rank-1 update rewrites (|coef| > 1e-16, src/simplex.ts:31).  While a counter is set, every kernel ADDS the R
+ * of each pivot to d_rows[per_lp ? LP index within the call : 0] (device memory, uint64, zeroed by the caller):
+ * yalps_solve_batch_device and yalps_solve_replicas per LP or in total, branch-and-cut node waves in total only.
+ * The tensor-memory kernel runs a counting instantiation while the counter is set, so set it for a measuring pass,
+ * not for the timed one.  NULL switches the counter off.
+ */
+int yalps_set_row_counter(yalps_ctx *ctx, uint64_t *d_rows, int32_t per_lp);
+
 /* Pinned host memory for callers that want zero-staging transfers. */
 int yalps_host_alloc(yalps_ctx *ctx, uint64_t bytes, void **out);
 int yalps_host_free(yalps_ctx *ctx, void *ptr);
@@ -296,6 +306,11 @@ int yalps_probe_division(yalps_ctx *ctx, int64_t n, uint64_t seed, int32_t mode,
 /* Shared-memory stream microbenchmark: bytes moved per second by ld/st.shared.f64 on all SMs
  * (the measured denominator of the K1 roofline).  Returns GB/s in *gbs. */
 int yalps_measure_smem_bandwidth(yalps_ctx *ctx, double *gbs, double *sm_clock_mhz);
+/* Bare host-to-device copy of `bytes` from a PINNED host buffer into a device scratch buffer, `reps` times over
+ * `nstreams` (1 or 2) streams: seconds per repetition.  bench.py runs it on all ranks at once to print the ceiling
+ * the box's PCIe / host-memory fabric puts on the end-to-end rate (e2e.h2d_ceiling_gbs). */
+int yalps_measure_h2d_bandwidth(yalps_ctx *ctx, const void *pinned_host, uint64_t bytes, int32_t reps, int32_t nstreams,
+                                double *seconds);
 /* Tensor-memory stream microbenchmark: bytes read + written per second by tcgen05.ld/st.32x32b.x32 with the
  * multiply-subtract of the rank-1 update in between, 16 warps per SM (what bounds K1t's row pass). */
 int yalps_measure_tmem_bandwidth(yalps_ctx *ctx, double *gbs, double *sm_clock_mhz);

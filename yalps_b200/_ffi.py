@@ -50,6 +50,7 @@ SIGNATURES = {
     "yalps_set_row_groups": (C.c_int, [_vp, C.c_int32]),
     "yalps_probe_division": (C.c_int, [_vp, C.c_int64, C.c_uint64, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "yalps_launch_count": (C.c_int64, [_vp]),
+    "yalps_set_row_counter": (C.c_int, [_vp, _vp, C.c_int32]),
     "yalps_host_alloc": (C.c_int, [_vp, C.c_uint64, C.POINTER(_vp)]),
     "yalps_host_free": (C.c_int, [_vp, _vp]),
     "yalps_solve_batch": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int32, _vp, C.POINTER(Options), _vp, _vp, _vp, _vp,
@@ -96,6 +97,7 @@ SIGNATURES = {
     "yalps_round_to_precision": (C.c_int, [_vp, C.c_int64, _vp, C.c_double, _vp]),
     "yalps_measure_smem_bandwidth": (C.c_int, [_vp, _dp, _dp]),
     "yalps_measure_tmem_bandwidth": (C.c_int, [_vp, _dp, _dp]),
+    "yalps_measure_h2d_bandwidth": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int32, C.c_int32, _dp]),
 }
 
 _lib = None

@@ -315,6 +315,7 @@ int bnb_solve_nodes_impl(yalps_ctx *ctx, int64_t n, const int32_t *cut_offsets, 
   a.cut_var = (const int *)d_var;
   a.cut_val = (const double *)d_val;
   fill_options(a, opt);
+  a.rows_out = ctx->rows_per_lp ? nullptr : ctx->d_rows;  // node waves only feed a total (their LP indices are wave-local)
   if (use_grid_path(ctx, n, plan)) {
     // few large nodes: assemble them in HBM (K3), then give each node the whole grid (K4)
     if (!d_work) {
@@ -354,7 +355,7 @@ int bnb_solve_nodes_impl(yalps_ctx *ctx, int64_t n, const int32_t *cut_offsets, 
       if ((rc = launch_grid(ctx, hj, W, (double *)d_work + (size_t)j * Hcap * W, opt, (int *)d_status + j,
                             (double *)d_value + j, (long long *)d_piv + 2 * j, (double *)d_rhs + (size_t)j * Hcap,
                             (int *)d_pos + (size_t)j * (W + Hcap), (int *)d_vr + (size_t)j * (W + Hcap), sj,
-                            (const int *)R.var.p, W + R.H, share, lanes > 1 ? "_l" + std::to_string(l) : "")))
+                            (const int *)R.var.p, W + R.H, share, lanes > 1 ? "_l" + std::to_string(l) : "", a.rows_out)))
         return rc;
     }
     if (lanes > 1) {

@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_simplex_cluster(const Batc
     res.status = ST_CYCLED;
     res.value = d_nan();
     res.p1 = res.p2 = 0;
+    res.rows = 0;  // this CTA's share of the rewritten rows (CTA 0 also counts the objective row)
     int phase = 1, parity = 0, xpar = 0, hist_len = 0;
     long long iter = 0;
     const double precision = a.precision;
@@ -400,6 +401,7 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_simplex_cluster(const Batc
         __syncthreads();
         const int R = *cnt;
         const bool any_partial = __any_sync(0xffffffffu, partial);
+        res.rows += (unsigned)(R + ((rank == 0 && fabs(coef0) > kTiny) ? 1 : 0));
         CT_MARK(3);
 
         if (rg == NWR - 1) {
@@ -460,6 +462,7 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_simplex_cluster(const Batc
 
     // ---- outputs (every CTA its own rows; CTA 0 the scalars, the objective row and the basis)
     cluster.sync();
+    if (a.rows_out && tid == 0 && res.rows != 0) atomicAdd(a.rows_out + (a.rows_per_lp ? lp : 0), res.rows);
     if (rank == 0) {
       if (tid == 0) {
         if (a.status) a.status[lp] = res.status;

@@ -57,6 +57,7 @@ struct GridArgs {
   int hist_cap;
   int *flags;                  // [2] cycle / history-overflow verdict of CTA 0, by iteration parity
   unsigned long long *barrier; // grid barrier arrival counter, zeroed before the launch
+  unsigned long long *rows_out; // optional: rows rewritten by the updates are ADDED here (roofline diagnostics)
 };
 
 constexpr int kGridThreads = 1024;
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(kGridThreads, 1) k_simplex_grid(const GridArgs
   int status = ST_CYCLED;
   double value = d_nan();
   long long p1 = 0, p2 = 0, iter = 0;
+  unsigned long long rows_mine = 0;
   int phase = 1, parity = 0, hist_len = 0;
 
   for (;;) {
@@ -244,7 +246,9 @@ __global__ void __launch_bounds__(kGridThreads, 1) k_simplex_grid(const GridArgs
     }
     for (int r = tid; r < H; r += NT) {
       const double coef = colbuf[r];
-      colbuf[r] = (r != row && fabs(coef) > kTiny) ? coef : 0.0;
+      const bool on = r != row && fabs(coef) > kTiny;
+      colbuf[r] = on ? coef : 0.0;
+      rows_mine += on;  // every CTA builds the whole column: CTA 0 reports the count
     }
     __syncthreads();
     // ---- the same rank-1 update on the private objective row / RHS column copies
@@ -347,6 +351,7 @@ __global__ void __launch_bounds__(kGridThreads, 1) k_simplex_grid(const GridArgs
       a.pivots[1] = p2;
     }
   }
+  if (a.rows_out && blockIdx.x == 0 && rows_mine != 0) atomicAdd(a.rows_out, rows_mine);
   if (a.rhs_out)
     for (int r = blockIdx.x * NT + tid; r < H; r += gridDim.x * NT) a.rhs_out[r] = M[(size_t)r * W];
   if (a.pos_out)

@@ -30,6 +30,10 @@ struct BatchArgs {
   long long *pivots;
   double *rhs_out;
   int *pos_out, *var_out;
+  // optional diagnostics for the roofline: rows rewritten by the rank-1 updates, summed over the pivots of
+  // an LP, ADDED (atomically) to rows_out[rows_per_lp ? lp : 0]; the host zeroes the buffer
+  unsigned long long *rows_out;
+  int rows_per_lp;
   const int *var_in;  // optional initial variableAtPosition, packed like var_out (null: the identity, src/tableau.ts:95-98)
   // node mode
   const double *root;
@@ -277,6 +281,7 @@ __global__ void __launch_bounds__(NWC *NWR * 32, min_ctas_per_sm(NWC, NWR)) k_si
         a.pivots[2 * lp + 1] = res.p2;
       }
     }
+    if (a.rows_out && res.rows != 0 && (!kSplit || tid == 0)) atomicAdd(a.rows_out + (a.rows_per_lp ? lp : 0), res.rows);
     if (a.rhs_out)
       for (int r = tid; r < H; r += NT) a.rhs_out[roff + r] = t.b[(size_t)r * ldb];
 #ifdef YALPS_TIMING

@@ -16,7 +16,10 @@ int tmem_kernel_ctas_per_sm(int Hcap) { return tall(Hcap) ? TmemShape<2>::kCtasP
 size_t tmem_kernel_dynamic_smem(int Hcap) { return (size_t)(227 * 1024) / (tmem_kernel_ctas_per_sm(Hcap) + 1) + 1024; }
 size_t tmem_stream_dynamic_smem() { return tmem_kernel_dynamic_smem(1); }
 
-const void *tmem_kernel_fn(int Hcap) { return tall(Hcap) ? (const void *)k_simplex_tmem<2> : (const void *)k_simplex_tmem<1>; }
+const void *tmem_kernel_fn(int Hcap, bool count_rows) {
+  if (count_rows) return tall(Hcap) ? (const void *)k_simplex_tmem<2, true> : (const void *)k_simplex_tmem<1, true>;
+  return tall(Hcap) ? (const void *)k_simplex_tmem<2> : (const void *)k_simplex_tmem<1>;
+}
 
 // Tensor-memory stream: every lane reads and rewrites its eight-row blocks (tcgen05.ld/st.32x32b.x32) with the
 // multiply-subtract of the rank-1 update in between.  bytes = grid * 128 lanes * iters * 128 columns * 4 B * 2.
@@ -77,10 +80,17 @@ cudaError_t launch_tmem_stream(int grid, int iters, double *sink, cudaStream_t s
 }
 
 cudaError_t launch_simplex_tmem(const BatchArgs &args, int grid, cudaStream_t stream) {
-  if (tall(args.Hcap))
-    k_simplex_tmem<2><<<grid, kTmemWarps * 32, tmem_kernel_dynamic_smem(args.Hcap), stream>>>(args);
-  else
-    k_simplex_tmem<1><<<grid, kTmemWarps * 32, tmem_kernel_dynamic_smem(args.Hcap), stream>>>(args);
+  const size_t smem = tmem_kernel_dynamic_smem(args.Hcap);
+  if (args.rows_out) {  // diagnostics instantiation: same code plus the rewritten-row counter
+    if (tall(args.Hcap))
+      k_simplex_tmem<2, true><<<grid, kTmemWarps * 32, smem, stream>>>(args);
+    else
+      k_simplex_tmem<1, true><<<grid, kTmemWarps * 32, smem, stream>>>(args);
+  } else if (tall(args.Hcap)) {
+    k_simplex_tmem<2><<<grid, kTmemWarps * 32, smem, stream>>>(args);
+  } else {
+    k_simplex_tmem<1><<<grid, kTmemWarps * 32, smem, stream>>>(args);
+  }
   return cudaGetLastError();
 }
 

@@ -148,6 +148,9 @@ struct LpResult {
   int status;
   double value;
   long long p1, p2;
+  // rows rewritten by the rank-1 updates (R of SURVEY 8d, summed over the pivots): THIS THREAD's share in K1/K2 (every
+  // thread counts the rows whose pivot-column cell it handled), the whole LP's total in the row-split kernels
+  unsigned long long rows;
 };
 
 // src/simplex.ts:44-63 after the push: does the history end in two identical runs of length 6..len/2 ?
@@ -253,7 +256,7 @@ __device__ __forceinline__ void update_all(double *__restrict__ Abase, int ldA, 
 
 // src/simplex.ts:5-39.
 template <int NW, int KC, int VW>
-__device__ __forceinline__ void pivot_cta(const LpView &t, const Scratch &s, int row, int col) {
+__device__ __forceinline__ int pivot_cta(const LpView &t, const Scratch &s, int row, int col) {
   constexpr int NT = NW * 32;
   constexpr int RU = KC == 1 ? 8 : (KC == 2 ? 4 : (KC <= 4 ? 2 : 1));
   const int tid = threadIdx.x;
@@ -317,6 +320,7 @@ __device__ __forceinline__ void pivot_cta(const LpView &t, const Scratch &s, int
   }
   const bool any_partial = (VW == 2) && (NW == 1 ? __any_sync(0xffffffffu, partial) : __syncthreads_or((int)partial));
   // old pivot column, -coef/q, and the RHS cell of the pivot row (:19 for c = 0, :28-36): one division each
+  int rewritten = 0;  // rows of mine that the update touches
   for (int r = tid; r < H; r += NT) {
     const double coef = A[(size_t)r * ldA + jc];
     const double num = (r == row) ? b[(size_t)row * ldb] : -coef;
@@ -334,6 +338,7 @@ __device__ __forceinline__ void pivot_cta(const LpView &t, const Scratch &s, int
     } else {
       s.colbuf[r] = nz ? coef : 0.0;  // row skip (:31)
       s.colnew[(size_t)r * s.ldc] = quo;
+      rewritten += nz;
     }
   }
   if (tid == 0) {  // basis bookkeeping (:7-12)
@@ -380,6 +385,7 @@ __device__ __forceinline__ void pivot_cta(const LpView &t, const Scratch &s, int
     }
   }
   cta_sync<NW>();
+  return rewritten;
 }
 
 // src/simplex.ts:106-142 (phase1) falling through to 66-103 (phase2); the whole CTA executes this uniformly.
@@ -397,6 +403,7 @@ __device__ __forceinline__ LpResult simplex_cta(const LpView &t, const Scratch &
   res.status = ST_CYCLED;
   res.value = d_nan();
   res.p1 = res.p2 = 0;
+  res.rows = 0;
   int phase = 1, parity = 0, hist_len = 0;
   long long iter = 0;
 
@@ -521,7 +528,7 @@ __device__ __forceinline__ LpResult simplex_cta(const LpView &t, const Scratch &
       if (history_has_cycle<NT>(s.hist, hist_len)) break;  // "cycled", NaN
     }
 
-    pivot_cta<NW, KC, VW>(t, s, row, col);
+    res.rows += (unsigned)pivot_cta<NW, KC, VW>(t, s, row, col);
     if (phase == 1)
       res.p1++;
     else

@@ -108,7 +108,7 @@ __device__ __forceinline__ void update_split(double *__restrict__ Ac, int ldA, i
 
 // src/simplex.ts:5-39.
 template <int NWC, int KC, int NWR, int VW>
-__device__ __forceinline__ void pivot_split(const LpView &t, const SplitScratch &s, int row, int col) {
+__device__ __forceinline__ int pivot_split(const LpView &t, const SplitScratch &s, int row, int col) {
   constexpr int NTC = NWC * 32, NT = NTC * NWR;
   constexpr int RU = (VW == 1) ? (KC >= 8 ? 1 : 8 / KC) : (KC >= 4 ? 1 : 4 / KC);
   const int tid = threadIdx.x, lane = tid & 31;
@@ -238,6 +238,7 @@ __device__ __forceinline__ void pivot_split(const LpView &t, const SplitScratch 
   __syncthreads();
   YT_MARK(7);
   if (tid == 0) *s.cnt = 0;  // next written after the barrier of the next cross-warp selection
+  return R;
 }
 
 // src/simplex.ts:106-142 (phase1) falling through to 66-103 (phase2); the whole CTA executes this uniformly.
@@ -260,6 +261,7 @@ __device__ __forceinline__ LpResult simplex_cta_split(const LpView &t, const Spl
   res.status = ST_CYCLED;
   res.value = d_nan();
   res.p1 = res.p2 = 0;
+  res.rows = 0;
   int phase = 1, parity = 0, hist_len = 0;
   long long iter = 0;
 
@@ -401,7 +403,7 @@ __device__ __forceinline__ LpResult simplex_cta_split(const LpView &t, const Spl
       if (history_has_cycle<NT>(s.hist, hist_len)) break;  // "cycled", NaN
     }
 
-    pivot_split<NWC, KC, NWR, VW>(t, s, row, col);
+    res.rows += (unsigned)pivot_split<NWC, KC, NWR, VW>(t, s, row, col);
     if (phase == 1)
       res.p1++;
     else

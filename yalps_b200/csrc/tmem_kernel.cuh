@@ -229,7 +229,9 @@ __device__ __forceinline__ void tmem_rows_sparse(unsigned tbase, unsigned mask, 
   }
 }
 
-template <int HR>
+// kCount: a second instantiation that also counts the rows every pivot rewrites (roofline diagnostics, launched only
+// when a row counter is set); the production instantiation carries no trace of it.
+template <int HR, bool kCount = false>
 __global__ void __launch_bounds__(kTmemWarps * 32, TmemShape<HR>::kCtasPerSm) k_simplex_tmem(const BatchArgs a) {
   using S = TmemShape<HR>;
   __shared__ __align__(16) TmemWarpSmem<HR> s_warp[kTmemWarps];
@@ -326,6 +328,7 @@ __global__ void __launch_bounds__(kTmemWarps * 32, TmemShape<HR>::kCtasPerSm) k_
 
     int status = ST_CYCLED;
     double value = d_nan();
+    unsigned long long rows_rewritten = 0;
     long long p1 = 0, iter = 0;
     int phase = 1;
 
@@ -535,6 +538,7 @@ __global__ void __launch_bounds__(kTmemWarps * 32, TmemShape<HR>::kCtasPerSm) k_
         const bool dense = __all_sync(0xffffffffu, (st0 || own0 || !v0) && (st1 || own1 || !v1));
         const TmemPivot pv{pn0, pn1, st0, st1, own0, own1};
         if (dense && on_mask == 0xffffffffu) {  // the common case of a dense LP: every block takes the fast form
+          if (kCount) rows_rewritten += (unsigned)(H - 2 + (act0 ? 1 : 0));  // every row but the pivot row
           if (ec == 0) {
             for (int blk = 0; blk < nblocks; blk++) tmem_block_fast<0>(tbase + 32u * (unsigned)blk, cb + 1 + 8 * blk, pv);
           } else {
@@ -548,6 +552,7 @@ __global__ void __launch_bounds__(kTmemWarps * 32, TmemShape<HR>::kCtasPerSm) k_
             act[h] = __ballot_sync(0xffffffffu, coef_mine[h] != 0.0);
             nact += __popc(act[h]);
           }
+          if (kCount) rows_rewritten += (unsigned)(nact + (act0 ? 1 : 0));
           if (4 * nact <= H - 1) {  // sparse pivot column: touch the active rows only
 #pragma unroll
             for (int h = 0; h < HR; h++) tmem_rows_sparse(tbase, act[h], 1 + 32 * h, cb, pv);
@@ -579,6 +584,7 @@ __global__ void __launch_bounds__(kTmemWarps * 32, TmemShape<HR>::kCtasPerSm) k_
         a.pivots[2 * lp + 1] = p2;
       }
       if (a.rhs_out) a.rhs_out[roff] = b0;
+      if (kCount && a.rows_out) atomicAdd(a.rows_out + (a.rows_per_lp ? lp : 0), rows_rewritten);
     }
 #pragma unroll
     for (int h = 0; h < HR; h++)

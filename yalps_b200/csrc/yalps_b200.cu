@@ -84,6 +84,8 @@ struct yalps_ctx {
   bool keep_final = false;         // solve_host (n == 1): leave the final tableau on the device, no D2H copy of it
   double *kept_final = nullptr;    // ... and where it is (valid until the next batch call on this ctx)
   int wave = 256;  // upper bound of the adaptive look-ahead of the branch-and-cut driver
+  unsigned long long *d_rows = nullptr;  // roofline diagnostics: device counter(s) of rewritten rows (yalps_set_row_counter)
+  int rows_per_lp = 0;
   // pooled device buffers (index = purpose * 2 + pipeline slot)
   std::unordered_map<std::string, DevBuf> pool;
   std::unordered_map<std::string, DevBuf> pinned;
@@ -268,6 +270,7 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
     plan->k = nullptr;
     plan->smem = tmem_kernel_dynamic_smem(Hcap);
     CU(ctx, raise_smem_limit(ctx->device, tmem_kernel_fn(Hcap), (int)plan->smem));
+    if (ctx->d_rows) CU(ctx, raise_smem_limit(ctx->device, tmem_kernel_fn(Hcap, true), (int)plan->smem));
     const long long ctas = (long long)tmem_kernel_ctas_per_sm(Hcap) * ctx->prop.multiProcessorCount;
     plan->grid = (int)std::max(1LL, std::min(ctas, n));  // few LPs: one per CTA (the kernel deals LP i to CTA i % grid)
     return 0;
@@ -383,6 +386,7 @@ int hist_capacity(const yalps_options *opt) {
 // Enqueue one kernel launch for `args` (device pointers filled in by the caller).
 int launch_simplex(yalps_ctx *ctx, const LaunchPlan &plan, BatchArgs &args, const std::string &slot,
                    cudaStream_t stream) {
+  if (!args.rows_out && ctx->d_rows && !ctx->rows_per_lp) args.rows_out = ctx->d_rows;  // total mode: every launch of the ctx
   args.counter = nullptr;
   const long long solvers = plan.tmem ? (long long)plan.grid * tmem_kernel_warps() : plan.grid;  // K1t: one LP per warp
   if (args.n > solvers) {  // more LPs than CTAs: dynamic queue (pivot counts vary per LP)
@@ -470,6 +474,7 @@ int plan_cluster(yalps_ctx *ctx, int Hcap, int Wcap, ClusterPlan *plan) {
 
 int launch_cluster(yalps_ctx *ctx, const ClusterPlan &plan, BatchArgs &args, const std::string &slot, cudaStream_t stream) {
   const int ncl = (int)std::max<long long>(1, std::min<long long>(plan.clusters, args.n));
+  if (!args.rows_out && ctx->d_rows && !ctx->rows_per_lp) args.rows_out = ctx->d_rows;
   args.counter = nullptr;
   args.hist = nullptr;
   if (args.check_cycles) {
@@ -527,6 +532,8 @@ int maybe_cluster(yalps_ctx *ctx, long long n, int Hcap, int Wcap, const LaunchP
 }
 
 void fill_options(BatchArgs &a, const yalps_options *opt) {
+  a.rows_out = nullptr;
+  a.rows_per_lp = 0;
   a.precision = opt->precision;
   a.max_pivots = opt->max_pivots;
   a.check_cycles = opt->check_cycles ? 1 : 0;
@@ -634,6 +641,13 @@ int yalps_set_row_groups(yalps_ctx *ctx, int32_t row_groups) {
 
 int64_t yalps_launch_count(const yalps_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int yalps_set_row_counter(yalps_ctx *ctx, uint64_t *d_rows, int32_t per_lp) {
+  if (!ctx) return YALPS_ERR_ARGUMENT;
+  ctx->d_rows = (unsigned long long *)d_rows;
+  ctx->rows_per_lp = per_lp ? 1 : 0;
+  return 0;
+}
+
 int yalps_host_alloc(yalps_ctx *ctx, uint64_t bytes, void **out) {
   if (!ctx || !out) return YALPS_ERR_ARGUMENT;
   CU(ctx, cudaSetDevice(ctx->device));
@@ -651,7 +665,7 @@ int yalps_host_free(yalps_ctx *ctx, void *ptr) {
 static int launch_grid(yalps_ctx *ctx, int H, int W, double *d_M, const yalps_options *opt, int *d_status,
                        double *d_value, long long *d_pivots, double *d_rhs, int *d_pos, int *d_var,
                        cudaStream_t stream, const int *d_init_var = nullptr, int init_n = 0, int max_ctas = 0,
-                       const std::string &slot = "") {
+                       const std::string &slot = "", unsigned long long *d_rows = nullptr) {
   const GridSmem L(H, W);
   if (L.total > (size_t)ctx->smem_optin)
     return fail(ctx, YALPS_ERR_TOO_LARGE, "tableau %dx%d: pivot row/column staging exceeds shared memory", H, W);
@@ -691,6 +705,7 @@ static int launch_grid(yalps_ctx *ctx, int H, int W, double *d_M, const yalps_op
   a.var = d_var;
   a.init_var = d_init_var;
   a.init_n = init_n;
+  a.rows_out = d_rows ? d_rows : ((ctx->d_rows && !ctx->rows_per_lp) ? ctx->d_rows : nullptr);
   if (int rc = dev_ensure(ctx, "grid_flags" + slot, 64, &p)) return rc;
   a.flags = (int *)p;
   a.barrier = (unsigned long long *)((char *)p + 32);
@@ -711,7 +726,7 @@ static int launch_grid(yalps_ctx *ctx, int H, int W, double *d_M, const yalps_op
 static int solve_batch_device_impl(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, const double *d_matrices,
                                    double *d_work, const yalps_options *opt, int32_t *d_status, double *d_value,
                                    int64_t *d_pivots, double *d_rhs_out, int32_t *d_pos_out, int32_t *d_var_out,
-                                   double *d_matrices_out, void *stream, const std::string &slot) {
+                                   double *d_matrices_out, void *stream, const std::string &slot, int64_t rows_base = 0) {
   if (!ctx) return YALPS_ERR_ARGUMENT;
   if (n < 0 || height < 1 || width < 1 || !opt || (n > 0 && !d_matrices))
     return fail(ctx, YALPS_ERR_ARGUMENT, "bad arguments (n=%lld, %dx%d)", (long long)n, height, width);
@@ -756,6 +771,8 @@ static int solve_batch_device_impl(yalps_ctx *ctx, int64_t n, int32_t height, in
   a.pos_out = d_pos_out;
   a.var_out = d_var_out;
   fill_options(a, opt);
+  a.rows_out = ctx->d_rows ? ctx->d_rows + (ctx->rows_per_lp ? rows_base : 0) : nullptr;
+  a.rows_per_lp = ctx->rows_per_lp;
   if (int rc = maybe_cluster(ctx, n, height, width, nullptr, a, slot, (cudaStream_t)stream)) return rc < 0 ? rc : 0;
   LaunchPlan plan;
   if (int rc = plan_launch(ctx, n, height, width, opt->check_cycles != 0, &plan, density, true)) return rc;
@@ -771,7 +788,8 @@ static int solve_batch_device_impl(yalps_ctx *ctx, int64_t n, int32_t height, in
                                d_value ? d_value + i : nullptr, d_pivots ? (long long *)d_pivots + 2 * i : nullptr,
                                d_rhs_out ? d_rhs_out + i * height : nullptr,
                                d_pos_out ? d_pos_out + i * (width + height) : nullptr,
-                               d_var_out ? d_var_out + i * (width + height) : nullptr, st, nullptr, 0, 0, slot))
+                               d_var_out ? d_var_out + i * (width + height) : nullptr, st, nullptr, 0, 0, slot,
+                               ctx->d_rows ? ctx->d_rows + (ctx->rows_per_lp ? rows_base + i : 0) : nullptr))
         return rc;
     }
     if (d_matrices_out && d_matrices_out != d_work)
@@ -1270,7 +1288,7 @@ int yalps_solve_replicas(yalps_ctx *ctx, int64_t n, int32_t height, int32_t widt
     ctx->launches++;
     if ((rc = solve_batch_device_impl(ctx, cn, height, width, (const double *)d_work, (double *)d_work, opt,
                                       (int32_t *)d_status, (double *)d_value, (int64_t *)d_piv, (double *)d_rhs,
-                                      (int32_t *)d_pos, (int32_t *)d_var, nullptr, st, s)))
+                                      (int32_t *)d_pos, (int32_t *)d_var, nullptr, st, s, begin)))
       return rc;
     if (status) CU(ctx, cudaMemcpyAsync(status + begin, d_status, (size_t)cn * 4, cudaMemcpyDeviceToHost, st));
     if (value) CU(ctx, cudaMemcpyAsync(value + begin, d_value, (size_t)cn * 8, cudaMemcpyDeviceToHost, st));
@@ -1401,6 +1419,28 @@ int yalps_measure_smem_bandwidth(yalps_ctx *ctx, double *gbs, double *sm_clock_m
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
     *sm_clock_mhz = khz / 1000.0;
   }
+  return 0;
+}
+
+int yalps_measure_h2d_bandwidth(yalps_ctx *ctx, const void *pinned_host, uint64_t bytes, int32_t reps, int32_t nstreams,
+                                double *seconds) {
+  if (!ctx || !pinned_host || !seconds || bytes == 0 || reps < 1 || nstreams < 1 || nstreams > 2)
+    return ctx ? fail(ctx, YALPS_ERR_ARGUMENT, "bad arguments") : YALPS_ERR_ARGUMENT;
+  CU(ctx, cudaSetDevice(ctx->device));
+  void *d;
+  if (int rc = dev_ensure(ctx, "h2d_probe", bytes, &d)) return rc;
+  const size_t part = ((bytes / nstreams) + 255) & ~(size_t)255;
+  CU(ctx, cudaDeviceSynchronize());
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int r = 0; r < reps; r++)
+    for (int k = 0; k < nstreams; k++) {
+      const size_t off = (size_t)k * part;
+      if (off >= bytes) break;
+      const size_t len = std::min(part, (size_t)bytes - off);
+      CU(ctx, cudaMemcpyAsync((char *)d + off, (const char *)pinned_host + off, len, cudaMemcpyHostToDevice, ctx->streams[k]));
+    }
+  for (int k = 0; k < nstreams; k++) CU(ctx, cudaStreamSynchronize(ctx->streams[k]));
+  *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / reps;
   return 0;
 }
 

@@ -86,6 +86,10 @@ class Engine:
     def launch_count(self) -> int:
         return int(self._lib.yalps_launch_count(self._ctx))
 
+    def set_row_counter(self, d_rows: int = 0, per_lp: bool = False):
+        """Device uint64 counter(s) the kernels add the rewritten rows of every pivot to (0 = off)."""
+        self._check(self._lib.yalps_set_row_counter(self._ctx, C.c_void_p(d_rows) if d_rows else None, int(per_lp)))
+
     def pinned_empty(self, shape, dtype) -> np.ndarray:
         """numpy array over page-locked memory (freed with the engine's process)."""
         dtype = np.dtype(dtype)
@@ -345,6 +349,13 @@ class Engine:
         g, c = C.c_double(), C.c_double()
         self._check(self._lib.yalps_measure_tmem_bandwidth(self._ctx, C.byref(g), C.byref(c)))
         return g.value, c.value
+
+    def measure_h2d_seconds(self, pinned: np.ndarray, reps: int = 3, nstreams: int = 2) -> float:
+        """Seconds per bare host-to-device copy of the whole (pinned) array."""
+        sec = C.c_double()
+        self._check(self._lib.yalps_measure_h2d_bandwidth(self._ctx, _ptr(pinned), pinned.nbytes, reps, nstreams,
+                                                          C.byref(sec)))
+        return sec.value
 
     def measure_smem_bandwidth(self) -> tuple:
         g, c = C.c_double(), C.c_double()
