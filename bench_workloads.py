@@ -51,9 +51,14 @@ def pivot_bytes(H, W, pivots, rows):
     return 16.0 * W * (pivots + rows) + pivots * 8.0 * (2 * (H - 1) + 2 * (W - 1))
 
 
-def ncu_traffic(name):
+def ncu_traffic(name, lps=None):
+    """DRAM bytes per launch from a committed ncu --set full summary; captures taken on a smaller launch of the same
+    kernel carry `dram_bytes_per_lp` and are scaled to the `lps` LPs of the benchmarked launch."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", name)))["dram_bytes_per_launch"]
+        j = json.load(open(os.path.join(ROOT, "profiles", name)))
+        if lps is not None and "dram_bytes_per_lp" in j:
+            return j["dram_bytes_per_lp"] * lps
+        return j["dram_bytes_per_launch"]
     except (OSError, KeyError, ValueError):
         return None
 
@@ -83,10 +88,10 @@ def _counter(torch, eng, fn):
     return int(c.item())
 
 
-def config3(torch, eng, name, n, hbm_peak, cpu_cores):
-    """n RHS-perturbed replicas of a Netlib model, HBM-resident working copies (the automatic policy picks the kernel).
-    The timed step = copy of the pristine replicas into the working buffer is EXCLUDED (device-to-device copy timed
-    separately and subtracted is not needed: the kernel solves from `d` into `work` itself)."""
+def config3(torch, eng, name, n, hbm_peak, cpu_cores, l2_peak):
+    """n RHS-perturbed replicas of a Netlib model, working copies in HBM (the automatic policy picks the kernel).
+    One step = one launch: the kernel reads the pristine replicas from `d`, writes its working copy into `work` and
+    solves there, so the tableau crosses HBM once in and once out per LP."""
     from yalps_b200.engine import make_options
     from oracle import lib as O
     g = netlib_base(name)
@@ -145,12 +150,20 @@ def config3(torch, eng, name, n, hbm_peak, cpu_cores):
                     f"working copies in HBM ({n * cells * 8 / 1e9:.1f} GB, larger than L2), BASELINE.json configs[2]",
         "ms": ms, "pivots_per_s": pivots / ms * 1e3, "lps_per_s": n / ms * 1e3, "pivots": pivots, "optimal": optimal,
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": ncu_traffic(f"r02_k2s_{name.lower()}_ncu_summary.json"),
+        "roofline": {"bound": "l2", "achieved": achieved, "peak": l2_peak, "unit": "GB/s", "frac": achieved / l2_peak,
+                     "peak_source": "measured live: ld-mul-sub-st stream over a 48 MB L2-resident buffer "
+                                    "(yalps_measure_l2_bandwidth)",
+                     "traffic": ncu_traffic(f"r02_k2s_{name.lower()}_ncu_summary.json", n),
+                     "traffic_note": "dram__bytes_read+write of the same kernel (ncu --set full on a launch of a quarter of "
+                                     "the LPs, scaled per LP; profiles/r02_k2s_*_ncu_summary.json)",
                      "bytes_formula": "16*W*(pivots + rows_rewritten) + pivots*8*(2(H-1)+2(W-1)), SURVEY 8(d)",
                      "rows_rewritten": rows, "mean_rows_per_pivot": rows / max(pivots, 1), "rows_dense": H - 1,
-                     "note": "R counted on the device; the kernel is bound by the per-pivot dependent chain of one CTA "
-                             "per LP (latency), not by HBM: the working set of the resident CTAs lives in L2"},
+                     "hbm": {"achieved": achieved, "peak": hbm_peak, "frac": achieved / hbm_peak,
+                             "note": "the SURVEY 8(d) bytes against the HBM peak can exceed 1: a working copy "
+                                     f"({cells * 8 / 1e3:.0f} KB) stays in L2 for the ~{pivots // max(n, 1)} pivots its CTA "
+                                     "spends on it, so HBM only sees the tableau once in and once out (`traffic`)"},
+                     "note": "R counted on the device.  The medium that serves the per-pivot bytes is L2, hence the "
+                             "denominator; the kernel itself is bound by the per-pivot dependent chain of one CTA per LP"},
         "e2e": {"api": "yalps_solve_replicas (base tableau once + n*H right-hand sides from pinned host memory; "
                        "status/value/pivots/RHS/basis back)", "ms": e2e_s * 1e3, "lps_per_s": n / e2e_s,
                 "pivots_per_s": pivots / e2e_s, "h2d_bytes_per_step": cells * 8 + n * H * 8,
@@ -204,7 +217,7 @@ def config4(torch, eng, hbm_peak):
     return out
 
 
-def config5(torch, eng, hbm_peak):
+def config5(torch, eng, hbm_peak, l2_peak):
     """One large dense LP on the whole GPU (K4): the 4097x8193 synthetic tableau (268.5 MB > L2) for a capped number of
     pivots, and Netlib 25FV47 (1338x1572, L2-resident) to the end."""
     from yalps_b200.engine import make_options
@@ -251,7 +264,9 @@ def config5(torch, eng, hbm_peak):
                          "traffic": ncu_traffic("r02_k4_ncu_summary.json") if not netlib else None,
                          "rows_rewritten": rows, "mean_rows_per_pivot": rows / max(p, 1), "rows_dense": H - 1,
                          "note": None if not netlib else "L2-resident and sparse: bound by the grid barriers of a pivot, "
-                                                         "not by bandwidth"},
+                                                         "not by bandwidth",
+                         "l2": None if not netlib else {"achieved": alg / (ms * 1e-3) / 1e9, "peak": l2_peak,
+                                                        "frac": alg / (ms * 1e-3) / 1e9 / l2_peak}},
         }
         if netlib:  # the reference's own outcome on this model: infeasible after 3110 phase-1 pivots
             entry["matches_oracle_golden"] = bool(int(st.item()) == g["status"] and
@@ -273,9 +288,10 @@ def config5(torch, eng, hbm_peak):
 
 def run_all(torch, eng, hbm_peak, cpu_cores):
     out = []
+    l2_peak = eng.measure_l2_bandwidth()
     for name, n in (("SC105", 32768), ("ADLITTLE", 65536)):
-        out.append(config3(torch, eng, name, n, hbm_peak, cpu_cores))
+        out.append(config3(torch, eng, name, n, hbm_peak, cpu_cores, l2_peak))
         torch.cuda.empty_cache()
     out.extend(config4(torch, eng, hbm_peak))
-    out.extend(config5(torch, eng, hbm_peak))
+    out.extend(config5(torch, eng, hbm_peak, l2_peak))
     return out

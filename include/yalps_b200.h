@@ -306,6 +306,9 @@ int yalps_probe_division(yalps_ctx *ctx, int64_t n, uint64_t seed, int32_t mode,
 /* Shared-memory stream microbenchmark: bytes moved per second by ld/st.shared.f64 on all SMs
  * (the measured denominator of the K1 roofline).  Returns GB/s in *gbs. */
 int yalps_measure_smem_bandwidth(yalps_ctx *ctx, double *gbs, double *sm_clock_mhz);
+/* L2 stream microbenchmark: read + write GB/s of the rank-1 update's ld-mul-sub-st pattern over a `bytes`-sized buffer
+ * that stays in L2 (the denominator for working copies that are L2-resident while their CTA works on them). */
+int yalps_measure_l2_bandwidth(yalps_ctx *ctx, uint64_t bytes, double *gbs);
 /* Bare host-to-device copy of `bytes` from a PINNED host buffer into a device scratch buffer, `reps` times over
  * `nstreams` (1 or 2) streams: seconds per repetition.  bench.py runs it on all ranks at once to print the ceiling
  * the box's PCIe / host-memory fabric puts on the end-to-end rate (e2e.h2d_ceiling_gbs). */

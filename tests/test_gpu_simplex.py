@@ -491,8 +491,132 @@ def test_full_size_batch_properties(engine):
     sample = np.random.default_rng(0).choice(n, 512, replace=False)
     mats = d.view(n, H * W)[torch.from_numpy(sample).cuda()].cpu().numpy()
     exp = oracle_batch(mats, H, W)
+    assert np.array_equal(exp["status"], st.cpu().numpy()[sample])
+    assert same_bits(exp["value"], val.cpu().numpy()[sample])
     assert np.array_equal(exp["pivots"], piv.cpu().numpy()[sample])
     assert same_bits(exp["rhs"], rhs.cpu().numpy()[sample]) and np.array_equal(exp["pos"], pos.cpu().numpy()[sample])
+    assert np.array_equal(exp["var"], var.cpu().numpy()[sample])
+
+
+@pytest.mark.parametrize("name,n", [("SC105", 32768), ("ADLITTLE", 65536)])
+def test_config3_full_size_sample_against_oracle_on_the_automatic_path(engine, name, n):
+    """BASELINE.json config 3 at the size bench.py runs per launch, on the AUTOMATIC path (the row-split HBM/L2
+    kernel): a random sample of 1,024 replicas against the oracle on every output, plus size-independent properties
+    over the whole batch (all optimal, inverse permutations, value = roundToPrecision(M[0,0]), primal feasibility)."""
+    import torch
+    g = NL.get(name)
+    H, W = g["height"], g["width"]
+    d = torch.empty(n * H * W, dtype=torch.float64, device="cuda")
+    engine.generate_replicas_device(0, n, g["matrix"], H, W, g["row_groups"], d.data_ptr())
+    work = torch.empty_like(d)
+    st = torch.empty(n, dtype=torch.int32, device="cuda")
+    val = torch.empty(n, dtype=torch.float64, device="cuda")
+    piv = torch.empty(n, 2, dtype=torch.int64, device="cuda")
+    rhs = torch.empty(n, H, dtype=torch.float64, device="cuda")
+    pos = torch.empty(n, W + H, dtype=torch.int32, device="cuda")
+    var = torch.empty(n, W + H, dtype=torch.int32, device="cuda")
+    rows = torch.zeros(n, dtype=torch.int64, device="cuda")
+    engine.set_row_counter(rows.data_ptr(), per_lp=True)
+    try:
+        engine.solve_batch_device(n, H, W, d.data_ptr(), d_work=work.data_ptr(), d_status=st.data_ptr(),
+                                  d_value=val.data_ptr(), d_pivots=piv.data_ptr(), d_rhs=rhs.data_ptr(),
+                                  d_pos=pos.data_ptr(), d_var=var.data_ptr(),
+                                  stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+    finally:
+        engine.set_row_counter(0)
+    assert bool((st == 0).all())
+    idx = torch.arange(W + H, device="cuda", dtype=torch.int64).expand(n, -1)
+    assert bool((torch.gather(pos.long(), 1, var.long()) == idx).all())
+    assert bool((rhs[:, 1:] >= -1e-8).all())
+    assert same_bits(engine.round_to_precision(rhs[:, 0].cpu().numpy(), 1e-8), val.cpu().numpy())
+    sample = np.sort(np.random.default_rng(3).choice(n, 1024, replace=False))
+    mats = d.view(n, H * W)[torch.from_numpy(sample).cuda()].cpu().numpy()
+    exp = O.simplex_batch(mats, W, H, nthreads=16)
+    assert np.array_equal(exp["status"], st.cpu().numpy()[sample])
+    assert same_bits(exp["value"], val.cpu().numpy()[sample])
+    assert np.array_equal(exp["pivots"], piv.cpu().numpy()[sample])
+    assert same_bits(exp["rhs"], rhs.cpu().numpy()[sample])
+    assert np.array_equal(exp["pos"], pos.cpu().numpy()[sample]) and np.array_equal(exp["var"], var.cpu().numpy()[sample])
+    # the device row counter (roofline diagnostics): between 1 and H-1 rows per pivot, per LP
+    r = rows.cpu().numpy()
+    p = piv.sum(dim=1).cpu().numpy()
+    assert (r >= p).all() and (r <= p * (H - 1)).all()
+
+
+def count_rewritten_rows(mats, H, W):
+    """R of SURVEY 8(d) summed over the pivots of each LP, from the oracle stepped one pivot at a time."""
+    out = []
+    for m0 in mats:
+        m = m0.copy()
+        pos = np.arange(W + H, dtype=np.int32)
+        var = pos.copy()
+        total = 0
+        for phase_budget in range(10 ** 6):
+            before = m.reshape(H, W).copy()
+            st, _, piv = O.simplex(m, W, H, pos, var, max_pivots=1)
+            if sum(piv) == 0:
+                break
+            changed = (before.view(np.uint64) != m.reshape(H, W).view(np.uint64)).any(axis=1)
+            # a rewritten row changes at least its pivot-column cell (it becomes -coef/q != coef unless q == -1)
+            total += int(changed.sum()) - 1  # minus the pivot row
+            if st != 4:
+                break
+        out.append(total)
+    return out
+
+
+def test_row_counter_matches_a_cpu_count(engine):
+    """yalps_set_row_counter: the rows rewritten per LP, per kernel family, against the oracle stepped pivot by pivot
+    (rows whose bits change; dense random tableaus, where a rewritten row always changes)."""
+    import torch
+    m_, nv, n = 12, 20, 40
+    H, W = m_ + 1, nv + 1
+    mats = O.generate_synthetic(4100, n, m_, nv, 3)
+    d = torch.from_numpy(mats.reshape(-1)).cuda()
+    work = torch.empty_like(d)
+    piv = torch.empty(n, 2, dtype=torch.int64, device="cuda")
+    pos = torch.empty(n, W + H, dtype=torch.int32, device="cuda")
+    var = torch.empty(n, W + H, dtype=torch.int32, device="cuda")
+    exp = None
+    for path, threads, rgroups in ((E.PATH_TMEM, 0, 0), (E.PATH_SMEM, 32, 0), (E.PATH_SMEM, 128, 4), (E.PATH_GMEM, 64, 0),
+                                   (E.PATH_GMEM, 128, 2), (E.PATH_CLUSTER, 0, 0)):
+        rows = torch.zeros(n, dtype=torch.int64, device="cuda")
+        engine.set_tuning(path, threads, rgroups)
+        engine.set_row_counter(rows.data_ptr(), per_lp=True)
+        try:
+            engine.solve_batch_device(n, H, W, d.data_ptr(), d_work=work.data_ptr(), d_pivots=piv.data_ptr(),
+                                      d_pos=pos.data_ptr(), d_var=var.data_ptr(),
+                                      stream=torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+        finally:
+            engine.set_row_counter(0)
+            engine.set_tuning(E.PATH_AUTO, 0, 0)
+        got = rows.cpu().numpy().tolist()
+        if exp is None:
+            # every LP runs to the end under the default budget, so stepping one pivot at a time is the same trajectory
+            exp = count_rewritten_rows(mats[:8], H, W)
+            assert got[:8] == exp, (path, got[:8], exp)
+            first = got
+        assert got == first, f"path {path} threads {threads} row groups {rgroups}"
+
+
+def test_netlib_ok_list_with_infinite_pivot_budget(engine):
+    """The reference's own benchmark runner calls solve with maxPivots: Infinity (benchmarks/runners.ts:10).  For the
+    models its harness handles, neither phase reaches the default budget, so the unbounded-budget trajectory is the
+    golden one: status, value, pivot counts, final basis and RHS bits."""
+    checked = 0
+    for name in NL.names:
+        g = NL.get(name)
+        if g["list"] == 2 or max(g["pivots"]) >= 8192:  # list: 0 = small, 1 = the harness's ok list, 2 = its "cannot handle" list
+            continue
+        got = engine.solve_batch(g["matrix"], g["height"], g["width"],
+                                 E.make_options(check_cycles=g["check_cycles"], max_pivots=math.inf))
+        assert got["status"][0] == g["status"] and tuple(got["pivots"][0]) == g["pivots"], name
+        assert same_value(got["value"][0], g["value"]), name
+        assert np.array_equal(got["pos"][0], g["final_pos"]) and same_bits(got["rhs"][0], g["final_rhs"]), name
+        checked += 1
+    assert checked >= 30
 
 
 # ---------------------------------------------------------------------------------------------- K1t tensor-memory kernel

@@ -97,6 +97,7 @@ SIGNATURES = {
     "yalps_round_to_precision": (C.c_int, [_vp, C.c_int64, _vp, C.c_double, _vp]),
     "yalps_measure_smem_bandwidth": (C.c_int, [_vp, _dp, _dp]),
     "yalps_measure_tmem_bandwidth": (C.c_int, [_vp, _dp, _dp]),
+    "yalps_measure_l2_bandwidth": (C.c_int, [_vp, C.c_uint64, _dp]),
     "yalps_measure_h2d_bandwidth": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int32, C.c_int32, _dp]),
 }
 

@@ -198,6 +198,19 @@ __global__ void k_round_to_precision(long long n, const double *x, double precis
   if (i < n) out[i] = round_to_precision(x[i], precision);
 }
 
+// L2 stream: every thread reads and rewrites 16-byte cells of a buffer that fits L2, `iters` times over
+// (the ld - mul - sub - st pattern of the rank-1 update on an L2-resident working copy).  bytes = words*8 * iters * 2.
+__global__ void k_l2_stream(double2 *buf, size_t n2, int iters, double coef) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (int it = 0; it < iters; it++)
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n2; k += stride) {
+      double2 x = __ldcg(buf + k);
+      x.x = __dsub_rn(x.x, __dmul_rn(coef, 1e-9));
+      x.y = __dsub_rn(x.y, __dmul_rn(coef, 2e-9));
+      __stcg(buf + k, x);
+    }
+}
+
 // Shared-memory stream: every thread reads and rewrites 8-byte cells of a CTA-private buffer.
 // bytes = grid * iters * words * 16.
 __global__ void k_smem_stream(int words, int iters, double *sink) {

@@ -1422,6 +1422,35 @@ int yalps_measure_smem_bandwidth(yalps_ctx *ctx, double *gbs, double *sm_clock_m
   return 0;
 }
 
+int yalps_measure_l2_bandwidth(yalps_ctx *ctx, uint64_t bytes, double *gbs) {
+  if (!ctx || !gbs || bytes < 4096) return YALPS_ERR_ARGUMENT;
+  CU(ctx, cudaSetDevice(ctx->device));
+  void *d;
+  if (int rc = dev_ensure(ctx, "l2_probe", bytes, &d)) return rc;
+  cudaStream_t st = ctx->streams[0];
+  CU(ctx, cudaMemsetAsync(d, 0, bytes, st));
+  const int iters = 50, grid = ctx->prop.multiProcessorCount * 8;
+  cudaEvent_t e0, e1;
+  CU(ctx, cudaEventCreate(&e0));
+  CU(ctx, cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    CU(ctx, cudaEventRecord(e0, st));
+    k_l2_stream<<<grid, 256, 0, st>>>((double2 *)d, bytes / 16, iters, 0.5);
+    CU(ctx, cudaEventRecord(e1, st));
+    CU(ctx, cudaEventSynchronize(e1));
+    CU(ctx, cudaGetLastError());
+    ctx->launches++;
+    float ms = 0;
+    CU(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0) best = std::min(best, ms);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *gbs = (double)(bytes / 16 * 16) * iters * 2.0 / (best * 1e-3) / 1e9;
+  return 0;
+}
+
 int yalps_measure_h2d_bandwidth(yalps_ctx *ctx, const void *pinned_host, uint64_t bytes, int32_t reps, int32_t nstreams,
                                 double *seconds) {
   if (!ctx || !pinned_host || !seconds || bytes == 0 || reps < 1 || nstreams < 1 || nstreams > 2)

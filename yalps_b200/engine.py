@@ -350,6 +350,12 @@ class Engine:
         self._check(self._lib.yalps_measure_tmem_bandwidth(self._ctx, C.byref(g), C.byref(c)))
         return g.value, c.value
 
+    def measure_l2_bandwidth(self, nbytes: int = 48 << 20) -> float:
+        """GB/s (read + write) of an update-like stream over an L2-resident buffer."""
+        g = C.c_double()
+        self._check(self._lib.yalps_measure_l2_bandwidth(self._ctx, int(nbytes), C.byref(g)))
+        return g.value
+
     def measure_h2d_seconds(self, pinned: np.ndarray, reps: int = 3, nstreams: int = 2) -> float:
         """Seconds per bare host-to-device copy of the whole (pinned) array."""
         sec = C.c_double()
