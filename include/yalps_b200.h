@@ -221,6 +221,11 @@ int yalps_bnb_solve_nodes(yalps_ctx *ctx, int64_t n, const int32_t *cut_offsets,
 int yalps_branch_and_cut(yalps_ctx *ctx, const int32_t *ints, int32_t nints, double sign, double init_result,
                          const yalps_options *opt, int32_t *status, double *result, int32_t *out_height,
                          double *rhs_out, int32_t *pos_out, int32_t *var_out, int64_t *stats);
+/* Where the search loop runs: 0 (default) = inside one persistent kernel (csrc/bnb_kernel.cuh: a scheduler CTA replays
+ * the reference's loop, the other CTAs evaluate node LPs) when the node tableaus fit one CTA's shared memory, otherwise
+ * -- and whenever a device pool overflows -- the host wave driver; 1 = host wave driver only; 2 = device kernel only
+ * (YALPS_ERR_TOO_LARGE when the search does not fit).  Both produce the reference's search node for node. */
+int yalps_bnb_set_mode(yalps_ctx *ctx, int32_t mode);
 /* Upper bound of the speculative look-ahead per wave (default 256; the driver adapts the actual width, starting at
  * 16, to how much of each wave the replay consumes). */
 int yalps_bnb_set_wave(yalps_ctx *ctx, int32_t wave);

@@ -295,3 +295,53 @@ def test_more_restrictive_constraint_that_does_not_conflict(engine, case):
     new_model = {**model, "constraints": list(model["constraints"]) + [(key, {"min": mn, "max": mx})]}
     restricted = yalps_b200.solve(new_model, options, engine=engine)
     assert _same_as_oracle(new_model, options, restricted)
+
+
+# ------------------------------------------------------------------------------------------------ device-resident search
+MILP = [c for c in CASES if c["oracle"]["nodes"] > 0]
+
+
+@pytest.mark.parametrize("case", MILP, ids=[c["name"] for c in MILP])
+def test_device_resident_search_equals_the_wave_driver_and_the_oracle(case):
+    """csrc/bnb_kernel.cuh (the replay loop of src/branchAndCut.ts:122-164 inside one persistent kernel) against the host
+    wave driver and the oracle: status, result, variables, node and node-pivot counts, final basis and RHS bits."""
+    o = case["oracle"]
+    eng = yalps_b200.Engine(0)
+    try:
+        out = {}
+        for mode in (1, 2):
+            eng.set_bnb_mode(mode)
+            info = {}
+            try:
+                sol = yalps_b200.solve(case["model"], case["options"], engine=eng, info=info)
+            except E.YalpsError as e:
+                assert mode == 2 and e.code == -3, e  # node tableaus beyond one CTA's shared memory: wave driver only
+                assert case["name"] in ("Monster 2", "Vendor Selection")
+                continue
+            out[mode] = (sol, info)
+            assert sol["status"] == o["status"] and same_value(sol["result"], o["result"]), mode
+            assert [list(v) for v in sol["variables"]] == [list(v) for v in o["variables"]], mode
+            assert info["nodes"] == o["nodes"] and info["node_pivots"] == o["node_pivots"], mode
+            assert np.array_equal(info["final_pos"], o["final_pos"]) and same_bits(info["final_rhs"], o["final_rhs"]), mode
+        if 2 in out:
+            assert out[2][1]["waves"] == 1  # one launch for the whole search
+            assert out[1][1]["max_cuts"] == out[2][1]["max_cuts"] and out[1][1]["max_heap"] == out[2][1]["max_heap"]
+        else:
+            assert case["name"] in ("Monster 2", "Vendor Selection")
+    finally:
+        eng.close()
+
+
+def test_device_resident_search_options(engine):
+    """tolerance, maxIterations and timeout inside the device scheduler (src/branchAndCut.ts:114-116,122,162,167-173)."""
+    c = next(x for x in CASES if x["name"] == "Fancy Stock Cutting Problem")
+    for extra in ({"tolerance": 0.05}, {"tolerance": 0.5}, {"maxIterations": 5}, {"maxIterations": 40}, {"timeout": 0}):
+        opts = {**c["options"], **extra}
+        ref = M.solve(c["model"], {**M.DEFAULT_OPTIONS, **opts})
+        engine.set_bnb_mode(2)
+        try:
+            sol = yalps_b200.solve(c["model"], opts, engine=engine)
+        finally:
+            engine.set_bnb_mode(0)
+        assert sol["status"] == ref["status"] and same_value(sol["result"], ref["result"]), extra
+        assert [list(v) for v in sol["variables"]] == [list(v) for v in ref["variables"]], extra

@@ -92,6 +92,7 @@ SIGNATURES = {
     "yalps_branch_and_cut": (C.c_int, [_vp, _vp, C.c_int32, C.c_double, C.c_double, C.POINTER(Options), _ip, _dp, _ip,
                                        _vp, _vp, _vp, _vp]),
     "yalps_bnb_set_wave": (C.c_int, [_vp, C.c_int32]),
+    "yalps_bnb_set_mode": (C.c_int, [_vp, C.c_int32]),
     "yalps_solve": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, _vp, C.c_int32, C.c_double, C.POINTER(Options), _ip, _dp,
                               _ip, _vp, _vp, _vp, _ip, _dp, _vp, _vp]),
     "yalps_round_to_precision": (C.c_int, [_vp, C.c_int64, _vp, C.c_double, _vp]),

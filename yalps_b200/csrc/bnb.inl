@@ -204,6 +204,12 @@ int yalps_bnb_set_root(yalps_ctx *ctx, int32_t height, int32_t width, const doub
   return upload_root_host(ctx, height, width, matrix, pos, var, max_extra_rows);
 }
 
+int yalps_bnb_set_mode(yalps_ctx *ctx, int32_t mode) {
+  if (!ctx || mode < 0 || mode > 2) return YALPS_ERR_ARGUMENT;
+  ctx->bnb_mode = mode;
+  return 0;
+}
+
 int yalps_bnb_set_wave(yalps_ctx *ctx, int32_t wave) {
   if (!ctx || wave < 1) return YALPS_ERR_ARGUMENT;
   ctx->wave = wave;
@@ -408,6 +414,145 @@ int yalps_branch_and_cut(yalps_ctx *ctx, const int32_t *ints, int32_t nints, dou
 
 namespace {
 
+// The whole search in one persistent launch (bnb_kernel.cuh).  Returns 0 when the search ran to its end on the device
+// (outputs filled), 1 when this search is not for the device kernel (node tableaus beyond one CTA's shared memory,
+// checkCycles) or one of its pools overflowed -- the caller then runs the wave driver --, < 0 on errors.
+int device_search(yalps_ctx *ctx, const int32_t *ints, int32_t nints, double sign, double init_result, int32_t init_var,
+                  double init_val, const yalps_options *opt, int32_t *status, double *result, int32_t *out_height,
+                  double *rhs_out, int32_t *pos_out, int32_t *var_out, int64_t *stats) {
+  Root &R = ctx->root;
+  const int W = R.W, H = R.H;
+  if (opt->check_cycles) return 1;
+  const BnbConfig *cfg = bnb_config_for(W);
+  if (!cfg) return 1;
+  const int nw = cfg->nwc * cfg->nwr;
+  // cut rows a node may carry on the device: as many as shared memory allows, at most 2*|integers| (:108) and 96
+  const size_t smem_room = (size_t)ctx->smem_optin - 4096;  // the kernel's static shared memory (staged cut list)
+  int extra = std::min(2 * nints, kBnbMaxCuts);
+  while (extra >= 8 && SmemLayout(H + extra, W, true, nw, true).total > smem_room) extra -= 8;
+  if (extra < std::min(2 * nints, 8)) return 1;
+  const int Hcap = H + extra;
+  const size_t worker_smem = SmemLayout(Hcap, W, true, nw, true).total;
+  const size_t smem = std::max(worker_smem, (size_t)96 << 10);
+  const int heap_cap = (int)(smem / 12);
+  CU(ctx, raise_smem_limit(ctx->device, cfg->fn, (int)smem));
+  const std::string okey = "bnb:" + std::to_string((size_t)cfg->fn) + ":" + std::to_string(smem);
+  int occ = 0;
+  auto it = ctx->occ_cache.find(okey);
+  if (it == ctx->occ_cache.end()) {
+    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cfg->fn, nw * 32, smem));
+    ctx->occ_cache[okey] = occ;
+  } else {
+    occ = it->second;
+  }
+  if (occ < 1) return 1;
+  // one scheduler + at most 64 workers: a search keeps a few dozen node LPs in flight at most (two new nodes per replay
+  // step), and four concurrent searches (yalps_multi_solve_many) must be able to be co-resident on one GPU
+  const int grid = std::min(occ * ctx->prop.multiProcessorCount, 1 + 64);
+  if (grid < 2) return 1;
+
+  double max_nodes = 2.0 * opt->max_iterations + 4.0;
+  const int node_cap = (int)std::min(max_nodes, 65536.0);
+  const unsigned long long cut_cap = 1ULL << 20;
+  const int cand_cap = 2048;
+  void *d_ctl, *d_nodes, *d_cuts, *d_crhs, *d_cpos, *d_cvar, *d_ints, *d_rank;
+  int rc;
+  if ((rc = dev_ensure(ctx, "kb_ctl", sizeof(BnbControl), &d_ctl))) return rc;
+  if ((rc = dev_ensure(ctx, "kb_nodes", (size_t)node_cap * sizeof(BnbNode), &d_nodes))) return rc;
+  if ((rc = dev_ensure(ctx, "kb_cuts", (size_t)cut_cap * sizeof(BnbCut), &d_cuts))) return rc;
+  if ((rc = dev_ensure(ctx, "kb_crhs", (size_t)cand_cap * Hcap * 8, &d_crhs))) return rc;
+  if ((rc = dev_ensure(ctx, "kb_cpos", (size_t)cand_cap * (W + Hcap) * 4, &d_cpos))) return rc;
+  if ((rc = dev_ensure(ctx, "kb_cvar", (size_t)cand_cap * (W + Hcap) * 4, &d_cvar))) return rc;
+  if ((rc = dev_ensure(ctx, "kb_ints", (size_t)std::max(nints, 1) * 4, &d_ints))) return rc;
+  if ((rc = dev_ensure(ctx, "kb_rank", (size_t)(W + H) * 4, &d_rank))) return rc;
+  // one pinned staging block: [ints | int_rank] up, control block + best candidate down
+  const size_t up_bytes = (size_t)(nints + W + H) * 4;
+  const size_t down_bytes = sizeof(BnbControl) + (size_t)Hcap * 8 + (size_t)2 * (W + Hcap) * 4;
+  void *h_up, *h_down;
+  if ((rc = pin_ensure(ctx, "kb_h_up", up_bytes + 16, &h_up))) return rc;
+  if ((rc = pin_ensure(ctx, "kb_h_down", down_bytes + 16, &h_down))) return rc;
+  int32_t *h_ints = (int32_t *)h_up, *h_rank = h_ints + nints;
+  std::memcpy(h_ints, ints, (size_t)nints * 4);
+  for (int k = 0; k < W + H; k++) h_rank[k] = -1;
+  for (int i = nints - 1; i >= 0; i--)
+    if (ints[i] >= 0 && ints[i] < W + H) h_rank[ints[i]] = i;  // first occurrence wins, like the reference's scan
+  cudaStream_t st = ctx->streams[0];
+  CU(ctx, cudaMemcpyAsync(d_ints, h_ints, (size_t)nints * 4, cudaMemcpyHostToDevice, st));
+  CU(ctx, cudaMemcpyAsync(d_rank, h_rank, (size_t)(W + H) * 4, cudaMemcpyHostToDevice, st));
+  CU(ctx, cudaMemsetAsync(d_ctl, 0, sizeof(BnbControl), st));
+
+  BnbArgs a{};
+  a.root = (const double *)R.m.p;
+  a.root_pos = (const int *)R.pos.p;
+  a.root_var = (const int *)R.var.p;
+  a.H = H;
+  a.W = W;
+  a.Hcap = Hcap;
+  a.ints = (const int *)d_ints;
+  a.int_rank = (const int *)d_rank;
+  a.nints = nints;
+  a.sign = sign;
+  a.init_result = init_result;
+  a.init_var = init_var;
+  a.init_value = init_val;
+  a.precision = opt->precision;
+  a.max_pivots = opt->max_pivots;
+  a.tolerance = opt->tolerance;
+  a.timeout_ms = opt->timeout_ms;
+  a.max_iterations = opt->max_iterations;
+  a.ctl = (BnbControl *)d_ctl;
+  a.nodes = (BnbNode *)d_nodes;
+  a.node_cap = node_cap;
+  a.cuts = (BnbCut *)d_cuts;
+  a.cut_cap = cut_cap;
+  a.cand_rhs = (double *)d_crhs;
+  a.cand_pos = (int *)d_cpos;
+  a.cand_var = (int *)d_cvar;
+  a.cand_cap = cand_cap;
+  a.heap_cap = heap_cap;
+  a.rows_out = ctx->rows_per_lp ? nullptr : ctx->d_rows;
+  const auto t0 = std::chrono::steady_clock::now();
+  CU(ctx, launch_bnb(cfg, a, grid, smem, st));
+  ctx->launches++;
+  BnbControl *hc = (BnbControl *)h_down;
+  CU(ctx, cudaMemcpyAsync(hc, d_ctl, sizeof(BnbControl), cudaMemcpyDeviceToHost, st));
+  CU(ctx, cudaStreamSynchronize(st));
+  if (hc->overflow) return 1;  // a pool ran out: the wave driver has no such limits
+  if (hc->found) {
+    if (hc->best_cand < 0) return fail(ctx, YALPS_ERR_CUDA, "device search: incumbent without candidate arrays");
+    const int h = hc->best_height;
+    double *h_rhs = (double *)((char *)h_down + sizeof(BnbControl));
+    int32_t *h_pos = (int32_t *)(h_rhs + Hcap), *h_var = h_pos + (W + Hcap);
+    CU(ctx, cudaMemcpyAsync(h_rhs, (double *)d_crhs + (size_t)hc->best_cand * Hcap, (size_t)h * 8, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaMemcpyAsync(h_pos, (int *)d_cpos + (size_t)hc->best_cand * (W + Hcap), (size_t)(W + h) * 4, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaMemcpyAsync(h_var, (int *)d_cvar + (size_t)hc->best_cand * (W + Hcap), (size_t)(W + h) * 4, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    *out_height = h;
+    std::memcpy(rhs_out, h_rhs, (size_t)h * 8);
+    std::memcpy(pos_out, h_pos, (size_t)(W + h) * 4);
+    std::memcpy(var_out, h_var, (size_t)(W + h) * 4);
+  } else {  // bestTableau = root (:119)
+    *out_height = H;
+    std::memcpy(rhs_out, R.h_rhs.data(), (size_t)H * 8);
+    std::memcpy(pos_out, R.h_pos.data(), (size_t)(W + H) * 4);
+    std::memcpy(var_out, R.h_var.data(), (size_t)(W + H) * 4);
+  }
+  *status = hc->status;
+  *result = hc->result;
+  if (stats) {
+    const int64_t us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+    stats[0] = hc->iters;
+    stats[1] = hc->node_pivots;
+    stats[2] = hc->max_cuts;
+    stats[3] = hc->max_heap;
+    stats[4] = 1;  // one launch
+    stats[5] = hc->created;
+    stats[6] = us;
+    stats[7] = us;
+  }
+  return 0;
+}
+
 int branch_and_cut_impl(yalps_ctx *ctx, const WaveEval *wave_eval, const WaveHook *wave_hook, const int32_t *ints,
                         int32_t nints, double sign, double init_result, const yalps_options *opt, int32_t *status,
                         double *result, int32_t *out_height, double *rhs_out, int32_t *pos_out, int32_t *var_out,
@@ -452,6 +597,14 @@ int branch_and_cut_impl(yalps_ctx *ctx, const WaveEval *wave_eval, const WaveHoo
   }
   if (2 * nints > R.max_extra)
     return fail(ctx, YALPS_ERR_ARGUMENT, "root was set with max_extra_rows=%d < 2*|integers|=%d", R.max_extra, 2 * nints);
+  // searches whose node LPs fit one CTA run entirely on the device (bnb_kernel.cuh); everything else, and any search
+  // that overflows the device pools, takes the wave driver below
+  if (!wave_eval && ctx->bnb_mode != 1) {
+    const int rc = device_search(ctx, ints, nints, sign, init_result, init_var, init_val, opt, status, result, out_height,
+                                 rhs_out, pos_out, var_out, stats);
+    if (rc <= 0) return rc;
+    if (ctx->bnb_mode == 2) return fail(ctx, YALPS_ERR_TOO_LARGE, "this search does not fit the device-resident branch-and-cut kernel");
+  }
 
   std::vector<Branch> arena;
   arena.reserve(4096);

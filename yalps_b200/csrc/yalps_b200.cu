@@ -32,6 +32,7 @@
 #include "cluster_kernel.cuh"
 #include "grid_kernel.cuh"
 #include "tmem_launch.h"
+#include "bnb_launch.h"
 
 using namespace yalps;
 
@@ -84,6 +85,7 @@ struct yalps_ctx {
   bool keep_final = false;         // solve_host (n == 1): leave the final tableau on the device, no D2H copy of it
   double *kept_final = nullptr;    // ... and where it is (valid until the next batch call on this ctx)
   int wave = 256;  // upper bound of the adaptive look-ahead of the branch-and-cut driver
+  int bnb_mode = 0;  // 0: device-resident search when it fits, else host waves; 1: host waves only; 2: device only
   unsigned long long *d_rows = nullptr;  // roofline diagnostics: device counter(s) of rewritten rows (yalps_set_row_counter)
   int rows_per_lp = 0;
   // pooled device buffers (index = purpose * 2 + pipeline slot)

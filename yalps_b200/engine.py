@@ -79,6 +79,10 @@ class Engine:
         self._check(self._lib.yalps_set_tuning(self._ctx, path, threads_per_lp))
         self._check(self._lib.yalps_set_row_groups(self._ctx, row_groups))
 
+    def set_bnb_mode(self, mode: int):
+        """0 = device-resident search when it fits (default), 1 = host wave driver only, 2 = device kernel only."""
+        self._check(self._lib.yalps_bnb_set_mode(self._ctx, int(mode)))
+
     def set_wave(self, wave: int):
         self._check(self._lib.yalps_bnb_set_wave(self._ctx, int(wave)))
 
