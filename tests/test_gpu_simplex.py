@@ -808,3 +808,28 @@ def test_ragged_batch_with_many_small_lps_on_the_automatic_path(engine):
         assert same_value(g["value"], e["value"][0])
         assert np.array_equal(g["pos"], e["pos"][0]) and np.array_equal(g["var"], e["var"][0])
         assert same_bits(g["rhs"], e["rhs"][0]) and same_bits(g["matrix"], e["matrices"][0]), s
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_cluster_kernel_tma_staging_variants_are_bit_exact(mode):
+    """KC with the winner's pivot row staged by cp.async.bulk (1) or by one multicast bulk copy into every CTA of the
+    cluster (2) instead of the ld.global.cg loop: same bits (the A/B of profiles/r02_kc_tma_ab.jsonl)."""
+    import os
+    import yalps_b200
+    os.environ["YALPS_KC_TMA"] = str(mode)
+    try:
+        eng = yalps_b200.Engine(0)
+    finally:
+        del os.environ["YALPS_KC_TMA"]
+    try:
+        eng.set_tuning(E.PATH_CLUSTER, 0)
+        for (m, nv, neg, n) in ((200, 260, 30, 3), (90, 400, 10, 2), (300, 150, 80, 2)):
+            mats = O.generate_synthetic(6100 + m, n, m, nv, neg)
+            assert_batch_equal(eng.solve_batch(mats, m + 1, nv + 1, want_matrices=True), oracle_batch(mats, m + 1, nv + 1),
+                               f"KC tma mode {mode} {m}x{nv}")
+        g = NL.get("SC205")
+        got = eng.solve_batch(g["matrix"], g["height"], g["width"])
+        assert got["status"][0] == g["status"] and tuple(got["pivots"][0]) == g["pivots"]
+        assert np.array_equal(got["pos"][0], g["final_pos"]) and same_bits(got["rhs"][0], g["final_rhs"])
+    finally:
+        eng.close()

@@ -81,13 +81,54 @@ __device__ __forceinline__ Best block_best_full(unsigned long long key, int idx,
   return warp_best<kMax>(hi, lo, id);
 }
 
+// ---- TMA (bulk asynchronous copy) staging of the winner's row, selectable at run time for the A/B of north_star (b):
+//   mode 0  every thread loads 16-byte chunks from the L2 scratch (ld.global.cg) and stores them to shared memory
+//   mode 1  one thread per CTA issues ONE cp.async.bulk global -> shared of the whole row, completion on an mbarrier
+//   mode 2  the winner's owner issues ONE cp.async.bulk ... .multicast::cluster that lands the row in the shared
+//           memory of every CTA of the cluster (each CTA's own mbarrier counts the bytes)
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_multicast(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar,
+                                                   unsigned short cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+
 // Cluster-wide winning row.  Every CTA posts its local winner into slot [rank] of every CTA's exchange buffer and
 // publishes that candidate's row (padded layout, ldA cells) to scratch[xpar][rank]; after the barrier every CTA
 // stages the winner's row into prow_s.  Returns kNone (nothing staged) when no CTA had a candidate.
 template <bool kMax, int NW>
 __device__ __forceinline__ int cluster_select(cg::cluster_group &cluster, int C, int rank, unsigned long long key, int idx,
                                               unsigned *red, int &parity, uint4 *xch, int &xpar, const double *A, int ldA,
-                                              double *scratch, double *prow_s) {
+                                              double *scratch, double *prow_s, int tma_mode = 0,
+                                              unsigned long long *mbar = nullptr, unsigned *mphase = nullptr) {
   constexpr int NT = NW * 32;
   const Best w = block_best_full<kMax, NW>(key, idx, red, parity);
   uint4 *slots = xch + xpar * kMaxCluster;
@@ -97,6 +138,7 @@ __device__ __forceinline__ int cluster_select(cg::cluster_group &cluster, int C,
     const double2 *src = reinterpret_cast<const double2 *>(A + (size_t)((w.idx - 1) / C) * ldA);
     double2 *dst = reinterpret_cast<double2 *>(pub + (size_t)rank * ldA);
     for (int c = threadIdx.x; c < ldA / 2; c += NT) __stcg(dst + c, src[c]);
+    if (tma_mode) asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy stores before async-proxy (TMA) reads
   }
   if ((int)threadIdx.x < C) {
     uint4 *dst = cluster.map_shared_rank(slots + rank, threadIdx.x);
@@ -109,10 +151,24 @@ __device__ __forceinline__ int cluster_select(cg::cluster_group &cluster, int C,
   if (lane < C) e = slots[lane];
   const int row = warp_best<kMax>(e.x, e.y, (int)e.z).idx;
   if (row != kNone) {
-    const double2 *src = reinterpret_cast<const double2 *>(pub + (size_t)((row - 1) % C) * ldA);
-    double2 *dst = reinterpret_cast<double2 *>(prow_s);
-    for (int c = threadIdx.x; c < ldA / 2; c += NT) dst[c] = __ldcg(src + c);
-    __syncthreads();
+    const int owner = (row - 1) % C;
+    const double2 *src = reinterpret_cast<const double2 *>(pub + (size_t)owner * ldA);
+    if (tma_mode == 0) {
+      double2 *dst = reinterpret_cast<double2 *>(prow_s);
+      for (int c = threadIdx.x; c < ldA / 2; c += NT) dst[c] = __ldcg(src + c);
+      __syncthreads();
+    } else {
+      const unsigned bytes = (unsigned)ldA * 8u;  // ldA is even: a multiple of 16 bytes, rows are 16-byte aligned
+      if (threadIdx.x == 0) {
+        mbar_expect_tx(mbar, bytes);  // every CTA arms its own barrier
+        if (tma_mode == 1)
+          bulk_g2s(prow_s, src, bytes, mbar);
+        else if (rank == owner)
+          bulk_g2s_multicast(prow_s, src, bytes, mbar, (unsigned short)((1u << C) - 1u));
+      }
+      mbar_wait(mbar, *mphase);
+      *mphase ^= 1u;
+    }
   }
   return row;
 }
@@ -177,6 +233,10 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_simplex_cluster(const Batc
       if (tid == 0) *cnt = 0;
       cp_async_wait_all();
     }
+    __shared__ __align__(8) unsigned long long s_mbar;
+    unsigned mphase = 0;
+    const int tma_mode = a.tma_mode;
+    if (tma_mode && tid == 0) mbar_init(&s_mbar, 1);
     __syncthreads();
     cluster.sync();
 
@@ -212,7 +272,7 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_simplex_cluster(const Batc
           }
         }
         row = cluster_select<false, NW>(cluster, C, rank, bi == kNone ? no_key<false>() : order_key(bv), bi, red, parity, xch, xpar,
-                                        A, ldA, scratch, prow_s);
+                                        A, ldA, scratch, prow_s, tma_mode, &s_mbar, &mphase);
         CT_MARK(0);
         if (row == kNone) {  // feasible: phase 2 with a fresh counter and history (:120, :67-69)
           phase = 2;
@@ -298,7 +358,7 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_simplex_cluster(const Batc
           }
         }
         row = cluster_select<false, NW>(cluster, C, rank, bi == kNone ? no_key<false>() : order_key(bv), bi, red, parity, xch, xpar,
-                                        A, ldA, scratch, prow_s);
+                                        A, ldA, scratch, prow_s, tma_mode, &s_mbar, &mphase);
         CT_MARK(1);
         if (row == kNone) {
           res.status = ST_UNBOUNDED;

@@ -49,6 +49,7 @@ struct BatchArgs {
   int hist_cap;
   unsigned long long *counter;
   double *cl_scratch;  // cluster kernel: per cluster 2 * C * ldA doubles (published candidate pivot rows)
+  int tma_mode;        // cluster kernel: how the winner's row is staged (0 ld.global.cg, 1 cp.async.bulk, 2 multicast)
 };
 
 // Shared-memory carve-up, identical on host and device.

@@ -85,6 +85,7 @@ struct yalps_ctx {
   bool keep_final = false;         // solve_host (n == 1): leave the final tableau on the device, no D2H copy of it
   double *kept_final = nullptr;    // ... and where it is (valid until the next batch call on this ctx)
   int wave = 256;  // upper bound of the adaptive look-ahead of the branch-and-cut driver
+  int kc_tma = 0;    // KC: staging of the winner's pivot row (YALPS_KC_TMA: 0 ld.global.cg, 1 cp.async.bulk, 2 multicast)
   int bnb_mode = 0;  // 0: device-resident search when it fits, else host waves; 1: host waves only; 2: device only
   unsigned long long *d_rows = nullptr;  // roofline diagnostics: device counter(s) of rewritten rows (yalps_set_row_counter)
   int rows_per_lp = 0;
@@ -490,6 +491,7 @@ int launch_cluster(yalps_ctx *ctx, const ClusterPlan &plan, BatchArgs &args, con
     if (int rc = dev_ensure(ctx, "cl_scratch" + slot, per_cluster * ncl, &scr)) return rc;
     args.cl_scratch = (double *)scr;
   }
+  args.tma_mode = ctx->kc_tma;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(ncl * plan.C));
   cfg.blockDim = dim3((unsigned)(plan.k->nw * plan.k->nwr * 32));
@@ -583,6 +585,7 @@ int yalps_create(int device, yalps_ctx **out) {
     return fail(nullptr, YALPS_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device,
                 ctx->prop.major, ctx->prop.minor);
   ctx->smem_optin = (int)ctx->prop.sharedMemPerBlockOptin;
+  if (const char *env = getenv("YALPS_KC_TMA")) ctx->kc_tma = std::max(0, std::min(2, atoi(env)));
   for (int i = 0; i < 2; i++) {
     if ((e = cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking)) != cudaSuccess)
       return fail(nullptr, YALPS_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
