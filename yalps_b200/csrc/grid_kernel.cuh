@@ -117,6 +117,10 @@ __global__ void __launch_bounds__(kGridThreads, 1) k_simplex_grid(const GridArgs
   long long p1 = 0, p2 = 0, iter = 0;
   unsigned long long rows_mine = 0;
   int phase = 1, parity = 0, hist_len = 0;
+  // this thread's candidates for the next first selection, collected by the fused stage of the previous pivot
+  bool have_carry = false;
+  double carry_cv = -INF, carry_rv = INF;
+  int carry_ci = kNone, carry_ri = kNone;
 
   for (;;) {
     if (!((double)iter < a.max_pivots)) break;
@@ -125,11 +129,16 @@ __global__ void __launch_bounds__(kGridThreads, 1) k_simplex_grid(const GridArgs
       // leaving row from the private RHS copy (:111-119)
       double bv = INF;
       int bi = kNone;
-      for (int r = 1 + tid; r < H; r += NT) {
-        const double v = bcol[r];
-        if (v < -precision && v < bv) {
-          bv = v;
-          bi = r;
+      if (have_carry) {  // collected while the previous pivot was applied to the private RHS copy
+        bv = carry_rv;
+        bi = carry_ri;
+      } else {
+        for (int r = 1 + tid; r < H; r += NT) {
+          const double v = bcol[r];
+          if (v < -precision && v < bv) {
+            bv = v;
+            bi = r;
+          }
         }
       }
       row = block_best<false, NW>(bi == kNone ? no_key<false>() : order_key(bv), bi, red, parity);
@@ -164,11 +173,16 @@ __global__ void __launch_bounds__(kGridThreads, 1) k_simplex_grid(const GridArgs
       // entering column from the private objective row (:71-79)
       double bv = -INF;
       int bi = kNone;
-      for (int c = 1 + tid; c < W; c += NT) {
-        const double v = row0[c];
-        if (v > precision && v > bv) {
-          bv = v;
-          bi = c;
+      if (have_carry) {  // collected while the previous pivot was applied to the private objective row
+        bv = carry_cv;
+        bi = carry_ci;
+      } else {
+        for (int c = 1 + tid; c < W; c += NT) {
+          const double v = row0[c];
+          if (v > precision && v > bv) {
+            bv = v;
+            bi = c;
+          }
         }
       }
       col = block_best<true, NW>(bi == kNone ? no_key<true>() : order_key(bv), bi, red, parity);
@@ -228,53 +242,72 @@ __global__ void __launch_bounds__(kGridThreads, 1) k_simplex_grid(const GridArgs
       if (verdict) break;
     }
 
-    // ---- normalise the staged pivot row in place (src/simplex.ts:16-25); column: 0 = row left alone (:29,:31)
+    // ---- ONE fused stage over the staged pivot row and column (every cell is handled by exactly one thread, so no
+    // barrier is needed between its parts): normalise the row in place (src/simplex.ts:16-25) and collect its non-zero
+    // flags; apply the pivot to the private objective-row copy; reduce the pivot column to "0 = row left alone"
+    // (:29,:31); apply the pivot to the private RHS copy; and carry this thread's candidates for the NEXT pivot's
+    // first selection (largest reduced cost above precision / most negative RHS), which saves that scan.
     const double q = prow[col];
     const double coef0 = colbuf[0];  // objective-row cell of the pivot column, before colbuf is rewritten
+    const double braw = prow[0];     // RHS cell of the pivot row (column 0 is never the pivot column)
     __syncthreads();
-    for (int cbase = warp * 32; cbase < W; cbase += NT) {
-      const int c = cbase + lane;
-      bool nz = false;
-      if (c < W) {
-        const double v = (c == col) ? 1.0 : prow[c];
-        nz = fabs(v) > kTiny;
-        prow[c] = nz ? __ddiv_rn(v, q) : 0.0;
-        if (c == col) nz = false;  // the pivot column gets -coef/q instead (:36)
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, nz);
-      if (lane == 0) nzmask[cbase >> 5] = m;
-    }
-    for (int r = tid; r < H; r += NT) {
-      const double coef = colbuf[r];
-      const bool on = r != row && fabs(coef) > kTiny;
-      colbuf[r] = on ? coef : 0.0;
-      rows_mine += on;  // every CTA builds the whole column: CTA 0 reports the count
-    }
-    __syncthreads();
-    // ---- the same rank-1 update on the private objective row / RHS column copies
     {
       const bool act0 = fabs(coef0) > kTiny;  // row 0 is never the pivot row
-      const double p0 = prow[0];
-      const bool nz0 = (nzmask[0] & 1u) != 0u;  // column 0 is never the pivot column
-      if (act0) {
-        for (int c = tid; c < W; c += NT) {
-          if ((nzmask[c >> 5] >> (c & 31)) & 1u)
-            row0[c] = __dsub_rn(row0[c], __dmul_rn(coef0, prow[c]));
-          else if (c == col)
-            row0[c] = __ddiv_rn(-coef0, q);
+      const bool nz0 = fabs(braw) > kTiny;
+      const double p0 = nz0 ? __ddiv_rn(braw, q) : 0.0;  // every thread for itself: the same division, the same bits
+      carry_cv = -INF;
+      carry_ci = kNone;
+      for (int cbase = warp * 32; cbase < W; cbase += NT) {
+        const int c = cbase + lane;
+        bool nz = false;
+        if (c < W) {
+          const double v = (c == col) ? 1.0 : prow[c];
+          nz = fabs(v) > kTiny;
+          const double pn = nz ? __ddiv_rn(v, q) : 0.0;
+          prow[c] = pn;
+          if (c == col) nz = false;  // the pivot column gets -coef/q instead (:36)
+          double o = row0[c];
+          if (act0) {
+            if (nz)
+              o = __dsub_rn(o, __dmul_rn(coef0, pn));
+            else if (c == col)
+              o = __ddiv_rn(-coef0, q);
+            row0[c] = o;
+          }
+          if (c == 0) bcol[0] = o;  // the corner cell belongs to both copies
+          if (c >= 1 && o > precision && o > carry_cv) {  // (:71-79), ascending c per thread: strict > keeps the first
+            carry_cv = o;
+            carry_ci = c;
+          }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, nz);
+        if (lane == 0) nzmask[cbase >> 5] = m;
+      }
+      carry_rv = INF;
+      carry_ri = kNone;
+      for (int r = tid; r < H; r += NT) {
+        const double coef = colbuf[r];
+        const bool on = r != row && fabs(coef) > kTiny;
+        colbuf[r] = on ? coef : 0.0;
+        rows_mine += on;  // every CTA builds the whole column: CTA 0 reports the count
+        if (r >= 1) {
+          double bnew = bcol[r];
+          if (r == row) {
+            bnew = p0;
+            bcol[r] = bnew;
+          } else if (on && nz0) {
+            bnew = __dsub_rn(bnew, __dmul_rn(coef, p0));
+            bcol[r] = bnew;
+          }
+          if (bnew < -precision && bnew < carry_rv) {  // (:111-119)
+            carry_rv = bnew;
+            carry_ri = r;
+          }
         }
       }
-      for (int r = 1 + tid; r < H; r += NT) {
-        if (r == row) {
-          bcol[r] = p0;
-        } else {
-          const double coef = colbuf[r];
-          if (coef != 0.0 && nz0) bcol[r] = __dsub_rn(bcol[r], __dmul_rn(coef, p0));
-        }
-      }
-      __syncthreads();
-      if (tid == 0) bcol[0] = row0[0];  // the corner cell belongs to both copies
+      have_carry = true;
     }
+    __syncthreads();
     if (blockIdx.x == 0 && tid == 0) {  // basis bookkeeping (:7-12)
       const int leaving = a.var[W + row];
       a.var[W + row] = a.var[col];
