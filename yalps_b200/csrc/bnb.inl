@@ -143,6 +143,12 @@ int upload_root_host(yalps_ctx *ctx, int32_t height, int32_t width, const double
   R.max_extra = max_extra_rows;
   R.h_rhs.resize(height);
   for (int r = 0; r < height; r++) R.h_rhs[r] = matrix[(size_t)r * width];
+  {
+    const size_t step = std::max<size_t>(1, cells / 65536);
+    size_t seen = 0, nz = 0;
+    for (size_t k = 0; k < cells; k += step, seen++) nz += matrix[k] != 0.0;
+    R.density = seen ? (double)nz / (double)seen : 1.0;
+  }
   R.h_pos.assign(pos, pos + nv);
   R.h_var.assign(var, var + nv);
   R.valid = true;
@@ -173,7 +179,15 @@ int adopt_root_device(yalps_ctx *ctx, int32_t height, int32_t width, const doubl
   CU(ctx, cudaMemcpyAsync(R.m.p, d_matrix, cells * 8, cudaMemcpyDeviceToDevice, st));
   CU(ctx, cudaMemcpyAsync(R.pos.p, pos, nv * 4, cudaMemcpyHostToDevice, st));
   CU(ctx, cudaMemcpyAsync(R.var.p, var, nv * 4, cudaMemcpyHostToDevice, st));
+  void *hp, *dp;
+  if (int rc = pin_ensure(ctx, "density_probe", 64, &hp)) return rc;
+  if (int rc = pin_device_ptr(ctx, hp, &dp)) return rc;
+  ((int *)hp)[0] = ((int *)hp)[1] = 0;
+  k_sample_density<<<1, 256, 0, st>>>((const double *)R.m.p, (long long)cells, std::max<long long>(1, (long long)cells / 65536), (int *)dp);
+  CU(ctx, cudaGetLastError());
+  ctx->launches++;
   CU(ctx, cudaStreamSynchronize(st));
+  R.density = ((int *)hp)[0] ? (double)((int *)hp)[1] / (double)((int *)hp)[0] : 1.0;
   R.H = height;
   R.W = width;
   R.max_extra = max_extra_rows;
@@ -254,6 +268,30 @@ int bnb_solve_nodes_impl(yalps_ctx *ctx, int64_t n, const int32_t *cut_offsets, 
   if ((long long)Hcap * W >= (1LL << 31)) return fail(ctx, YALPS_ERR_TOO_LARGE, "(height+cuts)*width must be < 2^31");
   LaunchPlan plan;
   if (int rc = plan_launch(ctx, n, Hcap, W, opt->check_cycles != 0, &plan)) return rc;
+  // Big, very sparse nodes (Monster-class models: ~1 % non-zeros, ~10 rows rewritten per pivot): the row-split HBM/L2
+  // kernel with one CTA per node compacts the few active rows and needs no grid barrier -- 5.8 us per pivot for every
+  // node of the wave at once, against 9.5 us per pivot and node on K4 (scripts/big_sparse_paths.py).  Denser nodes
+  // (Vendor Selection: 28 % non-zeros at the root optimum) stay on K4.
+  bool sparse_split = false;
+  if (!plan.resident && ctx->tune_path == YALPS_PATH_AUTO && ctx->tune_threads <= 0 && ctx->tune_rows <= 0 &&
+      R.density < 0.03 && use_grid_path(ctx, n, plan)) {
+    if (const KernelEntry *k = pick_kernel(8, 2, W, false)) {
+      if (k->nwr == 2) {
+        const size_t smem_k = SmemLayout(Hcap, W, false, k->nw * k->nwr, true).total;
+        if (smem_k <= (size_t)ctx->smem_optin) {
+          CU(ctx, raise_smem_limit(ctx->device, (const void *)k->global, (int)smem_k));
+          int occ = 0;
+          CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k->global, k->nw * k->nwr * 32, smem_k));
+          if (occ >= 1) {
+            plan.k = k;
+            plan.smem = smem_k;
+            plan.grid = (int)std::max<long long>(1, std::min<long long>((long long)occ * ctx->prop.multiProcessorCount, n));
+            sparse_split = true;
+          }
+        }
+      }
+    }
+  }
 
   cudaStream_t st = ctx->streams[0];
   int rc;
@@ -271,7 +309,9 @@ int bnb_solve_nodes_impl(yalps_ctx *ctx, int64_t n, const int32_t *cut_offsets, 
   if ((rc = pin_ensure(ctx, "nd_h_out", out_bytes + 8, &h_out))) return rc;
   // small waves: the kernel reads the cut lists and writes its results straight through the mapped pinned
   // buffers (zero-copy), so a wave is launch + synchronise; big waves use one explicit copy per direction
-  const bool zero_copy = in_bytes + out_bytes <= ((size_t)1 << 20);
+  // (only for shared-memory resident nodes: the HBM/L2-resident kernels and K4 keep variableAtPosition in the output
+  // buffer while they pivot, and that must not be host memory)
+  const bool zero_copy = plan.resident && in_bytes + out_bytes <= ((size_t)1 << 20);
   if (zero_copy) {
     if ((rc = pin_device_ptr(ctx, h_in, &d_inb))) return rc;
     if ((rc = pin_device_ptr(ctx, h_out, &d_outb))) return rc;
@@ -322,7 +362,18 @@ int bnb_solve_nodes_impl(yalps_ctx *ctx, int64_t n, const int32_t *cut_offsets, 
   a.cut_val = (const double *)d_val;
   fill_options(a, opt);
   a.rows_out = ctx->rows_per_lp ? nullptr : ctx->d_rows;  // node waves only feed a total (their LP indices are wave-local)
-  if (use_grid_path(ctx, n, plan)) {
+  if (sparse_split) {
+    // assemble the nodes grid-wide (K3), then one row-split CTA per node on the assembled working copies
+    const int gx = std::max(1, std::min(ctx->prop.multiProcessorCount * 4, (int)(((size_t)R.H * W + 255) / 256)));
+    const int gy = (int)std::min<int64_t>(n, 65535);
+    k_assemble_nodes<<<dim3(gx, gy), 256, 0, st>>>(n, R.H, W, Hcap, (const double *)R.m.p, (const int *)R.pos.p,
+                                                   (const int *)d_off, (const double *)d_sign, (const int *)d_var,
+                                                   (const double *)d_val, (double *)d_work);
+    CU(ctx, cudaGetLastError());
+    ctx->launches++;
+    a.assembled = 1;
+    if ((rc = launch_simplex(ctx, plan, a, "nd", st))) return rc;
+  } else if (use_grid_path(ctx, n, plan)) {
     // few large nodes: assemble them in HBM (K3), then give each node the whole grid (K4)
     if (!d_work) {
       if ((rc = dev_ensure(ctx, "nd_work", mat_bytes, &d_work))) return rc;

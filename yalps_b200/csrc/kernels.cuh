@@ -38,6 +38,7 @@ struct BatchArgs {
   // node mode
   const double *root;
   const int *root_pos, *root_var;
+  int assembled;  // node mode: a.work already holds root + cut rows (k_assemble_nodes ran first)
   const int *cut_off;
   const double *cut_sign;
   const int *cut_var;
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(NWC *NWR * 32, min_ctas_per_sm(NWC, NWR)) k_si
           sB += 8u * (unsigned)ldb * NW;
         }
       }
-    } else if (src != a.work + moff) {
+    } else if (src != a.work + moff && !(a.mode == kModeNodes && a.assembled)) {
       const size_t cells = (size_t)rootH * W;
       double *dst = a.work + moff;
       for (size_t k = tid; k < cells; k += NT) dst[k] = src[k];
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(NWC *NWR * 32, min_ctas_per_sm(NWC, NWR)) k_si
     if (a.mode == kModeNodes) {
       // applyCuts (src/branchAndCut.ts:22-61): one row per cut below the root rows
       const int cbeg = a.cut_off[lp];
-      for (int i = 0; i < ncuts; i++) {
+      for (int i = 0; i < (a.assembled ? 0 : ncuts); i++) {
         const double sign = a.cut_sign[cbeg + i], value = a.cut_val[cbeg + i];
         const int p = a.root_pos[a.cut_var[cbeg + i]];
         const int r = rootH + i;

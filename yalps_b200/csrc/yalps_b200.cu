@@ -62,6 +62,7 @@ struct DevBuf {
 struct Root {
   bool valid = false;
   int H = 0, W = 0, max_extra = 0;
+  double density = 1.0;  // fraction of non-zero cells of (a sample of) the root-optimal tableau
   DevBuf m, pos, var;
   std::vector<double> h_m;  // host copy of column 0 is enough for the driver, but keep rhs + pos + var
   std::vector<double> h_rhs;
