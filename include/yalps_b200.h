@@ -83,7 +83,7 @@ enum yalps_path {
                              is staged from there, DSMEM carries only the 16-byte selection records
                              (csrc/cluster_kernel.cuh) */
   YALPS_PATH_TMEM = 6, /* K1t: one LP per warp, tableau resident in tensor memory (tcgen05.ld/st as a lane-private
-                          scratchpad; at most 65 x 65, no checkCycles), csrc/tmem_kernel.cuh */
+                          scratchpad; at most 65 x 65), csrc/tmem_kernel.cuh */
   /* 4 is retired (a register-resident experiment that never beat K1) and rejected by yalps_set_tuning */
 };
 

@@ -833,3 +833,38 @@ def test_cluster_kernel_tma_staging_variants_are_bit_exact(mode):
         assert np.array_equal(got["pos"][0], g["final_pos"]) and same_bits(got["rhs"][0], g["final_rhs"])
     finally:
         eng.close()
+
+
+def test_tensor_memory_kernel_with_check_cycles(engine):
+    """K1t with checkCycles: true (src/simplex.ts:44-63): the instantiation with a per-warp history.  The Chvatal LP
+    must stop as "cycled" exactly where the reference does; LPs that do not cycle are unchanged by the option; and a
+    mixed batch keeps every LP's own history (one LP per warp, several LPs per warp in sequence)."""
+    chvatal = np.array([[0, 10, -57, -9, -24], [0, 0.5, -5.5, -2.5, 9], [0, 0.5, -1.5, -0.5, 1], [1, 1, 0, 0, 0]], float)
+    engine.set_tuning(E.PATH_TMEM, 0)
+    try:
+        for mp in (8192, math.inf, 7, 30):
+            m = chvatal.reshape(1, -1).copy()
+            exp = oracle_batch(m, 4, 5, check_cycles=True, max_pivots=mp)
+            got = engine.solve_batch(m, 4, 5, E.make_options(check_cycles=True, max_pivots=mp), want_matrices=True)
+            assert_batch_equal(got, exp, f"tmem chvatal maxPivots={mp}")
+        assert exp["status"][0] == 4
+        # 700 copies interleaved with ordinary LPs of the same shape: more LPs than warps, histories must not leak
+        rng = np.random.default_rng(11)
+        n = 1400
+        mats = O.generate_synthetic(321, n, 3, 4, 1)
+        mats[::2] = chvatal.reshape(-1)
+        exp = oracle_batch(mats, 4, 5, check_cycles=True)
+        got = engine.solve_batch(mats, 4, 5, E.make_options(check_cycles=True), want_matrices=True)
+        assert_batch_equal(got, exp, "tmem mixed batch with checkCycles")
+        assert (exp["status"][::2] == 4).all()
+        for (m_, nv, neg, k) in ((32, 64, 8, 300), (50, 40, 10, 64), (12, 20, 12, 100)):
+            mats = O.generate_synthetic(555 + m_, k, m_, nv, neg)
+            exp = oracle_batch(mats, m_ + 1, nv + 1, check_cycles=True)
+            got = engine.solve_batch(mats, m_ + 1, nv + 1, E.make_options(check_cycles=True), want_matrices=True)
+            assert_batch_equal(got, exp, f"tmem checkCycles {m_}x{nv}")
+    finally:
+        engine.set_tuning(E.PATH_AUTO, 0)
+    # the automatic path now keeps small checkCycles batches on the tensor-memory kernel as well
+    mats = O.generate_synthetic(9, 500, 20, 30, 5)
+    assert_batch_equal(engine.solve_batch(mats, 21, 31, E.make_options(check_cycles=True), want_matrices=True),
+                       oracle_batch(mats, 21, 31, check_cycles=True), "auto path with checkCycles")

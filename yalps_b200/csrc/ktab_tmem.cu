@@ -16,7 +16,11 @@ int tmem_kernel_ctas_per_sm(int Hcap) { return tall(Hcap) ? TmemShape<2>::kCtasP
 size_t tmem_kernel_dynamic_smem(int Hcap) { return (size_t)(227 * 1024) / (tmem_kernel_ctas_per_sm(Hcap) + 1) + 1024; }
 size_t tmem_stream_dynamic_smem() { return tmem_kernel_dynamic_smem(1); }
 
-const void *tmem_kernel_fn(int Hcap, bool count_rows) {
+const void *tmem_kernel_fn(int Hcap, bool count_rows, bool cycles) {
+  if (cycles) {
+    if (count_rows) return tall(Hcap) ? (const void *)k_simplex_tmem<2, true, true> : (const void *)k_simplex_tmem<1, true, true>;
+    return tall(Hcap) ? (const void *)k_simplex_tmem<2, false, true> : (const void *)k_simplex_tmem<1, false, true>;
+  }
   if (count_rows) return tall(Hcap) ? (const void *)k_simplex_tmem<2, true> : (const void *)k_simplex_tmem<1, true>;
   return tall(Hcap) ? (const void *)k_simplex_tmem<2> : (const void *)k_simplex_tmem<1>;
 }
@@ -81,7 +85,19 @@ cudaError_t launch_tmem_stream(int grid, int iters, double *sink, cudaStream_t s
 
 cudaError_t launch_simplex_tmem(const BatchArgs &args, int grid, cudaStream_t stream) {
   const size_t smem = tmem_kernel_dynamic_smem(args.Hcap);
-  if (args.rows_out) {  // diagnostics instantiation: same code plus the rewritten-row counter
+  if (args.check_cycles) {  // the instantiations with the cycle history
+    const bool t = tall(args.Hcap);
+    if (args.rows_out) {
+      if (t)
+        k_simplex_tmem<2, true, true><<<grid, kTmemWarps * 32, smem, stream>>>(args);
+      else
+        k_simplex_tmem<1, true, true><<<grid, kTmemWarps * 32, smem, stream>>>(args);
+    } else if (t) {
+      k_simplex_tmem<2, false, true><<<grid, kTmemWarps * 32, smem, stream>>>(args);
+    } else {
+      k_simplex_tmem<1, false, true><<<grid, kTmemWarps * 32, smem, stream>>>(args);
+    }
+  } else if (args.rows_out) {  // diagnostics instantiation: same code plus the rewritten-row counter
     if (tall(args.Hcap))
       k_simplex_tmem<2, true><<<grid, kTmemWarps * 32, smem, stream>>>(args);
     else

@@ -231,7 +231,9 @@ __device__ __forceinline__ void tmem_rows_sparse(unsigned tbase, unsigned mask, 
 
 // kCount: a second instantiation that also counts the rows every pivot rewrites (roofline diagnostics, launched only
 // when a row counter is set); the production instantiation carries no trace of it.
-template <int HR, bool kCount = false>
+// kCycles: the instantiation with the checkCycles history (src/simplex.ts:44-63: one buffer of (leaving, entering)
+// variable pairs per warp in HBM, tested after every push by the 32 lanes); launched only for checkCycles: true.
+template <int HR, bool kCount = false, bool kCycles = false>
 __global__ void __launch_bounds__(kTmemWarps * 32, TmemShape<HR>::kCtasPerSm) k_simplex_tmem(const BatchArgs a) {
   using S = TmemShape<HR>;
   __shared__ __align__(16) TmemWarpSmem<HR> s_warp[kTmemWarps];
@@ -331,6 +333,8 @@ __global__ void __launch_bounds__(kTmemWarps * 32, TmemShape<HR>::kCtasPerSm) k_
     unsigned long long rows_rewritten = 0;
     long long p1 = 0, iter = 0;
     int phase = 1;
+    int hist_len = 0;
+    int *hist = kCycles ? a.hist + ((size_t)blockIdx.x * kTmemWarps + warp) * 2 * (size_t)a.hist_cap : nullptr;
 
     // read-only pass: cells of column c in rows 0..H-1 -> colx (its owner lane reads them, one tcgen05.ld per block)
     auto extract_column = [&](int c) {
@@ -372,6 +376,7 @@ __global__ void __launch_bounds__(kTmemWarps * 32, TmemShape<HR>::kCtasPerSm) k_
         }
         if (row == kNone) {  // feasible: phase 2 with a fresh counter (:120, :67-69)
           phase = 2;
+          hist_len = 0;  // a fresh history per phase (:67-69)
           p1 = iter;
           iter = 0;
           continue;
@@ -460,6 +465,31 @@ __global__ void __launch_bounds__(kTmemWarps * 32, TmemShape<HR>::kCtasPerSm) k_
         tm_load_row(tbase, row, pr0, pr1);
       }
 
+      if (kCycles) {  // (:98, :137): push (leaving, entering), then look for two identical runs of length 6..len/2
+        if (hist_len >= a.hist_cap) {
+          status = ST_ERR_HISTORY;
+          break;
+        }
+        if (lane == 0) {
+          hist[2 * hist_len] = var[W + row];
+          hist[2 * hist_len + 1] = var[col];
+        }
+        hist_len++;
+        __syncwarp();
+        bool found = false;
+        for (int Lc = 6 + lane; Lc <= hist_len / 2 && !found; Lc += 32) {
+          bool cyc = true;
+          for (int i = 0; i < Lc; i++) {
+            const int item = hist_len - 1 - i;
+            if (hist[2 * item] != hist[2 * (item - Lc)] || hist[2 * item + 1] != hist[2 * (item - Lc) + 1]) {
+              cyc = false;
+              break;
+            }
+          }
+          found = cyc;
+        }
+        if (__any_sync(0xffffffffu, found)) break;  // "cycled", NaN
+      }
       // ---- pivot(row, col) (:5-39)
       const int jc = col - 1, lc = jc >> 1, ec = jc & 1;
       const double q = colx[row];

@@ -12,7 +12,7 @@ int tmem_kernel_warps();         // LPs in flight per CTA (one per warp)
 bool tmem_kernel_is_tall(int Hcap);       // more than 33 rows: the 256-column shape (8 LPs per SM instead of 16)
 int tmem_kernel_ctas_per_sm(int Hcap);    // 512 TMEM columns / allocation per CTA
 size_t tmem_kernel_dynamic_smem(int Hcap);  // padding request that keeps residency at tmem_kernel_ctas_per_sm()
-const void *tmem_kernel_fn(int Hcap, bool count_rows = false);  // for cudaFuncSetAttribute (dynamic shared-memory limit, per device)
+const void *tmem_kernel_fn(int Hcap, bool count_rows = false, bool cycles = false);  // for cudaFuncSetAttribute (dynamic shared-memory limit, per device)
 const void *tmem_stream_fn();
 int tmem_stream_ctas_per_sm();
 size_t tmem_stream_dynamic_smem();

@@ -268,19 +268,20 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
                                         // the HBM-resident K2; very sparse AFIRO 36x33 (0.1) only while one wave of
                                         // 8 LPs per SM covers the batch, beyond that K2 is 20-30 % faster
                                         : (density < 0.0 || density >= 0.15 || n <= 8LL * ctx->prop.multiProcessorCount)));
-  if (allow_tmem && tmem_kernel_fits(Hcap, Wcap) && !check_cycles && (tune_path == YALPS_PATH_TMEM || tmem_auto)) {
+  if (allow_tmem && tmem_kernel_fits(Hcap, Wcap) && (tune_path == YALPS_PATH_TMEM || tmem_auto)) {
     plan->tmem = true;
     plan->resident = true;
     plan->k = nullptr;
     plan->smem = tmem_kernel_dynamic_smem(Hcap);
-    CU(ctx, raise_smem_limit(ctx->device, tmem_kernel_fn(Hcap), (int)plan->smem));
-    if (ctx->d_rows) CU(ctx, raise_smem_limit(ctx->device, tmem_kernel_fn(Hcap, true), (int)plan->smem));
-    const long long ctas = (long long)tmem_kernel_ctas_per_sm(Hcap) * ctx->prop.multiProcessorCount;
+    CU(ctx, raise_smem_limit(ctx->device, tmem_kernel_fn(Hcap, false, check_cycles), (int)plan->smem));
+    if (ctx->d_rows) CU(ctx, raise_smem_limit(ctx->device, tmem_kernel_fn(Hcap, true, check_cycles), (int)plan->smem));
+    // checkCycles: one history buffer per warp, so one CTA per SM bounds the memory (4 warps x 2 x hist_cap ints each)
+    const long long ctas = (long long)(check_cycles ? 1 : tmem_kernel_ctas_per_sm(Hcap)) * ctx->prop.multiProcessorCount;
     plan->grid = (int)std::max(1LL, std::min(ctas, n));  // few LPs: one per CTA (the kernel deals LP i to CTA i % grid)
     return 0;
   }
   if (tune_path == YALPS_PATH_TMEM)
-    return fail(ctx, YALPS_ERR_TOO_LARGE, "tableau %dx%d does not fit the tensor-memory kernel (max %dx%d, no checkCycles, no node mode)",
+    return fail(ctx, YALPS_ERR_TOO_LARGE, "tableau %dx%d does not fit the tensor-memory kernel (max %dx%d, no node mode)",
                 Hcap, Wcap, 65, 65);
   plan->resident = resident;
   plan->k = nullptr;
@@ -401,7 +402,8 @@ int launch_simplex(yalps_ctx *ctx, const LaunchPlan &plan, BatchArgs &args, cons
   }
   if (args.check_cycles) {
     void *hist = nullptr;
-    if (int rc = dev_ensure(ctx, "hist" + slot, (size_t)plan.grid * 2 * args.hist_cap * sizeof(int), &hist)) return rc;
+    const size_t per_cta = (size_t)(plan.tmem ? tmem_kernel_warps() : 1) * 2 * args.hist_cap * sizeof(int);  // K1t: per warp
+    if (int rc = dev_ensure(ctx, "hist" + slot, (size_t)plan.grid * per_cta, &hist)) return rc;
     args.hist = (int *)hist;
   } else {
     args.hist = nullptr;
