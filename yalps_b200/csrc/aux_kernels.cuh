@@ -108,6 +108,227 @@ __global__ void k_expand_replicas(long long n, int H, int W, const double *base,
   }
 }
 
+// ---- replica path sharing (yalps_solve_replicas) -----------------------------------------------------------------
+// n replicas of one tableau differ only in column 0.  Everything else of the tableau -- objective row, pivot rows and
+// columns, the basis bookkeeping -- evolves identically for every replica that makes the same pivot choices, and those
+// choices depend on a replica's own data only through its RHS column: the leaving row of phase 1 (most negative RHS),
+// the ratio test of phase 2, and the moment phase 1 ends.  So ONE replica (the leader: the base tableau itself) is
+// solved with a trace -- per pivot the choice, the pivot element and the raw pivot column, plus tableau snapshots --
+// and every other replica FOLLOWS it carrying only its RHS column (one warp per replica, H doubles in shared memory):
+// per pivot it re-derives its own choice from the trace and its RHS, applies the pivot to its RHS with the reference's
+// operations (src/simplex.ts:16-36 restricted to column 0), and stops following at the first step where its choice
+// differs from the leader's.  From there it continues alone: its tableau is the leader's snapshot of that step with its
+// own column 0, handed to the ordinary kernels together with (phase, pivot counters) to resume.  Results are those of
+// solving every replica on its own, bit for bit; the coefficient updates of a shared path are simply not repeated.
+struct FollowArgs {
+  long long n;
+  int H, W, Hp;
+  const double *rhs_in;   // [n][H]
+  const int *steps;       // [K + 1][4]: phase, row, col, terminal flag
+  const double *q;        // [K]
+  const double *colraw;   // [K][Hp]
+  const int *leader_var;  // variableAtPosition of the leader's final tableau
+  int K;                  // pivots recorded
+  int leader_done;        // the trace ends with the leader's own termination (not with a full trace buffer)
+  int leader_status;
+  double precision, max_pivots;
+  int *status;
+  double *value;
+  long long *pivots;
+  double *rhs_out;        // [n][H]: final RHS of a replica that finished on the path, its RHS at the fork otherwise
+  int *pos_out, *var_out; // [n][W + H] (nullable)
+  int *fork_count;        // number of replicas that left the path
+  int *fork_ids;          // [n] their indices, in arrival order
+  int *fork_step;         // [n] (indexed by replica) the step at which it left
+  long long *fork_resume; // [n][3] (indexed by replica) phase and pivot counters at that step
+};
+
+constexpr int kFollowWarps = 8;
+
+__global__ void __launch_bounds__(kFollowWarps * 32) k_replica_follow(const FollowArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int H = a.H, W = a.W;
+  double *b = reinterpret_cast<double *>(smem_raw) + (size_t)warp * a.Hp;
+  const double precision = a.precision, INF = d_inf();
+  const long long budget =
+      !(a.max_pivots > 0.0) ? 0LL : (a.max_pivots >= 9.0e18 ? 0x7fffffffffffffffLL : (long long)ceil(a.max_pivots));
+  const int end_phase = a.steps[4 * a.K], end_row = a.steps[4 * a.K + 1], end_col = a.steps[4 * a.K + 2];
+  for (long long i = (long long)blockIdx.x * kFollowWarps + warp; i < a.n; i += (long long)gridDim.x * kFollowWarps) {
+    for (int r = lane; r < H; r += 32) b[r] = a.rhs_in[(size_t)i * H + r];
+    __syncwarp();
+    int phase = 1, k = 0, status = ST_CYCLED;
+    long long p1 = 0, p2 = 0, iter = 0;
+    double value = d_nan();
+    bool forked = false;
+    for (;;) {
+      if (iter >= budget) break;  // "cycled" (:102,:141): on the shared path the leader ends the same way
+      int row = kNone;
+      if (phase == 1) {
+        double bv = INF;
+        int bi = kNone;
+        for (int r = 1 + lane; r < H; r += 32) {  // (:111-119)
+          const double v = b[r];
+          if (v < -precision && v < bv) {
+            bv = v;
+            bi = r;
+          }
+        }
+        const unsigned long long key = bi == kNone ? no_key<false>() : order_key(bv);
+        row = warp_best<false>((unsigned)(key >> 32), (unsigned)key, bi).idx;
+        if (row == kNone) {  // (:120)
+          phase = 2;
+          iter = 0;
+          continue;
+        }
+        if (k == a.K) {  // the leader stopped here: same verdict only if it had chosen the same row and found no column
+          if (a.leader_done && end_phase == 1 && a.leader_status == ST_INFEASIBLE && end_row == row)
+            status = ST_INFEASIBLE;
+          else
+            forked = true;
+          break;
+        }
+        if (a.steps[4 * k] != 1 || a.steps[4 * k + 1] != row) {  // (the column follows from the row and shared data)
+          forked = true;
+          break;
+        }
+      } else {
+        if (k == a.K) {  // entering column and candidate rows depend on shared data only
+          if (a.leader_done && end_phase == 2 && a.leader_status == ST_OPTIMAL) {
+            status = ST_OPTIMAL;
+            value = round_to_precision(b[0], precision);
+          } else if (a.leader_done && end_phase == 2 && a.leader_status == ST_UNBOUNDED) {
+            status = ST_UNBOUNDED;
+            value = (double)end_col;
+          } else {
+            forked = true;
+          }
+          break;
+        }
+        if (a.steps[4 * k] != 2) {
+          forked = true;
+          break;
+        }
+        const double *colk = a.colraw + (size_t)k * a.Hp;
+        double bv = INF;
+        int bi = kNone;
+        for (int r = 1 + lane; r < H; r += 32) {  // ratio test (:83-95)
+          const double v = colk[r];
+          if (v > precision) {
+            const double ratio = div_rn(b[r], v);
+            if (ratio < INF) {
+              const double kk = (ratio <= precision) ? -INF : ratio;
+              if (bi == kNone || kk < bv) {
+                bv = kk;
+                bi = r;
+              }
+            }
+          }
+        }
+        const unsigned long long key = bi == kNone ? no_key<false>() : order_key(bv);
+        row = warp_best<false>((unsigned)(key >> 32), (unsigned)key, bi).idx;
+        if (row != a.steps[4 * k + 1]) {  // (kNone included: the ordinary kernel gives the verdict)
+          forked = true;
+          break;
+        }
+      }
+      // ---- pivot k applied to column 0 (:16-36): b[row] = |b[row]| > 1e-16 ? b[row] / q : 0, and for every other row
+      // with |coef| > 1e-16, b[r] -= coef * b[row] when column 0 is among the pivot row's non-zero cells
+      {
+        const double *colk = a.colraw + (size_t)k * a.Hp;
+        const double braw = b[row];
+        const bool nz0 = fabs(braw) > kTiny;
+        const double p0 = nz0 ? __ddiv_rn(braw, a.q[k]) : 0.0;
+        __syncwarp();
+        for (int r = lane; r < H; r += 32) {
+          if (r == row) {
+            b[r] = p0;
+          } else if (nz0) {
+            const double coef = colk[r];
+            if (fabs(coef) > kTiny) b[r] = __dsub_rn(b[r], __dmul_rn(coef, p0));
+          }
+        }
+        __syncwarp();
+      }
+      if (phase == 1)
+        p1++;
+      else
+        p2++;
+      iter++;
+      k++;
+    }
+    for (int r = lane; r < H; r += 32) a.rhs_out[(size_t)i * H + r] = b[r];
+    if (forked) {
+      if (lane == 0) {
+        a.fork_step[i] = k;
+        a.fork_resume[3 * i] = phase;
+        a.fork_resume[3 * i + 1] = p1;
+        a.fork_resume[3 * i + 2] = p2;
+        a.fork_ids[atomicAdd(a.fork_count, 1)] = (int)i;
+      }
+    } else {
+      if (lane == 0) {
+        if (a.status) a.status[i] = status;
+        if (a.value) a.value[i] = value;
+        if (a.pivots) {
+          a.pivots[2 * i] = p1;
+          a.pivots[2 * i + 1] = p2;
+        }
+      }
+      for (int p = lane; p < W + H; p += 32) {
+        const int v = a.leader_var[p];
+        if (a.var_out) a.var_out[(size_t)i * (W + H) + p] = v;
+        if (a.pos_out) a.pos_out[(size_t)i * (W + H) + v] = p;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// Forked replicas [first, first + m) of the fork list: private tableau = leader snapshot of the fork step with the
+// replica's own column 0; variableAtPosition of that step; resume state.
+__global__ void k_replica_materialise(int first, int m, int H, int W, const int *fork_ids, const int *fork_step,
+                                      const long long *fork_resume, const double *rhs_state, const double *snap,
+                                      const int *snap_var, double *work, int *var_in, long long *resume) {
+  const size_t cells = (size_t)H * W;
+  for (int f = blockIdx.y; f < m; f += gridDim.y) {
+    const int i = fork_ids[first + f], k = fork_step[i];
+    const double *src = snap + (size_t)k * cells;
+    double *dst = work + (size_t)f * cells;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < cells; e += (size_t)gridDim.x * blockDim.x) {
+      const int r = (int)(e / W), c = (int)(e - (size_t)r * W);
+      dst[e] = c == 0 ? rhs_state[(size_t)i * H + r] : src[e];
+    }
+    if (blockIdx.x == 0) {
+      for (int p = threadIdx.x; p < W + H; p += blockDim.x) var_in[(size_t)f * (W + H) + p] = snap_var[(size_t)k * (W + H) + p];
+      if (threadIdx.x < 3) resume[3 * f + threadIdx.x] = fork_resume[3 * i + threadIdx.x];
+    }
+  }
+}
+
+// Results of the forked replicas [first, first + m) (compact, as solved) back to their replica slots.
+__global__ void k_replica_scatter(int first, int m, int H, int W, const int *fork_ids, const int *c_status,
+                                  const double *c_value, const long long *c_pivots, const double *c_rhs, const int *c_pos,
+                                  const int *c_var, int *status, double *value, long long *pivots, double *rhs_out,
+                                  int *pos_out, int *var_out) {
+  for (int f = blockIdx.x; f < m; f += gridDim.x) {
+    const size_t i = (size_t)fork_ids[first + f];
+    if (threadIdx.x == 0) {
+      if (status) status[i] = c_status[f];
+      if (value) value[i] = c_value[f];
+      if (pivots) {
+        pivots[2 * i] = c_pivots[2 * f];
+        pivots[2 * i + 1] = c_pivots[2 * f + 1];
+      }
+    }
+    for (int r = threadIdx.x; r < H; r += blockDim.x) rhs_out[i * H + r] = c_rhs[(size_t)f * H + r];
+    for (int p = threadIdx.x; p < W + H; p += blockDim.x) {
+      if (pos_out) pos_out[i * (W + H) + p] = c_pos[(size_t)f * (W + H) + p];
+      if (var_out) var_out[i * (W + H) + p] = c_var[(size_t)f * (W + H) + p];
+    }
+  }
+}
+
 // Incumbent min-allreduce, the part inside one GPU: the logical ranks that share this GPU are reduced by ONE kernel
 // over all their slots (never by launches that wait for one another); slot[k] then goes through ncclAllReduce(min)
 // across the distinct GPUs and is broadcast back to the rank slots.

@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
     t.ldA = t.ldb = SmemLayout::ld_for(W);
     t.b = t.A + (t.ldA - 2);
     t.var = reinterpret_cast<int *>(smem_raw + L.off_var);
-    SplitScratch ss;
+    SplitScratch ss{};
     ss.cc = reinterpret_cast<double *>(smem_raw + L.off_cc);
     ss.list = reinterpret_cast<int *>(smem_raw + L.off_list);
     ss.cnt = reinterpret_cast<int *>(smem_raw + L.off_cnt);

@@ -34,6 +34,13 @@ struct BatchArgs {
   // an LP, ADDED (atomically) to rows_out[rows_per_lp ? lp : 0]; the host zeroes the buffer
   unsigned long long *rows_out;
   int rows_per_lp;
+  // optional per-LP resume state, 3 long long per LP: [phase, pivots done in phase 1, in phase 2] (replica path sharing)
+  const long long *resume;
+  // optional trace of ONE LP (n == 1): see SplitScratch (simplex_split.cuh); only the row-split kernels record it
+  int *tr_steps;
+  double *tr_q, *tr_col, *tr_snap;
+  int *tr_var;
+  int tr_hp, tr_cap;
   const int *var_in;  // optional initial variableAtPosition, packed like var_out (null: the identity, src/tableau.ts:95-98)
   // node mode
   const double *root;
@@ -186,6 +193,14 @@ __global__ void __launch_bounds__(NWC *NWR * 32, min_ctas_per_sm(NWC, NWR)) k_si
     ss.red = s.red;
     ss.hist = s.hist;
     ss.hist_cap = s.hist_cap;
+    s.resume = ss.resume = a.resume ? a.resume + 3 * lp : nullptr;
+    ss.tr_steps = a.tr_steps;
+    ss.tr_q = a.tr_q;
+    ss.tr_col = a.tr_col;
+    ss.tr_snap = a.tr_snap;
+    ss.tr_var = a.tr_var;
+    ss.tr_hp = a.tr_hp;
+    ss.tr_cap = a.tr_cap;
     if (kSplit && tid == 0) *ss.cnt = 0;
 #ifdef YALPS_TIMING
     long long yt_local[16];

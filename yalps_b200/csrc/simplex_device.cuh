@@ -142,6 +142,7 @@ struct Scratch {
   unsigned *red;      // [192] cross-warp reduction scratch (NW > 1 only)
   int *hist;       // [2*hist_cap] (leaving var, entering var) pairs, checkCycles only
   int hist_cap;
+  const long long *resume;  // nullable: [phase, pivots done in phase 1, in phase 2] of a trajectory to continue
 };
 
 struct LpResult {
@@ -406,6 +407,12 @@ __device__ __forceinline__ LpResult simplex_cta(const LpView &t, const Scratch &
   res.rows = 0;
   int phase = 1, parity = 0, hist_len = 0;
   long long iter = 0;
+  if (s.resume) {  // continue a trajectory: same phase, same per-phase counter
+    phase = (int)s.resume[0];
+    res.p1 = s.resume[1];
+    res.p2 = s.resume[2];
+    iter = phase == 1 ? res.p1 : res.p2;
+  }
 
   for (;;) {
     if (!((double)iter < max_pivots)) break;  // per-phase budget exhausted -> "cycled" (:102,:141)

@@ -40,6 +40,17 @@ struct SplitScratch {
   unsigned *red;  // [192] cross-warp reduction scratch
   int *hist;
   int hist_cap;
+  // resume (nullable): [phase, pivots already done in phase 1, in phase 2] -- the LP continues a trajectory that was
+  // followed elsewhere up to this tableau (replica path sharing, aux_kernels.cuh)
+  const long long *resume;
+  // trace (nullable, one LP per launch): per pivot k the choice and the raw pivot column, and a snapshot of the
+  // tableau and of variableAtPosition BEFORE pivot k; entry K (= number of pivots) describes how the LP ended
+  int *tr_steps;       // [cap + 1][4]: phase, row, col, 0  (kNone where nothing was chosen)
+  double *tr_q;        // [cap]
+  double *tr_col;      // [cap][tr_hp]
+  double *tr_snap;     // [cap + 1][H * W], reference layout
+  int *tr_var;         // [cap + 1][W + H]
+  int tr_hp, tr_cap;
 #ifdef YALPS_TIMING
   long long *yt;  // [16] per-thread phase cycle counters (debug builds only)
 #endif
@@ -264,10 +275,28 @@ __device__ __forceinline__ LpResult simplex_cta_split(const LpView &t, const Spl
   res.rows = 0;
   int phase = 1, parity = 0, hist_len = 0;
   long long iter = 0;
+  if (s.resume) {  // continue a trajectory: same phase, same per-phase counter
+    phase = (int)s.resume[0];
+    res.p1 = s.resume[1];
+    res.p2 = s.resume[2];
+    iter = phase == 1 ? res.p1 : res.p2;
+  }
+  int end_row = kNone, end_col = kNone;  // what the terminal step had chosen (trace)
+  // snapshot of the tableau (reference layout) and of variableAtPosition into trace slot k
+  auto trace_snapshot = [&](long long k) {
+    const int W = t.W;
+    double *dst = s.tr_snap + (size_t)k * H * W;
+    for (int e = tid; e < H * W; e += NT) {
+      const int r = e / W, c = e - r * W;
+      dst[e] = c == 0 ? b[(size_t)r * ldb] : A[(size_t)r * ldA + (c - 1)];
+    }
+    int *dv = s.tr_var + (size_t)k * (W + H);
+    for (int i = tid; i < W + H; i += NT) dv[i] = t.var[i];
+  };
 
   for (;;) {
     if (iter >= budget) break;  // per-phase budget exhausted -> "cycled" (:102,:141)
-    int row, col;
+    int row = kNone, col = kNone;
     if (phase == 1) {
       // leaving row: first index of the most negative RHS below -precision (:111-119)
       double bv = INF;
@@ -327,6 +356,7 @@ __device__ __forceinline__ LpResult simplex_cta_split(const LpView &t, const Spl
       YT_MARK(1);
       if (col == kNone) {
         res.status = ST_INFEASIBLE;
+        end_row = row;
         break;
       }
     } else {
@@ -385,7 +415,23 @@ __device__ __forceinline__ LpResult simplex_cta_split(const LpView &t, const Spl
       if (row == kNone) {
         res.status = ST_UNBOUNDED;
         res.value = (double)col;
+        end_col = col;
         break;
+      }
+    }
+
+    if (s.tr_steps) {  // trace: the choice, the pivot element, the raw pivot column, the tableau before the pivot
+      const long long k = res.p1 + res.p2;
+      if (k < s.tr_cap) {
+        if (tid == 0) {
+          s.tr_steps[4 * k] = phase;
+          s.tr_steps[4 * k + 1] = row;
+          s.tr_steps[4 * k + 2] = col;
+          s.tr_steps[4 * k + 3] = 0;
+          s.tr_q[k] = A[(size_t)row * ldA + (col - 1)];
+        }
+        for (int r = tid; r < H; r += NT) s.tr_col[(size_t)k * s.tr_hp + r] = A[(size_t)r * ldA + (col - 1)];
+        trace_snapshot(k);
       }
     }
 
@@ -409,6 +455,18 @@ __device__ __forceinline__ LpResult simplex_cta_split(const LpView &t, const Spl
     else
       res.p2++;
     iter++;
+  }
+  if (s.tr_steps) {  // how the LP ended, and the final tableau
+    const long long k = res.p1 + res.p2;
+    if (k <= s.tr_cap) {
+      if (tid == 0) {
+        s.tr_steps[4 * k] = phase;
+        s.tr_steps[4 * k + 1] = end_row;
+        s.tr_steps[4 * k + 2] = end_col;
+        s.tr_steps[4 * k + 3] = 1;
+      }
+      trace_snapshot(k);
+    }
   }
   return res;
 }
