@@ -300,6 +300,23 @@ int yalps_multi_solve_many(yalps_multi *m, int64_t n_models, const int32_t *heig
                            int32_t searches_per_device, int32_t *status, double *result, int32_t *out_height,
                            double *rhs_out, int32_t *pos_out, int32_t *var_out);
 
+/*
+ * ONE large LP over all the ranks of m (north_star (c) widened from the grid of one GPU to the GPUs of
+ * one box): simplex() of src/simplex.ts:99-142 on one height x width tableau whose rows are dealt round robin to the
+ * ranks (row r -> rank r % ndev), so ndev GPUs hold -- and update -- a tableau ndev times the size one could.  One
+ * persistent cooperative kernel per rank; per pivot the pivot column is all-gathered and the raw pivot row broadcast by
+ * stores into the peers' memory (NVLink / NVSwitch peer access, cudaDeviceEnablePeerAccess) from inside those kernels,
+ * published with system-scope release flags: no host round trip and no collective call per pivot.  Every rank makes the
+ * same pivot choice from private copies of the objective row and RHS column, so the trajectory -- and every output bit
+ * -- is that of yalps_solve_batch(n = 1).  matrix is a HOST array (reference layout); outputs as yalps_solve_batch for
+ * n = 1, matrix_out (nullable) receives the final tableau; kernel_ms (nullable) the device time of the slowest rank's
+ * kernel (CUDA events).  Fails with YALPS_ERR_CUDA when two GPUs of m have no peer path or the ranks' kernels could not
+ * run at the same time (every in-kernel wait has a ~2 s budget, so a missing peer cannot hang a GPU).
+ */
+int yalps_multi_solve_large(yalps_multi *m, int32_t height, int32_t width, const double *matrix,
+                            const yalps_options *opt, int32_t *status, double *value, int64_t *pivots, double *rhs_out,
+                            int32_t *pos_out, int32_t *var_out, double *matrix_out, double *kernel_ms);
+
 /* roundToPrecision (src/util.ts:1-4) evaluated on the device for n values (parity probe). */
 int yalps_round_to_precision(yalps_ctx *ctx, int64_t n, const double *x, double precision, double *out);
 

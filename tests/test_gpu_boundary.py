@@ -290,3 +290,84 @@ def test_solve_many_on_several_gpus_equals_solve(multi):
     for c, s in zip(default, sols):
         assert s["status"] == c["oracle"]["status"] and same_value(s["result"], c["oracle"]["result"]), c["name"]
         assert [list(v) for v in s["variables"]] == [list(v) for v in c["oracle"]["variables"]], c["name"]
+
+
+# ------------------------------------------------------------------------------- one large LP over the ranks (8f-3)
+def _large_equal(got, exp, what):
+    assert got["status"] == int(exp["status"][0]), what
+    assert same_value(got["value"], exp["value"][0]), what
+    assert got["pivots"] == tuple(int(x) for x in exp["pivots"][0]), what
+    assert np.array_equal(got["pos"], exp["pos"][0]) and np.array_equal(got["var"], exp["var"][0]), what
+    assert same_bits(got["rhs"], exp["rhs"][0]), what
+
+
+def _oracle_one(mats, H, W, **kw):
+    work = mats.copy()
+    exp = O.simplex_batch(work, W, H, **kw)
+    exp["matrices"] = work
+    return exp
+
+
+@pytest.mark.parametrize("m_,nv,neg", [(32, 64, 6), (5, 3, 2), (100, 300, 40), (300, 90, 100), (1, 1, 0), (0, 4, 0)])
+def test_large_lp_over_the_ranks_is_bit_exact(multi, m_, nv, neg):
+    """yalps_multi_solve_large: rows dealt round robin over the ranks, pivot row / column exchanged through peer memory
+    from inside one persistent kernel per rank -- every output bit against the oracle, final tableau included."""
+    H, W = m_ + 1, nv + 1
+    mats = O.generate_synthetic(4100, 1, m_, nv, neg) if m_ else np.array([[0.0, 1.0, -2.0, 0.0, 3.0]])
+    exp = _oracle_one(mats, H, W)
+    got = multi.solve_large(mats, H, W, want_matrix=True)
+    _large_equal(got, exp, f"large {H}x{W}")
+    assert same_bits(got["matrix"], exp["matrices"].reshape(-1)), "final tableau"
+    assert got["kernel_ms"] > 0.0
+
+
+def test_large_lp_statuses_budgets_and_check_cycles(multi):
+    t = np.array([[0, 10, -57, -9, -24], [0, 0.5, -5.5, -2.5, 9], [0, 0.5, -1.5, -0.5, 1], [1, 1, 0, 0, 0]], float)
+    for kw in ({"check_cycles": True}, {"check_cycles": False, "max_pivots": 9}, {"max_pivots": 0}, {"max_pivots": 2.5}):
+        m = t.reshape(1, -1).copy()
+        exp = _oracle_one(m, 4, 5, **kw)
+        got = multi.solve_large(m, 4, 5, E.make_options(**kw), want_matrix=True)
+        _large_equal(got, exp, f"large {kw}")
+        assert same_bits(got["matrix"], exp["matrices"].reshape(-1))
+    # infeasible and unbounded
+    for mat, H, W in ((np.array([[0.0, 1.0], [-1.0, 1.0]]), 2, 2), (np.array([[0.0, 1.0, 1.0], [4.0, -1.0, 1.0]]), 2, 3)):
+        exp = _oracle_one(mat.reshape(1, -1), H, W)
+        got = multi.solve_large(mat, H, W)
+        _large_equal(got, exp, f"large status {int(exp['status'][0])}")
+
+
+def test_large_lp_netlib_and_more_ranks(engine):
+    """Sparse Netlib models (row skip, long phase 1) over 2, 3 and 4 ranks: the rank count must not change a bit."""
+    import torch
+    ndev = torch.cuda.device_count()
+    nl = load_netlib()
+    for world in (2, 3, 4):
+        devs = [i % ndev for i in range(world)]
+        with yalps_b200.MultiEngine(devs) as me:
+            for name in ("AFIRO", "SC105", "ADLITTLE"):
+                g = nl.get(name)
+                got = me.solve_large(g["matrix"], g["height"], g["width"], E.make_options(check_cycles=g["check_cycles"]))
+                assert got["status"] == g["status"] and got["pivots"] == g["pivots"], (name, world)
+                assert same_value(got["value"], g["value"]) and np.array_equal(got["pos"], g["final_pos"])
+                assert same_bits(got["rhs"], g["final_rhs"]), (name, world)
+            mats = O.generate_synthetic(77, 1, 200, 500, 30)
+            exp = _oracle_one(mats, 201, 501)
+            _large_equal(me.solve_large(mats, 201, 501), exp, f"200x500 on {world} ranks")
+
+
+def test_large_lp_equals_the_grid_kernel_at_size(engine, multi):
+    """1025 x 2049 (16.8 MB), 40 pivots: the multi-rank kernel against the single-GPU grid kernel and the oracle."""
+    import torch
+    m_, nv, cap = 1024, 2048, 40
+    H, W = m_ + 1, nv + 1
+    d = torch.empty(H * W, dtype=torch.float64, device="cuda")
+    engine.generate_synthetic_device(0, 1, m_, nv, d.data_ptr())
+    torch.cuda.synchronize()
+    mats = d.cpu().numpy().reshape(1, -1)
+    opt = E.make_options(max_pivots=cap)
+    exp = _oracle_one(mats, H, W, max_pivots=cap)
+    got = multi.solve_large(mats, H, W, opt, want_matrix=True)
+    _large_equal(got, exp, "1025x2049")
+    assert same_bits(got["matrix"], exp["matrices"].reshape(-1))
+    one = engine.solve_batch(mats, H, W, opt, want_matrices=True)
+    assert same_bits(one["matrices"][0], got["matrix"])

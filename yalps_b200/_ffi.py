@@ -80,6 +80,8 @@ SIGNATURES = {
                                     C.c_int32, _ip, _dp, _ip, _vp, _vp, _vp, _ip, _dp, _vp, _vp]),
     "yalps_multi_solve_many": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(Options), C.c_int32,
                                          _vp, _vp, _vp, _vp, _vp, _vp]),
+    "yalps_multi_solve_large": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, C.POINTER(Options), _ip, _dp, _vp, _vp, _vp, _vp,
+                                          _vp, _dp]),
     "yalps_solve_batch_device": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, C.POINTER(Options), _vp,
                                            _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "yalps_generate_synthetic_device": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32,

@@ -110,6 +110,7 @@ struct yalps_multi {
   std::vector<ncclComm_t> comms;
   NcclApi nccl;
   int64_t allreduces = 0;
+  bool peers_enabled = false;  // cudaDeviceEnablePeerAccess between all distinct GPUs (yalps_multi_solve_large)
 };
 
 namespace {
@@ -569,6 +570,219 @@ int yalps_multi_solve_many(yalps_multi *m, int64_t n_models, const int32_t *heig
   }
   if (rc) m->error = first_error;
   return rc;
+}
+
+// ---- one large LP over all ranks: multigrid_kernel.cuh ---------------------------------------------
+namespace {
+
+struct LargeRank {
+  double *M = nullptr, *colx = nullptr, *rowx = nullptr, *value = nullptr, *rhs = nullptr;
+  unsigned long long *sync = nullptr;  // [G] column flags, [kMaxRowParts] row flags, barrier, 2 verdict ints
+  int *var = nullptr, *pos = nullptr, *status = nullptr, *hist = nullptr;
+  long long *piv = nullptr;
+  int Hl = 0, grid = 0;
+  float ms = 0.f;
+  int32_t h_status = 0;
+  long long giveup[6] = {0, 0, 0, 0, 0, 0};
+};
+
+int enable_peers(yalps_multi *m) {
+  if (m->peers_enabled) return 0;
+  for (int a : m->gpus)
+    for (int b : m->gpus) {
+      if (a == b) continue;
+      int can = 0;
+      MCU(m, cudaDeviceCanAccessPeer(&can, a, b));
+      if (!can) return mfail(m, YALPS_ERR_CUDA, "GPU %d cannot access the memory of GPU %d (no peer path)", a, b);
+      MCU(m, cudaSetDevice(a));
+      const cudaError_t e = cudaDeviceEnablePeerAccess(b, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        return mfail(m, YALPS_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d) failed: %s", a, b, cudaGetErrorString(e));
+      (void)cudaGetLastError();
+    }
+  m->peers_enabled = true;
+  return 0;
+}
+
+}  // namespace
+
+int yalps_multi_solve_large(yalps_multi *m, int32_t height, int32_t width, const double *matrix, const yalps_options *opt,
+                            int32_t *status, double *value, int64_t *pivots, double *rhs_out, int32_t *pos_out,
+                            int32_t *var_out, double *matrix_out, double *kernel_ms) {
+  if (!m) return YALPS_ERR_ARGUMENT;
+  if (height < 1 || width < 1 || !opt || !matrix) return mfail(m, YALPS_ERR_ARGUMENT, "bad arguments");
+  const int G = (int)m->devices.size();
+  const int H = height, W = width;
+  if (G > kMaxGridRanks) return mfail(m, YALPS_ERR_ARGUMENT, "at most %d ranks share one LP", kMaxGridRanks);
+  if ((long long)H + W >= (1LL << 31)) return mfail(m, YALPS_ERR_TOO_LARGE, "height + width must be < 2^31");
+  if (int rc = enable_peers(m)) return rc;
+  const GridSmem L(H, W);
+  const int Hlmax = (H + G - 1) / G, Wpad = (W + 1) & ~1;
+  std::vector<LargeRank> R(G);
+  std::vector<int> ranks_on_gpu(G, 1);
+  for (int r = 0; r < G; r++) {
+    int cnt = 0;
+    for (int q = 0; q < G; q++) cnt += m->devices[q] == m->devices[r];
+    ranks_on_gpu[r] = cnt;
+  }
+  // ---- phase A: every rank allocates, clears its flags and takes its rows (global row r -> rank r % G, local r / G)
+  int rc = run_on_ranks(m, [&](int r, yalps_ctx *ctx) -> int {
+    LargeRank &k = R[r];
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (L.total > (size_t)ctx->smem_optin)
+      return fail(ctx, YALPS_ERR_TOO_LARGE, "tableau %dx%d: pivot row/column staging exceeds shared memory", H, W);
+    int coop = 0;
+    CU(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
+    if (!coop) return fail(ctx, YALPS_ERR_CUDA, "device does not support cooperative launches");
+    CU(ctx, raise_smem_limit(ctx->device, (const void *)k_simplex_grid_multi, (int)L.total));
+    int occ = 0;
+    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_simplex_grid_multi, kGridThreads, L.total));
+    if (occ < 1) return fail(ctx, YALPS_ERR_TOO_LARGE, "grid kernel does not fit on an SM");
+    k.Hl = r < H ? (H - r + G - 1) / G : 0;
+    // the ranks that share a GPU share its SMs (all their kernels must be resident at once: they wait for one another)
+    int grid = ctx->prop.multiProcessorCount * occ / ranks_on_gpu[r];
+    {
+      const long long items = (long long)std::max(k.Hl, 1) * ((W + kSegCols - 1) / kSegCols);
+      grid = (int)std::min<long long>(grid, std::max(1LL, (items + 2 * kGridWarps - 1) / (2 * kGridWarps)));
+    }
+    if (const char *env = getenv("YALPS_GRID_CTAS")) grid = std::min(grid, std::max(1, atoi(env)));
+    grid = std::max(grid, G);  // CTA d of a rank is its sender to rank d
+    if (grid > ctx->prop.multiProcessorCount * occ / ranks_on_gpu[r])
+      return fail(ctx, YALPS_ERR_TOO_LARGE, "%d ranks on GPU %d leave fewer than %d co-resident CTAs per rank", ranks_on_gpu[r],
+                  ctx->device, G);
+    k.grid = grid;
+    void *p;
+    int e;
+    if ((e = dev_ensure(ctx, "lg_M", std::max<size_t>(1, (size_t)k.Hl) * W * 8, &p))) return e;
+    k.M = (double *)p;
+    if ((e = dev_ensure(ctx, "lg_colx", (size_t)2 * G * Hlmax * 8, &p))) return e;
+    k.colx = (double *)p;
+    if ((e = dev_ensure(ctx, "lg_rowx", (size_t)2 * Wpad * 8, &p))) return e;
+    k.rowx = (double *)p;
+    if ((e = dev_ensure(ctx, "lg_sync", (size_t)(kMaxGridRanks + kMaxRowParts + 12) * 8, &p))) return e;
+    k.sync = (unsigned long long *)p;
+    if ((e = dev_ensure(ctx, "lg_var", (size_t)(W + H) * 4, &p))) return e;
+    k.var = (int *)p;
+    if ((e = dev_ensure(ctx, "lg_pos", (size_t)(W + H) * 4, &p))) return e;
+    k.pos = (int *)p;
+    if ((e = dev_ensure(ctx, "lg_rhs", (size_t)H * 8, &p))) return e;
+    k.rhs = (double *)p;
+    if ((e = dev_ensure(ctx, "lg_res", 64, &p))) return e;
+    k.status = (int *)p;
+    k.value = (double *)((char *)p + 8);
+    k.piv = (long long *)((char *)p + 16);
+    if (opt->check_cycles) {
+      if ((e = dev_ensure(ctx, "lg_hist", (size_t)2 * hist_capacity(opt) * sizeof(int), &p))) return e;
+      k.hist = (int *)p;
+    }
+    cudaStream_t st = ctx->streams[0];
+    CU(ctx, cudaMemsetAsync(k.sync, 0, (size_t)(kMaxGridRanks + kMaxRowParts + 12) * 8, st));
+    if (k.Hl > 0)
+      CU(ctx, cudaMemcpy2DAsync(k.M, (size_t)W * 8, matrix + (size_t)r * W, (size_t)G * W * 8, (size_t)W * 8, k.Hl,
+                                cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    return 0;
+  });
+  if (rc) return rc;
+  // ---- phase B: one cooperative kernel per rank; the kernels exchange pivot rows and columns through peer memory
+  int row_parts = kMaxRowParts;
+  for (int r = 0; r < G; r++) row_parts = std::min(row_parts, std::max(1, R[r].grid / G));
+  if (const char *env = getenv("YALPS_LARGE_ROW_PARTS")) row_parts = std::max(1, std::min(row_parts, atoi(env)));
+  // Every rank launches before any rank issues a call that waits for its own kernel (a device-to-host copy into
+  // pageable memory blocks inside the driver; a rank whose launch queued up behind such a call would never start, and
+  // the kernels wait for one another).
+  std::atomic<int> launched{0};
+  std::vector<cudaEvent_t> ev0(G), ev1(G);
+  std::vector<long long *> d_giveup(G, nullptr);
+  auto launch = [&](int r, yalps_ctx *ctx) -> int {
+    LargeRank &k = R[r];
+    CU(ctx, cudaSetDevice(ctx->device));
+    MultiGridArgs a{};
+    a.M = k.M;
+    a.H = H;
+    a.W = W;
+    a.G = G;
+    a.g = r;
+    a.Hl = k.Hl;
+    a.Hlmax = Hlmax;
+    a.Wpad = Wpad;
+    a.row_parts = row_parts;
+    for (int q = 0; q < G; q++) {
+      a.colx[q] = R[q].colx;
+      a.rowx[q] = R[q].rowx;
+      a.colflag[q] = R[q].sync;
+      a.rowflag[q] = R[q].sync + kMaxGridRanks;
+    }
+    a.barrier = k.sync + kMaxGridRanks + kMaxRowParts;
+    a.flags = (int *)(k.sync + kMaxGridRanks + kMaxRowParts + 2);
+    a.var = k.var;
+    a.pos_out = k.pos;
+    a.rhs_out = k.rhs;
+    a.status = k.status;
+    a.value = k.value;
+    a.pivots = k.piv;
+    a.precision = opt->precision;
+    a.max_pivots = opt->max_pivots;
+    a.check_cycles = opt->check_cycles ? 1 : 0;
+    a.hist = k.hist;
+    a.hist_cap = hist_capacity(opt);
+    a.rows_out = (r == 0 && ctx->d_rows && !ctx->rows_per_lp) ? ctx->d_rows : nullptr;
+    a.spin_limit = (long long)(2.0 * ctx->prop.clockRate * 1e3);  // ~2 s of SM clock
+    a.giveup = (long long *)(k.sync + kMaxGridRanks + kMaxRowParts + 4);
+    cudaStream_t st = ctx->streams[0];
+    d_giveup[r] = a.giveup;
+    CU(ctx, cudaEventCreate(&ev0[r]));  // (the ctx's own events are created without timing)
+    CU(ctx, cudaEventCreate(&ev1[r]));
+    CU(ctx, cudaEventRecord(ev0[r], st));
+    void *params[] = {&a};
+    CU(ctx, cudaLaunchCooperativeKernel((void *)k_simplex_grid_multi, dim3(k.grid), dim3(kGridThreads), params, L.total, st));
+    ctx->launches++;
+    CU(ctx, cudaEventRecord(ev1[r], st));
+    return 0;
+  };
+  rc = run_on_ranks(m, [&](int r, yalps_ctx *ctx) -> int {
+    LargeRank &k = R[r];
+    const int lrc = launch(r, ctx);
+    launched.fetch_add(1);
+    while (launched.load() < G) std::this_thread::yield();
+    if (lrc) return lrc;
+    cudaStream_t st = ctx->streams[0];
+    CU(ctx, cudaMemcpyAsync(&k.h_status, k.status, 4, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaMemcpyAsync(k.giveup, d_giveup[r], sizeof k.giveup, cudaMemcpyDeviceToHost, st));
+    if (r == 0) {
+      if (status) CU(ctx, cudaMemcpyAsync(status, k.status, 4, cudaMemcpyDeviceToHost, st));
+      if (value) CU(ctx, cudaMemcpyAsync(value, k.value, 8, cudaMemcpyDeviceToHost, st));
+      if (pivots) CU(ctx, cudaMemcpyAsync(pivots, k.piv, 16, cudaMemcpyDeviceToHost, st));
+      if (rhs_out) CU(ctx, cudaMemcpyAsync(rhs_out, k.rhs, (size_t)H * 8, cudaMemcpyDeviceToHost, st));
+      if (pos_out) CU(ctx, cudaMemcpyAsync(pos_out, k.pos, (size_t)(W + H) * 4, cudaMemcpyDeviceToHost, st));
+      if (var_out) CU(ctx, cudaMemcpyAsync(var_out, k.var, (size_t)(W + H) * 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (matrix_out && k.Hl > 0)
+      CU(ctx, cudaMemcpy2DAsync(matrix_out + (size_t)r * W, (size_t)G * W * 8, k.M, (size_t)W * 8, (size_t)W * 8, k.Hl,
+                                cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    CU(ctx, cudaEventElapsedTime(&k.ms, ev0[r], ev1[r]));
+    cudaEventDestroy(ev0[r]);
+    cudaEventDestroy(ev1[r]);
+    return 0;
+  });
+  if (rc) return rc;
+  float ms = 0.f;
+  for (int r = 0; r < G; r++) {
+    ms = std::max(ms, R[r].ms);
+    if (R[r].h_status == ST_ERR_PEER)
+      return mfail(m, YALPS_ERR_CUDA,
+                   "rank %d (GPU %d) gave up waiting for a peer (wait %lld, exchange %lld, phase %lld, CTA %lld, after %lld + %lld "
+                   "pivots): the %d kernels were not running at the same time",
+                   r, m->devices[r], R[r].giveup[0], R[r].giveup[1], R[r].giveup[2], R[r].giveup[3], R[r].giveup[4],
+                   R[r].giveup[5], G);
+    if (R[r].h_status != R[0].h_status)
+      return mfail(m, YALPS_ERR_CUDA, "ranks disagree on the outcome (rank 0: %d, rank %d: %d)", R[0].h_status, r, R[r].h_status);
+  }
+  if (R[0].h_status == ST_ERR_HISTORY)
+    return mfail(m, YALPS_ERR_HISTORY, "checkCycles history exhausted (more than 262144 pivots in a phase)");
+  if (kernel_ms) *kernel_ms = ms;
+  return 0;
 }
 
 }  // extern "C"

@@ -11,6 +11,7 @@
 #include <nccl.h>  // types and prototypes only: libnccl.so.2 is opened at run time (multi.inl)
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -31,6 +32,7 @@
 #include "aux_kernels.cuh"
 #include "cluster_kernel.cuh"
 #include "grid_kernel.cuh"
+#include "multigrid_kernel.cuh"
 #include "tmem_launch.h"
 #include "bnb_launch.h"
 

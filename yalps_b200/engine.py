@@ -481,6 +481,24 @@ class MultiEngine:
                  "rhs": rhs[roffs[i]:roffs[i + 1]], "pos": pos[poffs[i]:poffs[i + 1]], "var": var[poffs[i]:poffs[i + 1]],
                  "matrix": mats[offs[i]:offs[i + 1]] if want_matrices else None} for i in range(n)]
 
+    def solve_large(self, matrix: np.ndarray, height: int, width: int, options: Optional[Options] = None,
+                    want_matrix: bool = False) -> dict:
+        """ONE LP with its rows dealt round robin over the ranks (yalps_multi_solve_large): peer-memory exchange of the
+        pivot row and column from inside one persistent kernel per GPU.  Outputs as solve_batch for n = 1."""
+        opt = options or make_options()
+        m = np.ascontiguousarray(matrix, np.float64).reshape(-1)
+        if m.size != height * width:
+            raise ValueError("matrix must hold height * width cells")
+        status, value, ms = C.c_int32(), C.c_double(), C.c_double()
+        piv = np.zeros(2, np.int64)
+        rhs, pos, var = np.empty(height), np.empty(width + height, np.int32), np.empty(width + height, np.int32)
+        mat = np.empty(height * width, np.float64) if want_matrix else None
+        self._check(self._lib.yalps_multi_solve_large(self._m, height, width, _ptr(m), C.byref(opt), C.byref(status),
+                                                      C.byref(value), _ptr(piv), _ptr(rhs), _ptr(pos), _ptr(var),
+                                                      _ptr(mat), C.byref(ms)))
+        return {"status": status.value, "value": value.value, "pivots": (int(piv[0]), int(piv[1])), "rhs": rhs,
+                "pos": pos, "var": var, "matrix": mat, "kernel_ms": ms.value}
+
     def incumbent_allreduce(self, local: Sequence[float]) -> np.ndarray:
         """Min-allreduce of one fp64 per rank (NCCL across the distinct GPUs)."""
         loc = np.ascontiguousarray(local, np.float64)
