@@ -84,6 +84,9 @@ enum yalps_path {
                              (csrc/cluster_kernel.cuh) */
   YALPS_PATH_TMEM = 6, /* K1t: one LP per warp, tableau resident in tensor memory (tcgen05.ld/st as a lane-private
                           scratchpad; at most 65 x 65), csrc/tmem_kernel.cuh */
+  YALPS_PATH_GRID_RESIDENT = 7, /* KG: one LP across the whole grid with the tableau resident in the SMs' shared memory
+                                   (up to ~25 MB: 148 x 227 KB), one grid barrier per pivot; the automatic choice for the
+                                   tableaus K4 used to take that fit (csrc/cluster_kernel.cuh, kGrid) */
   /* 4 is retired (a register-resident experiment that never beat K1) and rejected by yalps_set_tuning */
 };
 

@@ -1,4 +1,5 @@
-"""One dense LP through the grid kernel (K4), in place on the device, for profiling and A/B runs:
+"""One dense LP through the grid kernel (K4) or, with YALPS_CASE_PATH=7, the grid-resident kernel (KG), in place on the
+device, for profiling and A/B runs:
     python scripts/k4_case.py [m] [n] [max_pivots] [netlib name]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -23,7 +24,8 @@ work = torch.empty_like(d)
 piv = torch.empty(1, 2, dtype=torch.int64, device="cuda")
 opt = E.make_options(max_pivots=cap)
 stream = torch.cuda.current_stream().cuda_stream
-eng.set_tuning(E.PATH_GRID, 0)
+path = int(os.environ.get('YALPS_CASE_PATH', E.PATH_GRID))
+eng.set_tuning(path, 0)
 for _ in range(3):
     work.copy_(d)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -32,5 +34,5 @@ for _ in range(3):
     e1.record()
     torch.cuda.synchronize()
     p = int(piv.sum().item())
-    print(f"{os.environ.get('YALPS_B200_LIB', 'lib')[-12:]} {H}x{W}: {p} pivots, {e0.elapsed_time(e1) * 1e3 / max(p, 1):.2f} us/pivot")
+    print(f"{os.environ.get('YALPS_B200_LIB', 'lib')[-12:]} path {path} {H}x{W}: {p} pivots, {e0.elapsed_time(e1) * 1e3 / max(p, 1):.2f} us/pivot")
 eng.close()

@@ -130,7 +130,7 @@ def mid_trajectory_states(n, m, nv, neg, first, k):
 @pytest.mark.parametrize("path,m,nv,neg,n", [(E.PATH_TMEM, 32, 64, 6, 200), (E.PATH_TMEM, 50, 40, 10, 64),
                                              (E.PATH_SMEM, 32, 64, 6, 96), (E.PATH_SMEM, 90, 120, 20, 24),
                                              (E.PATH_GMEM, 60, 80, 9, 40), (E.PATH_CLUSTER, 200, 260, 30, 3),
-                                             (E.PATH_GRID, 70, 300, 10, 2), (E.PATH_AUTO, 20, 30, 5, 5),
+                                             (E.PATH_GRID, 70, 300, 10, 2), (E.PATH_GRID_RESIDENT, 70, 300, 10, 2), (E.PATH_AUTO, 20, 30, 5, 5),
                                              (E.PATH_AUTO, 32, 64, 8, 1000)])
 def test_caller_supplied_basis_on_every_kernel_path(engine, path, m, nv, neg, n):
     H, W = m + 1, nv + 1

@@ -400,6 +400,55 @@ def test_grid_kernel_check_cycles_and_budget(engine):
         engine.set_tuning(E.PATH_AUTO, 0)
 
 
+# ---------------------------------------------------------------------- KG: grid-wide, resident in shared memory
+@pytest.mark.parametrize("m,nv,neg", [(32, 64, 6), (5, 3, 2), (100, 300, 40), (300, 90, 100), (1, 1, 0), (700, 1500, 90)])
+def test_grid_resident_kernel_bit_exact(engine, m, nv, neg):
+    """One LP across the whole grid with its rows resident in the SMs' shared memory (one grid barrier per pivot),
+    forced on small inputs so the oracle is quick; 4 LPs run one after the other inside the one launch."""
+    n = 4 if m < 500 else 1
+    mats = O.generate_synthetic(4000, n, m, nv, neg)
+    exp = oracle_batch(mats, m + 1, nv + 1)
+    engine.set_tuning(E.PATH_GRID_RESIDENT, 0)
+    try:
+        got = engine.solve_batch(mats, m + 1, nv + 1, want_matrices=True)
+    finally:
+        engine.set_tuning(E.PATH_AUTO, 0)
+    assert_batch_equal(got, exp, f"grid-resident {m}x{nv}")
+
+
+def test_grid_resident_kernel_check_cycles_and_budget(engine):
+    t = np.array([[0, 10, -57, -9, -24], [0, 0.5, -5.5, -2.5, 9], [0, 0.5, -1.5, -0.5, 1], [1, 1, 0, 0, 0]], float)
+    engine.set_tuning(E.PATH_GRID_RESIDENT, 0)
+    try:
+        for kw in ({"check_cycles": True}, {"check_cycles": False, "max_pivots": 9}, {"max_pivots": 0}):
+            m = t.reshape(1, -1).copy()
+            exp = oracle_batch(m, 4, 5, **kw)
+            got = engine.solve_batch(m, 4, 5, E.make_options(**kw), want_matrices=True)
+            assert_batch_equal(got, exp, f"grid-resident {kw}")
+    finally:
+        engine.set_tuning(E.PATH_AUTO, 0)
+
+
+def test_grid_resident_is_the_automatic_choice_beyond_a_cluster(engine):
+    """1025 x 2049 (16.8 MB) no longer fits a 16-CTA cluster: the automatic path must give the K4 bits (and, by
+    test_config5_full_size_capped_pivots_against_oracle, the oracle's) while launching exactly one kernel."""
+    import torch
+    m, nv, cap = 1024, 2048, 25
+    H, W = m + 1, nv + 1
+    d = torch.empty(H * W, dtype=torch.float64, device="cuda")
+    engine.generate_synthetic_device(0, 1, m, nv, d.data_ptr())
+    torch.cuda.synchronize()
+    mats = d.cpu().numpy().reshape(1, -1)
+    opt = E.make_options(max_pivots=cap)
+    auto = engine.solve_batch(mats, H, W, opt, want_matrices=True)
+    engine.set_tuning(E.PATH_GRID, 0)
+    try:
+        k4 = engine.solve_batch(mats, H, W, opt, want_matrices=True)
+    finally:
+        engine.set_tuning(E.PATH_AUTO, 0)
+    assert_batch_equal(auto, k4, "KG vs K4")
+
+
 def test_large_dense_lp_takes_the_grid_path(engine):
     """A tableau beyond shared memory with n = 1 (config 5 in miniature): auto path == K4."""
     m, nv = 400, 900

@@ -18,6 +18,13 @@
 //   * the pivot row is normalised redundantly in registers by every thread that needs its cells (one shared
 //     reciprocal, fastdiv.cuh); the owner writes the normalised row back into its shared memory.
 // Per pivot: one cluster barrier and four CTA barriers, against two full grid barriers for K4.
+//
+// KG (kGrid = true): the same kernel with the "cluster" widened to the WHOLE GRID of a cooperative launch -- up to one
+// CTA per SM, the tableau resident in their 148 x 227 KB of shared memory (tableaus up to ~25 MB: 1025 x 2049,
+// Netlib 25FV47), so the rank-1 update never leaves the SMs.  The cluster barrier becomes a grid barrier (one per
+// pivot, release/acquire on an L2 counter) and the 16-byte selection records travel through an L2 slot array instead
+// of DSMEM; candidate rows go through the L2 scratch exactly as in KC.  K4 pays two grid barriers, two dependent L2
+// trips and an L2-bound update per pivot for such tableaus.
 #pragma once
 
 #include <cooperative_groups.h>
@@ -29,6 +36,7 @@ namespace yalps {
 namespace cg = cooperative_groups;
 
 constexpr int kMaxCluster = 16;
+constexpr int kGiveUp = -2;  // grid_select: a record never arrived
 
 struct ClusterSmem {
   size_t off_A, off_obj, off_prow, off_cc, off_list, off_cnt, off_misc, off_red, off_xch, off_var, total;
@@ -173,15 +181,152 @@ __device__ __forceinline__ int cluster_select(cg::cluster_group &cluster, int C,
   return row;
 }
 
-template <int NWC, int KC, int NWR>
+// Grid-wide barrier of a cooperative launch: one release reduction and an acquire spin by thread 0 between two CTA
+// barriers (the CTA barrier makes the other threads' writes part of what the release publishes).
+__device__ __forceinline__ void grid_sync_lean(unsigned long long *counter, unsigned long long &epoch) {
+  __syncthreads();
+  epoch++;
+  if (threadIdx.x == 0) {
+    const unsigned long long goal = epoch * gridDim.x;
+    asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(counter) : "memory");
+    unsigned long long seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(counter) : "memory");
+    } while (seen < goal);
+  }
+  __syncthreads();
+}
+
+// cluster_select for the grid-wide kernel, WITHOUT a barrier: a selection record is one 16-byte slot
+//   A = key[63:16] << 16 | seq,   B = key[15:0] << 48 | idx << 16 | seq
+// whose 8-byte halves each carry the 16-bit sequence number of the exchange (flag in data, as NCCL's LL protocol: a half
+// is valid the moment its sequence matches), written by thread 0 after a fence that orders the CTA's published
+// candidate row before it.  Warp 0 of every CTA polls all C slots (lane j takes j, j + 32, ...), picks the winner
+// (best key, lowest index on ties, as warp_best), fences and hands the row index to the CTA; the winner's row is then
+// staged from the L2 scratch.  Slots and scratch are double-buffered by exchange parity: a CTA can only be one exchange
+// ahead of the slowest one, because it needs that CTA's next record, which is written after that CTA has finished
+// reading the current buffers.  (First version: counter barrier + sequential record reads, 10,000 cycles per
+// selection on 25FV47; see profiles/.)
+template <bool kMax, int NW>
+__device__ __forceinline__ int grid_select(int C, int rank, unsigned long long key, int idx, unsigned *red, int &parity,
+                                           uint4 *gslots, unsigned &xcount, const double *A, int ldA, double *scratch,
+                                           double *prow_s, int *s_row, long long *yt = nullptr, long long *yt_last = nullptr) {
+  constexpr int NT = NW * 32;
+  // (timing builds: yt[6] = candidate row published + records pushed (warp 0), yt[7] += winner's row staged; the wait in between
+  // lands in the caller's selection slot)
+#define GS_MARK(k) do { if (yt) { const long long now_ = clock64(); yt[k] += now_ - *yt_last; *yt_last = now_; } } while (0)
+  constexpr int kMaxPerLane = 5;  // C <= 160
+  const Best w = block_best_full<kMax, NW>(key, idx, red, parity);
+  xcount++;
+  const int xpar = (int)(xcount & 1u);
+  const unsigned long long seq = (unsigned long long)(xcount % 65535u) + 1ULL;  // never 0 (the cleared state)
+  // inbox[xpar][receiver][sender]: every CTA polls lines nobody else polls (a first version had all CTAs poll one
+  // shared array of C records: 148 x 148 reads of the same 19 lines per round, 6,000 cycles of waiting per selection)
+  ulonglong2 *inbox = reinterpret_cast<ulonglong2 *>(gslots) + (size_t)xpar * C * C;
+  ulonglong2 *slots = inbox + (size_t)rank * C;
+  double *pub = scratch + (size_t)xpar * C * ldA;
+  if (w.idx != kNone) {
+    const double2 *src = reinterpret_cast<const double2 *>(A + (size_t)((w.idx - 1) / C) * ldA);
+    double2 *dst = reinterpret_cast<double2 *>(pub + (size_t)rank * ldA);
+    for (int c = threadIdx.x; c < ldA / 2; c += NT) __stcg(dst + c, src[c]);
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    {
+      const unsigned long long k = ((unsigned long long)w.hi << 32) | w.lo;
+      const unsigned long long ra = (k & ~0xffffULL) | seq;
+      const unsigned long long rb = ((k & 0xffffULL) << 48) | ((unsigned long long)(unsigned)w.idx << 16) | seq;
+      __threadfence();  // the candidate row (all threads' stores, ordered by the CTA barrier) before the records
+#pragma unroll
+      for (int u = 0; u < kMaxPerLane; u++)
+        if (lane + 32 * u < C)
+          asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(inbox + (size_t)(lane + 32 * u) * C + rank), "l"(ra), "l"(rb)
+                       : "memory");
+    }
+    GS_MARK(6);
+    const unsigned long long nk = no_key<kMax>();
+    unsigned long long bk = nk;
+    int bi = kNone;
+    unsigned pending = 0, spins = 0;
+#pragma unroll
+    for (int u = 0; u < kMaxPerLane; u++)
+      if (lane + 32 * u < C) pending |= 1u << u;
+    while (pending) {
+      if (++spins > (1u << 22)) {  // seconds: a CTA of the grid is gone (cannot happen in a cooperative launch)
+        bi = kGiveUp;
+        break;
+      }
+      unsigned long long ra[kMaxPerLane], rb[kMaxPerLane];
+#pragma unroll
+      for (int u = 0; u < kMaxPerLane; u++)
+        if ((pending >> u) & 1u)
+          asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(ra[u]), "=l"(rb[u]) : "l"(slots + lane + 32 * u) : "memory");
+#pragma unroll
+      for (int u = 0; u < kMaxPerLane; u++)
+        if (((pending >> u) & 1u) && (ra[u] & 0xffffULL) == seq && (rb[u] & 0xffffULL) == seq) {
+          pending &= ~(1u << u);
+          const unsigned long long k = (ra[u] & ~0xffffULL) | (rb[u] >> 48);
+          const int i = (int)(unsigned)(rb[u] >> 16);
+          if (i != kNone && (bi == kNone || (kMax ? k > bk : k < bk) || (k == bk && i < bi))) {
+            bk = k;
+            bi = i;
+          }
+        }
+    }
+    const bool gave_up = __any_sync(0xffffffffu, bi == kGiveUp);
+    if (bi == kNone || gave_up) bk = nk;
+    const int row = gave_up ? kGiveUp : warp_best<kMax>((unsigned)(bk >> 32), (unsigned)bk, gave_up ? kNone : bi).idx;
+    __threadfence();  // the winner's published row is visible to whoever reads it after the CTA barrier below
+    if (lane == 0) *s_row = row;
+  }
+  __syncthreads();
+  const int row = *s_row;
+  if (yt) {  // the wait belongs to the caller's slot: restart the clock for the staging part
+    const long long now_ = clock64();
+    yt[8] += now_ - *yt_last;
+    *yt_last = now_;
+  }
+  if (row != kNone && row != kGiveUp) {
+    const int owner = (row - 1) % C;
+    const double2 *src = reinterpret_cast<const double2 *>(pub + (size_t)owner * ldA);
+    double2 *dst = reinterpret_cast<double2 *>(prow_s);
+    const int n2 = ldA / 2;
+    for (int c0 = 0; c0 < n2; c0 += 4 * NT) {  // four 16-byte loads in flight per thread
+      double2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (c0 + u * NT + (int)threadIdx.x < n2) v[u] = __ldcg(src + c0 + u * NT + threadIdx.x);
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (c0 + u * NT + (int)threadIdx.x < n2) dst[c0 + u * NT + threadIdx.x] = v[u];
+    }
+    __syncthreads();
+  }
+  GS_MARK(7);
+#undef GS_MARK
+  return row;
+}
+
+template <int NWC, int KC, int NWR, bool kGrid = false>
 __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_simplex_cluster(const BatchArgs a) {
   constexpr int NTC = NWC * 32, NW = NWC * NWR, NT = NW * 32, VW = 2;
   constexpr int RU = KC >= 4 ? 1 : 4 / KC;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cg::cluster_group cluster = cg::this_cluster();
-  const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int C = kGrid ? (int)gridDim.x : (int)cluster.num_blocks();
+  const int rank = kGrid ? (int)blockIdx.x : (int)cluster.block_rank();
   const int tid = threadIdx.x, lane = tid & 31, ctid = tid % NTC, rg = tid / NTC;
-  const long long cid = blockIdx.x / C, ncl = gridDim.x / C;
+  const long long cid = kGrid ? 0 : blockIdx.x / C, ncl = kGrid ? 1 : gridDim.x / C;  // KG: the LPs one after the other
+  unsigned long long epoch = 0;
+  unsigned xcount = 0;  // KG: selections so far in this launch (sequence numbers of the record slots)
+  __shared__ int s_row;
+  auto scope_sync = [&]() {
+    if (kGrid)
+      grid_sync_lean(a.counter, epoch);
+    else
+      cluster.sync();
+  };
   const double INF = d_inf();
 
   for (long long lp0 = cid; lp0 < a.n; lp0 += ncl) {
@@ -235,10 +380,10 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_simplex_cluster(const Batc
     }
     __shared__ __align__(8) unsigned long long s_mbar;
     unsigned mphase = 0;
-    const int tma_mode = a.tma_mode;
+    const int tma_mode = kGrid ? 0 : a.tma_mode;
     if (tma_mode && tid == 0) mbar_init(&s_mbar, 1);
     __syncthreads();
-    cluster.sync();
+    scope_sync();
 
     LpResult res;
     res.status = ST_CYCLED;
@@ -254,8 +399,10 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_simplex_cluster(const Batc
 #ifdef YALPS_TIMING
     long long yt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, yt_last = clock64();
 #define CT_MARK(k) do { const long long now_ = clock64(); yt[k] += now_ - yt_last; yt_last = now_; } while (0)
+#define GS_TIMING_ARGS , yt, &yt_last
 #else
 #define CT_MARK(k)
+#define GS_TIMING_ARGS
 #endif
     for (;;) {
       if (iter >= budget) break;  // per-phase budget exhausted -> "cycled" (:102,:141)
@@ -271,9 +418,17 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_simplex_cluster(const Batc
             bi = 1 + rank + l * C;
           }
         }
-        row = cluster_select<false, NW>(cluster, C, rank, bi == kNone ? no_key<false>() : order_key(bv), bi, red, parity, xch, xpar,
-                                        A, ldA, scratch, prow_s, tma_mode, &s_mbar, &mphase);
+        if (kGrid)
+          row = grid_select<false, NW>(C, rank, bi == kNone ? no_key<false>() : order_key(bv), bi, red, parity, a.gx_slots, xcount,
+                                       A, ldA, scratch, prow_s, &s_row GS_TIMING_ARGS);
+        else
+          row = cluster_select<false, NW>(cluster, C, rank, bi == kNone ? no_key<false>() : order_key(bv), bi, red, parity, xch,
+                                          xpar, A, ldA, scratch, prow_s, tma_mode, &s_mbar, &mphase);
         CT_MARK(0);
+        if (kGrid && row == kGiveUp) {
+          res.status = ST_ERR_PEER;
+          break;
+        }
         if (row == kNone) {  // feasible: phase 2 with a fresh counter and history (:120, :67-69)
           phase = 2;
           iter = 0;
@@ -357,9 +512,17 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_simplex_cluster(const Batc
             }
           }
         }
-        row = cluster_select<false, NW>(cluster, C, rank, bi == kNone ? no_key<false>() : order_key(bv), bi, red, parity, xch, xpar,
-                                        A, ldA, scratch, prow_s, tma_mode, &s_mbar, &mphase);
+        if (kGrid)
+          row = grid_select<false, NW>(C, rank, bi == kNone ? no_key<false>() : order_key(bv), bi, red, parity, a.gx_slots, xcount,
+                                       A, ldA, scratch, prow_s, &s_row GS_TIMING_ARGS);
+        else
+          row = cluster_select<false, NW>(cluster, C, rank, bi == kNone ? no_key<false>() : order_key(bv), bi, red, parity, xch,
+                                          xpar, A, ldA, scratch, prow_s, tma_mode, &s_mbar, &mphase);
         CT_MARK(1);
+        if (kGrid && row == kGiveUp) {
+          res.status = ST_ERR_PEER;
+          break;
+        }
         if (row == kNone) {
           res.status = ST_UNBOUNDED;
           res.value = (double)col;
@@ -521,7 +684,7 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_simplex_cluster(const Batc
     }
 
     // ---- outputs (every CTA its own rows; CTA 0 the scalars, the objective row and the basis)
-    cluster.sync();
+    scope_sync();
     if (a.rows_out && tid == 0 && res.rows != 0) atomicAdd(a.rows_out + (a.rows_per_lp ? lp : 0), res.rows);
     if (rank == 0) {
       if (tid == 0) {
@@ -544,10 +707,11 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_simplex_cluster(const Batc
       for (int l = tid; l < nloc; l += NT) a.rhs_out[roff + 1 + rank + l * C] = A[(size_t)l * ldA + bslot];
 #ifdef YALPS_TIMING
     __syncthreads();
-    if (a.rhs_out && rank == 0 && (tid == 0 || tid == NT - 1)) {  // debug builds only: overwrite the RHS output (H >= 18)
-      double *o = a.rhs_out + roff + (tid == 0 ? 0 : 9);
+    if (a.rhs_out && rank == 0 && (tid == 0 || tid == NT - 1)) {  // debug builds only: overwrite the RHS output (H >= 20)
+      double *o = a.rhs_out + roff + (tid == 0 ? 0 : 10);
       for (int k = 0; k < 8; k++) o[k] = (double)yt[k];
       o[8] = (double)(res.p1 + res.p2);
+      o[9] = (double)yt[8];  // KG: wait for the selection records
     }
 #endif
     if (a.mat_out) {
@@ -557,7 +721,7 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_simplex_cluster(const Batc
         for (int c = lane; c < W; c += 32) dr[c] = (c == 0) ? sA[bslot] : sA[c - 1];
       }
     }
-    cluster.sync();  // nobody may start overwriting its shared memory while a peer is still in this LP
+    scope_sync();  // nobody may start overwriting its shared memory while a peer is still in this LP
   }
 }
 

@@ -19,6 +19,6 @@ const KernelEntry *kernel_table_base(int *count);
 const KernelEntry *kernel_table_split_a(int *count);
 const KernelEntry *kernel_table_split_b(int *count);
 const KernelEntry *kernel_table_split_c(int *count);
-const KernelEntry *kernel_table_cluster(int *count);  // KC (cluster_kernel.cuh): `resident` only
+const KernelEntry *kernel_table_cluster(int *count);  // cluster_kernel.cuh: `resident` = KC, `global` = KG (grid-resident)
 
 }  // namespace yalps

@@ -58,6 +58,7 @@ struct BatchArgs {
   unsigned long long *counter;
   double *cl_scratch;  // cluster kernel: per cluster 2 * C * ldA doubles (published candidate pivot rows)
   int tma_mode;        // cluster kernel: how the winner's row is staged (0 ld.global.cg, 1 cp.async.bulk, 2 multicast)
+  uint4 *gx_slots;     // grid-resident kernel (KG): [2][gridDim.x][gridDim.x] selection records (inbox per CTA); `counter` is its grid barrier
 };
 
 // Shared-memory carve-up, identical on host and device.

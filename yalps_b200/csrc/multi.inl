@@ -576,8 +576,9 @@ int yalps_multi_solve_many(yalps_multi *m, int64_t n_models, const int32_t *heig
 namespace {
 
 struct LargeRank {
-  double *M = nullptr, *colx = nullptr, *rowx = nullptr, *value = nullptr, *rhs = nullptr;
-  unsigned long long *sync = nullptr;  // [G] column flags, [kMaxRowParts] row flags, barrier, 2 verdict ints
+  double *M = nullptr, *value = nullptr, *rhs = nullptr;
+  uint4 *colx = nullptr, *rowx = nullptr;  // exchange buffers of 16-byte {data, sequence} slots
+  unsigned long long *sync = nullptr;  // grid barrier counter, 2 verdict ints, give-up record
   int *var = nullptr, *pos = nullptr, *status = nullptr, *hist = nullptr;
   long long *piv = nullptr;
   int Hl = 0, grid = 0;
@@ -655,10 +656,11 @@ int yalps_multi_solve_large(yalps_multi *m, int32_t height, int32_t width, const
     int e;
     if ((e = dev_ensure(ctx, "lg_M", std::max<size_t>(1, (size_t)k.Hl) * W * 8, &p))) return e;
     k.M = (double *)p;
-    if ((e = dev_ensure(ctx, "lg_colx", (size_t)2 * G * Hlmax * 8, &p))) return e;
-    k.colx = (double *)p;
-    if ((e = dev_ensure(ctx, "lg_rowx", (size_t)2 * Wpad * 8, &p))) return e;
-    k.rowx = (double *)p;
+    const size_t colx_bytes = (size_t)2 * G * Hlmax * 16, rowx_bytes = (size_t)2 * Wpad * 16;
+    if ((e = dev_ensure(ctx, "lg_colx", colx_bytes, &p))) return e;
+    k.colx = (uint4 *)p;
+    if ((e = dev_ensure(ctx, "lg_rowx", rowx_bytes, &p))) return e;
+    k.rowx = (uint4 *)p;
     if ((e = dev_ensure(ctx, "lg_sync", (size_t)(kMaxGridRanks + kMaxRowParts + 12) * 8, &p))) return e;
     k.sync = (unsigned long long *)p;
     if ((e = dev_ensure(ctx, "lg_var", (size_t)(W + H) * 4, &p))) return e;
@@ -677,6 +679,8 @@ int yalps_multi_solve_large(yalps_multi *m, int32_t height, int32_t width, const
     }
     cudaStream_t st = ctx->streams[0];
     CU(ctx, cudaMemsetAsync(k.sync, 0, (size_t)(kMaxGridRanks + kMaxRowParts + 12) * 8, st));
+    CU(ctx, cudaMemsetAsync(k.colx, 0, colx_bytes, st));  // sequence numbers of an earlier call must not look current
+    CU(ctx, cudaMemsetAsync(k.rowx, 0, rowx_bytes, st));
     if (k.Hl > 0)
       CU(ctx, cudaMemcpy2DAsync(k.M, (size_t)W * 8, matrix + (size_t)r * W, (size_t)G * W * 8, (size_t)W * 8, k.Hl,
                                 cudaMemcpyHostToDevice, st));
@@ -710,8 +714,6 @@ int yalps_multi_solve_large(yalps_multi *m, int32_t height, int32_t width, const
     for (int q = 0; q < G; q++) {
       a.colx[q] = R[q].colx;
       a.rowx[q] = R[q].rowx;
-      a.colflag[q] = R[q].sync;
-      a.rowflag[q] = R[q].sync + kMaxGridRanks;
     }
     a.barrier = k.sync + kMaxGridRanks + kMaxRowParts;
     a.flags = (int *)(k.sync + kMaxGridRanks + kMaxRowParts + 2);

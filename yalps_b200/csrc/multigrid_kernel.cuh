@@ -8,12 +8,16 @@
 //   * every CTA of every rank keeps the private shared-memory copies of the objective row and of the RHS column that
 //     K4 keeps, and makes the pivot choice redundantly from them -- the ranks agree on (row, col) without a
 //     candidate exchange, because they all look at the same bits;
-//   * per pivot two things cross the fabric, both pushed by their owners with plain stores into the receivers'
-//     exchange buffers and published with a system-scope release store of the pivot's sequence number:
+//   * per pivot two things cross the fabric, both pushed by their owners with stores into the receivers' exchange
+//     buffers:
 //       - the pivot column: every rank sends its H/G cells to every rank (an all-gather of H*8 bytes);
 //       - the raw pivot row: its owner sends W*8 bytes to every other rank (a broadcast), in `row_parts` slices
 //         pushed by different CTAs;
-//     receivers spin on flags in their OWN memory (ld.acquire.sys) and read the buffers with ld.global.cg;
+//     every cell travels as ONE 16-byte store {low word, sequence, high word, sequence} (the flag-in-data protocol of
+//     NCCL's LL: each 8-byte half is valid the moment its sequence number matches), so there is no fence and no
+//     separate flag on the way: a cell costs one one-way trip over NVLink; receivers poll the slots in their OWN memory
+//     with volatile 16-byte loads (first version: data, fence.sys, release flag, acquire spin = 8 us per exchange on
+//     two B200s; this one: see profiles/);
 //   * exchange buffers are double-buffered by pivot parity: a rank can only be one exchange ahead of the slowest one
 //     (it needs that rank's share of the next pivot column), so a buffer is never rewritten while someone reads it;
 //   * the update of the local rows and the two local grid barriers per pivot are K4's.
@@ -27,7 +31,6 @@ namespace yalps {
 
 constexpr int kMaxGridRanks = 16;
 constexpr int kMaxRowParts = 8;
-constexpr int ST_ERR_PEER = -5;
 
 struct MultiGridArgs {
   double *M;  // local rows, Hl x W (global row g + G * lr at local row lr), updated in place
@@ -35,10 +38,8 @@ struct MultiGridArgs {
   int G, g;   // ranks, this rank
   int Hl, Hlmax, Wpad;
   int row_parts;
-  double *colx[kMaxGridRanks];              // per rank: [2][G][Hlmax] pivot-column shares, indexed by sender
-  double *rowx[kMaxGridRanks];              // per rank: [2][Wpad] raw pivot row
-  unsigned long long *colflag[kMaxGridRanks];  // per rank: [G] sequence number of the newest share of each sender
-  unsigned long long *rowflag[kMaxGridRanks];  // per rank: [kMaxRowParts] the same for the slices of the pivot row
+  uint4 *colx[kMaxGridRanks];  // per rank: [2][G][Hlmax] slots, pivot-column shares indexed by sender
+  uint4 *rowx[kMaxGridRanks];  // per rank: [2][Wpad] slots, raw pivot row
   int *var;
   int *pos_out;
   double *rhs_out;
@@ -56,22 +57,26 @@ struct MultiGridArgs {
   long long *giveup;     // [8] where the first CTA of this rank that gave up was: wait id, sequence, phase, CTA, row, col
 };
 
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+// One cell of an exchange buffer: {low word, sequence, high word, sequence}; 8-byte halves are written atomically.
+__device__ __forceinline__ void ll_store(uint4 *slot, double v, unsigned seq) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(slot), "r"((unsigned)__double2loint(v)), "r"(seq),
+               "r"((unsigned)__double2hiint(v)), "r"(seq)
+               : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-// one thread: wait until *flag >= goal; false when the budget ran out
-__device__ __forceinline__ bool spin_until(const unsigned long long *flag, unsigned long long goal, long long limit) {
-  if (ld_acquire_sys(flag) >= goal) return true;
-  const long long t0 = clock64();
+// Polls a slot of this rank's own buffer until both halves carry `seq`; false when the cycle budget ran out.
+__device__ __forceinline__ bool ll_load(const uint4 *slot, unsigned seq, double &v, long long limit) {
+  unsigned lo, f1, hi, f2;
+  long long t0 = 0;
   for (;;) {
-    if (ld_acquire_sys(flag) >= goal) return true;
-    if (clock64() - t0 > limit) return false;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f1), "=r"(hi), "=r"(f2) : "l"(slot) : "memory");
+    if (f1 == seq && f2 == seq) break;
+    if (t0 == 0)
+      t0 = clock64();
+    else if (clock64() - t0 > limit)
+      return false;
   }
+  v = __hiloint2double((int)hi, (int)lo);
+  return true;
 }
 
 // K4's grid barrier with a budget; *dead (shared memory) is set when it runs out.  Returns with the CTA synchronised.
@@ -128,25 +133,25 @@ __global__ void __launch_bounds__(kGridThreads, 1) k_simplex_grid_multi(const Mu
   auto gather_column = [&](int c, unsigned long long seq, int par) -> bool {
     if ((int)blockIdx.x < G) {
       const int dst = blockIdx.x;
-      double *out = a.colx[dst] + ((size_t)par * G + g) * Hlmax;
-      for (int lr = tid; lr < Hl; lr += NT) out[lr] = M[(size_t)lr * W + c];
-      __syncthreads();
-      if (tid == 0) {
-        __threadfence_system();
-        st_release_sys(a.colflag[dst] + g, seq);
-      }
+      uint4 *out = a.colx[dst] + ((size_t)par * G + g) * Hlmax;
+      for (int lr = tid; lr < Hl; lr += NT) ll_store(out + lr, M[(size_t)lr * W + c], (unsigned)seq);
     }
-    if (tid < G && !spin_until(a.colflag[g] + tid, seq, limit)) dead = 100 + tid;
-    __syncthreads();
-    if (dead) return false;
-    const double *in = a.colx[g] + (size_t)par * G * Hlmax;
+    const uint4 *in = a.colx[g] + (size_t)par * G * Hlmax;
+    bool ok = true;
     for (int idx = tid; idx < G * Hlmax; idx += NT) {
       const int src = idx / Hlmax, lr = idx - src * Hlmax;
       const int r = lr * G + src;
-      if (r < H) colbuf[r] = __ldcg(in + idx);
+      double v;
+      if (r < H) {
+        if (ok && ll_load(in + idx, (unsigned)seq, v, limit))
+          colbuf[r] = v;
+        else
+          ok = false;
+      }
     }
+    if (!ok) dead = 100;
     __syncthreads();
-    return true;
+    return !dead;
   };
   // the owner's sender CTAs push the raw pivot row to the other ranks
   auto push_row = [&](int lrow, unsigned long long seq, int par) {
@@ -155,18 +160,12 @@ __global__ void __launch_bounds__(kGridThreads, 1) k_simplex_grid_multi(const Mu
       if (dst != g) {
         const int per = (((W + RP - 1) / RP) + 1) & ~1;
         const int c0 = part * per, c1 = min(W, c0 + per);
-        double *out = a.rowx[dst] + (size_t)par * a.Wpad;
+        uint4 *out = a.rowx[dst] + (size_t)par * a.Wpad;
         const double *src = M + (size_t)lrow * W;
-        for (int c = c0 + tid; c < c1; c += NT) out[c] = src[c];
-        __syncthreads();
-        if (tid == 0) {
-          __threadfence_system();
-          st_release_sys(a.rowflag[dst] + part, seq);
-        }
+        for (int c = c0 + tid; c < c1; c += NT) ll_store(out + c, src[c], (unsigned)seq);
       }
     }
   };
-
   // private copies of the objective row (rank 0 owns row 0: a row broadcast) and of the RHS column (a column gather)
   {
     // (sequence number 1 -> parity 1, like every later exchange: buffer = parity of the sequence number)
@@ -174,12 +173,16 @@ __global__ void __launch_bounds__(kGridThreads, 1) k_simplex_grid_multi(const Mu
     if (g == 0) {
       for (int c = tid; c < W; c += NT) row0[c] = M[c];
     } else {
-      if (tid < RP && !spin_until(a.rowflag[g] + tid, 1, limit)) dead = 200 + tid;
-      __syncthreads();
-      if (!dead) {
-        const double *in = a.rowx[g] + a.Wpad;
-        for (int c = tid; c < W; c += NT) row0[c] = __ldcg(in + c);
+      const uint4 *in = a.rowx[g] + a.Wpad;
+      bool ok = true;
+      for (int c = tid; c < W; c += NT) {
+        double v;
+        if (ok && ll_load(in + c, 1u, v, limit))
+          row0[c] = v;
+        else
+          ok = false;
       }
+      if (!ok) dead = 200;
     }
     __syncthreads();
     if (!dead && gather_column(0, 1, 1))
@@ -225,15 +228,20 @@ __global__ void __launch_bounds__(kGridThreads, 1) k_simplex_grid_multi(const Mu
           scan(c, coef);
         }
       } else {
-        if (tid < RP && !spin_until(a.rowflag[g] + tid, s, limit)) dead = 300 + tid;
+        const uint4 *in = a.rowx[g] + (size_t)par * a.Wpad;
+        bool ok = true;
+        for (int c = tid; c < W; c += NT) {
+          double coef;
+          if (ok && ll_load(in + c, (unsigned)s, coef, limit)) {
+            prow[c] = coef;
+            scan(c, coef);
+          } else {
+            ok = false;
+          }
+        }
+        if (!ok) dead = 300;
         __syncthreads();
         if (dead) return false;
-        const double *in = a.rowx[g] + (size_t)par * a.Wpad;
-        for (int c = tid; c < W; c += NT) {
-          const double coef = __ldcg(in + c);
-          prow[c] = coef;
-          scan(c, coef);
-        }
       }
       return true;
     };

@@ -42,6 +42,7 @@ enum : int {
   ST_TIMEDOUT = 3,
   ST_CYCLED = 4,
   ST_ERR_HISTORY = -4,
+  ST_ERR_PEER = -5,  // grid-wide / multi-GPU kernels: a participant of an exchange never showed up (spin budget exhausted)
 };
 
 __device__ __forceinline__ double d_inf() { return __longlong_as_double(0x7ff0000000000000LL); }

@@ -236,7 +236,7 @@ struct LaunchPlan {
 int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycles, LaunchPlan *plan,
                 double density = -1.0, bool allow_tmem = false) {
   // a forced cluster path is resolved by maybe_cluster(); what it cannot take is planned as in automatic mode
-  const int tune_path = ctx->tune_path == YALPS_PATH_CLUSTER ? (int)YALPS_PATH_AUTO : ctx->tune_path;
+  const int tune_path = (ctx->tune_path == YALPS_PATH_CLUSTER || ctx->tune_path == YALPS_PATH_GRID_RESIDENT) ? (int)YALPS_PATH_AUTO : ctx->tune_path;
   SmemLayout Lr(Hcap, Wcap, true, 32), Lg(Hcap, Wcap, false, 32);
   bool resident = Lr.total <= (size_t)ctx->smem_optin;
   // (throughput mode only: with at most two LPs per SM the shared-memory row-split kernels are 3x faster than K2 on
@@ -438,7 +438,7 @@ int plan_cluster(yalps_ctx *ctx, int Hcap, int Wcap, ClusterPlan *plan) {
   const KernelEntry *tab = kernel_table_cluster(&count);
   const KernelEntry *k = nullptr;
   for (int i = 0; i < count && !k; i++)
-    if ((long long)tab[i].nw * 32 * tab[i].kc * 2 >= std::max(Wcap - 1, 1)) k = &tab[i];
+    if (tab[i].resident && (long long)tab[i].nw * 32 * tab[i].kc * 2 >= std::max(Wcap - 1, 1)) k = &tab[i];
   if (!k) return 0;
   for (int C = 2; C <= kMaxCluster; C *= 2) {
     const ClusterSmem L(Hcap, Wcap, C);
@@ -513,6 +513,98 @@ int launch_cluster(yalps_ctx *ctx, const ClusterPlan &plan, BatchArgs &args, con
   return 0;
 }
 
+// ---- KG: the cluster kernel with the whole cooperative grid as its "cluster" (tableau resident in the SMs' shared memory)
+struct GridResPlan {
+  const KernelEntry *k = nullptr;
+  int C = 0;  // CTAs (one per SM at most)
+  size_t smem = 0;
+};
+
+int plan_gridres(yalps_ctx *ctx, int Hcap, int Wcap, GridResPlan *plan) {
+  plan->k = nullptr;
+  int count = 0, coop = 0;
+  const KernelEntry *tab = kernel_table_cluster(&count);
+  const KernelEntry *k = nullptr;
+  // narrowest kernel that covers the width; among those the one with the most threads (YALPS_KG_THREADS caps them)
+  int max_threads = 512;
+  if (const char *env = getenv("YALPS_KG_THREADS")) max_threads = atoi(env);
+  for (int i = 0; i < count; i++) {
+    const long long cap = (long long)tab[i].nw * 32 * tab[i].kc * 2;
+    const int threads = tab[i].nw * tab[i].nwr * 32;
+    if (!tab[i].global || cap < std::max(Wcap - 1, 1) || threads > max_threads) continue;
+    const long long kcap = k ? (long long)k->nw * 32 * k->kc * 2 : 0;
+    if (!k || cap < kcap || (cap == kcap && threads > k->nw * k->nwr * 32)) k = &tab[i];
+  }
+  if (!k) return 0;
+  CU(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
+  if (!coop) return 0;
+  int C = std::max(1, std::min(std::min(ctx->prop.multiProcessorCount, 160), Hcap - 1));  // (grid_select: 5 slots per lane)
+  if (const char *env = getenv("YALPS_KG_CTAS")) C = std::max(1, std::min(C, atoi(env)));
+  const ClusterSmem L(Hcap, Wcap, C);
+  if (L.total > (size_t)ctx->smem_optin) return 0;
+  CU(ctx, raise_smem_limit(ctx->device, (const void *)k->global, (int)L.total));
+  const std::string key = "kg:" + std::to_string((size_t)(void *)k->global) + ":" + std::to_string(L.total);
+  int occ = 0;
+  auto it = ctx->occ_cache.find(key);
+  if (it != ctx->occ_cache.end()) {
+    occ = it->second;
+  } else {
+    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)k->global, k->nw * k->nwr * 32, L.total));
+    ctx->occ_cache[key] = occ;
+  }
+  if ((long long)occ * ctx->prop.multiProcessorCount < C) return 0;
+  plan->k = k;
+  plan->C = C;
+  plan->smem = L.total;
+  return 0;
+}
+
+int launch_gridres(yalps_ctx *ctx, const GridResPlan &plan, BatchArgs &args, const std::string &slot, cudaStream_t stream) {
+  if (!args.rows_out && ctx->d_rows && !ctx->rows_per_lp) args.rows_out = ctx->d_rows;
+  args.hist = nullptr;
+  if (args.check_cycles) {
+    void *hist = nullptr;
+    if (int rc = dev_ensure(ctx, "hist_kg" + slot, (size_t)plan.C * 2 * args.hist_cap * sizeof(int), &hist)) return rc;
+    args.hist = (int *)hist;
+  }
+  void *p = nullptr;
+  const size_t ldA = (size_t)SmemLayout::ld_for(args.Wcap);
+  if (int rc = dev_ensure(ctx, "kg_scratch" + slot, (size_t)2 * plan.C * ldA * sizeof(double), &p)) return rc;
+  args.cl_scratch = (double *)p;
+  const size_t inbox_bytes = (size_t)2 * plan.C * plan.C * sizeof(uint4);  // [2][receiver][sender] selection records
+  if (int rc = dev_ensure(ctx, "kg_slots" + slot, inbox_bytes + 64, &p)) return rc;
+  args.gx_slots = (uint4 *)p;
+  args.counter = (unsigned long long *)((char *)p + inbox_bytes);
+  // slots: sequence numbers of an earlier launch must not look current; counter: the grid barrier's arrival count
+  CU(ctx, cudaMemsetAsync(p, 0, inbox_bytes + 64, stream));
+  args.tma_mode = 0;
+  void *params[] = {&args};
+  CU(ctx, cudaLaunchCooperativeKernel((const void *)plan.k->global, dim3((unsigned)plan.C),
+                                      dim3((unsigned)(plan.k->nw * plan.k->nwr * 32)), params, plan.smem, stream));
+  ctx->launches++;
+  return 0;
+}
+
+// The batches K4 would take (few LPs beyond one SM's -- and one cluster's -- shared memory) go to KG when the tableau
+// fits the shared memory of the whole grid.  1: launched, 0: not applicable, < 0: error.
+int maybe_gridres(yalps_ctx *ctx, long long n, int Hcap, int Wcap, const LaunchPlan *plan, BatchArgs &a, const std::string &slot,
+                  cudaStream_t stream) {
+  const bool forced = ctx->tune_path == YALPS_PATH_GRID_RESIDENT;
+  if (!forced) {
+    if (!plan || ctx->tune_path != YALPS_PATH_AUTO || !use_grid_path(ctx, n, *plan)) return 0;
+    if (getenv("YALPS_NO_KG")) return 0;
+  }
+  GridResPlan gp;
+  if (int rc = plan_gridres(ctx, Hcap, Wcap, &gp)) return rc;
+  if (!gp.k) {
+    if (forced)
+      return fail(ctx, YALPS_ERR_TOO_LARGE, "tableau %dx%d does not fit the shared memory of the grid (or is wider than 2049)", Hcap, Wcap);
+    return 0;
+  }
+  if (int rc = launch_gridres(ctx, gp, a, slot, stream)) return rc;
+  return 1;
+}
+
 // Few LPs that do not fit one SM's shared memory: KC when they fit a cluster's (tune_path AUTO or CLUSTER).
 bool want_cluster(const yalps_ctx *ctx, long long n, const LaunchPlan &plan, const ClusterPlan &cp) {
   if (!cp.k) return false;
@@ -526,6 +618,7 @@ bool want_cluster(const yalps_ctx *ctx, long long n, const LaunchPlan &plan, con
 int maybe_cluster(yalps_ctx *ctx, long long n, int Hcap, int Wcap, const LaunchPlan *plan, BatchArgs &a,
                   const std::string &slot, cudaStream_t stream) {
   const bool forced = ctx->tune_path == YALPS_PATH_CLUSTER;
+  if (ctx->tune_path == YALPS_PATH_GRID_RESIDENT) return plan ? 0 : maybe_gridres(ctx, n, Hcap, Wcap, nullptr, a, slot, stream);
   if (!plan && !forced) return 0;
   if (plan && (forced || ctx->tune_path != YALPS_PATH_AUTO || plan->resident || plan->tmem)) return 0;
   ClusterPlan cp;
@@ -534,7 +627,7 @@ int maybe_cluster(yalps_ctx *ctx, long long n, int Hcap, int Wcap, const LaunchP
     if (!cp.k)
       return fail(ctx, YALPS_ERR_TOO_LARGE, "tableau %dx%d does not fit the shared memory of a %d-CTA cluster", Hcap, Wcap, kMaxCluster);
   } else if (!want_cluster(ctx, n, *plan, cp)) {
-    return 0;
+    return maybe_gridres(ctx, n, Hcap, Wcap, plan, a, slot, stream);  // beyond a cluster: the whole grid's shared memory (KG)
   }
   if (int rc = launch_cluster(ctx, cp, a, slot, stream)) return rc;
   return 1;
@@ -554,6 +647,8 @@ int check_device_status(yalps_ctx *ctx, const int32_t *status, long long n) {
   for (long long i = 0; i < n; i++)
     if (status[i] == ST_ERR_HISTORY)
       return fail(ctx, YALPS_ERR_HISTORY, "checkCycles history exhausted for LP %lld (more than 262144 pivots in a phase)", i);
+    else if (status[i] == ST_ERR_PEER)
+      return fail(ctx, YALPS_ERR_CUDA, "LP %lld: an in-kernel exchange between the CTAs of the grid timed out", i);
   return 0;
 }
 
@@ -635,7 +730,7 @@ int yalps_device_info(const yalps_ctx *ctx, int32_t *sm_count, int32_t *smem_per
 
 int yalps_set_tuning(yalps_ctx *ctx, int32_t path, int32_t threads_per_lp) {
   if (!ctx) return YALPS_ERR_ARGUMENT;
-  if (path < 0 || path > YALPS_PATH_TMEM || path == 4) return fail(ctx, YALPS_ERR_ARGUMENT, "bad path %d", path);
+  if (path < 0 || path > YALPS_PATH_GRID_RESIDENT || path == 4) return fail(ctx, YALPS_ERR_ARGUMENT, "bad path %d", path);
   ctx->tune_path = path;
   ctx->tune_threads = threads_per_lp;
   return 0;
@@ -906,7 +1001,7 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
       for (long long k = 0; k < c0; k += step, seen++) nz += m0[k] != 0.0;
       small_density = seen ? (double)nz / (double)seen : 1.0;
     }
-    if (!ctx->keep_final && in_b + out_b + desc_b <= ((size_t)768 << 10) && ctx->tune_path != YALPS_PATH_GRID && ctx->tune_path != YALPS_PATH_CLUSTER &&
+    if (!ctx->keep_final && in_b + out_b + desc_b <= ((size_t)768 << 10) && ctx->tune_path != YALPS_PATH_GRID && ctx->tune_path != YALPS_PATH_CLUSTER && ctx->tune_path != YALPS_PATH_GRID_RESIDENT &&
         plan_launch(ctx, n, Hcap, Wcap, opt->check_cycles != 0, &plan, small_density, true) == 0 && (plan.k || plan.tmem) && plan.resident) {
       auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
       size_t o = 0;

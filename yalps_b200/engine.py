@@ -17,7 +17,7 @@ from ._ffi import Options, YalpsError
 
 STATUS_NAMES = ("optimal", "infeasible", "unbounded", "timedout", "cycled")  # enum yalps_status
 
-PATH_AUTO, PATH_SMEM, PATH_GMEM, PATH_GRID, PATH_CLUSTER, PATH_TMEM = 0, 1, 2, 3, 5, 6
+PATH_AUTO, PATH_SMEM, PATH_GMEM, PATH_GRID, PATH_CLUSTER, PATH_TMEM, PATH_GRID_RESIDENT = 0, 1, 2, 3, 5, 6, 7
 
 
 def _ptr(a: Optional[np.ndarray]):
