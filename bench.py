@@ -374,7 +374,26 @@ def run_native(args):
         }
         if world == 1 and args.workload == "config2" and not args.no_secondary:
             line["secondary"] = BW.run_all(torch, eng, hbm_peak, cores)
+        if world > 1 and args.workload == "config2" and not args.no_secondary:
+            # strong scaling of ONE large LP over the N GPUs, driven by this process alone (the other ranks wait on the
+            # host, their GPUs idle: a NCCL barrier kernel would sit on the SMs the cooperative kernels need)
+            try:
+                del d_in, d_rhs, d_pos, d_var
+                torch.cuda.empty_cache()
+                line["multi_gpu_large_lp"] = BW.config5_multi(torch, eng, list(range(world)))
+            except Exception as e:  # the headline must survive a failure of the extra measurement
+                line["multi_gpu_large_lp"] = {"error": f"{type(e).__name__}: {e}"}
         emit_line(line)
+    if world > 1 and args.workload == "config2" and not args.no_secondary:
+        from datetime import timedelta
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            store.set("yalps_large_lp_done", "1")
+        else:
+            try:
+                store.wait(["yalps_large_lp_done"], timedelta(seconds=300))
+            except Exception:
+                pass
     eng.close()
     if dist is not None:
         dist.destroy_process_group()

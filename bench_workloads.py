@@ -136,6 +136,19 @@ def config3(torch, eng, name, n, hbm_peak, cpu_cores, l2_peak):
     for _ in range(reps):
         eng.solve_replicas(g["matrix"], h_rhs, H, W, opt, out=out)
     e2e_s = (time.perf_counter() - t0) / reps
+    forks = eng.replica_forks
+    shared_bits = (out["pivots"].copy(), out["rhs"].copy(), out["pos"].copy())
+    # the same call with path sharing off: every replica expanded to its own working copy and solved from scratch
+    eng.set_replica_sharing(False)
+    try:
+        eng.solve_replicas(g["matrix"], h_rhs, H, W, opt, out=out)
+        t0 = time.perf_counter()
+        eng.solve_replicas(g["matrix"], h_rhs, H, W, opt, out=out)
+        e2e_plain_s = time.perf_counter() - t0
+    finally:
+        eng.set_replica_sharing(True)
+    sharing_same = bool(np.array_equal(shared_bits[0], out["pivots"]) and np.array_equal(shared_bits[2], out["pos"]) and
+                        np.array_equal(shared_bits[1].view(np.uint64), out["rhs"].view(np.uint64)))
 
     # CPU port on a bounded sample, all cores
     cn = min(n, 64 * cpu_cores)
@@ -167,7 +180,14 @@ def config3(torch, eng, name, n, hbm_peak, cpu_cores, l2_peak):
         "e2e": {"api": "yalps_solve_replicas (base tableau once + n*H right-hand sides from pinned host memory; "
                        "status/value/pivots/RHS/basis back)", "ms": e2e_s * 1e3, "lps_per_s": n / e2e_s,
                 "pivots_per_s": pivots / e2e_s, "h2d_bytes_per_step": cells * 8 + n * H * 8,
-                "d2h_bytes_per_step": n * (4 + 8 + 16 + H * 8 + 2 * (W + H) * 4)},
+                "d2h_bytes_per_step": n * (4 + 8 + 16 + H * 8 + 2 * (W + H) * 4),
+                "path_sharing": {"replicas_that_left_the_shared_path": forks, "of": n,
+                                 "ms_without_sharing": e2e_plain_s * 1e3, "speedup": e2e_plain_s / e2e_s,
+                                 "bit_identical_to_without": sharing_same,
+                                 "note": "the replicas follow the recorded pivot trace of the base tableau with their RHS "
+                                         "column only and continue alone from the leader's snapshot where they would choose "
+                                         "differently (include/yalps_b200.h: yalps_set_replica_sharing); `ms` above is WITH "
+                                         "sharing, the kernel-only line of this workload is the plain HBM-resident batch"}},
         "cpu_baseline": {"value": int(ref["pivots"].sum()) / cpu_dt, "unit": "pivots/s", "lps_per_s": cn / cpu_dt,
                          "cores": cpu_cores, "kind": "port", "sample": f"the first {cn} replicas, {cpu_dt:.2f} s",
                          "bit_identical_to_gpu": same},
@@ -218,13 +238,16 @@ def config4(torch, eng, hbm_peak):
 
 
 def config5(torch, eng, hbm_peak, l2_peak):
-    """One large dense LP on the whole GPU (K4): the 4097x8193 synthetic tableau (268.5 MB > L2) for a capped number of
-    pivots, and Netlib 25FV47 (1338x1572, L2-resident) to the end."""
+    """One large LP on the whole GPU: the 4097x8193 synthetic tableau (268.5 MB > L2: K4, rows in HBM) for a capped
+    number of pivots; the 1025x2049 one (16.8 MB) and Netlib 25FV47 (1338x1572, to the end) on KG, the grid-resident
+    kernel that keeps the rows in the SMs' shared memory."""
     from yalps_b200.engine import make_options
     from oracle import lib as O
     out = []
     stream = torch.cuda.current_stream().cuda_stream
-    cases = [("synthetic 4096x8192", None, 4096, 8192, 48.0), ("Netlib 25FV47", "25FV47", 0, 0, math.inf)]
+    cases = [("synthetic 4096x8192", None, 4096, 8192, 48.0), ("synthetic 1024x2048", None, 1024, 2048, 200.0),
+             ("Netlib 25FV47", "25FV47", 0, 0, math.inf)]
+    smem_peak = eng.measure_smem_bandwidth()[0]
     for label, netlib, m, nv, cap in cases:
         if netlib:
             g = netlib_base(netlib)
@@ -253,7 +276,10 @@ def config5(torch, eng, hbm_peak, l2_peak):
         ms = _events(torch, step, reps=2, warm=0) - copy_ms
         p = int(piv.sum().item())
         alg = pivot_bytes(H, W, p, rows)
+        resident = H * W * 8 < 24e6 and W <= 2049  # what plan_gridres (csrc/yalps_b200.cu) accepts: KG instead of K4
         entry = {
+            "kernel": "k_simplex_cluster<..., kGrid> (KG: rows resident in the shared memory of all SMs, one all-to-all of "
+                      "selection records per pivot)" if resident else "k_simplex_grid (K4: rows in HBM/L2, two grid barriers per pivot)",
             "workload": f"config5: one LP on the whole GPU, {label} (tableau {H}x{W}, {H * W * 8 / 1e6:.1f} MB, "
                         f"{'larger than' if H * W * 8 > 126e6 else 'resident in'} L2), BASELINE.json configs[4]"
                         + (f"; first {int(cap)} pivots per phase" if math.isfinite(cap) else "; full solve"),
@@ -261,17 +287,21 @@ def config5(torch, eng, hbm_peak, l2_peak):
             "status": int(st.item()), "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak,
-                         "traffic": ncu_traffic("r02_k4_ncu_summary.json") if not netlib else None,
+                         "traffic": ncu_traffic("r02_k4_ncu_summary.json") if not resident else
+                         (ncu_traffic("r02_kg_ncu_summary.json") if not netlib else None),
                          "rows_rewritten": rows, "mean_rows_per_pivot": rows / max(p, 1), "rows_dense": H - 1,
-                         "note": None if not netlib else "L2-resident and sparse: bound by the grid barriers of a pivot, "
-                                                         "not by bandwidth",
-                         "l2": None if not netlib else {"achieved": alg / (ms * 1e-3) / 1e9, "peak": l2_peak,
-                                                        "frac": alg / (ms * 1e-3) / 1e9 / l2_peak}},
+                         "note": None if not resident else "rows never leave shared memory: bound by the latency of one all-to-all "
+                                                           "of selection records through L2 per pivot, not by bandwidth; "
+                                                           "the smem view is the medium's own roofline",
+                         "smem": None if not resident else {"achieved": alg / (ms * 1e-3) / 1e9, "peak": smem_peak,
+                                                            "frac": alg / (ms * 1e-3) / 1e9 / smem_peak},
+                         "l2": None if not resident else {"achieved": alg / (ms * 1e-3) / 1e9, "peak": l2_peak,
+                                                          "frac": alg / (ms * 1e-3) / 1e9 / l2_peak}},
         }
         if netlib:  # the reference's own outcome on this model: infeasible after 3110 phase-1 pivots
             entry["matches_oracle_golden"] = bool(int(st.item()) == g["status"] and
                                                   tuple(int(x) for x in piv[0].tolist()) == g["pivots"])
-        else:
+        elif not resident:
             k = 6  # CPU port: the first k pivots of the same tableau, one thread (a pivot is a sequential rank-1 update)
             host = d.cpu().numpy().copy()
             posv = np.arange(W + H, dtype=np.int32)
@@ -295,3 +325,54 @@ def run_all(torch, eng, hbm_peak, cpu_cores):
     out.extend(config4(torch, eng, hbm_peak))
     out.extend(config5(torch, eng, hbm_peak, l2_peak))
     return out
+
+
+def config5_multi(torch, eng, devices, m=4096, nv=8192, cap=48.0):
+    """the config-5 tableau with its rows dealt over several GPUs (yalps_multi_solve_large, K4m), driven
+    by ONE process; device time of the slowest rank's kernel, against K4 on one GPU on the same tableau, bit for bit."""
+    import yalps_b200
+    from yalps_b200.engine import make_options
+    H, W = m + 1, nv + 1
+    stream = torch.cuda.current_stream().cuda_stream
+    d = torch.empty(H * W, dtype=torch.float64, device="cuda")
+    eng.generate_synthetic_device(0, 1, m, nv, d.data_ptr(), stream=stream)
+    torch.cuda.synchronize()
+    mats = d.cpu().numpy().reshape(1, -1)
+    opt = make_options(max_pivots=cap)
+    work = torch.empty_like(d)
+    piv = torch.empty(1, 2, dtype=torch.int64, device="cuda")
+
+    def one_gpu():
+        eng.solve_batch_device(1, H, W, work.data_ptr(), opt, d_work=work.data_ptr(), d_pivots=piv.data_ptr(), stream=stream)
+
+    best1 = None
+    for _ in range(3):
+        work.copy_(d)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        one_gpu()
+        e1.record()
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1)
+        best1 = t if best1 is None else min(best1, t)
+    p = int(piv.sum().item())
+    ref_bits = work.cpu().numpy().view(np.uint64)
+    del d
+    with yalps_b200.MultiEngine(devices) as me:
+        ms = None
+        launches0 = me.launch_count
+        for _ in range(3):
+            got = me.solve_large(mats, H, W, opt, want_matrix=True)
+            ms = got["kernel_ms"] if ms is None else min(ms, got["kernel_ms"])
+        launches = (me.launch_count - launches0) // 3
+    same = bool(np.array_equal(got["matrix"].view(np.uint64), ref_bits) and sum(got["pivots"]) == p)
+    return {
+        "workload": f"config5 over {len(devices)} GPUs (SURVEY 8f-3): one LP, synthetic {m}x{nv} (tableau {H}x{W}, "
+                    f"{H * W * 8 / 1e6:.1f} MB), rows dealt round robin over the GPUs, first {int(cap)} pivots; one process, "
+                    f"one persistent kernel per GPU, pivot row / column exchanged by peer-memory stores inside the kernels",
+        "api": "yalps_multi_solve_large", "n_gpus": len(devices), "pivots": p,
+        "ms": ms, "us_per_pivot": ms * 1e3 / max(p, 1), "pivots_per_s": p / ms * 1e3, "gpu_launches": launches,
+        "one_gpu": {"kernel": "K4", "ms": best1, "us_per_pivot": best1 * 1e3 / max(p, 1)},
+        "speedup_vs_one_gpu": best1 / ms, "bit_identical_to_one_gpu": same, "scaling": "strong",
+        "timing": "CUDA events around each rank's kernel, max over ranks, best of 3",
+    }

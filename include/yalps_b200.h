@@ -162,6 +162,18 @@ int yalps_solve_replicas(yalps_ctx *ctx, int64_t n, int32_t height, int32_t widt
                          const double *rhs, const yalps_options *opt, int32_t *status, double *value, int64_t *pivots,
                          double *rhs_out, int32_t *pos_out, int32_t *var_out);
 
+/* Replica path sharing (default on).  The replicas of yalps_solve_replicas differ only in column 0, and a pivot choice
+ * depends on a replica's own data only through that column (most negative RHS in phase 1, ratio test in phase 2): the
+ * base tableau is solved once with a recorded trace, every replica follows it carrying just its RHS column (one warp,
+ * H doubles) while it makes the same choices, and continues alone -- from the leader's tableau of that step with its own
+ * column 0, same phase, same pivot counters -- the moment it would choose differently.  Every output bit is that of
+ * solving the replica on its own (src/simplex.ts:99-142); the coefficient updates of the shared stretch are simply not
+ * repeated.  Not used with checkCycles or a forced kernel path.  yalps_replica_forks: how many replicas of the last
+ * call left the shared path (-1: sharing was not used). */
+int yalps_set_replica_sharing(yalps_ctx *ctx, int32_t on);
+int64_t yalps_replica_forks(const yalps_ctx *ctx);
+
+
 /* Ragged batch: LP i is heights[i] x widths[i] at matrices[mat_offsets[i]];
  * rhs_out is packed by cumulative heights, pos_out/var_out by cumulative (width+height). */
 int yalps_solve_ragged(yalps_ctx *ctx, int64_t n, const int32_t *heights, const int32_t *widths,

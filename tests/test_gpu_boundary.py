@@ -194,6 +194,78 @@ def test_replicas_equal_the_expanded_batch_and_the_oracle(engine, name, n):
     assert same_bits(got["rhs"][:48], exp["rhs"]) and np.array_equal(got["pos"][:48], exp["pos"])
 
 
+def _replica_case(base, H, W, n, eps, seed):
+    rng = np.random.default_rng(seed)
+    rhs = np.tile(base.reshape(H, W)[:, 0], (n, 1)) * (1.0 + eps * (2.0 * rng.random((n, H)) - 1.0))
+    mats = np.tile(base, (n, 1))
+    mats.reshape(n, H, W)[:, :, 0] = rhs
+    return rhs, mats
+
+
+@pytest.mark.parametrize("name,n,eps,kw", [
+    ("SC105", 700, 1e-2, {}), ("ADLITTLE", 500, 1e-2, {}), ("AFIRO", 400, 1e-2, {}),
+    ("SC105", 300, 0.0, {}),                      # every replica IS the leader: nobody leaves the path
+    ("SC105", 300, 0.9, {}),                      # wild right-hand sides: forks from the first steps on
+    ("ADLITTLE", 300, 1e-2, {"max_pivots": 20}),  # the leader ends "cycled" on its budget, in phase 1 or 2
+    ("ADLITTLE", 300, 1e-2, {"max_pivots": 61}),
+    ("SC105", 300, 1e-3, {"precision": 1e-6}),
+    ("KLEIN1", 200, 1e-2, {}),                    # an infeasible leader
+])
+def test_replica_path_sharing_is_bit_exact(engine, name, n, eps, kw):
+    """yalps_solve_replicas with path sharing (the replicas follow the recorded trace of the base tableau with their RHS
+    column only and continue alone from the leader's snapshot where they would choose differently) against the oracle's
+    solve of every replica on its own: every output, bit for bit -- and against the same call with sharing off."""
+    g = load_netlib().get(name)
+    H, W = g["height"], g["width"]
+    base = g["matrix"]
+    rhs, mats = _replica_case(base, H, W, n, eps, 11)
+    opt = E.make_options(**kw)
+    got = engine.solve_replicas(base, rhs, H, W, opt)
+    forks = engine.replica_forks
+    assert forks >= 0, "path sharing was not used"
+    if eps == 0.0:
+        assert forks == 0
+    work = mats.copy()
+    exp = O.simplex_batch(work, W, H, **kw)
+    for k in ("status", "pivots", "pos", "var"):
+        assert np.array_equal(got[k], exp[k]), (name, k, forks)
+    assert same_bits(got["rhs"], exp["rhs"]), (name, forks)
+    nan = np.isnan(exp["value"])
+    assert np.array_equal(np.isnan(got["value"]), nan) and same_bits(got["value"][~nan], exp["value"][~nan])
+    engine.set_replica_sharing(False)
+    try:
+        off = engine.solve_replicas(base, rhs, H, W, opt)
+        assert engine.replica_forks == -1
+    finally:
+        engine.set_replica_sharing(True)
+    for k in ("status", "pivots", "pos", "var"):
+        assert np.array_equal(got[k], off[k]), k
+    assert same_bits(got["rhs"], off["rhs"])
+
+
+def test_replica_path_sharing_synthetic_phase2_and_statuses(engine):
+    """A dense synthetic base (phase 2 only; perturbed replicas fork in the ratio test), an unbounded one, and a base whose
+    trace does not fit the snapshot memory (KB-size trace capacity is exercised through a huge pivot budget)."""
+    for (m_, nv, neg, n, eps) in ((20, 30, 0, 400, 1e-2), (40, 60, 8, 300, 5e-2), (12, 9, 3, 300, 0.3)):
+        H, W = m_ + 1, nv + 1
+        base = O.generate_synthetic(900 + m_, 1, m_, nv, neg)[0]
+        rhs, mats = _replica_case(base, H, W, n, eps, 3)
+        got = engine.solve_replicas(base, rhs, H, W)
+        assert engine.replica_forks >= 0
+        exp = O.simplex_batch(mats.copy(), W, H)
+        for k in ("status", "pivots", "pos", "var"):
+            assert np.array_equal(got[k], exp[k]), (m_, k)
+        assert same_bits(got["rhs"], exp["rhs"])
+    base = np.array([[0.0, 1.0, 1.0], [4.0, -1.0, 1.0], [2.0, -2.0, 1.0]]).reshape(-1)  # unbounded along column 1
+    rhs = np.array([[0.0, 4.0, 2.0], [0.0, 1.0, 7.0], [0.0, -3.0, 2.0], [0.0, 4.0, -2.0]])
+    mats = np.tile(base, (4, 1))
+    mats.reshape(4, 3, 3)[:, :, 0] = rhs
+    got = engine.solve_replicas(base, rhs, 3, 3)
+    exp = O.simplex_batch(mats.copy(), 3, 3)
+    assert np.array_equal(got["status"], exp["status"]) and np.array_equal(got["pivots"], exp["pivots"])
+    assert same_bits(got["rhs"], exp["rhs"]) and np.array_equal(got["pos"], exp["pos"])
+
+
 # ------------------------------------------------------------------------------------------------ several GPUs, one process
 def rank_devices():
     import torch

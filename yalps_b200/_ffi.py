@@ -63,6 +63,8 @@ SIGNATURES = {
                                            _vp, _vp, _vp, _vp]),
     "yalps_solve_replicas": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, C.POINTER(Options), _vp, _vp, _vp,
                                        _vp, _vp, _vp]),
+    "yalps_set_replica_sharing": (C.c_int, [_vp, C.c_int32]),
+    "yalps_replica_forks": (C.c_int64, [_vp]),
     "yalps_create_multi": (C.c_int, [_ip, C.c_int32, C.POINTER(_vp)]),
     "yalps_destroy_multi": (None, [_vp]),
     "yalps_multi_last_error": (C.c_char_p, [_vp]),

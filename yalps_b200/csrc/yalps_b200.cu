@@ -90,6 +90,8 @@ struct yalps_ctx {
   int wave = 256;  // upper bound of the adaptive look-ahead of the branch-and-cut driver
   int kc_tma = 0;    // KC: staging of the winner's pivot row (YALPS_KC_TMA: 0 ld.global.cg, 1 cp.async.bulk, 2 multicast)
   int bnb_mode = 0;  // 0: device-resident search when it fits, else host waves; 1: host waves only; 2: device only
+  int64_t replica_forks = -1;  // last yalps_solve_replicas call: replicas that left the shared path (-1: sharing not used)
+  int replica_sharing = 1;  // yalps_solve_replicas: follow the base tableau's pivot path while a replica makes the same choices
   unsigned long long *d_rows = nullptr;  // roofline diagnostics: device counter(s) of rewritten rows (yalps_set_row_counter)
   int rows_per_lp = 0;
   // pooled device buffers (index = purpose * 2 + pipeline slot)
@@ -1351,6 +1353,201 @@ int yalps_solve_ragged_basis(yalps_ctx *ctx, int64_t n, const int32_t *heights, 
                     pos_out, var_out, matrices_out, pos_in, var_in);
 }
 
+// ---- replica path sharing (aux_kernels.cuh: k_replica_follow) ------------------------------------------------------
+// The leader (the base tableau itself) is solved once by a row-split kernel that records its trace; see the comment
+// above FollowArgs for why following it gives every replica its own result, bit for bit.
+struct ReplicaTrace {
+  bool ok = false;
+  int K = 0, Hp = 0, cap = 0, leader_done = 0, leader_status = 0;
+  int *steps = nullptr, *var = nullptr;
+  double *q = nullptr, *col = nullptr, *snap = nullptr;
+  double density = -1.0;
+};
+
+static int replica_leader_trace(yalps_ctx *ctx, int H, int W, const double *base_host, const double *d_base,
+                                const yalps_options *opt, cudaStream_t st, ReplicaTrace *tr) {
+  tr->ok = false;
+  if (!ctx->replica_sharing || opt->check_cycles || getenv("YALPS_NO_REPLICA_SHARING")) return 0;
+  if (ctx->tune_path != YALPS_PATH_AUTO) return 0;  // a forced kernel path means "measure that kernel"
+  const size_t cells = (size_t)H * W, pv = (size_t)H + W;
+  const SmemLayout Lg(H, W, false, 32);
+  if (Lg.total > (size_t)ctx->smem_optin) return 0;  // the forks need a one-CTA-per-LP kernel
+  // trace capacity: both phases of the budget, bounded by 512 MiB of snapshots
+  const double budget = !(opt->max_pivots > 0.0) ? 0.0 : std::min(opt->max_pivots, 1.0e6);
+  long long cap = (long long)std::min(2.0 * std::ceil(budget), 4096.0);
+  cap = std::min<long long>(cap, (long long)(((size_t)512 << 20) / (cells * 8)) - 1);
+  if (cap < 8) return 0;
+  LaunchPlan plan;
+  if (int rc = plan_launch(ctx, 1, H, W, false, &plan, -1.0, false)) return rc;
+  if (plan.tmem || !plan.k || plan.k->nwr < 2) return 0;  // only the row-split kernels record a trace
+  size_t nz = 0;
+  for (size_t i = 0; i < cells; i++) nz += base_host[i] != 0.0;
+  tr->density = (double)nz / (double)cells;
+  tr->Hp = (H + 1) & ~1;
+  tr->cap = (int)cap;
+  void *p;
+  int rc;
+  if ((rc = dev_ensure(ctx, "rs_steps", (size_t)(cap + 1) * 4 * sizeof(int), &p))) return rc;
+  tr->steps = (int *)p;
+  if ((rc = dev_ensure(ctx, "rs_q", (size_t)cap * 8, &p))) return rc;
+  tr->q = (double *)p;
+  if ((rc = dev_ensure(ctx, "rs_col", (size_t)cap * tr->Hp * 8, &p))) return rc;
+  tr->col = (double *)p;
+  if ((rc = dev_ensure(ctx, "rs_snap", (size_t)(cap + 1) * cells * 8, &p))) return rc;
+  tr->snap = (double *)p;
+  if ((rc = dev_ensure(ctx, "rs_var", (size_t)(cap + 1) * pv * sizeof(int), &p))) return rc;
+  tr->var = (int *)p;
+  void *d_lwork, *d_lres, *d_lpv;
+  if ((rc = dev_ensure(ctx, "rs_lwork", cells * 8, &d_lwork))) return rc;
+  if ((rc = dev_ensure(ctx, "rs_lres", 64, &d_lres))) return rc;
+  if ((rc = dev_ensure(ctx, "rs_lpv", 2 * pv * sizeof(int), &d_lpv))) return rc;
+  BatchArgs a{};
+  a.n = 1;
+  a.mode = kModeBatch;
+  a.H = a.Hcap = H;
+  a.W = a.Wcap = W;
+  a.in = d_base;
+  a.work = (double *)d_lwork;
+  a.status = (int *)d_lres;
+  a.value = (double *)((char *)d_lres + 8);
+  a.pivots = (long long *)((char *)d_lres + 16);
+  a.pos_out = (int *)d_lpv;
+  a.var_out = (int *)d_lpv + pv;
+  fill_options(a, opt);
+  a.tr_steps = tr->steps;
+  a.tr_q = tr->q;
+  a.tr_col = tr->col;
+  a.tr_snap = tr->snap;
+  a.tr_var = tr->var;
+  a.tr_hp = tr->Hp;
+  a.tr_cap = tr->cap;
+  if ((rc = launch_simplex(ctx, plan, a, "rs_lead", st))) return rc;
+  struct {
+    int status, pad;
+    double value;
+    long long p1, p2;
+  } res;
+  CU(ctx, cudaMemcpyAsync(&res, d_lres, sizeof res, cudaMemcpyDeviceToHost, st));
+  CU(ctx, cudaStreamSynchronize(st));
+  if (res.status == ST_ERR_HISTORY) return 0;
+  const long long K = res.p1 + res.p2;
+  // a trace that did not fit ends one step early: snapshots exist for the states BEFORE pivots 0 .. cap - 1 only
+  tr->leader_done = K <= cap;
+  tr->K = (int)(K <= cap ? K : cap - 1);
+  tr->leader_status = res.status;
+  tr->ok = true;
+  return 0;
+}
+
+// One chunk of replicas whose right-hand sides are in d_rin: followers first, then the replicas that left the path
+// (tableau = the leader's snapshot of the fork step + their own column 0) through the ordinary batch kernels.
+static int replica_chunk_shared(yalps_ctx *ctx, const ReplicaTrace &tr, int64_t cn, int H, int W, const double *d_rin,
+                                double *d_work, const yalps_options *opt, int *d_status, double *d_value, long long *d_piv,
+                                double *d_rhs, int *d_pos, int *d_var, cudaStream_t st, const std::string &s,
+                                int64_t *forks_out) {
+  const size_t cells = (size_t)H * W, pv = (size_t)H + W;
+  void *p, *hp;
+  int rc;
+  if ((rc = dev_ensure(ctx, "rs_fcount" + s, 64, &p))) return rc;
+  int *d_fcount = (int *)p;
+  if ((rc = dev_ensure(ctx, "rs_fids" + s, (size_t)cn * 4, &p))) return rc;
+  int *d_fids = (int *)p;
+  if ((rc = dev_ensure(ctx, "rs_fstep" + s, (size_t)cn * 4, &p))) return rc;
+  int *d_fstep = (int *)p;
+  if ((rc = dev_ensure(ctx, "rs_fres" + s, (size_t)cn * 24, &p))) return rc;
+  long long *d_fres = (long long *)p;
+  if ((rc = pin_ensure(ctx, "rs_fcount_h" + s, 64, &hp))) return rc;
+  CU(ctx, cudaMemsetAsync(d_fcount, 0, 4, st));
+  FollowArgs fa{};
+  fa.n = cn;
+  fa.H = H;
+  fa.W = W;
+  fa.Hp = tr.Hp;
+  fa.rhs_in = d_rin;
+  fa.steps = tr.steps;
+  fa.q = tr.q;
+  fa.colraw = tr.col;
+  fa.leader_var = tr.var + (size_t)tr.K * pv;
+  fa.K = tr.K;
+  fa.leader_done = tr.leader_done;
+  fa.leader_status = tr.leader_status;
+  fa.precision = opt->precision;
+  fa.max_pivots = opt->max_pivots;
+  fa.status = d_status;
+  fa.value = d_value;
+  fa.pivots = d_piv;
+  fa.rhs_out = d_rhs;
+  fa.pos_out = d_pos;
+  fa.var_out = d_var;
+  fa.fork_count = d_fcount;
+  fa.fork_ids = d_fids;
+  fa.fork_step = d_fstep;
+  fa.fork_resume = d_fres;
+  const int grid = (int)std::min<int64_t>((cn + kFollowWarps - 1) / kFollowWarps, (int64_t)ctx->prop.multiProcessorCount * 8);
+  k_replica_follow<<<grid, kFollowWarps * 32, (size_t)kFollowWarps * tr.Hp * 8, st>>>(fa);
+  CU(ctx, cudaGetLastError());
+  ctx->launches++;
+  CU(ctx, cudaMemcpyAsync(hp, d_fcount, 4, cudaMemcpyDeviceToHost, st));
+  CU(ctx, cudaStreamSynchronize(st));
+  const int nf = *(int *)hp;
+  if (forks_out) *forks_out += nf;
+  if (nf == 0) return 0;
+  // compact buffers of the forked replicas
+  if ((rc = dev_ensure(ctx, "rs_cvin" + s, (size_t)nf * pv * 4, &p))) return rc;
+  int *c_vin = (int *)p;
+  if ((rc = dev_ensure(ctx, "rs_cres" + s, (size_t)nf * 24, &p))) return rc;
+  long long *c_resume = (long long *)p;
+  if ((rc = dev_ensure(ctx, "rs_cstatus" + s, (size_t)nf * 4, &p))) return rc;
+  int *c_status = (int *)p;
+  if ((rc = dev_ensure(ctx, "rs_cvalue" + s, (size_t)nf * 8, &p))) return rc;
+  double *c_value = (double *)p;
+  if ((rc = dev_ensure(ctx, "rs_cpiv" + s, (size_t)nf * 16, &p))) return rc;
+  long long *c_piv = (long long *)p;
+  if ((rc = dev_ensure(ctx, "rs_crhs" + s, (size_t)nf * H * 8, &p))) return rc;
+  double *c_rhs = (double *)p;
+  if ((rc = dev_ensure(ctx, "rs_cpos" + s, (size_t)nf * pv * 4, &p))) return rc;
+  int *c_pos = (int *)p;
+  if ((rc = dev_ensure(ctx, "rs_cvar" + s, (size_t)nf * pv * 4, &p))) return rc;
+  int *c_var = (int *)p;
+  {
+    const dim3 g((unsigned)std::min<size_t>((cells + 255) / 256, 64), (unsigned)std::min(nf, 32768));
+    k_replica_materialise<<<g, 256, 0, st>>>(0, nf, H, W, d_fids, d_fstep, d_fres, d_rhs, tr.snap, tr.var, d_work, c_vin, c_resume);
+    CU(ctx, cudaGetLastError());
+    ctx->launches++;
+  }
+  LaunchPlan plan;
+  if ((rc = plan_launch(ctx, nf, H, W, false, &plan, tr.density, false))) return rc;
+  if (use_grid_path(ctx, nf, plan) || plan.tmem || !plan.k) {  // few large forks: one CTA per LP on the HBM-resident kernel
+    const int keep = ctx->tune_path;
+    ctx->tune_path = YALPS_PATH_GMEM;
+    rc = plan_launch(ctx, nf, H, W, false, &plan, tr.density, false);
+    ctx->tune_path = keep;
+    if (rc) return rc;
+  }
+  BatchArgs a{};
+  a.n = nf;
+  a.mode = kModeBatch;
+  a.H = a.Hcap = H;
+  a.W = a.Wcap = W;
+  a.in = d_work;
+  a.work = d_work;
+  a.status = c_status;
+  a.value = c_value;
+  a.pivots = c_piv;
+  a.rhs_out = c_rhs;
+  a.pos_out = c_pos;
+  a.var_out = c_var;
+  a.var_in = c_vin;
+  a.resume = c_resume;
+  fill_options(a, opt);
+  if ((rc = launch_simplex(ctx, plan, a, "rs_fork" + s, st))) return rc;
+  k_replica_scatter<<<(unsigned)std::min(nf, ctx->prop.multiProcessorCount * 8), 128, 0, st>>>(
+      0, nf, H, W, d_fids, c_status, c_value, c_piv, c_rhs, c_pos, c_var, d_status, d_value, d_piv, d_rhs, d_pos, d_var);
+  CU(ctx, cudaGetLastError());
+  ctx->launches++;
+  return 0;
+}
+
 int yalps_solve_replicas(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, const double *base,
                          const double *rhs, const yalps_options *opt, int32_t *status, double *value, int64_t *pivots,
                          double *rhs_out, int32_t *pos_out, int32_t *var_out) {
@@ -1365,6 +1562,9 @@ int yalps_solve_replicas(yalps_ctx *ctx, int64_t n, int32_t height, int32_t widt
   int rc;
   if ((rc = dev_ensure(ctx, "rep_base", cells * 8, &d_base))) return rc;
   CU(ctx, cudaMemcpy(d_base, base, cells * 8, cudaMemcpyHostToDevice));
+  ReplicaTrace trace;
+  if ((rc = replica_leader_trace(ctx, height, width, base, (const double *)d_base, opt, ctx->streams[0], &trace))) return rc;
+  ctx->replica_forks = trace.ok ? 0 : -1;
   // two pipeline slots of at most ~1.5 GiB of working copies each: the H2D of chunk k+1's right-hand sides and the
   // D2H of chunk k-1's results overlap the solve of chunk k
   const int64_t per_chunk = std::max<int64_t>(1, std::min<int64_t>((n + 1) / 2 > 4096 ? (n + 7) / 8 : n,
@@ -1386,15 +1586,22 @@ int yalps_solve_replicas(yalps_ctx *ctx, int64_t n, int32_t height, int32_t widt
     if ((rc = dev_ensure(ctx, "pos" + s, (size_t)cn * pv * 4, &d_pos))) return rc;
     if ((rc = dev_ensure(ctx, "var" + s, (size_t)cn * pv * 4, &d_var))) return rc;
     CU(ctx, cudaMemcpyAsync(d_rin, rhs + (size_t)begin * height, (size_t)cn * height * 8, cudaMemcpyHostToDevice, st));
-    const size_t total = (size_t)cn * cells;
-    const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)ctx->prop.multiProcessorCount * 16);
-    k_expand_replicas<<<grid, 256, 0, st>>>(cn, height, width, (const double *)d_base, (const double *)d_rin, (double *)d_work);
-    CU(ctx, cudaGetLastError());
-    ctx->launches++;
-    if ((rc = solve_batch_device_impl(ctx, cn, height, width, (const double *)d_work, (double *)d_work, opt,
-                                      (int32_t *)d_status, (double *)d_value, (int64_t *)d_piv, (double *)d_rhs,
-                                      (int32_t *)d_pos, (int32_t *)d_var, nullptr, st, s, begin)))
-      return rc;
+    if (trace.ok) {
+      if ((rc = replica_chunk_shared(ctx, trace, cn, height, width, (const double *)d_rin, (double *)d_work, opt, (int *)d_status,
+                                     (double *)d_value, (long long *)d_piv, (double *)d_rhs, (int *)d_pos, (int *)d_var, st, s,
+                                     &ctx->replica_forks)))
+        return rc;
+    } else {
+      const size_t total = (size_t)cn * cells;
+      const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)ctx->prop.multiProcessorCount * 16);
+      k_expand_replicas<<<grid, 256, 0, st>>>(cn, height, width, (const double *)d_base, (const double *)d_rin, (double *)d_work);
+      CU(ctx, cudaGetLastError());
+      ctx->launches++;
+      if ((rc = solve_batch_device_impl(ctx, cn, height, width, (const double *)d_work, (double *)d_work, opt,
+                                        (int32_t *)d_status, (double *)d_value, (int64_t *)d_piv, (double *)d_rhs,
+                                        (int32_t *)d_pos, (int32_t *)d_var, nullptr, st, s, begin)))
+        return rc;
+    }
     if (status) CU(ctx, cudaMemcpyAsync(status + begin, d_status, (size_t)cn * 4, cudaMemcpyDeviceToHost, st));
     if (value) CU(ctx, cudaMemcpyAsync(value + begin, d_value, (size_t)cn * 8, cudaMemcpyDeviceToHost, st));
     if (pivots) CU(ctx, cudaMemcpyAsync(pivots + 2 * begin, d_piv, (size_t)cn * 16, cudaMemcpyDeviceToHost, st));
@@ -1408,6 +1615,14 @@ int yalps_solve_replicas(yalps_ctx *ctx, int64_t n, int32_t height, int32_t widt
     if (used[i]) CU(ctx, cudaStreamSynchronize(ctx->streams[i]));
   return check_device_status(ctx, status, n);
 }
+
+int yalps_set_replica_sharing(yalps_ctx *ctx, int32_t on) {
+  if (!ctx) return YALPS_ERR_ARGUMENT;
+  ctx->replica_sharing = on ? 1 : 0;
+  return 0;
+}
+
+int64_t yalps_replica_forks(const yalps_ctx *ctx) { return ctx ? ctx->replica_forks : -1; }
 
 int yalps_generate_synthetic_device(yalps_ctx *ctx, int64_t first, int64_t n, int32_t m, int32_t nvars,
                                     int32_t neg_rows, uint32_t salt, double *d_out, void *stream) {

@@ -187,6 +187,15 @@ class Engine:
                                                    _ptr(out["rhs"]), _ptr(out["pos"]), _ptr(out["var"])))
         return out
 
+    def set_replica_sharing(self, on: bool = True):
+        """solve_replicas: follow the base tableau's pivot path while a replica makes the same choices (default on)."""
+        self._check(self._lib.yalps_set_replica_sharing(self._ctx, int(bool(on))))
+
+    @property
+    def replica_forks(self) -> int:
+        """Replicas of the last solve_replicas call that left the shared path (-1: sharing was not used)."""
+        return int(self._lib.yalps_replica_forks(self._ctx))
+
     def solve_ragged(self, tableaus: Sequence[np.ndarray], shapes: Sequence[tuple], options: Optional[Options] = None,
                      want_matrices: bool = False) -> list:
         """LPs of different shapes in one call.  tableaus[i] is float64 of height_i*width_i values."""
