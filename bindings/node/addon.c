@@ -193,6 +193,44 @@ static napi_value js_simplex(napi_env env, napi_callback_info info) {
   return rc_value(env, rc);
 }
 
+/* simplexLarge(multi, height, width, matrix, positionOfVariable, variableAtPosition, options, out[2]): simplex() on ONE
+ * fresh tableau whose rows are dealt over the GPUs of `multi` (yalps_multi_solve_large); the tableau is mutated in place
+ * and both permutation arrays are overwritten, as src/simplex.ts:144 does. */
+static napi_value js_simplex_large(napi_env env, napi_callback_info info) {
+  size_t argc = 8;
+  napi_value a[8];
+  NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+  if (argc < 8) {
+    napi_throw_type_error(env, "YALPS_B200", "simplexLarge needs 8 arguments");
+    return NULL;
+  }
+  yalps_multi *mu = (yalps_multi *)handle_arg(env, a[0], TAG_MULTI);
+  if (!mu) return NULL;
+  int32_t h = 0, w = 0;
+  napi_get_value_int32(env, a[1], &h);
+  napi_get_value_int32(env, a[2], &w);
+  if (h < 1 || w < 1) {
+    napi_throw_range_error(env, "YALPS_B200", "height and width must be positive");
+    return NULL;
+  }
+  const size_t cells = (size_t)h * (size_t)w, pv = (size_t)h + (size_t)w;
+  void *m, *pos, *vars, *out;
+  yalps_options o;
+  if (!typed_arg(env, a[3], napi_float64_array, cells, false, "matrix: Float64Array(height*width)", &m, NULL) ||
+      !typed_arg(env, a[4], napi_int32_array, pv, false, "positionOfVariable: Int32Array(width+height)", &pos, NULL) ||
+      !typed_arg(env, a[5], napi_int32_array, pv, false, "variableAtPosition: Int32Array(width+height)", &vars, NULL) ||
+      !read_options(env, a[6], &o) ||
+      !typed_arg(env, a[7], napi_float64_array, 2, false, "out: Float64Array(2)", &out, NULL))
+    return NULL;
+  int32_t status = 0;
+  double value = 0.0;
+  const int rc = yalps_multi_solve_large(mu, h, w, (const double *)m, &o, &status, &value, NULL, NULL, (int32_t *)pos,
+                                         (int32_t *)vars, (double *)m, NULL);
+  ((double *)out)[0] = (double)status;
+  ((double *)out)[1] = value;
+  return rc_value(env, rc);
+}
+
 static napi_value js_solve(napi_env env, napi_callback_info info) {
   size_t argc = 13;
   napi_value a[13];
@@ -303,6 +341,7 @@ NAPI_MODULE_INIT() {
       {"create", NULL, js_create, NULL, NULL, NULL, napi_default, NULL},
       {"createMulti", NULL, js_create_multi, NULL, NULL, NULL, napi_default, NULL},
       {"simplex", NULL, js_simplex, NULL, NULL, NULL, napi_default, NULL},
+      {"simplexLarge", NULL, js_simplex_large, NULL, NULL, NULL, napi_default, NULL},
       {"solve", NULL, js_solve, NULL, NULL, NULL, napi_default, NULL},
       {"solveMany", NULL, js_solve_many, NULL, NULL, NULL, napi_default, NULL},
       {"lastError", NULL, js_last_error, NULL, NULL, NULL, napi_default, NULL},

@@ -36,6 +36,18 @@ export const simplex = (tableau: Tableau, options: Required<Options>): [Solution
   return [STATUS[out[0]], out[1]]
 }
 
+// simplex() for ONE fresh tableau too large (or too slow) for one GPU: its rows are dealt over `devices`, one persistent
+// kernel per GPU, the pivot row and column travel through NVLink peer memory inside the kernels
+// (yalps_multi_solve_large).  Same in-place contract; the tableau must carry the identity permutation (src/tableau.ts:95-98).
+export const simplexLarge = (tableau: Tableau, options: Required<Options>, devices: number[]): [SolutionStatus, number] => {
+  const { width, height, matrix, positionOfVariable, variableAtPosition } = tableau
+  const out = new Float64Array(2)
+  const m = getMulti(devices)
+  const rc = native.simplexLarge(m, height, width, matrix, positionOfVariable, variableAtPosition, packOptions(options), out)
+  if (rc !== 0) throw new Error(native.lastError(m))
+  return [STATUS[out[0]], out[1]]
+}
+
 // New API: many models, ONE native call.  All root LPs run as one ragged device batch (sharded over `devices` when
 // several GPUs are given); models with integer variables whose root is optimal and fractional then run branch and
 // cut on the device side of the ABI, many searches concurrently (yalps_multi_solve_many).  Each result equals
