@@ -224,26 +224,34 @@ __device__ __forceinline__ int grid_select(int C, int rank, unsigned long long k
   // shared array of C records: 148 x 148 reads of the same 19 lines per round, 6,000 cycles of waiting per selection)
   ulonglong2 *inbox = reinterpret_cast<ulonglong2 *>(gslots) + (size_t)xpar * C * C;
   ulonglong2 *slots = inbox + (size_t)rank * C;
-  double *pub = scratch + (size_t)xpar * C * ldA;
-  if (w.idx != kNone) {
-    const double2 *src = reinterpret_cast<const double2 *>(A + (size_t)((w.idx - 1) / C) * ldA);
-    double2 *dst = reinterpret_cast<double2 *>(pub + (size_t)rank * ldA);
-    for (int c = threadIdx.x; c < ldA / 2; c += NT) __stcg(dst + c, src[c]);
+  // candidate rows travel as flag-in-data slots too: one 16-byte {low word, sequence, high word, sequence} per cell
+  // (the 32-bit exchange counter), so neither the publisher nor the readers need a fence and the records can leave
+  // BEFORE the row is written (a version with plain row stores + fence + records spent 2,700 cycles publishing)
+  uint4 *pub = reinterpret_cast<uint4 *>(scratch) + (size_t)xpar * C * ldA;
+  const unsigned rseq = xcount;
+  if (threadIdx.x < 32) {  // records first
+    const int lane = threadIdx.x;
+    const unsigned long long k = ((unsigned long long)w.hi << 32) | w.lo;
+    const unsigned long long ra = (k & ~0xffffULL) | seq;
+    const unsigned long long rb = ((k & 0xffffULL) << 48) | ((unsigned long long)(unsigned)w.idx << 16) | seq;
+#pragma unroll
+    for (int u = 0; u < kMaxPerLane; u++)
+      if (lane + 32 * u < C)
+        asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(inbox + (size_t)(lane + 32 * u) * C + rank), "l"(ra), "l"(rb)
+                     : "memory");
   }
-  __syncthreads();
+  if (w.idx != kNone) {
+    const double *src = A + (size_t)((w.idx - 1) / C) * ldA;
+    uint4 *dst = pub + (size_t)rank * ldA;
+    for (int c = threadIdx.x; c < ldA; c += NT) {
+      const double v = src[c];
+      asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c), "r"((unsigned)__double2loint(v)), "r"(rseq),
+                   "r"((unsigned)__double2hiint(v)), "r"(rseq)
+                   : "memory");
+    }
+  }
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
-    {
-      const unsigned long long k = ((unsigned long long)w.hi << 32) | w.lo;
-      const unsigned long long ra = (k & ~0xffffULL) | seq;
-      const unsigned long long rb = ((k & 0xffffULL) << 48) | ((unsigned long long)(unsigned)w.idx << 16) | seq;
-      __threadfence();  // the candidate row (all threads' stores, ordered by the CTA barrier) before the records
-#pragma unroll
-      for (int u = 0; u < kMaxPerLane; u++)
-        if (lane + 32 * u < C)
-          asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(inbox + (size_t)(lane + 32 * u) * C + rank), "l"(ra), "l"(rb)
-                       : "memory");
-    }
     GS_MARK(6);
     const unsigned long long nk = no_key<kMax>();
     unsigned long long bk = nk;
@@ -277,38 +285,47 @@ __device__ __forceinline__ int grid_select(int C, int rank, unsigned long long k
     const bool gave_up = __any_sync(0xffffffffu, bi == kGiveUp);
     if (bi == kNone || gave_up) bk = nk;
     const int row = gave_up ? kGiveUp : warp_best<kMax>((unsigned)(bk >> 32), (unsigned)bk, gave_up ? kNone : bi).idx;
-    // acquire: the winner's published row (written before its record, behind the publisher's fence) is visible to
-    // whoever reads it after the CTA barrier below.  One acquire load instead of a full fence (MEMBAR + L1 flush).
-    {
-      unsigned long long sink;
-      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(sink) : "l"(slots + rank) : "memory");
-      (void)sink;
-    }
     if (lane == 0) *s_row = row;
   }
   __syncthreads();
-  const int row = *s_row;
+  int row = *s_row;
   if (yt) {  // the wait belongs to the caller's slot: restart the clock for the staging part
     const long long now_ = clock64();
     yt[8] += now_ - *yt_last;
     *yt_last = now_;
   }
-  if (row != kNone && row != kGiveUp) {
+  bool bad = false;
+  if (row != kNone && row != kGiveUp) {  // the winner's row: every thread polls the slots of its own cells
     const int owner = (row - 1) % C;
-    const double2 *src = reinterpret_cast<const double2 *>(pub + (size_t)owner * ldA);
-    double2 *dst = reinterpret_cast<double2 *>(prow_s);
-    const int n2 = ldA / 2;
-    for (int c0 = 0; c0 < n2; c0 += 4 * NT) {  // four 16-byte loads in flight per thread
-      double2 v[4];
+    const uint4 *src = pub + (size_t)owner * ldA;
+    for (int c0 = 0; c0 < ldA; c0 += 8 * NT) {
+      unsigned pend = 0, spins = 0;
 #pragma unroll
-      for (int u = 0; u < 4; u++)
-        if (c0 + u * NT + (int)threadIdx.x < n2) v[u] = __ldcg(src + c0 + u * NT + threadIdx.x);
+      for (int u = 0; u < 8; u++)
+        if (c0 + u * NT + (int)threadIdx.x < ldA) pend |= 1u << u;
+      while (pend) {
+        if (++spins > (1u << 22)) {
+          bad = true;
+          break;
+        }
+        uint4 v[8];
 #pragma unroll
-      for (int u = 0; u < 4; u++)
-        if (c0 + u * NT + (int)threadIdx.x < n2) dst[c0 + u * NT + threadIdx.x] = v[u];
+        for (int u = 0; u < 8; u++)
+          if ((pend >> u) & 1u)
+            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w)
+                         : "l"(src + c0 + u * NT + threadIdx.x)
+                         : "memory");
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+          if (((pend >> u) & 1u) && v[u].y == rseq && v[u].w == rseq) {
+            pend &= ~(1u << u);
+            prow_s[c0 + u * NT + threadIdx.x] = __hiloint2double((int)v[u].z, (int)v[u].x);
+          }
+      }
     }
-    __syncthreads();
   }
+  if (__syncthreads_or(bad)) row = kGiveUp;
   GS_MARK(7);
 #undef GS_MARK
   return row;

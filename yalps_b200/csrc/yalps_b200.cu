@@ -571,8 +571,11 @@ int launch_gridres(yalps_ctx *ctx, const GridResPlan &plan, BatchArgs &args, con
   }
   void *p = nullptr;
   const size_t ldA = (size_t)SmemLayout::ld_for(args.Wcap);
-  if (int rc = dev_ensure(ctx, "kg_scratch" + slot, (size_t)2 * plan.C * ldA * sizeof(double), &p)) return rc;
+  // candidate rows as 16-byte flag-in-data slots {low word, sequence, high word, sequence}: [2][C][ldA]
+  const size_t pub_bytes = (size_t)2 * plan.C * ldA * sizeof(uint4);
+  if (int rc = dev_ensure(ctx, "kg_scratch" + slot, pub_bytes, &p)) return rc;
   args.cl_scratch = (double *)p;
+  CU(ctx, cudaMemsetAsync(p, 0, pub_bytes, stream));  // sequence numbers of an earlier launch must not look current
   const size_t inbox_bytes = (size_t)2 * plan.C * plan.C * sizeof(uint4);  // [2][receiver][sender] selection records
   if (int rc = dev_ensure(ctx, "kg_slots" + slot, inbox_bytes + 64, &p)) return rc;
   args.gx_slots = (uint4 *)p;
