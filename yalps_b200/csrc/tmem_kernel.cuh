@@ -262,6 +262,8 @@ __global__ void __launch_bounds__(kTmemWarps * 32, TmemShape<HR>::kCtasPerSm) k_
   if (a.max_pivots > 0.0) budget = a.max_pivots >= 9.0e18 ? 0x7fffffffffffffffLL : (long long)ceil(a.max_pivots);
 
   // static assignment (few LPs): LP i -> CTA i % grid, warp i / grid, so that a small batch spreads over the SMs
+  // (reading the queue one LP ahead, to prefetch the next tableau into L2 while the current one is solved, was measured
+  // 3.5 % SLOWER: the last LPs sit reserved by busy warps while others idle)
   for (long long static_lp = (long long)warp * gridDim.x + blockIdx.x;; static_lp += nwarps) {
     long long lp = static_lp;
     if (a.counter) {
@@ -301,25 +303,31 @@ __global__ void __launch_bounds__(kTmemWarps * 32, TmemShape<HR>::kCtasPerSm) k_
 #pragma unroll
     for (int h = 0; h < HR; h++) bv[h] = has_b[h] ? src[(size_t)(lane + 1 + 32 * h) * W] : 0.0;
     double b0 = src[0];
-    for (int blk = 0; blk < nblocks; blk++) {
-      const int r0 = 1 + 8 * blk;
-      double x[8][2];
-      const double *rp = src + (size_t)r0 * W + 1 + j0;
+    for (int blk = 0; blk < nblocks; blk += 2) {  // two blocks (32 loads per lane) in flight; a block past H-1 gets zeros
+      double x[2][8][2];
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
-        x[i][0] = (r0 + i < H && v0) ? rp[0] : 0.0;
-        x[i][1] = (r0 + i < H && v1) ? rp[1] : 0.0;
-        rp += W;
-      }
-      unsigned v[32];
+      for (int b = 0; b < 2; b++) {
+        const int r0 = 1 + 8 * (blk + b);
+        const double *rp = src + (size_t)r0 * W + 1 + j0;
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
-        v[2 * i] = (unsigned)__double2loint(x[i][0]);
-        v[2 * i + 1] = (unsigned)__double2hiint(x[i][0]);
-        v[16 + 2 * i] = (unsigned)__double2loint(x[i][1]);
-        v[16 + 2 * i + 1] = (unsigned)__double2hiint(x[i][1]);
+        for (int i = 0; i < 8; i++) {
+          x[b][i][0] = (r0 + i < H && v0) ? rp[0] : 0.0;
+          x[b][i][1] = (r0 + i < H && v1) ? rp[1] : 0.0;
+          rp += W;
+        }
       }
-      tm_st32(tbase + 32u * (unsigned)blk, v);
+#pragma unroll
+      for (int b = 0; b < 2; b++) {
+        unsigned v[32];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          v[2 * i] = (unsigned)__double2loint(x[b][i][0]);
+          v[2 * i + 1] = (unsigned)__double2hiint(x[b][i][0]);
+          v[16 + 2 * i] = (unsigned)__double2loint(x[b][i][1]);
+          v[16 + 2 * i + 1] = (unsigned)__double2hiint(x[b][i][1]);
+        }
+        tm_st32(tbase + 32u * (unsigned)(blk + b), v);
+      }
     }
     for (int k = lane; k < W + H; k += 32) var[k] = a.var_in ? a.var_in[poff + k] : k;
     // rows past H-1 in the last block of eight: zeros in TMEM, never read; a non-zero coefficient keeps the block on
@@ -341,10 +349,10 @@ __global__ void __launch_bounds__(kTmemWarps * 32, TmemShape<HR>::kCtasPerSm) k_
       const int l = (c - 1) >> 1, e = (c - 1) & 1;
       if (lane == l) colx[0] = e ? o1 : o0;
       tm_wait_st();  // the pivot-row store of the previous pivot
-      for (int blk = 0; blk < nblocks; blk += 2) {
+      for (int blk = 0; blk < nblocks; blk += 2) {  // (blocks past H-1 are allocated, zero and never read)
         unsigned u[32];
-        tm_ld16(tbase + 32u * (unsigned)blk + 16u * (unsigned)e, u);
-        tm_ld16(tbase + 32u * (unsigned)(blk + 1) + 16u * (unsigned)e, u + 16);  // (may be a block past H-1: never read)
+#pragma unroll
+        for (int b = 0; b < 2; b++) tm_ld16(tbase + 32u * (unsigned)(blk + b) + 16u * (unsigned)e, u + 16 * b);
         tm_wait_ld(u);
         if (lane == l) {
           uint4 *dst = reinterpret_cast<uint4 *>(colx + 1 + 8 * blk);
@@ -360,6 +368,7 @@ __global__ void __launch_bounds__(kTmemWarps * 32, TmemShape<HR>::kCtasPerSm) k_
       int row, col;
       double pr0, pr1;   // old pivot row cells of my two columns
       double cmine[HR];  // pivot-column cells of my RHS rows
+      double rcp_q;      // refined reciprocal of the pivot element: the selection's own division already computed it in one lane
       if (phase == 1) {
         // leaving row: first index of the most negative RHS below -precision (:111-119)
         {
@@ -386,9 +395,12 @@ __global__ void __launch_bounds__(kTmemWarps * 32, TmemShape<HR>::kCtasPerSm) k_
         tm_load_row(tbase, row, pr0, pr1);
         double best = -INF;
         int bi = kNone;
+        double rcp0, rcp1;
         {
           const bool c0 = v0 && pr0 < -precision, c1 = v1 && pr1 < -precision;
           RecipBatch d0(pr0, c0), d1(pr1, c1);
+          rcp0 = d0.r;
+          rcp1 = d1.r;
           double ratio0 = d0.quot(-o0, c0), ratio1 = d1.quot(-o1, c1);
           if (!(d0.ok && d1.ok)) {  // rare: exact division out of line
             ratio0 = div_rn_slow(-o0, pr0);
@@ -409,6 +421,7 @@ __global__ void __launch_bounds__(kTmemWarps * 32, TmemShape<HR>::kCtasPerSm) k_
           status = ST_INFEASIBLE;
           break;
         }
+        rcp_q = __shfl_sync(0xffffffffu, ((col - 1) & 1) ? rcp1 : rcp0, (col - 1) >> 1);  // q = M[row, col]: that lane's divisor
         extract_column(col);
 #pragma unroll
         for (int h = 0; h < HR; h++) cmine[h] = has_b[h] ? colx[lane + 1 + 32 * h] : 0.0;
@@ -441,10 +454,12 @@ __global__ void __launch_bounds__(kTmemWarps * 32, TmemShape<HR>::kCtasPerSm) k_
         {
           double keyv = INF;
           int bi = kNone;
+          double rcp[HR];
 #pragma unroll
           for (int h = 0; h < HR; h++) {
             bool cand = has_b[h] && cmine[h] > precision;
             RecipBatch dr(cmine[h], cand);
+            rcp[h] = dr.r;
             double ratio = dr.quot(bv[h], cand);
             if (!dr.ok) ratio = div_rn_slow(bv[h], cmine[h]);  // rare (e.g. a zero RHS): exact division out of line
             cand = cand && ratio < INF;                        // +inf and NaN never win
@@ -456,6 +471,7 @@ __global__ void __launch_bounds__(kTmemWarps * 32, TmemShape<HR>::kCtasPerSm) k_
           }
           const unsigned long long key = bi == kNone ? no_key<false>() : order_key(keyv);
           row = warp_best<false>((unsigned)(key >> 32), (unsigned)key, bi).idx;
+          rcp_q = __shfl_sync(0xffffffffu, (HR > 1 && row > 32) ? rcp[HR - 1] : rcp[0], (row - 1) & 31);  // q = M[row, col]
         }
         if (row == kNone) {
           status = ST_UNBOUNDED;
@@ -494,7 +510,7 @@ __global__ void __launch_bounds__(kTmemWarps * 32, TmemShape<HR>::kCtasPerSm) k_
       const int jc = col - 1, lc = jc >> 1, ec = jc & 1;
       const double q = colx[row];
       const double c0raw = colx[0];
-      RecipBatch rq(q);  // one reciprocal refinement and one acceptance branch for the four quotients of this lane
+      RecipBatch rq(q, rcp_q);  // one acceptance branch for the four quotients of this lane; the reciprocal is the selection's
       // normalised pivot row cells of my columns; the pivot cell itself becomes 1/q
       const bool own0 = lane == lc && ec == 0, own1 = lane == lc && ec == 1;
       const double x0 = own0 ? 1.0 : pr0, x1 = own1 ? 1.0 : pr1;
