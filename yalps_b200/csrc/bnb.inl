@@ -497,19 +497,27 @@ int device_search(yalps_ctx *ctx, const int32_t *ints, int32_t nints, double sig
     occ = it->second;
   }
   if (occ < 1) return 1;
-  // one scheduler + at most 64 workers: a search keeps a few dozen node LPs in flight at most (two new nodes per replay
-  // step), and four concurrent searches (yalps_multi_solve_many) must be able to be co-resident on one GPU
-  const int grid = std::min(occ * ctx->prop.multiProcessorCount, 1 + 64);
+  // one scheduler + one worker per remaining SM (speculative expansion keeps a few thousand node LPs queued); the
+  // concurrent searches of yalps_multi_solve_many share the SMs (ctx->bnb_workers) so that they are co-resident
+  int max_workers = ctx->bnb_workers > 0 ? ctx->bnb_workers : ctx->prop.multiProcessorCount - 1;
+  if (const char *env = getenv("YALPS_BNB_WORKERS")) max_workers = std::max(1, atoi(env));
+  const int grid = std::min(occ * ctx->prop.multiProcessorCount, 1 + max_workers);
   if (grid < 2) return 1;
 
+  // the replay creates at most 2 * maxIterations + 2 nodes; speculation (bnb_kernel.cuh) gets as many again
   double max_nodes = 2.0 * opt->max_iterations + 4.0;
-  const int node_cap = (int)std::min(max_nodes, 65536.0);
-  const unsigned long long cut_cap = 1ULL << 20;
-  const int cand_cap = 2048;
-  void *d_ctl, *d_nodes, *d_cuts, *d_crhs, *d_cpos, *d_cvar, *d_ints, *d_rank;
+  const int base_nodes = (int)std::min(max_nodes, 65536.0);
+  int spec_depth = 2;
+  if (const char *env = getenv("YALPS_BNB_SPEC")) spec_depth = std::max(0, atoi(env));
+  const int spec_cap = spec_depth > 0 ? base_nodes : 0;
+  const int node_cap = base_nodes + spec_cap;
+  const unsigned long long cut_cap = 1ULL << 21;
+  const int cand_cap = 4096;
+  void *d_ctl, *d_nodes, *d_queue, *d_cuts, *d_crhs, *d_cpos, *d_cvar, *d_ints, *d_rank;
   int rc;
   if ((rc = dev_ensure(ctx, "kb_ctl", sizeof(BnbControl), &d_ctl))) return rc;
   if ((rc = dev_ensure(ctx, "kb_nodes", (size_t)node_cap * sizeof(BnbNode), &d_nodes))) return rc;
+  if ((rc = dev_ensure(ctx, "kb_queue", (size_t)node_cap * sizeof(int), &d_queue))) return rc;
   if ((rc = dev_ensure(ctx, "kb_cuts", (size_t)cut_cap * sizeof(BnbCut), &d_cuts))) return rc;
   if ((rc = dev_ensure(ctx, "kb_crhs", (size_t)cand_cap * Hcap * 8, &d_crhs))) return rc;
   if ((rc = dev_ensure(ctx, "kb_cpos", (size_t)cand_cap * (W + Hcap) * 4, &d_cpos))) return rc;
@@ -531,6 +539,8 @@ int device_search(yalps_ctx *ctx, const int32_t *ints, int32_t nints, double sig
   CU(ctx, cudaMemcpyAsync(d_ints, h_ints, (size_t)nints * 4, cudaMemcpyHostToDevice, st));
   CU(ctx, cudaMemcpyAsync(d_rank, h_rank, (size_t)(W + H) * 4, cudaMemcpyHostToDevice, st));
   CU(ctx, cudaMemsetAsync(d_ctl, 0, sizeof(BnbControl), st));
+  CU(ctx, cudaMemsetAsync(d_queue, 0, (size_t)node_cap * sizeof(int), st));
+  CU(ctx, cudaMemsetAsync(d_nodes, 0xff, (size_t)node_cap * sizeof(BnbNode), st));  // the cleared state of the result blocks
 
   BnbArgs a{};
   a.root = (const double *)R.m.p;
@@ -554,6 +564,10 @@ int device_search(yalps_ctx *ctx, const int32_t *ints, int32_t nints, double sig
   a.ctl = (BnbControl *)d_ctl;
   a.nodes = (BnbNode *)d_nodes;
   a.node_cap = node_cap;
+  a.queue = (int *)d_queue;
+  a.sched_cap = base_nodes;
+  a.spec_cap = spec_cap;
+  a.spec_depth = spec_depth;
   a.cuts = (BnbCut *)d_cuts;
   a.cut_cap = cut_cap;
   a.cand_rhs = (double *)d_crhs;
@@ -568,6 +582,9 @@ int device_search(yalps_ctx *ctx, const int32_t *ints, int32_t nints, double sig
   BnbControl *hc = (BnbControl *)h_down;
   CU(ctx, cudaMemcpyAsync(hc, d_ctl, sizeof(BnbControl), cudaMemcpyDeviceToHost, st));
   CU(ctx, cudaStreamSynchronize(st));
+  if (getenv("YALPS_BNB_DEBUG"))
+    fprintf(stderr, "k_bnb scheduler: %lld iterations, %lld cycles, %lld waiting for results (%lld pops waited), %lld in pop()\n",
+            hc->iters, hc->t_total, hc->t_wait, hc->n_wait, hc->t_heap);
   if (hc->overflow) return 1;  // a pool ran out: the wave driver has no such limits
   if (hc->found) {
     if (hc->best_cand < 0) return fail(ctx, YALPS_ERR_CUDA, "device search: incumbent without candidate arrays");

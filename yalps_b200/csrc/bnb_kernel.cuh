@@ -17,8 +17,17 @@
 //     (cooperative launch), so the spin-waits are inside one kernel.
 // What the reference pops, prunes, accepts and branches on is reproduced exactly (the tests compare node and
 // node-pivot counts, final basis and RHS bits with the oracle); only the evaluation order of the node LPs differs.
+// SPECULATIVE EXPANSION: a search is a chain of dives -- the scheduler pops a node, branches, and the best node of the
+// heap is one of the two children it has just created, whose LP (~30 us) has not even started.  So a worker that finds
+// its node optimal and fractional creates the node's two children ITSELF (same cuts the scheduler would derive from the
+// same result, :141-156) and queues them for evaluation, `spec_depth` generations ahead of the replay at most and only
+// while the node's result is below the incumbent the scheduler has published (the reference's own test at :130, taken
+// at an earlier time: a superset of what the replay will branch on).  When the replay branches on such a node it adopts
+// the two children instead of creating them.  Node ids are pool indices (allocated by whoever creates the node): they
+// only name nodes, the heap order depends on keys and push order, which stay the reference's.
 // Capacity limits (node pool, cut pool, candidate pool, heap, cut rows per node) are reported through `overflow`; the
-// host then repeats the search with the wave driver, which has none.
+// host then repeats the search with the wave driver, which has none.  Speculation has its own share of the node pool
+// and simply stops when that is used up.
 #pragma once
 
 #include "kernels.cuh"
@@ -35,7 +44,10 @@ struct BnbCut {
 };
 
 struct __align__(64) BnbNode {
-  // ---- result block, written by the worker, read by the scheduler with four 16-byte loads (one round trip to L2)
+  // ---- result block: four 16-byte chunks, each written by the worker with ONE vector store and each self-validating
+  // against the cleared state of the pool (every byte 0xff before the launch: result / pivots / status / done can never
+  // hold that), so the scheduler reads a finished node in a single round trip to L2 -- four loads in flight, no
+  // acquire in front of them -- and simply reads again while a chunk is still in its cleared state
   double result;    // rounded objective (optimal) / NaN
   double bval;      // mostFractionalVar: value
   double bfrac;     //                    fraction
@@ -46,20 +58,28 @@ struct __align__(64) BnbNode {
   int cand;         // candidate slot (integer-feasible optimal node) or -1
   int cut_begin;
   int done;         // release-stored last
-  int pad0, pad1;
-  // ---- written by the scheduler when the branch is created
+  int child0, child1;  // the children a worker created speculatively (upper branch first, :155-156), -1: none
+  // ---- written by whoever creates the branch (the scheduler, or the worker that evaluated the parent)
   double eval;      // parent's rounded result (heap key, :155-156)
   double new_sign, new_value;
   int new_var;
   int parent;       // -1: child of the root
-  double pad2[3];
+  int depth;        // generations of speculation behind this node (0: created by the scheduler)
+  int pad1;
+  double pad2[2];
 };
 static_assert(sizeof(BnbNode) == 128, "BnbNode layout");
 
 struct BnbControl {
-  unsigned long long next_ticket;  // workers: atomicAdd
+  unsigned long long next_ticket;  // (unused since the two-queue dispatch; kept for the layout)
   unsigned long long cut_top;      // cut pool bump pointer
-  int created;                     // nodes created so far (release-stored by the scheduler)
+  double best_eval;                // the scheduler's incumbent (+inf while none): bound of the workers' speculation
+  // two evaluation queues: the scheduler's nodes (ids [0, sched_cap), single producer, no atomics on its path) are
+  // served before the speculative ones (ids [sched_cap, node_cap), produced by the workers)
+  int s_head;                      // scheduler queue: entries claimed by workers (CAS)
+  int p_head, p_tail;              // speculative queue: claimed (CAS) / appended (atomicAdd)
+  int spec_count;                  // nodes created speculatively so far
+  int created;                     // nodes created in total (written by the scheduler at the end)
   int stop;                        // the scheduler is done
   int cand_top;
   int overflow;                    // 1 nodes, 2 cuts, 4 candidates, 8 heap, 16 cut rows
@@ -67,6 +87,7 @@ struct BnbControl {
   int status, found, best_node, best_height, best_cand, pad;
   double result;
   long long iters, node_pivots, max_cuts, max_heap;
+  long long t_total, t_wait, n_wait, t_heap;  // scheduler cycles: whole loop / waiting for results / pops that waited / heap work
 };
 
 struct BnbArgs {
@@ -86,6 +107,9 @@ struct BnbArgs {
   BnbControl *ctl;
   BnbNode *nodes;
   int node_cap;
+  int *queue;              // [node_cap] node id + 1, 0 = not yet written (zeroed before the launch): the scheduler's
+                           // queue in [0, sched_cap), the speculative one in [sched_cap, node_cap)
+  int sched_cap, spec_cap, spec_depth;  // node_cap = sched_cap + spec_cap; generations of speculation ahead of the replay
   BnbCut *cuts;
   unsigned long long cut_cap;
   double *cand_rhs;        // [cand_cap][Hcap]
@@ -105,6 +129,19 @@ __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
+}
+
+// A worker's result block: everything it wrote for this node (cut list, candidate arrays, speculative children) is
+// fenced in front of four 16-byte stores, one per self-validating chunk (see BnbNode).
+__device__ __forceinline__ void publish_result(BnbNode *nd, double result, double bval, double bfrac, long long pivots, int status,
+                                               int bvar, int cut_len, int cand, int cut_begin, int child0, int child1) {
+  __threadfence();
+  asm volatile("st.volatile.global.v2.f64 [%0], {%1, %2};" ::"l"(&nd->result), "d"(result), "d"(bval) : "memory");
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(&nd->bfrac), "l"(__double_as_longlong(bfrac)), "l"(pivots) : "memory");
+  asm volatile("st.volatile.global.v4.s32 [%0], {%1, %2, %3, %4};" ::"l"(&nd->status), "r"(status), "r"(bvar), "r"(cut_len), "r"(cand)
+               : "memory");
+  asm volatile("st.volatile.global.v4.s32 [%0], {%1, %2, %3, %4};" ::"l"(&nd->cut_begin), "r"(cut_begin), "r"(1), "r"(child0), "r"(child1)
+               : "memory");
 }
 
 template <int NWC, int KC, int NWR>
@@ -167,25 +204,35 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
       *k_out = tk;
       return tidx;
     };
-    int created = 0;
+    int created = 0;  // the scheduler's own nodes: ids and queue slots [0, sched_cap), no atomics on this path
     auto create = [&](double eval, int parent, double sign, int var, double value) -> bool {
-      if (created >= a.node_cap) {
-        atomicOr(&ctl->overflow, 1);
-        return false;
-      }
       if (hn >= a.heap_cap) {
         atomicOr(&ctl->overflow, 8);
         return false;
       }
-      BnbNode *nd = a.nodes + created;
+      const int id = created;
+      if (id >= a.sched_cap) {
+        atomicOr(&ctl->overflow, 1);
+        return false;
+      }
+      created++;
+      BnbNode *nd = a.nodes + id;
       nd->eval = eval;
       nd->new_sign = sign;
       nd->new_value = value;
       nd->new_var = var;
       nd->parent = parent;
-      nd->done = 0;
-      push(eval, created);
-      created++;
+      nd->depth = 0;
+      push(eval, id);
+      st_release(a.queue + id, id + 1);  // release: the node record is visible to the worker that claims the entry
+      return true;
+    };
+    auto adopt = [&](double eval, int id) -> bool {  // a child a worker has created (and queued) already
+      if (hn >= a.heap_cap) {
+        atomicOr(&ctl->overflow, 8);
+        return false;
+      }
+      push(eval, id);
       return true;
     };
     const unsigned long long t_start = global_ns();
@@ -194,37 +241,51 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
       return (double)(global_ns() - t_start) * 1e-6 >= a.timeout_ms;
     };
 
+    *reinterpret_cast<volatile double *>(&ctl->best_eval) = d_inf();
     // the root's two children (:101-102)
     bool ok = create(a.init_result, -1, -1.0, a.init_var, ceil(a.init_value));
     ok = ok && create(a.init_result, -1, 1.0, a.init_var, floor(a.init_value));
-    st_release(&ctl->created, created);
 
     const double threshold = a.init_result * (1.0 - a.sign * a.tolerance);  // :114
     bool timedout = timed_out();
     bool found = false;
     double best_eval = d_inf();
-    int best_node = -1;
+    int best_node = -1, best_cand = -1, best_len = 0;
+    long long t_wait = 0, n_wait = 0, t_heap = 0;
+    const long long t_loop0 = clock64();
     double iter = 0;
     long long node_pivots = 0, max_cuts = 0, max_heap = 0;
     while (ok && iter < a.max_iterations && hn > 0 && best_eval >= threshold && !timedout) {  // :122
       if (hn > max_heap) max_heap = hn;
       double ev;
+      const long long tp0 = clock64();
       const int br = pop(&ev);
+      t_heap += clock64() - tp0;
       if (ev > best_eval) break;  // :124
       BnbNode *nd = a.nodes + br;
-      while (!ld_acquire(&nd->done)) {
+      // the worker's result block in one round trip (see BnbNode); a pool overflow voids results: checked with it
+      double r_result, r_bval, r_bfrac;
+      long long r_pivots;
+      int r_status, r_bvar, r_cut_len, r_cand, r_cut_begin, r_done, r_child0, r_child1, r_overflow;
+      const long long tw0 = clock64();
+      int tries = 0;
+      for (;;) {
+        tries++;
+        asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(r_result), "=d"(r_bval) : "l"(&nd->result) : "memory");
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=d"(r_bfrac), "=l"(r_pivots) : "l"(&nd->bfrac) : "memory");
+        asm volatile("ld.volatile.global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r_status), "=r"(r_bvar), "=r"(r_cut_len), "=r"(r_cand) : "l"(&nd->status) : "memory");
+        asm volatile("ld.volatile.global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r_cut_begin), "=r"(r_done), "=r"(r_child0), "=r"(r_child1) : "l"(&nd->cut_begin) : "memory");
+        asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(r_overflow) : "l"(&ctl->overflow) : "memory");
+        if (r_overflow) break;
+        if (__double_as_longlong(r_result) != -1LL && r_pivots != -1LL && r_status != -1 && r_done == 1) break;
       }
-      if (*reinterpret_cast<volatile int *>(&ctl->overflow)) {  // a pool ran out: this node's result may be void
+      t_wait += clock64() - tw0;
+      n_wait += tries > 1;
+      (void)r_cut_begin;
+      if (r_overflow) {  // a pool ran out: this node's result may be void
         ok = false;
         break;
       }
-      // the worker's result block in one round trip
-      double r_result, r_bval, r_bfrac;
-      long long r_pivots;
-      int r_status, r_bvar, r_cut_len, r_cand;
-      asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(r_result), "=d"(r_bval) : "l"(&nd->result) : "memory");
-      asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=d"(r_bfrac), "=l"(r_pivots) : "l"(&nd->bfrac) : "memory");
-      asm volatile("ld.volatile.global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r_status), "=r"(r_bvar), "=r"(r_cut_len), "=r"(r_cand) : "l"(&nd->status) : "memory");
       const int n_status = r_status;
       const double n_value = r_result;
       node_pivots += r_pivots;
@@ -236,12 +297,17 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
           found = true;
           best_eval = n_value;
           best_node = br;
+          best_cand = r_cand;
+          best_len = r_cut_len;
+          *reinterpret_cast<volatile double *>(&ctl->best_eval) = best_eval;  // the workers stop speculating above it
+        } else if (r_child0 >= 0) {  // branch (:141-156) on children the node's worker has created (and queued) already
+          ok = adopt(n_value, r_child0);        // upper first (:155)
+          ok = ok && adopt(n_value, r_child1);  // then lower (:156)
         } else {  // branch (:141-156); the workers build the children's cut lists
           const int variable = r_bvar;
           const double value = r_bval;
           ok = create(n_value, br, -1.0, variable, ceil(value));       // upper first (:155)
           ok = ok && create(n_value, br, 1.0, variable, floor(value));  // then lower (:156)
-          st_release(&ctl->created, created);  // release: the two node records above are visible before the count
         }
       }
       timedout = timed_out();  // :162
@@ -252,12 +318,17 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
     ctl->found = found ? 1 : 0;
     ctl->result = found ? best_eval : d_nan();
     ctl->best_node = best_node;
-    ctl->best_cand = best_node >= 0 ? *reinterpret_cast<volatile int *>(&a.nodes[best_node].cand) : -1;
-    ctl->best_height = best_node >= 0 ? rootH + *reinterpret_cast<volatile int *>(&a.nodes[best_node].cut_len) : rootH;
+    ctl->best_cand = best_node >= 0 ? best_cand : -1;
+    ctl->best_height = best_node >= 0 ? rootH + best_len : rootH;
     ctl->iters = (long long)iter;
     ctl->node_pivots = node_pivots;
     ctl->max_cuts = max_cuts;
     ctl->max_heap = max_heap;
+    ctl->t_total = clock64() - t_loop0;
+    ctl->t_wait = t_wait;
+    ctl->n_wait = n_wait;
+    ctl->t_heap = t_heap;
+    ctl->created = created + min(*reinterpret_cast<volatile int *>(&ctl->spec_count), a.spec_cap);
     if (!ok) atomicOr(&ctl->overflow, 32);  // the search was abandoned: the host repeats it with the wave driver
     __threadfence();
     st_release(&ctl->stop, 1);
@@ -269,23 +340,36 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
   unsigned long long rows_total = 0;
   for (;;) {
     if (tid == 0) {
-      const unsigned long long ticket = atomicAdd(&ctl->next_ticket, 1ULL);
+      // claim the next entry: the scheduler's queue first (the replay is waiting for those), then the speculative one
       int node = -1;
-      if (ticket < (unsigned long long)a.node_cap) {
-        for (;;) {
-          if ((unsigned long long)ld_acquire(&ctl->created) > ticket) {
-            node = (int)ticket;
-            break;
+      for (;;) {
+        const int h = *reinterpret_cast<volatile int *>(&ctl->s_head);
+        if (h < a.sched_cap) {
+          const int q = ld_acquire(a.queue + h);
+          if (q) {
+            if (atomicCAS(&ctl->s_head, h, h + 1) == h) {
+              node = q - 1;
+              break;
+            }
+            continue;
           }
-          if (ld_acquire(&ctl->stop)) {  // re-check: the last nodes may have been created just before the stop
-            if ((unsigned long long)ld_acquire(&ctl->created) > ticket) node = (int)ticket;
-            break;
-          }
-          __nanosleep(64);
         }
-        // nodes created before the stop but never needed are skipped once the scheduler is done
-        if (node >= 0 && ld_acquire(&ctl->stop)) node = -1;
+        const int hp = *reinterpret_cast<volatile int *>(&ctl->p_head);
+        if (hp < a.spec_cap) {
+          const int q = ld_acquire(a.queue + a.sched_cap + hp);
+          if (q) {
+            if (atomicCAS(&ctl->p_head, hp, hp + 1) == hp) {
+              node = q - 1;
+              break;
+            }
+            continue;
+          }
+        }
+        if (ld_acquire(&ctl->stop)) break;
+        __nanosleep(32);
       }
+      // nodes created before the stop but never needed are skipped once the scheduler is done
+      if (node >= 0 && ld_acquire(&ctl->stop)) node = -1;
       s_node = node;
     }
     __syncthreads();
@@ -367,15 +451,7 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
     if (ncuts < 0 || rootH + ncuts > a.Hcap) {
       if (tid == 0) {
         if (ncuts >= 0) atomicOr(&ctl->overflow, 16);
-        nd->cut_begin = 0;
-        nd->cut_len = 0;
-        nd->status = ST_CYCLED;
-        nd->result = d_nan();
-        nd->pivots = 0;
-        nd->bfrac = 0.0;
-        nd->cand = -1;
-        __threadfence();
-        st_release(&nd->done, 1);
+        publish_result(nd, d_nan(), 0.0, 0.0, 0, ST_CYCLED, 0, 0, -1, 0, -1, -1);
       }
       __syncthreads();
       continue;
@@ -512,17 +588,36 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
     }
     __syncthreads();
     if (tid == 0) {
-      nd->cut_begin = (int)s_cut_begin;
-      nd->cut_len = ncuts;
-      nd->status = res.status;
-      nd->result = res.value;
-      nd->pivots = res.p1 + res.p2;
-      nd->bvar = bvar;
-      nd->bval = bval;
-      nd->bfrac = bfrac;
-      nd->cand = cand;
-      __threadfence();
-      st_release(&nd->done, 1);
+      // speculative expansion (see the header): the two children the replay will create if it branches on this node
+      int c0 = -1, c1 = -1;
+      const int depth = __ldcg(&nd->depth);
+      if (res.status == ST_OPTIMAL && bfrac > a.precision && depth < a.spec_depth &&
+          res.value < *reinterpret_cast<volatile double *>(&ctl->best_eval) && !ld_acquire(&ctl->stop)) {
+        const int sp = atomicAdd(&ctl->spec_count, 2);
+        if (sp + 2 <= a.spec_cap) {
+          const int id = a.sched_cap + sp;
+          {
+            c0 = id;
+            c1 = id + 1;
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+              BnbNode *ch = a.nodes + id + k;
+              ch->eval = res.value;
+              ch->new_sign = k == 0 ? -1.0 : 1.0;                 // upper first (:155), then lower (:156)
+              ch->new_value = k == 0 ? ceil(bval) : floor(bval);
+              ch->new_var = bvar;
+              ch->parent = node;
+              ch->depth = depth + 1;
+            }
+          }
+        }
+      }
+      publish_result(nd, res.value, bval, bfrac, res.p1 + res.p2, res.status, bvar, ncuts, cand, (int)s_cut_begin, c0, c1);
+      if (c0 >= 0) {  // (release: this node's cut list and the children's records are visible to whoever claims them)
+        const int slot = atomicAdd(&ctl->p_tail, 2);
+        st_release(a.queue + a.sched_cap + slot, c0 + 1);
+        st_release(a.queue + a.sched_cap + slot + 1, c1 + 1);
+      }
     }
     __syncthreads();
   }

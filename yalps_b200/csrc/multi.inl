@@ -535,6 +535,8 @@ int yalps_multi_solve_many(yalps_multi *m, int64_t n_models, const int32_t *heig
     for (int r = 0; r < world; r++) {
       MultiWorker *mw = ensure_worker(m, r, w);
       if (!mw) return YALPS_ERR_CUDA;
+      // the per_dev searches of one GPU run at the same time: each gets its share of the SMs (scheduler CTA included)
+      mw->ctx->bnb_workers = std::max(8, mw->ctx->prop.multiProcessorCount / per_dev - 1);
       pool.push_back(mw);
     }
   std::mutex qmu;

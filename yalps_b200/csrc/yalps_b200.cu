@@ -90,6 +90,8 @@ struct yalps_ctx {
   int wave = 256;  // upper bound of the adaptive look-ahead of the branch-and-cut driver
   int kc_tma = 0;    // KC: staging of the winner's pivot row (YALPS_KC_TMA: 0 ld.global.cg, 1 cp.async.bulk, 2 multicast)
   int bnb_mode = 0;  // 0: device-resident search when it fits, else host waves; 1: host waves only; 2: device only
+  int bnb_workers = 0;  // device-resident search: worker CTAs (0 = one per SM beside the scheduler; yalps_multi_solve_many
+                        // shares the SMs between its concurrent searches)
   int64_t replica_forks = -1;  // last yalps_solve_replicas call: replicas that left the shared path (-1: sharing not used)
   int replica_sharing = 1;  // yalps_solve_replicas: follow the base tableau's pivot path while a replica makes the same choices
   unsigned long long *d_rows = nullptr;  // roofline diagnostics: device counter(s) of rewritten rows (yalps_set_row_counter)
