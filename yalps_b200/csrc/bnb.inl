@@ -585,6 +585,10 @@ int device_search(yalps_ctx *ctx, const int32_t *ints, int32_t nints, double sig
   if (getenv("YALPS_BNB_DEBUG"))
     fprintf(stderr, "k_bnb scheduler: %lld iterations, %lld cycles, %lld waiting for results (%lld pops waited), %lld in pop()\n",
             hc->iters, hc->t_total, hc->t_wait, hc->n_wait, hc->t_heap);
+  if (getenv("YALPS_BNB_DEBUG") && hc->w_nodes)
+    fprintf(stderr, "k_bnb workers: %llu nodes (finished before the stop), cycles per node: cut list %llu, assembly %llu, simplex %llu (%.1f pivots), mostFractionalVar + publish %llu\n",
+            hc->w_nodes, hc->w_cuts / hc->w_nodes, hc->w_asm / hc->w_nodes, hc->w_simplex / hc->w_nodes,
+            (double)hc->node_pivots / (double)std::max<long long>(hc->iters, 1), hc->w_post / hc->w_nodes);
   if (hc->overflow) return 1;  // a pool ran out: the wave driver has no such limits
   if (hc->found) {
     if (hc->best_cand < 0) return fail(ctx, YALPS_ERR_CUDA, "device search: incumbent without candidate arrays");

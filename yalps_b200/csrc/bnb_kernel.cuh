@@ -88,6 +88,7 @@ struct BnbControl {
   double result;
   long long iters, node_pivots, max_cuts, max_heap;
   long long t_total, t_wait, n_wait, t_heap;  // scheduler cycles: whole loop / waiting for results / pops that waited / heap work
+  unsigned long long w_nodes, w_cuts, w_asm, w_simplex, w_post;  // workers (thread 0, summed): nodes and cycles per stage
 };
 
 struct BnbArgs {
@@ -224,8 +225,17 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
       nd->parent = parent;
       nd->depth = 0;
       push(eval, id);
-      st_release(a.queue + id, id + 1);  // release: the node record is visible to the worker that claims the entry
       return true;
+    };
+    // the records of the nodes created since the last call become visible before their queue entries (one fence for the
+    // two children of a branch; the fence also orders the result block the scheduler has just read -- and with it the
+    // parent's cut list -- before the entries, for the workers that claim them)
+    int published = 0;
+    auto publish_created = [&]() {
+      if (published == created) return;
+      __threadfence();
+      for (; published < created; published++)
+        *reinterpret_cast<volatile int *>(a.queue + published) = published + 1;
     };
     auto adopt = [&](double eval, int id) -> bool {  // a child a worker has created (and queued) already
       if (hn >= a.heap_cap) {
@@ -245,6 +255,7 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
     // the root's two children (:101-102)
     bool ok = create(a.init_result, -1, -1.0, a.init_var, ceil(a.init_value));
     ok = ok && create(a.init_result, -1, 1.0, a.init_var, floor(a.init_value));
+    publish_created();
 
     const double threshold = a.init_result * (1.0 - a.sign * a.tolerance);  // :114
     bool timedout = timed_out();
@@ -257,27 +268,31 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
     long long node_pivots = 0, max_cuts = 0, max_heap = 0;
     while (ok && iter < a.max_iterations && hn > 0 && best_eval >= threshold && !timedout) {  // :122
       if (hn > max_heap) max_heap = hn;
-      double ev;
-      const long long tp0 = clock64();
-      const int br = pop(&ev);
-      t_heap += clock64() - tp0;
-      if (ev > best_eval) break;  // :124
-      BnbNode *nd = a.nodes + br;
-      // the worker's result block in one round trip (see BnbNode); a pool overflow voids results: checked with it
+      // the worker's result block in one round trip (see BnbNode); a pool overflow voids results: checked with it.  The
+      // node that pop() is about to return is the heap's top: its loads are issued first and travel while the heap is
+      // re-ordered (~1,300 cycles of shared-memory work that does not depend on them)
+      BnbNode *nd = a.nodes + hid[0];
       double r_result, r_bval, r_bfrac;
       long long r_pivots;
       int r_status, r_bvar, r_cut_len, r_cand, r_cut_begin, r_done, r_child0, r_child1, r_overflow;
-      const long long tw0 = clock64();
-      int tries = 0;
-      for (;;) {
-        tries++;
+      auto read_block = [&]() {
         asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(r_result), "=d"(r_bval) : "l"(&nd->result) : "memory");
         asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=d"(r_bfrac), "=l"(r_pivots) : "l"(&nd->bfrac) : "memory");
         asm volatile("ld.volatile.global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r_status), "=r"(r_bvar), "=r"(r_cut_len), "=r"(r_cand) : "l"(&nd->status) : "memory");
         asm volatile("ld.volatile.global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r_cut_begin), "=r"(r_done), "=r"(r_child0), "=r"(r_child1) : "l"(&nd->cut_begin) : "memory");
         asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(r_overflow) : "l"(&ctl->overflow) : "memory");
-        if (r_overflow) break;
-        if (__double_as_longlong(r_result) != -1LL && r_pivots != -1LL && r_status != -1 && r_done == 1) break;
+      };
+      read_block();
+      double ev;
+      const long long tp0 = clock64();
+      const int br = pop(&ev);
+      t_heap += clock64() - tp0;
+      if (ev > best_eval) break;  // :124
+      const long long tw0 = clock64();
+      int tries = 1;
+      while (!r_overflow && !(__double_as_longlong(r_result) != -1LL && r_pivots != -1LL && r_status != -1 && r_done == 1)) {
+        tries++;
+        read_block();
       }
       t_wait += clock64() - tw0;
       n_wait += tries > 1;
@@ -308,6 +323,7 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
           const double value = r_bval;
           ok = create(n_value, br, -1.0, variable, ceil(value));       // upper first (:155)
           ok = ok && create(n_value, br, 1.0, variable, floor(value));  // then lower (:156)
+          publish_created();
         }
       }
       timedout = timed_out();  // :162
@@ -338,6 +354,7 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
   // =========================== workers ===========================
   const SmemLayout L(a.Hcap, W, true, NW, true);
   unsigned long long rows_total = 0;
+  unsigned long long w_nodes = 0, w_cuts = 0, w_asm = 0, w_simplex = 0, w_post = 0;  // (thread 0; YALPS_BNB_DEBUG prints the sums)
   for (;;) {
     if (tid == 0) {
       // claim the next entry: the scheduler's queue first (the replay is waiting for those), then the speculative one
@@ -377,6 +394,7 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
     __syncthreads();
     if (node < 0) break;
     BnbNode *nd = a.nodes + node;
+    long long wt0 = clock64();
 
     // ---- the node's cut list from its parent's (:141-154): same-direction cuts on the branching variable are dropped.
     // Everything another CTA wrote during this launch is read through L2 (__ldcg): L1 lines may predate those writes.
@@ -447,6 +465,11 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
       }
     }
     __syncthreads();
+    if (tid == 0) {
+      const long long now = clock64();
+      w_cuts += now - wt0;
+      wt0 = now;
+    }
     const int ncuts = s_ncuts;
     if (ncuts < 0 || rootH + ncuts > a.Hcap) {
       if (tid == 0) {
@@ -524,10 +547,20 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
     }
     cp_async_wait_all();
     __syncthreads();
+    if (tid == 0) {
+      const long long now = clock64();
+      w_asm += now - wt0;
+      wt0 = now;
+    }
 
     // ---- simplex(tableau, options) (:127)
     const LpResult res = simplex_cta_split<NWC, KC, NWR, VW>(t, ss, a.precision, a.max_pivots, 0);
     __syncthreads();
+    if (tid == 0) {
+      const long long now = clock64();
+      w_simplex += now - wt0;
+      wt0 = now;
+    }
     rows_total += res.rows;
 
     // ---- mostFractionalVar (:64-85): first integer variable (in `integers` order) with the largest fraction
@@ -613,6 +646,8 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
         }
       }
       publish_result(nd, res.value, bval, bfrac, res.p1 + res.p2, res.status, bvar, ncuts, cand, (int)s_cut_begin, c0, c1);
+      w_post += clock64() - wt0;
+      w_nodes++;
       if (c0 >= 0) {  // (release: this node's cut list and the children's records are visible to whoever claims them)
         const int slot = atomicAdd(&ctl->p_tail, 2);
         st_release(a.queue + a.sched_cap + slot, c0 + 1);
@@ -622,6 +657,13 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
     __syncthreads();
   }
   if (a.rows_out && tid == 0 && rows_total) atomicAdd(a.rows_out, rows_total);
+  if (tid == 0 && w_nodes) {
+    atomicAdd(&ctl->w_nodes, w_nodes);
+    atomicAdd(&ctl->w_cuts, w_cuts);
+    atomicAdd(&ctl->w_asm, w_asm);
+    atomicAdd(&ctl->w_simplex, w_simplex);
+    atomicAdd(&ctl->w_post, w_post);
+  }
 }
 
 }  // namespace yalps
