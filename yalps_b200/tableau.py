@@ -29,9 +29,10 @@ def entries(obj) -> Iterable:
     Any other iterable is taken as an iterable of (key, value) pairs (Array / Map, src/tableau.ts:36).
     """
     if isinstance(obj, dict):
-        numeric = [k for k in obj if isinstance(k, str) and _INDEX_KEY.fullmatch(k) and int(k) < 4294967295]
+        # (cheap pre-test: a canonical array index starts with a digit)
+        numeric = [k for k in obj if isinstance(k, str) and k[:1].isdigit() and _INDEX_KEY.fullmatch(k) and int(k) < 4294967295]
         if not numeric:
-            return list(obj.items())
+            return obj.items()
         numeric.sort(key=int)
         seen = set(numeric)
         return [(k, obj[k]) for k in numeric] + [(k, v) for k, v in obj.items() if k not in seen]
@@ -133,22 +134,34 @@ def tableau_model(model: dict) -> TableauModel:
     matrix = np.zeros(height * width, dtype=np.float64)
 
     # coefficients: later duplicates of a key overwrite earlier ones (src/tableau.ts:100-117)
+    # one lookup per coefficient: key -> (row offset of the upper row or -1, row offset of the lower row or -1, is objective)
+    where: dict[Any, tuple] = {}
+    for key in lower:
+        u, l = up_row.get(key), lo_row.get(key)
+        if u is not None or l is not None:
+            where[key] = (-1 if u is None else u * width, -1 if l is None else l * width, False)
+    if objective is not None:
+        u, l, _ = where.get(objective, (-1, -1, False))
+        where[objective] = (u, l, True)
     idx: list[int] = []
     val: list[float] = []
+    add_idx, add_val, find = idx.append, val.append, where.get
     for col, (_, coefs) in enumerate(variables, start=1):
         for ckey, coef in entries(coefs):
+            hit = find(ckey)
+            if hit is None:
+                continue
             coef = float(coef)
-            if objective is not None and ckey == objective:
-                idx.append(col)
-                val.append(sign * coef)
-            r = up_row.get(ckey)
-            if r is not None:
-                idx.append(r * width + col)
-                val.append(coef)
-            r = lo_row.get(ckey)
-            if r is not None:
-                idx.append(r * width + col)
-                val.append(-coef)
+            u, l, is_obj = hit
+            if is_obj:
+                add_idx(col)
+                add_val(sign * coef)
+            if u >= 0:
+                add_idx(u + col)
+                add_val(coef)
+            if l >= 0:
+                add_idx(l + col)
+                add_val(-coef)
     if idx:
         # numpy fancy assignment applies repeated indices in order, so the last one wins like the reference
         matrix[np.asarray(idx, dtype=np.int64)] = np.asarray(val, dtype=np.float64)
