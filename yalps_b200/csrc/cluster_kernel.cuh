@@ -207,7 +207,7 @@ __device__ __forceinline__ void grid_sync_lean(unsigned long long *counter, unsi
 // ahead of the slowest one, because it needs that CTA's next record, which is written after that CTA has finished
 // reading the current buffers.  (First version: counter barrier + sequential record reads, 10,000 cycles per
 // selection on 25FV47; see profiles/.)
-template <bool kMax, int NW>
+template <bool kMax, int NW, int kRowU>
 __device__ __forceinline__ int grid_select(int C, int rank, unsigned long long key, int idx, unsigned *red, int &parity,
                                            uint4 *gslots, unsigned &xcount, const double *A, int ldA, double *scratch,
                                            double *prow_s, int *s_row, long long *yt = nullptr, long long *yt_last = nullptr) {
@@ -298,26 +298,28 @@ __device__ __forceinline__ int grid_select(int C, int rank, unsigned long long k
   if (row != kNone && row != kGiveUp) {  // the winner's row: every thread polls the slots of its own cells
     const int owner = (row - 1) % C;
     const uint4 *src = pub + (size_t)owner * ldA;
-    for (int c0 = 0; c0 < ldA; c0 += 8 * NT) {
+    // (kRowU = the most slots a thread of this instantiation can own: all of them in ONE flight -- 2049 columns / 256
+    // threads are 8.02 slots per thread, and a second pass for the last four cells was a second round trip to L2 per pivot)
+    for (int c0 = 0; c0 < ldA; c0 += kRowU * NT) {
       unsigned pend = 0, spins = 0;
 #pragma unroll
-      for (int u = 0; u < 8; u++)
+      for (int u = 0; u < kRowU; u++)
         if (c0 + u * NT + (int)threadIdx.x < ldA) pend |= 1u << u;
       while (pend) {
         if (++spins > (1u << 22)) {
           bad = true;
           break;
         }
-        uint4 v[8];
+        uint4 v[kRowU];
 #pragma unroll
-        for (int u = 0; u < 8; u++)
+        for (int u = 0; u < kRowU; u++)
           if ((pend >> u) & 1u)
             asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
                          : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w)
                          : "l"(src + c0 + u * NT + threadIdx.x)
                          : "memory");
 #pragma unroll
-        for (int u = 0; u < 8; u++)
+        for (int u = 0; u < kRowU; u++)
           if (((pend >> u) & 1u) && v[u].y == rseq && v[u].w == rseq) {
             pend &= ~(1u << u);
             prow_s[c0 + u * NT + threadIdx.x] = __hiloint2double((int)v[u].z, (int)v[u].x);
@@ -442,7 +444,7 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_simplex_cluster(const Batc
           }
         }
         if (kGrid)
-          row = grid_select<false, NW>(C, rank, bi == kNone ? no_key<false>() : order_key(bv), bi, red, parity, a.gx_slots, xcount,
+          row = grid_select<false, NW, (2 * KC * NTC + 4 + NT - 1) / NT>(C, rank, bi == kNone ? no_key<false>() : order_key(bv), bi, red, parity, a.gx_slots, xcount,
                                        A, ldA, scratch, prow_s, &s_row GS_TIMING_ARGS);
         else
           row = cluster_select<false, NW>(cluster, C, rank, bi == kNone ? no_key<false>() : order_key(bv), bi, red, parity, xch,
@@ -536,7 +538,7 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_simplex_cluster(const Batc
           }
         }
         if (kGrid)
-          row = grid_select<false, NW>(C, rank, bi == kNone ? no_key<false>() : order_key(bv), bi, red, parity, a.gx_slots, xcount,
+          row = grid_select<false, NW, (2 * KC * NTC + 4 + NT - 1) / NT>(C, rank, bi == kNone ? no_key<false>() : order_key(bv), bi, red, parity, a.gx_slots, xcount,
                                        A, ldA, scratch, prow_s, &s_row GS_TIMING_ARGS);
         else
           row = cluster_select<false, NW>(cluster, C, rank, bi == kNone ? no_key<false>() : order_key(bv), bi, red, parity, xch,
