@@ -465,22 +465,46 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_simplex_cluster(const Batc
         bv = -INF;
         bi = kNone;
         {
+          // (KC blocks of NT column pairs cover the row: NT >= NTC.  Branch-free batch form of the divisions, fastdiv.cuh:
+          // the quotients of a thread overlap and share one acceptance test; the exact division runs out of line)
           const double *prow = prow_s;
-          for (int j0 = VW * tid; j0 < Wm1; j0 += VW * NT) {
-            const double2 cf = *reinterpret_cast<const double2 *>(prow + j0);
-            const double2 ob = *reinterpret_cast<const double2 *>(obj + j0);
+          double ratio[KC][VW], coefs[KC][VW], nums[KC][VW];
+          unsigned use = 0;
+          bool ok = true;
+#pragma unroll
+          for (int k = 0; k < KC; k++) {
+            const int j0 = VW * (tid + NT * k);
+            double2 cf = make_double2(0.0, 0.0), ob = make_double2(0.0, 0.0);
+            if (j0 < Wm1) {
+              cf = *reinterpret_cast<const double2 *>(prow + j0);
+              ob = *reinterpret_cast<const double2 *>(obj + j0);
+            }
 #pragma unroll
             for (int e = 0; e < VW; e++) {
-              const double coef = e ? cf.y : cf.x;
-              if (j0 + e < Wm1 && coef < -precision) {
-                const double ratio = div_rn(-(e ? ob.y : ob.x), coef);
-                if (ratio > bv) {  // bv starts at -inf: -inf and NaN ratios never win, as in the reference
-                  bv = ratio;
-                  bi = j0 + e + 1;
-                }
-              }
+              coefs[k][e] = e ? cf.y : cf.x;
+              nums[k][e] = -(e ? ob.y : ob.x);
+              const bool u = j0 + e < Wm1 && coefs[k][e] < -precision;
+              RecipBatch d(coefs[k][e], u);
+              ratio[k][e] = d.quot(nums[k][e], u);
+              ok = ok && d.ok;
+              use |= (u ? 1u : 0u) << (k * VW + e);
             }
           }
+          if (!ok) {  // rare
+#pragma unroll
+            for (int k = 0; k < KC; k++)
+#pragma unroll
+              for (int e = 0; e < VW; e++)
+                if ((use >> (k * VW + e)) & 1u) ratio[k][e] = div_rn_slow(nums[k][e], coefs[k][e]);
+          }
+#pragma unroll
+          for (int k = 0; k < KC; k++)
+#pragma unroll
+            for (int e = 0; e < VW; e++)
+              if (((use >> (k * VW + e)) & 1u) && ratio[k][e] > bv) {  // bv starts at -inf: -inf and NaN ratios never win, as in the reference
+                bv = ratio[k][e];
+                bi = VW * (tid + NT * k) + e + 1;
+              }
         }
         col = block_best<true, NW>(bi == kNone ? no_key<true>() : order_key(bv), bi, red, parity);
         CT_MARK(1);
