@@ -610,27 +610,50 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_simplex_cluster(const Batc
         if (tid < nloc) cell0 = A[(size_t)tid * ldA + jc];
         const Recip rq(q);
 
+        // (branch-free batch form of the divisions, fastdiv.cuh: the quotients of a thread overlap and share ONE acceptance
+        // test -- a test-and-branch per quotient made this stage ~2,000 cycles of every CTA's critical path)
+        RecipBatch rb(q, rq.r);
         double p[KC][VW];
-        unsigned st = 0, full = 0, valid = 0, partial = 0;
+        unsigned st = 0, full = 0, valid = 0, partial = 0, live = 0;
         int jc_off = -1;
 #pragma unroll
         for (int k = 0; k < KC; k++) {
           const int j0 = VW * (ctid + NTC * k);
 #pragma unroll
           for (int e = 0; e < VW; e++) {
-            p[k][e] = 0.0;
             const int j = j0 + e;
+            const double x = (j == jc) ? 1.0 : (e ? v[k].y : v[k].x);
+            const bool use = j < Wm1 && fabs(x) > kTiny;
+            p[k][e] = rb.quot(x, use);
+            live |= (use ? 1u : 0u) << (k * VW + e);
             if (j < Wm1) {
               valid |= 1u << (k * VW + e);
               if (j == jc) jc_off = VW * NTC * k + e;
-              const double x = (j == jc) ? 1.0 : (e ? v[k].y : v[k].x);
-              if (fabs(x) > kTiny) {
-                p[k][e] = rq.quot(x);
-                st |= 1u << (k * VW + e);
-              }
-            } else if (j0 < Wm1) {
-              st |= 1u << (k * VW + e);  // padding cell next to the last column: rewriting it is harmless
             }
+          }
+        }
+        const bool nz0 = fabs(braw) > kTiny;
+        double p0 = rb.quot(braw, nz0);  // normalised RHS of the pivot row (:19 for c = 0)
+        if (!rb.ok) {  // rare: exact divisions out of line
+#pragma unroll
+          for (int k = 0; k < KC; k++)
+#pragma unroll
+            for (int e = 0; e < VW; e++)
+              if ((live >> (k * VW + e)) & 1u)
+                p[k][e] = div_rn_slow((VW * (ctid + NTC * k) + e == jc) ? 1.0 : (e ? v[k].y : v[k].x), q);
+          if (nz0) p0 = div_rn_slow(braw, q);
+        }
+        if (!nz0) p0 = 0.0;
+#pragma unroll
+        for (int k = 0; k < KC; k++) {
+          const int j0 = VW * (ctid + NTC * k);
+#pragma unroll
+          for (int e = 0; e < VW; e++) {
+            if (!((live >> (k * VW + e)) & 1u)) p[k][e] = 0.0;
+            if ((live >> (k * VW + e)) & 1u)
+              st |= 1u << (k * VW + e);
+            else if (j0 + e >= Wm1 && j0 < Wm1)
+              st |= 1u << (k * VW + e);  // padding cell next to the last column: rewriting it is harmless
           }
           const unsigned m = (st >> (k * VW)) & 3u;
           if (m == 3u)
@@ -638,8 +661,6 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_simplex_cluster(const Batc
           else if (m)
             partial = 1u;
         }
-        const bool nz0 = fabs(braw) > kTiny;
-        const double p0 = nz0 ? rq.quot(braw) : 0.0;  // normalised RHS of the pivot row (:19 for c = 0)
         CT_MARK(2);
 
         // ---- local pivot-column cells: -coef/q (:36) and the compacted list of local rows to rewrite (:31)
