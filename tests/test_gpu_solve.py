@@ -332,6 +332,33 @@ def test_device_resident_search_equals_the_wave_driver_and_the_oracle(case):
         eng.close()
 
 
+@pytest.mark.parametrize("spec,workers", [(0, 0), (1, 2), (3, 0), (5, 1), (2, 3)])
+def test_device_resident_search_speculation_depth_and_worker_count(monkeypatch, spec, workers):
+    """Speculative expansion (bnb_kernel.cuh) changes WHEN node LPs are evaluated, never what the replay pops: every
+    depth -- none, deeper than the default -- and every worker count, down to one CTA that has to serve both queues,
+    gives the oracle's search node for node."""
+    monkeypatch.setenv("YALPS_BNB_SPEC", str(spec))
+    if workers:
+        monkeypatch.setenv("YALPS_BNB_WORKERS", str(workers))
+    eng = yalps_b200.Engine(0)
+    try:
+        eng.set_bnb_mode(2)
+        for name in ("Large Farm MIP", "Knapsack 1", "Fancy Stock Cutting Problem", "Integer Wood Shop Problem"):
+            case = next(x for x in CASES if x["name"] == name)
+            o = case["oracle"]
+            info = {}
+            sol = yalps_b200.solve(case["model"], case["options"], engine=eng, info=info)
+            assert sol["status"] == o["status"] and same_value(sol["result"], o["result"]), name
+            assert [list(v) for v in sol["variables"]] == [list(v) for v in o["variables"]], name
+            assert info["nodes"] == o["nodes"] and info["node_pivots"] == o["node_pivots"], name
+            assert np.array_equal(info["final_pos"], o["final_pos"]) and same_bits(info["final_rhs"], o["final_rhs"]), name
+            assert info["waves"] == 1, name
+            if spec == 0:
+                assert info["device_nodes"] <= 2 * o["nodes"] + 2, name  # only what the replay itself creates
+    finally:
+        eng.close()
+
+
 def test_device_resident_search_options(engine):
     """tolerance, maxIterations and timeout inside the device scheduler (src/branchAndCut.ts:114-116,122,162,167-173)."""
     c = next(x for x in CASES if x["name"] == "Fancy Stock Cutting Problem")

@@ -583,8 +583,8 @@ int device_search(yalps_ctx *ctx, const int32_t *ints, int32_t nints, double sig
   CU(ctx, cudaMemcpyAsync(hc, d_ctl, sizeof(BnbControl), cudaMemcpyDeviceToHost, st));
   CU(ctx, cudaStreamSynchronize(st));
   if (getenv("YALPS_BNB_DEBUG"))
-    fprintf(stderr, "k_bnb scheduler: %lld iterations, %lld cycles, %lld waiting for results (%lld pops waited), %lld in pop()\n",
-            hc->iters, hc->t_total, hc->t_wait, hc->n_wait, hc->t_heap);
+    fprintf(stderr, "k_bnb scheduler: %lld iterations, %lld cycles, %lld waiting for results (%lld pops waited), %lld in pop(); overflow flags %d, %d nodes created (%d speculative), %d candidates, %llu cuts\n",
+            hc->iters, hc->t_total, hc->t_wait, hc->n_wait, hc->t_heap, hc->overflow, hc->created, hc->spec_count, hc->cand_top, hc->cut_top);
   if (getenv("YALPS_BNB_DEBUG") && hc->w_nodes)
     fprintf(stderr, "k_bnb workers: %llu nodes (finished before the stop), cycles per node: cut list %llu, assembly %llu, simplex %llu (%.1f pivots), mostFractionalVar + publish %llu\n",
             hc->w_nodes, hc->w_cuts / hc->w_nodes, hc->w_asm / hc->w_nodes, hc->w_simplex / hc->w_nodes,

@@ -297,6 +297,28 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
       t_wait += clock64() - tw0;
       n_wait += tries > 1;
       (void)r_cut_begin;
+      if (r_status == ST_ERR_POOL && !r_overflow) {
+        // a speculative node that a pool could not serve has become part of the replay: it is evaluated again as one of the
+        // replay's own nodes (result block back to its cleared state, generation 0, a slot of the scheduler's queue -- the
+        // slot's own node id stays unused) and awaited in place, so the heap never sees the difference
+        publish_created();
+        if (created >= a.sched_cap) {
+          atomicOr(&ctl->overflow, 1);
+          ok = false;
+          break;
+        }
+        asm volatile("st.volatile.global.v4.s32 [%0], {%1, %1, %1, %1};" ::"l"(&nd->result), "r"(-1) : "memory");
+        asm volatile("st.volatile.global.v4.s32 [%0], {%1, %1, %1, %1};" ::"l"(&nd->bfrac), "r"(-1) : "memory");
+        asm volatile("st.volatile.global.v4.s32 [%0], {%1, %1, %1, %1};" ::"l"(&nd->status), "r"(-1) : "memory");
+        asm volatile("st.volatile.global.v4.s32 [%0], {%1, %1, %1, %1};" ::"l"(&nd->cut_begin), "r"(-1) : "memory");
+        *reinterpret_cast<volatile int *>(&nd->depth) = 0;
+        __threadfence();
+        *reinterpret_cast<volatile int *>(a.queue + created) = br + 1;
+        created++;
+        published++;
+        do read_block();
+        while (!r_overflow && !(__double_as_longlong(r_result) != -1LL && r_pivots != -1LL && r_status != -1 && r_done == 1));
+      }
       if (r_overflow) {  // a pool ran out: this node's result may be void
         ok = false;
         break;
@@ -418,11 +440,13 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
       if (lane == 0) begin = atomicAdd(&ctl->cut_top, (unsigned long long)(plen + 1));
       begin = __shfl_sync(0xffffffffu, begin, 0);
       int n = 0;
+      // (a pool that runs out under a SPECULATIVE node only voids that node: the search is abandoned when -- if ever --
+      // the replay pops it)
       if (begin + plen + 1 > a.cut_cap) {
-        if (lane == 0) atomicOr(&ctl->overflow, 2);
+        if (lane == 0 && __ldcg(&nd->depth) == 0) atomicOr(&ctl->overflow, 2);
         n = -1;
       } else if (plen + 1 > kBnbMaxCuts) {
-        if (lane == 0) atomicOr(&ctl->overflow, 16);
+        if (lane == 0 && __ldcg(&nd->depth) == 0) atomicOr(&ctl->overflow, 16);
         n = -1;
       } else {
         for (int i0 = 0; i0 < plen; i0 += 32) {
@@ -473,8 +497,9 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
     const int ncuts = s_ncuts;
     if (ncuts < 0 || rootH + ncuts > a.Hcap) {
       if (tid == 0) {
-        if (ncuts >= 0) atomicOr(&ctl->overflow, 16);
-        publish_result(nd, d_nan(), 0.0, 0.0, 0, ST_CYCLED, 0, 0, -1, 0, -1, -1);
+        const bool spec = __ldcg(&nd->depth) > 0;
+        if (ncuts >= 0 && !spec) atomicOr(&ctl->overflow, 16);
+        publish_result(nd, d_nan(), 0.0, 0.0, 0, spec ? ST_ERR_POOL : ST_CYCLED, 0, 0, -1, 0, -1, -1);
       }
       __syncthreads();
       continue;
@@ -601,10 +626,16 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
     if (res.status == ST_OPTIMAL && bfrac <= a.precision) {  // incumbent candidate: what solution() reads (:175)
       __shared__ int s_cand;
       if (tid == 0) {
-        s_cand = atomicAdd(&ctl->cand_top, 1);
-        if (s_cand >= a.cand_cap) {
-          atomicOr(&ctl->overflow, 4);
-          s_cand = -1;
+        const bool spec = __ldcg(&nd->depth) > 0;
+        // (speculative nodes leave half of the pool to the replay's own nodes; one that finds no slot is void, see the cut pool)
+        if (spec && *reinterpret_cast<volatile int *>(&ctl->cand_top) >= a.cand_cap / 2) {
+          s_cand = -2;
+        } else {
+          s_cand = atomicAdd(&ctl->cand_top, 1);
+          if (s_cand >= a.cand_cap) {
+            if (!spec) atomicOr(&ctl->overflow, 4);
+            s_cand = -2;
+          }
         }
       }
       __syncthreads();
@@ -645,7 +676,8 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
           }
         }
       }
-      publish_result(nd, res.value, bval, bfrac, res.p1 + res.p2, res.status, bvar, ncuts, cand, (int)s_cut_begin, c0, c1);
+      publish_result(nd, res.value, bval, bfrac, res.p1 + res.p2, cand == -2 ? ST_ERR_POOL : res.status, bvar, ncuts, cand, (int)s_cut_begin, c0,
+                     c1);
       w_post += clock64() - wt0;
       w_nodes++;
       if (c0 >= 0) {  // (release: this node's cut list and the children's records are visible to whoever claims them)

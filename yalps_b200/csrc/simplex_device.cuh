@@ -43,6 +43,7 @@ enum : int {
   ST_CYCLED = 4,
   ST_ERR_HISTORY = -4,
   ST_ERR_PEER = -5,  // grid-wide / multi-GPU kernels: a participant of an exchange never showed up (spin budget exhausted)
+  ST_ERR_POOL = -6,  // device-resident branch and cut: a speculative node that a pool (cuts, cut rows, candidates) could not serve
 };
 
 __device__ __forceinline__ double d_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
