@@ -232,6 +232,13 @@ int yalps_bnb_solve_nodes(yalps_ctx *ctx, int64_t n, const int32_t *cut_offsets,
  * height+max_extra_rows).  stats[8] (optional): nodes evaluated by the replay, node pivots,
  * max cuts, max heap, waves, nodes solved on device (incl. unused speculation),
  * microseconds spent in device waves, microseconds total.
+ * When the node tableaus fit one CTA's shared memory the whole search runs inside one
+ * persistent kernel (csrc/bnb_kernel.cuh: scheduler CTA + worker CTAs that expand
+ * optimal fractional nodes speculatively); the result is the same search node for node.
+ * Tuning / diagnostics through the environment, read per search: YALPS_BNB_SPEC
+ * (generations of speculation, default 2, 0 = none), YALPS_BNB_WORKERS (worker CTAs,
+ * default one per SM beside the scheduler), YALPS_BNB_DEBUG=1 (scheduler and worker stage
+ * cycles and pool usage on stderr).
  */
 int yalps_branch_and_cut(yalps_ctx *ctx, const int32_t *ints, int32_t nints, double sign, double init_result,
                          const yalps_options *opt, int32_t *status, double *result, int32_t *out_height,
