@@ -334,20 +334,16 @@ __device__ __forceinline__ LpResult simplex_cta_split(const LpView &t, const Spl
       bv = -INF;
       bi = kNone;
       {
+        // (one cell per thread and step: a node LP of 101 columns on 256 threads has one division per thread instead of
+        // two in a row on 50 of them)
         const double *Arow = A + (size_t)row * ldA;
-        for (int j0 = VW * tid; j0 < Wm1; j0 += VW * NT) {
-          Cells<VW> cf, ob;
-          cf.load(Arow + j0);
-          ob.load(A + j0);
-#pragma unroll
-          for (int e = 0; e < VW; e++) {
-            const double coef = cf.get(e);
-            if (j0 + e < Wm1 && coef < -precision) {
-              const double ratio = div_rn(-ob.get(e), coef);
-              if (ratio > bv) {  // bv starts at -inf: -inf and NaN ratios never win, as in the reference
-                bv = ratio;
-                bi = j0 + e + 1;
-              }
+        for (int j = tid; j < Wm1; j += NT) {
+          const double coef = Arow[j];
+          if (coef < -precision) {
+            const double ratio = div_rn(-A[j], coef);
+            if (ratio > bv) {  // bv starts at -inf: -inf and NaN ratios never win, as in the reference
+              bv = ratio;
+              bi = j + 1;
             }
           }
         }
