@@ -65,8 +65,10 @@ struct __align__(64) BnbNode {
   int new_var;
   int parent;       // -1: child of the root
   int depth;        // generations of speculation behind this node (0: created by the scheduler)
+  int parent_cut_len;    // the parent's cut list (its creator knows it: one dependent L2 trip less for the worker)
+  int parent_cut_begin;
   int pad1;
-  double pad2[2];
+  double pad2;
 };
 static_assert(sizeof(BnbNode) == 128, "BnbNode layout");
 
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
       return tidx;
     };
     int created = 0;  // the scheduler's own nodes: ids and queue slots [0, sched_cap), no atomics on this path
-    auto create = [&](double eval, int parent, double sign, int var, double value) -> bool {
+    auto create = [&](double eval, int parent, double sign, int var, double value, int pbeg, int plen) -> bool {
       if (hn >= a.heap_cap) {
         atomicOr(&ctl->overflow, 8);
         return false;
@@ -224,6 +226,8 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
       nd->new_var = var;
       nd->parent = parent;
       nd->depth = 0;
+      nd->parent_cut_begin = pbeg;
+      nd->parent_cut_len = plen;
       push(eval, id);
       return true;
     };
@@ -253,8 +257,8 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
 
     *reinterpret_cast<volatile double *>(&ctl->best_eval) = d_inf();
     // the root's two children (:101-102)
-    bool ok = create(a.init_result, -1, -1.0, a.init_var, ceil(a.init_value));
-    ok = ok && create(a.init_result, -1, 1.0, a.init_var, floor(a.init_value));
+    bool ok = create(a.init_result, -1, -1.0, a.init_var, ceil(a.init_value), 0, 0);
+    ok = ok && create(a.init_result, -1, 1.0, a.init_var, floor(a.init_value), 0, 0);
     publish_created();
 
     const double threshold = a.init_result * (1.0 - a.sign * a.tolerance);  // :114
@@ -343,8 +347,8 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
         } else {  // branch (:141-156); the workers build the children's cut lists
           const int variable = r_bvar;
           const double value = r_bval;
-          ok = create(n_value, br, -1.0, variable, ceil(value));       // upper first (:155)
-          ok = ok && create(n_value, br, 1.0, variable, floor(value));  // then lower (:156)
+          ok = create(n_value, br, -1.0, variable, ceil(value), r_cut_begin, r_cut_len);       // upper first (:155)
+          ok = ok && create(n_value, br, 1.0, variable, floor(value), r_cut_begin, r_cut_len);  // then lower (:156)
           publish_created();
         }
       }
@@ -431,11 +435,8 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
       const int parent = __ldcg(&nd->parent);
       const int new_var = __ldcg(&nd->new_var);
       const double new_sign = __ldcg(&nd->new_sign), new_value = __ldcg(&nd->new_value);
-      int pbeg = 0, plen = 0;
-      if (parent >= 0) {
-        pbeg = __ldcg(&a.nodes[parent].cut_begin);
-        plen = __ldcg(&a.nodes[parent].cut_len);
-      }
+      const int pbeg = __ldcg(&nd->parent_cut_begin), plen = __ldcg(&nd->parent_cut_len);  // (0, 0 for the root's children)
+      (void)parent;
       unsigned long long begin = 0;
       if (lane == 0) begin = atomicAdd(&ctl->cut_top, (unsigned long long)(plen + 1));
       begin = __shfl_sync(0xffffffffu, begin, 0);
@@ -672,6 +673,8 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
               ch->new_var = bvar;
               ch->parent = node;
               ch->depth = depth + 1;
+              ch->parent_cut_begin = (int)s_cut_begin;
+              ch->parent_cut_len = ncuts;
             }
           }
         }
