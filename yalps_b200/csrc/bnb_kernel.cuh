@@ -381,11 +381,13 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
   const SmemLayout L(a.Hcap, W, true, NW, true);
   unsigned long long rows_total = 0;
   unsigned long long w_nodes = 0, w_cuts = 0, w_asm = 0, w_simplex = 0, w_post = 0;  // (thread 0; YALPS_BNB_DEBUG prints the sums)
+  int own_next = -1;  // (thread 0) the first child this worker has just created: it goes on with it without the queue
   for (;;) {
     if (tid == 0) {
       // claim the next entry: the scheduler's queue first (the replay is waiting for those), then the speculative one
-      int node = -1;
-      for (;;) {
+      int node = own_next;
+      own_next = -1;
+      while (node < 0) {
         const int h = *reinterpret_cast<volatile int *>(&ctl->s_head);
         if (h < a.sched_cap) {
           const int q = ld_acquire(a.queue + h);
@@ -684,9 +686,11 @@ __global__ void __launch_bounds__(NWC *NWR * 32, 1) k_bnb(const BnbArgs a) {
       w_post += clock64() - wt0;
       w_nodes++;
       if (c0 >= 0) {  // (release: this node's cut list and the children's records are visible to whoever claims them)
-        const int slot = atomicAdd(&ctl->p_tail, 2);
-        st_release(a.queue + a.sched_cap + slot, c0 + 1);
-        st_release(a.queue + a.sched_cap + slot + 1, c1 + 1);
+        // a dive goes through one of the two children next: this worker continues with the first one itself (no trip
+        // through the queue, no claim), the second one is queued for whoever is idle
+        const int slot = atomicAdd(&ctl->p_tail, 1);
+        st_release(a.queue + a.sched_cap + slot, c1 + 1);
+        own_next = c0;
       }
     }
     __syncthreads();
