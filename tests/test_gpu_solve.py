@@ -372,3 +372,73 @@ def test_device_resident_search_options(engine):
             engine.set_bnb_mode(0)
         assert sol["status"] == ref["status"] and same_value(sol["result"], ref["result"]), extra
         assert [list(v) for v in sol["variables"]] == [list(v) for v in ref["variables"]], extra
+
+
+def _solve_both_forms(engine, case, cells=None, values=None):
+    """yalps_solve on the dense image and yalps_solve_sparse on the ordered stores: every output must agree."""
+    opt = {**M.DEFAULT_OPTIONS, **case["options"]}
+    copt = E.make_options(opt["precision"], opt["maxPivots"], opt["checkCycles"], opt["tolerance"], opt["timeout"],
+                          opt["maxIterations"])
+    tm = yalps_b200.tableau_model(case["model"], 0)
+    t = tm.tableau
+    cells = t.cells if cells is None else cells
+    values = t.values if values is None else values
+    dense = np.zeros(t.height * t.width)
+    for c, v in zip(cells.tolist(), values.tolist()):
+        dense[c] = v
+    a = engine.solve_tableau(dense, t.height, t.width, tm.integers, tm.sign, copt)
+    b = engine.solve_tableau_sparse(cells, values, t.height, t.width, tm.integers, tm.sign, copt)
+    assert a["status"] == b["status"] and same_value(a["result"], b["result"]) and a["height"] == b["height"]
+    assert same_bits(a["rhs"], b["rhs"]) and np.array_equal(a["pos"], b["pos"]) and np.array_equal(a["var"], b["var"])
+    assert a["root_status"] == b["root_status"] and same_value(a["root_value"], b["root_value"])
+    assert a["root_pivots"] == b["root_pivots"]
+    assert a["stats"]["nodes"] == b["stats"]["nodes"] and a["stats"]["node_pivots"] == b["stats"]["node_pivots"]
+    return a, b
+
+
+@pytest.mark.parametrize("name", ["Monster Problem", "Monster 2", "Vendor Selection", "Large Farm MIP", "Knapsack 1"])
+def test_sparse_entry_equals_dense_entry(engine, name):
+    """yalps_solve_sparse (the stores of src/tableau.ts:100-134 instead of the zero-filled matrix; the device zeroes
+    and scatters) against yalps_solve on the dense image: big tableaus take the device scatter, tableaus under 768 KB
+    are densified inside the library."""
+    case = next(c for c in CASES if c["name"] == name)
+    a, _ = _solve_both_forms(engine, case)
+    o = case["oracle"]
+    assert E.STATUS_NAMES[a["status"]] == o["status"] and same_bits(a["rhs"], o["final_rhs"])
+
+
+def test_sparse_entry_applies_duplicate_cells_in_order(engine):
+    """A later store to the same cell wins (src/tableau.ts:101).  The device scatter is unordered, so the library has
+    to notice duplicates with different bits and resolve them: here every tenth store is preceded by a store of a
+    different value to the same cell, and one cell is finally overwritten (changing the model)."""
+    case = next(c for c in CASES if c["name"] == "Monster Problem")
+    t = yalps_b200.tableau_model(case["model"], 0).tableau
+    assert t.height * t.width * 8 > (768 << 10)  # the device-scatter path
+    cells, values = t.cells.tolist(), t.values.tolist()
+    dc, dv = [], []
+    for k, (c, v) in enumerate(zip(cells, values)):
+        if k % 10 == 0:
+            dc.append(c)
+            dv.append(v + 1.5)
+        dc.append(c)
+        dv.append(v)
+    plain, _ = _solve_both_forms(engine, case)
+    dup, _ = _solve_both_forms(engine, case, np.asarray(dc, np.int32), np.asarray(dv, np.float64))
+    assert same_bits(plain["rhs"], dup["rhs"]) and np.array_equal(plain["pos"], dup["pos"])
+    # identical duplicates need no resolution; a trailing overwrite (-0.0 over an objective coefficient) is honoured
+    k = next(i for i, c in enumerate(cells) if 0 < c < t.width and values[i] != 0.0)
+    _solve_both_forms(engine, case, np.asarray(cells + cells[:50] + [cells[k]], np.int32),
+                      np.asarray(values + values[:50] + [-0.0], np.float64))
+
+
+def test_sparse_entry_argument_errors_and_empty_list(engine):
+    copt = E.make_options()
+    with pytest.raises(RuntimeError, match="outside"):
+        engine.solve_tableau_sparse(np.asarray([5, 400000], np.int32), np.asarray([1.0, 1.0]), 400, 1000, [], 1.0, copt)
+    with pytest.raises(RuntimeError, match="outside"):
+        engine.solve_tableau_sparse(np.asarray([-1], np.int32), np.asarray([1.0]), 4, 4, [], 1.0, copt)
+    with pytest.raises(ValueError):
+        engine.solve_tableau_sparse(np.asarray([1, 2], np.int32), np.asarray([1.0]), 4, 4, [], 1.0, copt)
+    for h, w in ((4, 4), (400, 1000)):  # no stores at all: the zero tableau is optimal with value 0 on both paths
+        r = engine.solve_tableau_sparse(np.zeros(0, np.int32), np.zeros(0), h, w, [], 1.0, copt)
+        assert E.STATUS_NAMES[r["status"]] == "optimal" and r["result"] == 0.0 and not r["rhs"].any()

@@ -136,3 +136,34 @@ def test_integer_like_keys_follow_js_property_order():
     tm = tableau_model(model)
     assert [k for k, _ in tm.variables] == ["2", "10", "b"]
     assert_same(tm, M.tableau_model(model))
+
+
+@pytest.mark.parametrize("case", ALL, ids=[c["name"] for c in ALL])
+def test_sparse_form_is_the_dense_image(case):
+    """The (cells, values) form handed to yalps_solve_sparse is the ordered list of the stores src/tableau.ts:100-134
+    makes into its zero-filled matrix: replaying it gives the dense image bit for bit (signed zeros included)."""
+    dense = tableau_model(case["model"])
+    sparse = tableau_model(case["model"], 0)
+    t = sparse.tableau
+    assert t.matrix is None and t.cells.dtype == np.int32 and t.values.dtype == np.float64
+    assert t.cells.size == t.values.size and (t.cells.size == 0 or (0 <= t.cells.min() and t.cells.max() < t.width * t.height))
+    replay = np.zeros(t.width * t.height)
+    for c, v in zip(t.cells.tolist(), t.values.tolist()):  # in order, like update() calls
+        replay[c] = v
+    assert same_bits(replay, dense.tableau.matrix)
+    assert same_bits(t.dense(), dense.tableau.matrix) and t.matrix is not None
+    assert_same(sparse, M.tableau_model(case["model"]))
+
+
+def test_sparse_form_keeps_the_order_of_duplicate_coefficients():
+    """src/tableau.ts:101: a constraint key listed twice by one variable stores twice, the last store wins."""
+    model = {"direction": "minimize", "objective": "cost",
+             "constraints": [("a", {"max": 4}), ("b", {"min": 1, "max": 3})],
+             "variables": [("x", [("a", 1), ("cost", 2), ("a", 5), ("b", -0.0)]), ("y", [("b", 2), ("b", 7), ("cost", 0)])]}
+    sparse = tableau_model(model, 0)
+    t = sparse.tableau
+    assert len(set(t.cells.tolist())) < t.cells.size  # duplicates are kept, not resolved, in the sparse form
+    assert same_bits(tableau_model(model).tableau.matrix, t.dense())
+    assert_same(sparse, M.tableau_model(model))
+    m = t.dense().reshape(t.height, t.width)
+    assert m[1, 1] == 5.0 and m[2, 2] == 7.0 and m[3, 2] == -7.0 and np.signbit(m[0, 2]) and np.signbit(m[2, 1])

@@ -99,6 +99,8 @@ SIGNATURES = {
     "yalps_bnb_set_mode": (C.c_int, [_vp, C.c_int32]),
     "yalps_solve": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, _vp, C.c_int32, C.c_double, C.POINTER(Options), _ip, _dp,
                               _ip, _vp, _vp, _vp, _ip, _dp, _vp, _vp]),
+    "yalps_solve_sparse": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int64, _vp, _vp, _vp, C.c_int32, C.c_double,
+                                     C.POINTER(Options), _ip, _dp, _ip, _vp, _vp, _vp, _ip, _dp, _vp, _vp]),
     "yalps_round_to_precision": (C.c_int, [_vp, C.c_int64, _vp, C.c_double, _vp]),
     "yalps_measure_smem_bandwidth": (C.c_int, [_vp, _dp, _dp]),
     "yalps_measure_tmem_bandwidth": (C.c_int, [_vp, _dp, _dp]),

@@ -342,6 +342,24 @@ __global__ void k_incumbent_broadcast(double *slots, int k) {
   for (int i = 0; i < k; i++) slots[i] = m;
 }
 
+// Sparse producer boundary (yalps_solve_sparse): the initial tableau arrives as (cell, value) pairs over a zeroed
+// matrix -- what tableauModel (src/tableau.ts:88-134) writes into its zero-filled Float64Array, without the zeros.
+__global__ void k_scatter_cells(long long nnz, const int *__restrict__ cell, const double *__restrict__ val, double *M) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (long long)gridDim.x * blockDim.x)
+    M[cell[i]] = val[i];
+}
+
+// The reference's stores happen in order (a later duplicate of a cell wins, src/tableau.ts:100-117); the scatter above
+// is unordered.  Duplicates with different bits are the only case where that shows: then some pair does not find its
+// own value in the matrix, and the host repeats the call with the duplicates resolved.
+__global__ void k_verify_cells(long long nnz, const int *__restrict__ cell, const double *__restrict__ val,
+                               const double *__restrict__ M, int *mismatch) {
+  bool bad = false;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (long long)gridDim.x * blockDim.x)
+    bad |= __double_as_longlong(M[cell[i]]) != __double_as_longlong(val[i]);
+  if (bad) *mismatch = 1;
+}
+
 // Non-zero count of a sample of one tableau (kernel-path policy: sparse batches go to the HBM/L2-resident kernel).
 __global__ void k_sample_density(const double *m, long long cells, long long step, int *out /* [2]: seen, nz */) {
   int seen = 0, nz = 0;

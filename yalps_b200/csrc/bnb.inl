@@ -898,6 +898,7 @@ int yalps_solve(yalps_ctx *ctx, int32_t height, int32_t width, const double *mat
                                         (milp && !keep_on_device) ? final_m.data() : nullptr);
   ctx->keep_final = false;
   if (root_rc) return root_rc;
+  if (ctx->coo_nnz >= 0 && ctx->coo_dup) return 1;  // yalps_solve_sparse resolves the duplicates and calls again
   if (root_status) *root_status = st;
   if (root_value) *root_value = val;
   if (root_pivots) {
@@ -920,6 +921,59 @@ int yalps_solve(yalps_ctx *ctx, int32_t height, int32_t width, const double *mat
   }
   return yalps_branch_and_cut(ctx, ints, nints, sign, val, opt, status, result, out_height, rhs_out, pos_out, var_out,
                               stats);
+}
+
+int yalps_solve_sparse(yalps_ctx *ctx, int32_t height, int32_t width, int64_t nnz, const int32_t *cell, const double *val,
+                       const int32_t *ints, int32_t nints, double sign, const yalps_options *opt, int32_t *status,
+                       double *result, int32_t *out_height, double *rhs_out, int32_t *pos_out, int32_t *var_out,
+                       int32_t *root_status, double *root_value, int64_t *root_pivots, int64_t *stats) {
+  if (!ctx) return YALPS_ERR_ARGUMENT;
+  if (height < 1 || width < 1 || nnz < 0 || (nnz && (!cell || !val)))
+    return fail(ctx, YALPS_ERR_ARGUMENT, "bad arguments");
+  if ((long long)height * width >= (1LL << 31)) return fail(ctx, YALPS_ERR_TOO_LARGE, "height*width must be < 2^31");
+  const int32_t cells = (int32_t)((long long)height * width);
+  for (int64_t i = 0; i < nnz; i++)
+    if (cell[i] < 0 || cell[i] >= cells)
+      return fail(ctx, YALPS_ERR_ARGUMENT, "cell %lld = %d is outside the %dx%d tableau", (long long)i, cell[i], height, width);
+  // small tableaus take the zero-copy latency path of yalps_solve_batch, which reads a dense host image
+  if ((size_t)cells * 8 <= ((size_t)768 << 10)) {
+    std::vector<double> dense((size_t)cells, 0.0);
+    for (int64_t i = 0; i < nnz; i++) dense[cell[i]] = val[i];
+    return yalps_solve(ctx, height, width, dense.data(), ints, nints, sign, opt, status, result, out_height, rhs_out,
+                       pos_out, var_out, root_status, root_value, root_pivots, stats);
+  }
+  // the matrix argument below is a placeholder that is never dereferenced while coo_nnz >= 0 (solve_host scatters
+  // the pairs on the device instead of copying a host matrix)
+  ctx->coo_cell = cell;
+  ctx->coo_val = val;
+  ctx->coo_nnz = nnz;
+  ctx->coo_dup = 0;
+  int rc = yalps_solve(ctx, height, width, reinterpret_cast<const double *>(val ? (const void *)val : (const void *)ctx), ints,
+                       nints, sign, opt, status, result, out_height, rhs_out, pos_out, var_out, root_status, root_value,
+                       root_pivots, stats);
+  if (rc == 1) {  // duplicates with different values: keep the last store of every cell (src/tableau.ts:100-117), again
+    std::unordered_map<int32_t, int64_t> last;
+    last.reserve((size_t)nnz);
+    for (int64_t i = 0; i < nnz; i++) last[cell[i]] = i;
+    std::vector<int32_t> ucell;
+    std::vector<double> uval;
+    for (int64_t i = 0; i < nnz; i++)
+      if (last[cell[i]] == i) {
+        ucell.push_back(cell[i]);
+        uval.push_back(val[i]);
+      }
+    ctx->coo_cell = ucell.data();
+    ctx->coo_val = uval.data();
+    ctx->coo_nnz = (int64_t)ucell.size();
+    ctx->coo_dup = 0;
+    rc = yalps_solve(ctx, height, width, reinterpret_cast<const double *>((const void *)val), ints, nints, sign, opt, status,
+                     result, out_height, rhs_out, pos_out, var_out, root_status, root_value, root_pivots, stats);
+    if (rc == 1) rc = fail(ctx, YALPS_ERR_CUDA, "cell scatter did not verify after the duplicates were resolved");
+  }
+  ctx->coo_cell = nullptr;
+  ctx->coo_val = nullptr;
+  ctx->coo_nnz = -1;
+  return rc;
 }
 
 }  // extern "C"

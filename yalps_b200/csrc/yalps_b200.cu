@@ -87,6 +87,12 @@ struct yalps_ctx {
   cudaEvent_t fork_event = nullptr;
   bool keep_final = false;         // solve_host (n == 1): leave the final tableau on the device, no D2H copy of it
   double *kept_final = nullptr;    // ... and where it is (valid until the next batch call on this ctx)
+  // yalps_solve_sparse: solve_host (n == 1) builds its device tableau from these (cell, value) pairs instead of copying
+  // a dense host matrix (coo_nnz < 0: not in use); coo_dup reports that duplicates with different values were seen
+  const int32_t *coo_cell = nullptr;
+  const double *coo_val = nullptr;
+  int64_t coo_nnz = -1;
+  int coo_dup = 0;
   int wave = 256;  // upper bound of the adaptive look-ahead of the branch-and-cut driver
   int kc_tma = 0;    // KC: staging of the winner's pivot row (YALPS_KC_TMA: 0 ld.global.cg, 1 cp.async.bulk, 2 multicast)
   int bnb_mode = 0;  // 0: device-resident search when it fits, else host waves; 1: host waves only; 2: device only
@@ -1000,7 +1006,7 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
     LaunchPlan plan;
     // density of (a sample of) the first tableau: the latency-mode policy distinguishes dense from very sparse LPs
     double small_density = -1.0;
-    if (n > 0 && in_b + out_b + desc_b <= ((size_t)768 << 10)) {
+    if (ctx->coo_nnz < 0 && n > 0 && in_b + out_b + desc_b <= ((size_t)768 << 10)) {
       const double *m0 = matrices + (ragged ? mat_offsets[0] : 0);
       const long long c0 = ragged ? (long long)heights[0] * widths[0] : (long long)height * width;
       const long long step = std::max(1LL, c0 / 4096);
@@ -1008,7 +1014,7 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
       for (long long k = 0; k < c0; k += step, seen++) nz += m0[k] != 0.0;
       small_density = seen ? (double)nz / (double)seen : 1.0;
     }
-    if (!ctx->keep_final && in_b + out_b + desc_b <= ((size_t)768 << 10) && ctx->tune_path != YALPS_PATH_GRID && ctx->tune_path != YALPS_PATH_CLUSTER && ctx->tune_path != YALPS_PATH_GRID_RESIDENT &&
+    if (!ctx->keep_final && ctx->coo_nnz < 0 && in_b + out_b + desc_b <= ((size_t)768 << 10) && ctx->tune_path != YALPS_PATH_GRID && ctx->tune_path != YALPS_PATH_CLUSTER && ctx->tune_path != YALPS_PATH_GRID_RESIDENT &&
         plan_launch(ctx, n, Hcap, Wcap, opt->check_cycles != 0, &plan, small_density, true) == 0 && (plan.k || plan.tmem) && plan.resident) {
       auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
       size_t o = 0;
@@ -1118,6 +1124,8 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
       }
     }
     LaunchPlan plan;
+    const bool from_cells = ctx->coo_nnz >= 0 && n == 1 && !ragged;
+    if (from_cells) density = (double)ctx->coo_nnz / (double)((long long)height * width);
     if (density < 0.0) {  // sample the first tableau once
       const double *m0 = matrices + (ragged ? mat_offsets[0] : 0);
       const long long c0 = ragged ? (long long)heights[0] * widths[0] : (long long)height * width;
@@ -1159,6 +1167,30 @@ static int solve_host(yalps_ctx *ctx, int64_t n, int32_t height, int32_t width, 
           CU(ctx, cudaMemcpyAsync((double *)d_in + (moff[i] - moff[begin]), matrices + mat_offsets[i],
                                   (size_t)heights[i] * widths[i] * 8, cudaMemcpyHostToDevice, st));
       }
+    } else if (from_cells) {
+      // the (cell, value) pairs cross PCIe, the zeros are written by the device
+      const size_t nnz = (size_t)ctx->coo_nnz, val_off = (nnz * 4 + 15) & ~(size_t)15;
+      void *h_coo, *d_coo, *d_flag;
+      if ((rc = pin_ensure(ctx, "coo", val_off + nnz * 8 + 16, &h_coo))) return rc;
+      if ((rc = dev_ensure(ctx, "coo", val_off + nnz * 8 + 16, &d_coo))) return rc;
+      if ((rc = dev_ensure(ctx, "coo_flag", 4, &d_flag))) return rc;
+      if (nnz) {
+        std::memcpy(h_coo, ctx->coo_cell, nnz * 4);
+        std::memcpy((char *)h_coo + val_off, ctx->coo_val, nnz * 8);
+        CU(ctx, cudaMemcpyAsync(d_coo, h_coo, val_off + nnz * 8, cudaMemcpyHostToDevice, st));
+      }
+      CU(ctx, cudaMemsetAsync(d_in, 0, ccells * 8, st));
+      CU(ctx, cudaMemsetAsync(d_flag, 0, 4, st));
+      if (nnz) {
+        const int blocks = (int)std::min<size_t>((nnz + 255) / 256, (size_t)ctx->prop.multiProcessorCount * 8);
+        const int *d_cell = (const int *)d_coo;
+        const double *d_val = (const double *)((char *)d_coo + val_off);
+        k_scatter_cells<<<blocks, 256, 0, st>>>((long long)nnz, d_cell, d_val, (double *)d_in);
+        k_verify_cells<<<blocks, 256, 0, st>>>((long long)nnz, d_cell, d_val, (const double *)d_in, (int *)d_flag);
+        ctx->launches += 2;
+        CU(ctx, cudaGetLastError());
+      }
+      CU(ctx, cudaMemcpyAsync(&ctx->coo_dup, d_flag, 4, cudaMemcpyDeviceToHost, st));
     } else {
       CU(ctx, cudaMemcpyAsync(d_in, src, ccells * 8, cudaMemcpyHostToDevice, st));
     }

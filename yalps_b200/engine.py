@@ -293,9 +293,20 @@ class Engine:
                                                     _ptr(out["var"]), _ptr(out["matrices"])))
         return out
 
+    def solve_tableau_sparse(self, cells: np.ndarray, values: np.ndarray, height: int, width: int,
+                             integers: Sequence[int], sign: float, options: Optional[Options] = None) -> dict:
+        """solve_tableau on a tableau given as the ordered stores (cell = row*width + col, value) into a zero matrix
+        (yalps_solve_sparse): the zeros are neither built on the host nor shipped over PCIe."""
+        cells = np.ascontiguousarray(cells, np.int32).reshape(-1)
+        values = np.ascontiguousarray(values, np.float64).reshape(-1)
+        if cells.size != values.size:
+            raise ValueError("cells and values must have the same length")
+        return self.solve_tableau(values, height, width, integers, sign, options, cells=cells)
+
     def solve_tableau(self, matrix: np.ndarray, height: int, width: int, integers: Sequence[int], sign: float,
-                      options: Optional[Options] = None) -> dict:
-        """Numeric part of solve() (src/YALPS.ts:77-91): root simplex + branch and cut when needed."""
+                      options: Optional[Options] = None, cells: Optional[np.ndarray] = None) -> dict:
+        """Numeric part of solve() (src/YALPS.ts:77-91): root simplex + branch and cut when needed.
+        (`cells` given: `matrix` holds the values of the sparse form, see solve_tableau_sparse.)"""
         opt = options or make_options()
         m = np.ascontiguousarray(matrix, np.float64).reshape(-1)
         ints = np.ascontiguousarray(integers, np.int32)
@@ -307,10 +318,18 @@ class Engine:
         result, root_value = C.c_double(), C.c_double()
         root_piv = np.zeros(2, np.int64)
         stats = np.zeros(8, np.int64)
-        self._check(self._lib.yalps_solve(self._ctx, height, width, _ptr(m), _ptr(ints) if ints.size else None,
-                                          int(ints.size), float(sign), C.byref(opt), C.byref(status), C.byref(result),
-                                          C.byref(out_h), _ptr(rhs), _ptr(pos), _ptr(var), C.byref(root_status),
-                                          C.byref(root_value), _ptr(root_piv), _ptr(stats)))
+        if cells is None:
+            self._check(self._lib.yalps_solve(self._ctx, height, width, _ptr(m), _ptr(ints) if ints.size else None,
+                                              int(ints.size), float(sign), C.byref(opt), C.byref(status), C.byref(result),
+                                              C.byref(out_h), _ptr(rhs), _ptr(pos), _ptr(var), C.byref(root_status),
+                                              C.byref(root_value), _ptr(root_piv), _ptr(stats)))
+        else:
+            self._check(self._lib.yalps_solve_sparse(self._ctx, height, width, int(cells.size),
+                                                     _ptr(cells) if cells.size else None, _ptr(m) if m.size else None,
+                                                     _ptr(ints) if ints.size else None, int(ints.size), float(sign),
+                                                     C.byref(opt), C.byref(status), C.byref(result), C.byref(out_h),
+                                                     _ptr(rhs), _ptr(pos), _ptr(var), C.byref(root_status),
+                                                     C.byref(root_value), _ptr(root_piv), _ptr(stats)))
         h = out_h.value
         return {
             "status": status.value, "result": result.value, "height": h, "rhs": rhs[:h], "pos": pos[:width + h],

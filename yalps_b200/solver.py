@@ -17,7 +17,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from .engine import Engine, MultiEngine, STATUS_NAMES, make_options
-from .tableau import TableauModel, tableau_model
+from .tableau import SPARSE_OVER_BYTES, TableauModel, tableau_model
 
 # src/YALPS.ts:52-60
 _DEFAULTS = {
@@ -90,12 +90,18 @@ def _solution(tabmod: TableauModel, status: str, result: float, rhs, pos, var, o
 def solve(model: dict, options: Optional[dict] = None, *, engine: Optional[Engine] = None,
           info: Optional[dict] = None) -> dict:
     """Runs the solver on `model` (src/YALPS.ts:73-92).  `info`, if given, receives engine statistics."""
-    tabmod = tableau_model(model)
     opt = {**_DEFAULTS, **(options or {})}
     eng = engine or get_engine()
+    # big model tableaus are almost all zeros: they go to the device as (cell, value) pairs (yalps_solve_sparse) and
+    # never exist densely on the host; small ones take the library's zero-copy path as a dense image
+    sparse_ok = hasattr(eng, "solve_tableau_sparse")
+    tabmod = tableau_model(model, SPARSE_OVER_BYTES if sparse_ok else None)
     t = tabmod.tableau
-    # a MultiEngine shards the branch-and-bound frontier over its GPUs (same search, same result)
-    r = eng.solve_tableau(t.matrix, t.height, t.width, tabmod.integers, tabmod.sign, _c_options(opt))
+    if t.matrix is None:
+        r = eng.solve_tableau_sparse(t.cells, t.values, t.height, t.width, tabmod.integers, tabmod.sign, _c_options(opt))
+    else:
+        # a MultiEngine shards the branch-and-bound frontier over its GPUs (same search, same result)
+        r = eng.solve_tableau(t.matrix, t.height, t.width, tabmod.integers, tabmod.sign, _c_options(opt))
     if info is not None:
         info.update(r["stats"], root_status=STATUS_NAMES[r["root_status"]], root_value=r["root_value"],
                     root_pivots=r["root_pivots"], height=t.height, width=t.width, final_rhs=r["rhs"],

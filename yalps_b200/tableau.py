@@ -14,7 +14,7 @@ from __future__ import annotations
 import math
 import re
 from dataclasses import dataclass
-from typing import Any, Iterable
+from typing import Any, Iterable, Optional
 
 import numpy as np
 
@@ -58,11 +58,24 @@ def _field(constraint, name):
 class Tableau:
     """src/tableau.ts:9-15"""
 
-    matrix: np.ndarray  # float64[height*width], row-major
+    matrix: Optional[np.ndarray]  # float64[height*width], row-major; None while only the sparse form below exists
     width: int
     height: int
     position_of_variable: np.ndarray  # int32[width+height]
     variable_at_position: np.ndarray  # int32[width+height]
+    # the stores tableauModel makes into its zero-filled matrix, in order (cell = row*width + col; a later store to
+    # the same cell wins): what yalps_solve_sparse takes, so that big sparse models never exist densely on the host
+    cells: Optional[np.ndarray] = None  # int32[nnz]
+    values: Optional[np.ndarray] = None  # float64[nnz]
+
+    def dense(self) -> np.ndarray:
+        """The flat row-major matrix (built from the sparse form on first use)."""
+        if self.matrix is None:
+            m = np.zeros(self.height * self.width, dtype=np.float64)
+            if self.cells.size:
+                m[self.cells] = self.values  # repeated indices are applied in order: the last one wins
+            self.matrix = m
+        return self.matrix
 
 
 @dataclass
@@ -75,7 +88,13 @@ class TableauModel:
     integers: list  # variable ids (1-based columns) that must be integral
 
 
-def tableau_model(model: dict) -> TableauModel:
+# solve() keeps tableaus above this size (the library's zero-copy small-call limit) in the sparse form only
+SPARSE_OVER_BYTES = 768 << 10
+
+
+def tableau_model(model: dict, sparse_over_bytes: Optional[int] = None) -> TableauModel:
+    """`sparse_over_bytes`: tableaus larger than this are returned with `matrix=None` and only the (cells, values)
+    form filled in (`Tableau.dense()` materialises them); None = always dense, as the reference."""
     sign = -1.0 if model.get("direction") == "minimize" else 1.0
     objective = model.get("objective")
     variables = list(entries(model["variables"]))
@@ -131,7 +150,6 @@ def tableau_model(model: dict) -> TableauModel:
 
     width = nvars + 1
     height = rows + len(binary_cols)
-    matrix = np.zeros(height * width, dtype=np.float64)
 
     # coefficients: later duplicates of a key overwrite earlier ones (src/tableau.ts:100-117)
     # one lookup per coefficient: key -> (row offset of the upper row or -1, row offset of the lower row or -1, is objective)
@@ -162,15 +180,17 @@ def tableau_model(model: dict) -> TableauModel:
             if l >= 0:
                 add_idx(l + col)
                 add_val(-coef)
-    if idx:
-        # numpy fancy assignment applies repeated indices in order, so the last one wins like the reference
-        matrix[np.asarray(idx, dtype=np.int64)] = np.asarray(val, dtype=np.float64)
-    if rhs_rows:
-        matrix[np.asarray(rhs_rows, dtype=np.int64) * width] = np.asarray(rhs_vals, dtype=np.float64)
+    for r, v in zip(rhs_rows, rhs_vals):  # RHS cells (src/tableau.ts:119-127)
+        add_idx(r * width)
+        add_val(v)
     for k, col in enumerate(binary_cols):  # src/tableau.ts:130-134
         r = rows + k
-        matrix[r * width] = 1.0
-        matrix[r * width + col] = 1.0
+        idx += (r * width, r * width + col)
+        val += (1.0, 1.0)
 
     ident = np.arange(width + height, dtype=np.int32)
-    return TableauModel(Tableau(matrix, width, height, ident.copy(), ident.copy()), sign, variables, ints)
+    tableau = Tableau(None, width, height, ident.copy(), ident.copy(), np.asarray(idx, dtype=np.int32),
+                      np.asarray(val, dtype=np.float64))
+    if sparse_over_bytes is None or height * width * 8 <= sparse_over_bytes:
+        tableau.dense()
+    return TableauModel(tableau, sign, variables, ints)
