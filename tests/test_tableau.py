@@ -167,3 +167,62 @@ def test_sparse_form_keeps_the_order_of_duplicate_coefficients():
     assert_same(sparse, M.tableau_model(model))
     m = t.dense().reshape(t.height, t.width)
     assert m[1, 1] == 5.0 and m[2, 2] == 7.0 and m[3, 2] == -7.0 and np.signbit(m[0, 2]) and np.signbit(m[2, 1])
+
+
+def _both_builders(model):
+    """tableau_model through the native core (csrc/tabfast.c) and through the Python loops it restates."""
+    from yalps_b200 import tableau as T
+    assert T._NATIVE is not None, "yalps_b200/_tabfast*.so is missing: run `make -C yalps_b200/csrc`"
+    native = T.tableau_model(model, 0)
+    saved, T._NATIVE = T._NATIVE, None
+    try:
+        python = T.tableau_model(model, 0)
+    finally:
+        T._NATIVE = saved
+    a, b = native.tableau, python.tableau
+    assert (a.width, a.height) == (b.width, b.height) and native.integers == python.integers
+    assert np.array_equal(a.cells, b.cells) and same_bits(a.values, b.values)
+    return native
+
+
+@pytest.mark.parametrize("case", ALL, ids=[c["name"] for c in ALL])
+def test_native_builder_makes_the_same_stores_as_the_python_loops(case):
+    _both_builders(case["model"])
+
+
+def test_native_builder_on_the_corners_of_the_model_format():
+    class Con:  # any object with min / max / equal attributes is a constraint (src/types.ts:7-31)
+        def __init__(self, **kw):
+            self.__dict__.update(kw)
+
+    models = [
+        {"variables": {}, "constraints": {}},
+        # integer-like keys are iterated first, ascending (JS property order), in variables, constraints and coefficients
+        {"objective": "10", "direction": "minimize",
+         "constraints": {"b": {"max": 5}, "10": {"min": 1}, "2": {"equal": 3}, "02": {"max": 9}},
+         "variables": {"y": {"b": 1, "10": 2, "2": 3, "02": 4}, "7": {"2": "1.5", "b": -0.0}, "x": [("b", 2), ["2", 1]]},
+         "integers": ["7"], "binaries": {"x"}},
+        # objects, tuples, generators, keys without a finite bound, NaN bounds, merged duplicates, objective == constraint
+        {"objective": "c", "constraints": [("c", Con(max=10)), ("free", Con()), ("c", {"min": -2, "max": 12}),
+                                           ("nan", {"max": float("nan")}), ("e", Con(equal=4, min=0)), (3, {"min": 1}),
+                                           (3.0, {"max": 8})],
+         "variables": [("u", (p for p in [("c", 1), ("free", "7"), ("nan", 5), (3, 2), ("e", True)])),
+                       ("v", {"c": 2, "e": -1, 3: 0, "unknown": 1}), ("w", ())],
+         "binaries": True},
+        # coefficients of keys that have no row are never looked at (src/tableau.ts:104: `bounds != null` comes first)
+        {"constraints": {"a": {"max": 1}, "free": {}}, "variables": [("x", {"a": 1, "free": "junk", "other": object()})]},
+    ]
+    for model in models:
+        if isinstance(model["variables"], list):  # generators are consumed once: rebuild them per builder
+            def fresh():
+                return {**model, "variables": [(k, list(c) if not isinstance(c, (dict, tuple)) else c)
+                                               for k, c in model["variables"]]}
+            model = fresh()
+        tm = _both_builders(model)
+        if "free" not in model["constraints"] or isinstance(model["constraints"], list):
+            assert same_bits(tm.tableau.dense(), M.tableau_model(model).tableau.matrix)
+    for bad in ({"variables": [("x", [("a", "abc")])], "constraints": {"a": {"max": 1}}},
+                {"variables": [("x", [("a", 1, 2)])], "constraints": {"a": {"max": 1}}},
+                {"variables": [("x", [([], 1)])], "constraints": {"a": {"max": 1}}}):
+        with pytest.raises((ValueError, TypeError)):
+            tableau_model(bad)

@@ -18,6 +18,11 @@ from typing import Any, Iterable, Optional
 
 import numpy as np
 
+try:  # native core of the builder (csrc/tabfast.c, built by `make -C yalps_b200/csrc`); the loops below are the fallback
+    from . import _tabfast as _NATIVE
+except ImportError:  # pragma: no cover - the extension is part of the normal build
+    _NATIVE = None
+
 _INDEX_KEY = re.compile(r"0|[1-9][0-9]*")
 
 
@@ -88,36 +93,12 @@ class TableauModel:
     integers: list  # variable ids (1-based columns) that must be integral
 
 
-# solve() keeps tableaus above this size (the library's zero-copy small-call limit) in the sparse form only
-SPARSE_OVER_BYTES = 768 << 10
-
-
-def tableau_model(model: dict, sparse_over_bytes: Optional[int] = None) -> TableauModel:
-    """`sparse_over_bytes`: tableaus larger than this are returned with `matrix=None` and only the (cells, values)
-    form filled in (`Tableau.dense()` materialises them); None = always dense, as the reference."""
-    sign = -1.0 if model.get("direction") == "minimize" else 1.0
-    objective = model.get("objective")
-    variables = list(entries(model["variables"]))
-    nvars = len(variables)
-
-    # integer / binary marking (src/tableau.ts:57-71); binary wins over integer
-    ints: list[int] = []
-    binary_cols: list[int] = []
-    integers, binaries = model.get("integers"), model.get("binaries")
-    if integers is not None or binaries is not None:
-        bin_set = _as_set(binaries)
-        int_set = True if bin_set is True else _as_set(integers)
-        for col, (key, _) in enumerate(variables, start=1):
-            if bin_set is True or key in bin_set:
-                binary_cols.append(col)
-                ints.append(col)
-            elif int_set is True or key in int_set:
-                ints.append(col)
-
+def _stores_python(variables: list, constraints: list, objective, sign: float, width: int, binary_cols: list):
+    """The ordered stores of src/tableau.ts:73-134 as (cells, values, rows); specification of csrc/tabfast.c."""
     # merge constraints per key, first-seen order (src/tableau.ts:73-80)
     lower: dict[Any, float] = {}
     upper: dict[Any, float] = {}
-    for key, con in entries(model["constraints"]):
+    for key, con in constraints:
         eq = _field(con, "equal")
         lo = eq if eq is not None else _field(con, "min")
         hi = eq if eq is not None else _field(con, "max")
@@ -147,9 +128,6 @@ def tableau_model(model: dict, sparse_over_bytes: Optional[int] = None) -> Table
             rhs_rows.append(rows)
             rhs_vals.append(-lower[key])
             rows += 1
-
-    width = nvars + 1
-    height = rows + len(binary_cols)
 
     # coefficients: later duplicates of a key overwrite earlier ones (src/tableau.ts:100-117)
     # one lookup per coefficient: key -> (row offset of the upper row or -1, row offset of the lower row or -1, is objective)
@@ -188,9 +166,48 @@ def tableau_model(model: dict, sparse_over_bytes: Optional[int] = None) -> Table
         idx += (r * width, r * width + col)
         val += (1.0, 1.0)
 
+    return np.asarray(idx, dtype=np.int32), np.asarray(val, dtype=np.float64), rows
+
+
+# solve() keeps tableaus above this size (the library's zero-copy small-call limit) in the sparse form only
+SPARSE_OVER_BYTES = 768 << 10
+
+
+def tableau_model(model: dict, sparse_over_bytes: Optional[int] = None) -> TableauModel:
+    """`sparse_over_bytes`: tableaus larger than this are returned with `matrix=None` and only the (cells, values)
+    form filled in (`Tableau.dense()` materialises them); None = always dense, as the reference."""
+    sign = -1.0 if model.get("direction") == "minimize" else 1.0
+    objective = model.get("objective")
+    variables = list(entries(model["variables"]))
+    nvars = len(variables)
+
+    # integer / binary marking (src/tableau.ts:57-71); binary wins over integer
+    ints: list[int] = []
+    binary_cols: list[int] = []
+    integers, binaries = model.get("integers"), model.get("binaries")
+    if integers is not None or binaries is not None:
+        bin_set = _as_set(binaries)
+        int_set = True if bin_set is True else _as_set(integers)
+        for col, (key, _) in enumerate(variables, start=1):
+            if bin_set is True or key in bin_set:
+                binary_cols.append(col)
+                ints.append(col)
+            elif int_set is True or key in int_set:
+                ints.append(col)
+
+    width = nvars + 1
+    constraints = list(entries(model["constraints"]))
+    if _NATIVE is not None:
+        cells_b, values_b, rows = _NATIVE.build(variables, constraints, objective, sign, width, binary_cols, entries)
+        cells, values = np.frombuffer(cells_b, dtype=np.int32), np.frombuffer(values_b, dtype=np.float64)
+    else:
+        cells, values, rows = _stores_python(variables, constraints, objective, sign, width, binary_cols)
+    height = rows + len(binary_cols)
+    if height * width >= 2 ** 31:
+        raise OverflowError("height*width must be < 2^31 (src/tableau.ts:17)")
+
     ident = np.arange(width + height, dtype=np.int32)
-    tableau = Tableau(None, width, height, ident.copy(), ident.copy(), np.asarray(idx, dtype=np.int32),
-                      np.asarray(val, dtype=np.float64))
+    tableau = Tableau(None, width, height, ident.copy(), ident.copy(), cells, values)
     if sparse_over_bytes is None or height * width * 8 <= sparse_over_bytes:
         tableau.dense()
     return TableauModel(tableau, sign, variables, ints)
