@@ -16,6 +16,10 @@
  *       (yalps_solve_batch_basis with every output aliasing its input).
  *   solve(ctx, height, width, matrix, ints: Int32Array, sign, options, status: Int32Array(3), result: Float64Array(2),
  *         rhs: Float64Array(h+2k), pos: Int32Array(w+h+2k), vars: Int32Array(w+h+2k), stats: BigInt64Array(8)) -> rc
+ *   solveSparse(ctx, height, width, cells: Int32Array(nnz), values: Float64Array(nnz), ints, sign, options, status, result,
+ *               rhs, pos, vars, stats) -> rc
+ *       solve() with the tableau as the ordered update() stores of tableauModel (yalps_solve_sparse): big model
+ *       tableaus are almost all zeros, which are then neither allocated in JS nor sent over PCIe.
  *   solveMany(multi, heights: Int32Array(n), widths: Int32Array(n), offsets: BigInt64Array(n), matrices: Float64Array,
  *             intsOffsets: BigInt64Array(n+1), ints: Int32Array, signs: Float64Array(n), options,
  *             status: Int32Array(n), result: Float64Array(n), outHeight: Int32Array(n),
@@ -273,6 +277,52 @@ static napi_value js_solve(napi_env env, napi_callback_info info) {
   return rc_value(env, rc);
 }
 
+/* solveSparse(ctx, height, width, cells: Int32Array, values: Float64Array, ints, sign, options, status, result, rhs, pos,
+ * vars, stats): yalps_solve_sparse -- js_solve with the initial tableau as the ordered update() stores of tableauModel
+ * (src/tableau.ts:100-134) instead of the zero-filled Float64Array they land in. */
+static napi_value js_solve_sparse(napi_env env, napi_callback_info info) {
+  size_t argc = 14;
+  napi_value a[14];
+  NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+  if (argc < 14) {
+    napi_throw_type_error(env, "YALPS_B200", "solveSparse needs 14 arguments");
+    return NULL;
+  }
+  yalps_ctx *ctx = (yalps_ctx *)handle_arg(env, a[0], TAG_CTX);
+  if (!ctx) return NULL;
+  int32_t h = 0, w = 0;
+  double sign = 1.0;
+  napi_get_value_int32(env, a[1], &h);
+  napi_get_value_int32(env, a[2], &w);
+  napi_get_value_double(env, a[6], &sign);
+  if (h < 1 || w < 1) {
+    napi_throw_range_error(env, "YALPS_B200", "height and width must be positive");
+    return NULL;
+  }
+  void *cells, *values, *ints, *st, *res, *rhs, *pos, *vars, *stats;
+  size_t nnz = 0, nints = 0;
+  yalps_options o;
+  if (!typed_arg(env, a[3], napi_int32_array, 0, false, "cells: Int32Array", &cells, &nnz) ||
+      !typed_arg(env, a[4], napi_float64_array, nnz, false, "values: Float64Array(cells.length)", &values, NULL) ||
+      !typed_arg(env, a[5], napi_int32_array, 0, false, "ints: Int32Array", &ints, &nints) || !read_options(env, a[7], &o))
+    return NULL;
+  const size_t rows = (size_t)h + 2 * nints, pv = (size_t)w + rows;
+  if (!typed_arg(env, a[8], napi_int32_array, 3, false, "status: Int32Array(3)", &st, NULL) ||
+      !typed_arg(env, a[9], napi_float64_array, 2, false, "result: Float64Array(2)", &res, NULL) ||
+      !typed_arg(env, a[10], napi_float64_array, rows, false, "rhs: Float64Array(height + 2*ints.length)", &rhs, NULL) ||
+      !typed_arg(env, a[11], napi_int32_array, pv, false, "pos: Int32Array(width + height + 2*ints.length)", &pos, NULL) ||
+      !typed_arg(env, a[12], napi_int32_array, pv, false, "vars: Int32Array(width + height + 2*ints.length)", &vars, NULL) ||
+      !typed_arg(env, a[13], napi_bigint64_array, 8, true, "stats: BigInt64Array(8)", &stats, NULL))
+    return NULL;
+  int32_t *s3 = (int32_t *)st; /* [status, out_height, root_status] */
+  double *r2 = (double *)res;  /* [result, root_value] */
+  const int rc = yalps_solve_sparse(ctx, h, w, (int64_t)nnz, nnz ? (const int32_t *)cells : NULL,
+                                    nnz ? (const double *)values : NULL, nints ? (const int32_t *)ints : NULL,
+                                    (int32_t)nints, sign, &o, &s3[0], &r2[0], &s3[1], (double *)rhs, (int32_t *)pos,
+                                    (int32_t *)vars, &s3[2], &r2[1], NULL, (int64_t *)stats);
+  return rc_value(env, rc);
+}
+
 static napi_value js_solve_many(napi_env env, napi_callback_info info) {
   size_t argc = 15;
   napi_value a[15];
@@ -343,6 +393,7 @@ NAPI_MODULE_INIT() {
       {"simplex", NULL, js_simplex, NULL, NULL, NULL, napi_default, NULL},
       {"simplexLarge", NULL, js_simplex_large, NULL, NULL, NULL, napi_default, NULL},
       {"solve", NULL, js_solve, NULL, NULL, NULL, napi_default, NULL},
+      {"solveSparse", NULL, js_solve_sparse, NULL, NULL, NULL, napi_default, NULL},
       {"solveMany", NULL, js_solve_many, NULL, NULL, NULL, napi_default, NULL},
       {"lastError", NULL, js_last_error, NULL, NULL, NULL, napi_default, NULL},
   };

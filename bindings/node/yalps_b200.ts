@@ -48,6 +48,25 @@ export const simplexLarge = (tableau: Tableau, options: Required<Options>, devic
   return [STATUS[out[0]], out[1]]
 }
 
+// solve()'s numeric part (src/YALPS.ts:77-91) for a model whose tableau would be large and almost all zeros (Vendor
+// Selection: 22.6 MB for 9,801 stores).  `stores` is what tableauModel would have written with update(tableau, row, col,
+// value) (src/tableau.ts:100-134), in order, as cells[i] = row*width + col and values[i]; a maintainer gets them by
+// letting tableauModel push into two arrays instead of allocating `matrix` (later stores to a cell win, as there).
+// The device zeroes the matrix and scatters the stores (yalps_solve_sparse); results equal solve() on the dense tableau.
+export const solveStores = (
+  width: number, height: number, cells: Int32Array, values: Float64Array, integers: readonly number[], sign: number,
+  options: Required<Options>,
+): { status: SolutionStatus; result: number; height: number; rhs: Float64Array; pos: Int32Array; vars: Int32Array } => {
+  const k = integers.length
+  const status = new Int32Array(3), result = new Float64Array(2)
+  const rhs = new Float64Array(height + 2 * k)
+  const pos = new Int32Array(width + height + 2 * k), vars = new Int32Array(width + height + 2 * k)
+  const rc = native.solveSparse(getCtx(), height, width, cells, values, Int32Array.from(integers), sign,
+                                packOptions(options), status, result, rhs, pos, vars, undefined)
+  if (rc !== 0) throw new Error(native.lastError(getCtx()))
+  return { status: STATUS[status[0]], result: result[0], height: status[1], rhs, pos, vars }
+}
+
 // New API: many models, ONE native call.  All root LPs run as one ragged device batch (sharded over `devices` when
 // several GPUs are given); models with integer variables whose root is optimal and fractional then run branch and
 // cut on the device side of the ABI, many searches concurrently (yalps_multi_solve_many).  Each result equals
