@@ -17,7 +17,7 @@ collective: LPs are independent); the time is the max over ranks, the value the 
             measured live (north_star's denominator; K1 keeps the tableau in shared memory).  The automatic
             path for this workload is K1t, which keeps the tableau in TENSOR memory: its own stream bandwidth
             (tcgen05.ld/st, measured live too) and the HBM view are reported alongside
-`secondary` (N=1 only) BASELINE.json configs 3, 4 and 5 with the same fields per workload (bench_workloads.py)
+`secondary` (N=1 only) BASELINE.json configs 3, 4, 5 and 1 (AFIRO, last) with the same fields per workload (bench_workloads.py)
 `cpu_baseline` the CPU restatement of the reference loop (oracle/, C -O2 -ffp-contract=off; Node is not
             available) on the box's host cores, bounded sample of the same workload
 
