@@ -442,3 +442,40 @@ def test_sparse_entry_argument_errors_and_empty_list(engine):
     for h, w in ((4, 4), (400, 1000)):  # no stores at all: the zero tableau is optimal with value 0 on both paths
         r = engine.solve_tableau_sparse(np.zeros(0, np.int32), np.zeros(0), h, w, [], 1.0, copt)
         assert E.STATUS_NAMES[r["status"]] == "optimal" and r["result"] == 0.0 and not r["rhs"].any()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_sparse_entry_on_random_sparse_tableaus(engine, seed):
+    """yalps_solve_sparse against yalps_solve (dense image) and the oracle on random sparse tableaus above the 768 KB
+    limit -- phase 1, every terminal status the generator happens to hit, explicit zeros, negative zeros and duplicate
+    stores (the dense image is the in-order replay of the stores)."""
+    rng = np.random.default_rng(1000 + seed)
+    H, W = int(rng.integers(330, 420)), int(rng.integers(300, 380))
+    assert H * W * 8 > (768 << 10)
+    nnz = int(0.02 * H * W)
+    rows = rng.integers(1, H, nnz)
+    cols = rng.integers(1, W, nnz)
+    vals = np.round(rng.uniform(-1.0, 3.0, nnz), 3)
+    vals[rng.random(nnz) < 0.02] = 0.0
+    vals[rng.random(nnz) < 0.01] = -0.0
+    cells = [int(r) * W + int(c) for r, c in zip(rows, cols)]  # duplicates happen (about 1 % of the stores)
+    values = vals.tolist()
+    for c in range(1, W):  # objective row
+        cells.append(c)
+        values.append(float(np.round(rng.uniform(-0.5, 1.0), 3)))
+    for r in range(1, H):  # RHS, a few rows infeasible at the start (phase 1) when seed is odd
+        cells.append(r * W)
+        values.append(float(np.round(rng.uniform(1.0, 50.0), 2)) * (-1.0 if (seed & 1) and rng.random() < 0.03 else 1.0))
+    cells, values = np.asarray(cells, np.int32), np.asarray(values, np.float64)
+    dense = np.zeros(H * W)
+    for c, v in zip(cells.tolist(), values.tolist()):
+        dense[c] = v
+    copt = E.make_options()
+    a = engine.solve_tableau(dense, H, W, [], 1.0, copt)
+    b = engine.solve_tableau_sparse(cells, values, H, W, [], 1.0, copt)
+    assert a["status"] == b["status"] and same_value(a["result"], b["result"]) and a["root_pivots"] == b["root_pivots"]
+    assert same_bits(a["rhs"], b["rhs"]) and np.array_equal(a["pos"], b["pos"]) and np.array_equal(a["var"], b["var"])
+    work = dense.reshape(1, -1).copy()
+    exp = O.simplex_batch(work, W, H)
+    assert b["status"] == int(exp["status"][0]) and b["root_pivots"] == tuple(int(x) for x in exp["pivots"][0])
+    assert np.array_equal(b["pos"], exp["pos"][0]) and same_bits(b["rhs"], exp["rhs"][0])
