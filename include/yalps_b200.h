@@ -238,7 +238,8 @@ int yalps_bnb_solve_nodes(yalps_ctx *ctx, int64_t n, const int32_t *cut_offsets,
  * Tuning / diagnostics through the environment, read per search: YALPS_BNB_SPEC
  * (generations of speculation, default 2, 0 = none), YALPS_BNB_WORKERS (worker CTAs,
  * default one per SM beside the scheduler), YALPS_BNB_DEBUG=1 (scheduler and worker stage
- * cycles and pool usage on stderr).
+ * cycles and pool usage on stderr; for the wave driver: host microseconds per wave spent
+ * enqueueing, waiting for the device, copying out and replaying).
  */
 int yalps_branch_and_cut(yalps_ctx *ctx, const int32_t *ints, int32_t nints, double sign, double init_result,
                          const yalps_options *opt, int32_t *status, double *result, int32_t *out_height,

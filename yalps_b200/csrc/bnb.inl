@@ -253,6 +253,7 @@ int bnb_solve_nodes_impl(yalps_ctx *ctx, int64_t n, const int32_t *cut_offsets, 
   if (!R.valid) return fail(ctx, YALPS_ERR_ARGUMENT, "no root tableau: call yalps_bnb_set_root first");
   if (n < 0 || !opt || (n > 0 && !cut_offsets)) return fail(ctx, YALPS_ERR_ARGUMENT, "bad arguments");
   if (n == 0) return 0;
+  const auto tw0 = std::chrono::steady_clock::now();
   CU(ctx, cudaSetDevice(ctx->device));
   const int W = R.W;
   int maxcuts = std::max(0, min_maxcuts);
@@ -325,6 +326,7 @@ int bnb_solve_nodes_impl(yalps_ctx *ctx, int64_t n, const int32_t *cut_offsets, 
     std::memcpy((char *)h_in + in_sign, cut_sign, nc * 8);
     std::memcpy((char *)h_in + in_val, cut_value, nc * 8);
   }
+  const auto tw1 = std::chrono::steady_clock::now();
   if (!zero_copy) CU(ctx, cudaMemcpyAsync(d_inb, h_in, in_bytes, cudaMemcpyHostToDevice, st));
   void *d_off = (char *)d_inb + in_off, *d_var = (char *)d_inb + in_var, *d_sign = (char *)d_inb + in_sign,
        *d_val = (char *)d_inb + in_val;
@@ -426,7 +428,9 @@ int bnb_solve_nodes_impl(yalps_ctx *ctx, int64_t n, const int32_t *cut_offsets, 
   }
   if (!zero_copy) CU(ctx, cudaMemcpyAsync(h_out, d_outb, out_bytes, cudaMemcpyDeviceToHost, st));
   if (matrices_out) CU(ctx, cudaMemcpyAsync(matrices_out, d_out, mat_bytes, cudaMemcpyDeviceToHost, st));
+  const auto tw2 = std::chrono::steady_clock::now();
   CU(ctx, cudaStreamSynchronize(st));
+  const auto tw3 = std::chrono::steady_clock::now();
   const char *ho = (const char *)h_out;
   if (status) std::memcpy(status, ho + o_status, (size_t)n * 4);
   if (value) std::memcpy(value, ho + o_value, (size_t)n * 8);
@@ -434,6 +438,14 @@ int bnb_solve_nodes_impl(yalps_ctx *ctx, int64_t n, const int32_t *cut_offsets, 
   if (rhs_out) std::memcpy(rhs_out, ho + o_rhs, (size_t)n * Hcap * 8);
   if (pos_out) std::memcpy(pos_out, ho + o_pos, (size_t)n * (W + Hcap) * 4);
   if (var_out) std::memcpy(var_out, ho + o_var, (size_t)n * (W + Hcap) * 4);
+  {
+    const auto tw4 = std::chrono::steady_clock::now();
+    auto ns = [](auto a, auto b) { return (int64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count(); };
+    ctx->wave_ns[0] += ns(tw0, tw1);
+    ctx->wave_ns[1] += ns(tw1, tw2);
+    ctx->wave_ns[2] += ns(tw2, tw3);
+    ctx->wave_ns[3] += ns(tw3, tw4);
+  }
   return check_device_status(ctx, status, n);
 }
 
@@ -864,6 +876,15 @@ int branch_and_cut_impl(yalps_ctx *ctx, const WaveEval *wave_eval, const WaveHoo
   else
     write_best(R.h_rhs.data(), R.h_pos.data(), R.h_var.data(), H);  // bestTableau = root (:119)
   write_stats();
+  if (getenv("YALPS_BNB_DEBUG") && st_waves) {
+    const auto total = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_begin).count();
+    fprintf(stderr, "wave driver: %lld waves, %lld device nodes, %lld us in all; per wave (us): host before the first CUDA call %.1f, "
+                    "enqueue %.1f, wait %.1f, copy out %.1f, replay and wave set-up %.1f\n",
+            (long long)st_waves, (long long)st_devnodes, (long long)total, ctx->wave_ns[0] / 1e3 / st_waves,
+            ctx->wave_ns[1] / 1e3 / st_waves, ctx->wave_ns[2] / 1e3 / st_waves, ctx->wave_ns[3] / 1e3 / st_waves,
+            ((double)total - (ctx->wave_ns[0] + ctx->wave_ns[1] + ctx->wave_ns[2] + ctx->wave_ns[3]) / 1e3) / st_waves);
+  }
+  for (auto &x : ctx->wave_ns) x = 0;
   return 0;
 }
 

@@ -93,6 +93,8 @@ struct yalps_ctx {
   const double *coo_val = nullptr;
   int64_t coo_nnz = -1;
   int coo_dup = 0;
+  // YALPS_BNB_DEBUG: where the host spends a node wave (ns): before the first CUDA call, enqueueing, waiting, copying out
+  int64_t wave_ns[4] = {0, 0, 0, 0};
   int wave = 256;  // upper bound of the adaptive look-ahead of the branch-and-cut driver
   int kc_tma = 0;    // KC: staging of the winner's pivot row (YALPS_KC_TMA: 0 ld.global.cg, 1 cp.async.bulk, 2 multicast)
   int bnb_mode = 0;  // 0: device-resident search when it fits, else host waves; 1: host waves only; 2: device only
