@@ -22,6 +22,12 @@ for spec in sys.argv[1:]:
         d = torch.empty(H * W, dtype=torch.float64, device="cuda")
         eng.generate_synthetic_device(0, 1, m_, nv_, d.data_ptr())
         work = torch.empty_like(d)
+    elif name.startswith("MILP="):  # MILP=<case name>: the model's initial tableau on the HBM/L2-resident split kernel
+        import bench_workloads as BW
+        tb = yalps_b200.tableau_model(BW.milp_case(name[5:].replace("_", " "))["model"]).tableau
+        H, W = tb.height, tb.width
+        d = torch.from_numpy(tb.matrix.copy()).cuda()
+        work = torch.empty_like(d)
     else:
         g = NL.get(name); H, W = g["height"], g["width"]
         d = torch.from_numpy(np.asarray(g["matrix"], np.float64).reshape(-1).copy()).cuda()
@@ -32,7 +38,7 @@ for spec in sys.argv[1:]:
         labels = ["sel1", "sel2(+exchange)", "dsmem+normalise", "column+B1", "rhs+obj", "update", "cluster wait (KG: publish+record)",
                   "writeback+B2 (KG: + row staging)"]
     else:
-        eng.set_tuning(1, int(threads), int(rows))
+        eng.set_tuning(2 if name.startswith("MILP=") else 1, int(threads), int(rows))
     for _ in range(2):
         if work is not None:
             work.copy_(d)

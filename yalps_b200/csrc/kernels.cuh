@@ -67,7 +67,7 @@ struct BatchArgs {
 // the RHS cell and the per-pivot -coef/q scratch cell of a row live in its last two slots.
 // Split kernels (row groups, simplex_split.cuh) replace colbuf/colnew by the compacted active-row list.
 struct SmemLayout {
-  size_t off_A, off_colbuf, off_colnew, off_misc, off_red, off_var, off_cc, off_list, off_cnt, total;
+  size_t off_A, off_colbuf, off_colnew, off_misc, off_red, off_var, off_cc, off_list, off_cnt, off_bcol, total;
   int ldA;
   __host__ __device__ static int ld_for(int W) {
     int ld = (W - 1 + 2 + 1) & ~1;
@@ -99,6 +99,10 @@ struct SmemLayout {
     if (nw > 1) o += 192 * 4;
     off_var = o;
     if (resident) o += (size_t)(Wcap + Hcap) * 4;
+    // HBM/L2-resident split kernels keep the RHS column of their tableau in shared memory (see k_simplex)
+    o = (o + 15) & ~(size_t)15;
+    off_bcol = o;
+    if (!resident && split) o += (size_t)((Hcap + 1) & ~1) * 8;
     total = (o + 15) & ~(size_t)15;
   }
 };
@@ -284,6 +288,18 @@ __global__ void __launch_bounds__(NWC *NWR * 32, min_ctas_per_sm(NWC, NWR)) k_si
     }
     if (kResident) cp_async_wait_all();
     __syncthreads();
+    // HBM/L2-resident split kernels: the RHS column moves into shared memory for the whole solve.  It is the one
+    // strided column every pivot reads (leaving row of phase 1, ratio test of phase 2) and rewrites, and with it in
+    // shared memory the first selection of a phase-1 pivot -- all a branch-and-cut node LP consists of -- costs no trip
+    // to L2.  Same values, same operations; the column is written back behind the solve.
+    constexpr bool kBcolShared = !kResident && kSplit;
+    if (kBcolShared) {
+      double *bcol = reinterpret_cast<double *>(smem_raw + L.off_bcol);
+      for (int r = tid; r < H; r += NT) bcol[r] = t.b[(size_t)r * ldb];
+      __syncthreads();
+      t.b = bcol;
+      t.ldb = 1;
+    }
 
     LpResult res;
     if constexpr (kSplit)
@@ -301,7 +317,9 @@ __global__ void __launch_bounds__(NWC *NWR * 32, min_ctas_per_sm(NWC, NWR)) k_si
     }
     if (a.rows_out && res.rows != 0 && (!kSplit || tid == 0)) atomicAdd(a.rows_out + (a.rows_per_lp ? lp : 0), res.rows);
     if (a.rhs_out)
-      for (int r = tid; r < H; r += NT) a.rhs_out[roff + r] = t.b[(size_t)r * ldb];
+      for (int r = tid; r < H; r += NT) a.rhs_out[roff + r] = t.b[(size_t)r * t.ldb];
+    if (kBcolShared)  // column 0 of the working copy: whoever reads the final tableau finds it complete
+      for (int r = tid; r < H; r += NT) a.work[moff + (size_t)r * W] = t.b[r];
 #ifdef YALPS_TIMING
     __syncthreads();
     if (kSplit && a.rhs_out && (tid == 0 || tid == NT - 1 || tid == 32)) {
@@ -321,7 +339,7 @@ __global__ void __launch_bounds__(NWC *NWR * 32, min_ctas_per_sm(NWC, NWR)) k_si
         for (int r = tid >> 5; r < H; r += NW) {
           const double *sA = t.A + (size_t)r * ldA - 1;
           double *dr = dst + (size_t)r * W;
-          for (int c = tid & 31; c < W; c += 32) dr[c] = (c == 0) ? t.b[(size_t)r * ldb] : sA[c];
+          for (int c = tid & 31; c < W; c += 32) dr[c] = (c == 0) ? t.b[(size_t)r * t.ldb] : sA[c];
         }
       }
     }
