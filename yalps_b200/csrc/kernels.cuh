@@ -98,7 +98,7 @@ struct SmemLayout {
     off_red = o;
     if (nw > 1) o += 192 * 4;
     off_var = o;
-    if (resident) o += (size_t)(Wcap + Hcap) * 4;
+    if (resident || split) o += (size_t)(Wcap + Hcap) * 4;  // (split kernels: variableAtPosition on chip in either layout)
     // HBM/L2-resident split kernels keep the RHS column of their tableau in shared memory (see k_simplex)
     o = (o + 15) & ~(size_t)15;
     off_bcol = o;
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(NWC *NWR * 32, min_ctas_per_sm(NWC, NWR)) k_si
       t.A = a.work + moff + 1;
       t.b = a.work + moff;
       t.ldA = t.ldb = W;
-      t.var = a.var_out + poff;
+      t.var = kSplit ? reinterpret_cast<int *>(smem_raw + L.off_var) : a.var_out + poff;
     }
     s.colbuf = reinterpret_cast<double *>(smem_raw + L.off_colbuf);
     s.misc = reinterpret_cast<double *>(smem_raw + L.off_misc);
@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(NWC *NWR * 32, min_ctas_per_sm(NWC, NWR)) k_si
 #endif
     if (a.pos_out)  // positionOfVariable is the inverse permutation of variableAtPosition
       for (int k = tid; k < W + H; k += NT) a.pos_out[poff + t.var[k]] = k;
-    if (kResident && a.var_out)
+    if ((kResident || kSplit) && a.var_out)
       for (int k = tid; k < W + H; k += NT) a.var_out[poff + k] = t.var[k];
     if (a.mat_out) {
       double *dst = a.mat_out + moff;
