@@ -329,7 +329,10 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
         want_threads = 512, want_rows = 8;
       }
     } else if (!resident) {
-      if (cells >= 5000) want_threads = 128, want_rows = 2;
+      // (with the RHS column and the basis in shared memory a pivot of the split kernel waits on L2 less often, and one
+      // column warp per row group -- twice the cells per thread and row -- beats two: SC105 78.5 -> 81.8, ADLITTLE
+      // 139.8 -> 151.1 M pivots/s, profiles/r02u_sweep_config3.jsonl)
+      if (cells >= 5000) want_threads = Wcap <= 129 ? 64 : 128, want_rows = 2;
     }
   }
   plan->small_for_grid = !resident && cells < 40000;
