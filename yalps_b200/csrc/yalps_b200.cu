@@ -359,6 +359,7 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
       CU(ctx, raise_smem_limit(ctx->device, (const void *)(resident ? k->resident : k->global), (int)smem_c));
       int occ_c = it->second;
       if (check_cycles) occ_c = std::min(occ_c, 4);
+      if (const char *env = getenv("YALPS_CTAS_PER_SM")) occ_c = std::max(1, std::min(occ_c, atoi(env)));  // experiments
       long long grid_c = std::max(1LL, std::min((long long)occ_c * ctx->prop.multiProcessorCount, n));
       plan->resident = resident;
       plan->k = k;
@@ -379,6 +380,7 @@ int plan_launch(yalps_ctx *ctx, long long n, int Hcap, int Wcap, bool check_cycl
   if (occ < 1) return fail(ctx, YALPS_ERR_TOO_LARGE, "kernel does not fit on an SM (smem %zu)", smem);
   ctx->occ_cache[std::to_string((size_t)(void *)fn) + ":" + std::to_string(smem)] = occ;
   if (check_cycles) occ = std::min(occ, 4);  // bounds the history buffer
+  if (const char *env = getenv("YALPS_CTAS_PER_SM")) occ = std::max(1, std::min(occ, atoi(env)));  // experiments
   long long grid = (long long)occ * ctx->prop.multiProcessorCount;
   grid = std::max(1LL, std::min(grid, n));
   plan->resident = resident;
