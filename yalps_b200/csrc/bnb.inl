@@ -276,8 +276,10 @@ int bnb_solve_nodes_impl(yalps_ctx *ctx, int64_t n, const int32_t *cut_offsets, 
   bool sparse_split = false;
   if (!plan.resident && ctx->tune_path == YALPS_PATH_AUTO && ctx->tune_threads <= 0 && ctx->tune_rows <= 0 &&
       R.density < 0.03 && use_grid_path(ctx, n, plan)) {
-    if (const KernelEntry *k = pick_kernel(8, 2, W, false)) {
-      if (k->nwr == 2) {
+    int split_nwc = 8, split_nwr = 2;
+    if (const char *env = getenv("YALPS_NODE_SPLIT")) sscanf(env, "%d,%d", &split_nwc, &split_nwr);  // experiments: "column warps,row groups"
+    if (const KernelEntry *k = pick_kernel(split_nwc, split_nwr, W, false)) {
+      if (k->nwr == split_nwr) {
         const size_t smem_k = SmemLayout(Hcap, W, false, k->nw * k->nwr, true).total;
         if (smem_k <= (size_t)ctx->smem_optin) {
           CU(ctx, raise_smem_limit(ctx->device, (const void *)k->global, (int)smem_k));
