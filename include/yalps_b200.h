@@ -101,6 +101,11 @@ int yalps_set_tuning(yalps_ctx *ctx, int32_t path, int32_t threads_per_lp);
 /* Row groups per CTA for the shared-memory / HBM paths: > 1 selects the row-split latency kernels
  * (csrc/simplex_split.cuh: threads_per_lp / row_groups column threads x row_groups), 0 = automatic. */
 int yalps_set_row_groups(yalps_ctx *ctx, int32_t row_groups);
+/* Experiment switches read from the environment (results never depend on them, only the launch configuration):
+ * YALPS_CTAS_PER_SM=n caps the resident CTAs per SM of the k_simplex kernels; YALPS_NODE_SPLIT="w,r" sets column warps
+ * and row groups of the one-CTA-per-node kernel of big sparse node waves; YALPS_KC_TMA=0|1|2 the pivot-row staging of the
+ * cluster kernel; YALPS_KG_CTAS / YALPS_KG_THREADS / YALPS_NO_KG the grid-resident kernel; YALPS_GRID_CTAS the grid of K4;
+ * YALPS_LARGE_ROW_PARTS the row split of yalps_multi_solve_large; YALPS_NO_REPLICA_SHARING the replica path sharing. */
 /* Number of kernels launched by this ctx since creation (bench.py's gpu_launches). */
 int64_t yalps_launch_count(const yalps_ctx *ctx);
 
