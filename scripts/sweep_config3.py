@@ -11,6 +11,8 @@ eng = yalps_b200.Engine(0)
 stream = torch.cuda.current_stream().cuda_stream
 NL = load_netlib()
 combos = [(0, 0), (128, 1), (256, 1), (64, 2), (128, 2), (128, 4), (256, 2), (256, 4), (256, 8), (512, 8), (512, 16)]
+if os.environ.get('SWEEP_THIN'):
+    combos = [(0, 0), (32, 1), (64, 1), (64, 2)]
 if os.environ.get('SWEEP_K1_ONLY'):
     combos = [(0, 0), (64, 2), (128, 2), (128, 4), (256, 4), (256, 8), (512, 8)]
 if os.environ.get('SWEEP_K2_ONLY'):
@@ -22,7 +24,7 @@ for name, n in (("SC105", 16384), ("ADLITTLE", 32768), ("AFIRO", 65536), ("BLEND
     eng.generate_replicas_device(0, n, g["matrix"], H, W, g["row_groups"], d.data_ptr())
     work = torch.empty_like(d)
     st = torch.empty(n, dtype=torch.int32, device="cuda"); piv = torch.empty(n, 2, dtype=torch.int64, device="cuda")
-    for path, pn in (((E.PATH_AUTO, "auto"), (E.PATH_SMEM, "K1")) if os.environ.get("SWEEP_K1_ONLY") else ((E.PATH_AUTO, "auto"), (E.PATH_GMEM, "K2")) if os.environ.get("SWEEP_K2_ONLY") else ((E.PATH_AUTO, "auto"), (E.PATH_SMEM, "K1"), (E.PATH_GMEM, "K2"))):
+    for path, pn in (((E.PATH_AUTO, "auto"), (E.PATH_SMEM, "K1")) if os.environ.get("SWEEP_K1_ONLY") else ((E.PATH_AUTO, "auto"), (E.PATH_GMEM, "K2")) if (os.environ.get("SWEEP_K2_ONLY") or os.environ.get("SWEEP_THIN")) else ((E.PATH_AUTO, "auto"), (E.PATH_SMEM, "K1"), (E.PATH_GMEM, "K2"))):
         for threads, rows in (combos[:1] if path == E.PATH_AUTO else combos[1:]):
             eng.set_tuning(path, threads, rows)
             def run():
