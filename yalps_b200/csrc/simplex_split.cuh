@@ -140,6 +140,18 @@ __device__ __forceinline__ int pivot_split(const LpView &t, const SplitScratch &
   }
   double cell0 = 0.0;  // pivot-column cell of row `tid` (first pass of the column loop); RHS for the pivot row
   if (tid < H) cell0 = (tid == row) ? b[(size_t)row * ldb] : A[(size_t)tid * ldA + jc];
+  // HBM/L2-resident tableaus (VW == 1): the cells of the next passes of the column loop leave in the same flight -- a
+  // 64-thread CTA walks the 151 rows of SC105 in three passes, and each pass used to be a dependent trip to L2
+  constexpr int CX = (VW == 1) ? 2 : 0;
+  double cellx[CX > 0 ? CX : 1];
+  if constexpr (CX > 0) {
+#pragma unroll
+    for (int u = 0; u < CX; u++) {
+      const int r = tid + (u + 1) * NT;
+      cellx[u] = 0.0;
+      if (r < H) cellx[u] = (r == row) ? b[(size_t)row * ldb] : A[(size_t)r * ldA + jc];
+    }
+  }
   const Recip rq(q);
 
   // ---- normalise the pivot row into registers (:16-25), every row group for itself
@@ -174,12 +186,12 @@ __device__ __forceinline__ int pivot_split(const LpView &t, const SplitScratch &
   YT_MARK(2);
   // ---- pivot column: -coef/q per row (:36), normalised RHS of the pivot row (:19 for c = 0), and the
   // compacted list of rows the update rewrites (:31)
-  for (int r0 = 0; r0 < H; r0 += NT) {
+  auto column_pass = [&](const int r0, const double cell_in) {
     const int r = r0 + tid;
     bool act = false;
     double cell = 0.0, quo = 0.0;
     if (r < H) {
-      cell = r0 == 0 ? cell0 : ((r == row) ? b[(size_t)row * ldb] : A[(size_t)r * ldA + jc]);
+      cell = cell_in;
       const double num = (r == row) ? cell : -cell;
       const bool nz = fabs(num) > kTiny;  // also false for NaN, as in the reference
       quo = nz ? rq.quot(num) : 0.0;
@@ -201,6 +213,18 @@ __device__ __forceinline__ int pivot_split(const LpView &t, const SplitScratch &
         *reinterpret_cast<double2 *>(s.cc + 2 * k) = make_double2(cell, quo);
       }
     }
+  };
+  column_pass(0, cell0);
+  if constexpr (CX > 0) {
+#pragma unroll
+    for (int u = 0; u < CX; u++)
+      if ((u + 1) * NT < H) column_pass((u + 1) * NT, cellx[u]);
+  }
+  for (int r0 = (CX + 1) * NT; r0 < H; r0 += NT) {
+    const int r = r0 + tid;
+    double cell = 0.0;
+    if (r < H) cell = (r == row) ? b[(size_t)row * ldb] : A[(size_t)r * ldA + jc];
+    column_pass(r0, cell);
   }
   if (tid == 0) {  // basis bookkeeping (:7-12)
     const int leaving = t.var[t.W + row];
