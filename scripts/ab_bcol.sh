@@ -1,4 +1,4 @@
-for i in 1 2; do
+for i in 1; do
   for lib in base new; do
     if [ $lib = base ]; then export YALPS_B200_LIB=$PWD/yalps_b200/libyalps_base.so; else unset YALPS_B200_LIB; fi
     echo "== $lib"

@@ -361,15 +361,34 @@ __device__ __forceinline__ LpResult simplex_cta_split(const LpView &t, const Spl
         // (one cell per thread and step: a node LP of 101 columns on 256 threads has one division per thread instead of
         // two in a row on 50 of them)
         const double *Arow = A + (size_t)row * ldA;
-        for (int j = tid; j < Wm1; j += NT) {
-          const double coef = Arow[j];
+        auto cost_ratio = [&](const int j, const double coef, const double obj) {
           if (coef < -precision) {
-            const double ratio = div_rn(-A[j], coef);
+            const double ratio = div_rn(-obj, coef);
             if (ratio > bv) {  // bv starts at -inf: -inf and NaN ratios never win, as in the reference
               bv = ratio;
               bi = j + 1;
             }
           }
+        };
+        // HBM/L2-resident tableaus: pivot-row and objective-row cells of the first passes leave in one flight
+        constexpr int PX = (VW == 1) ? 2 : 0;
+        if constexpr (PX > 0) {
+          double cf[PX], ob[PX];
+#pragma unroll
+          for (int u = 0; u < PX; u++) {
+            const int j = tid + u * NT;
+            cf[u] = j < Wm1 ? Arow[j] : 0.0;
+            ob[u] = j < Wm1 ? A[j] : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < PX; u++) {
+            const int j = tid + u * NT;
+            if (j < Wm1) cost_ratio(j, cf[u], ob[u]);
+          }
+        }
+        for (int j = tid + PX * NT; j < Wm1; j += NT) {
+          const double coef = Arow[j];
+          if (coef < -precision) cost_ratio(j, coef, A[j]);
         }
       }
       col = block_best<true, NW>(bi == kNone ? no_key<true>() : order_key(bv), bi, s.red, parity);
@@ -417,8 +436,7 @@ __device__ __forceinline__ LpResult simplex_cta_split(const LpView &t, const Spl
       // <= precision if any, else first index of the minimum ratio.  Ratios <= precision get key -inf.
       bv = INF;
       bi = kNone;
-      for (int r = 1 + tid; r < H; r += NT) {
-        const double v = A[(size_t)r * ldA + (col - 1)];
+      auto ratio_test = [&](const int r, const double v) {
         if (v > precision) {
           const double ratio = div_rn(b[(size_t)r * ldb], v);
           if (ratio < INF) {  // +inf and NaN never win (`ratio < minRatio` with minRatio = Infinity)
@@ -429,7 +447,23 @@ __device__ __forceinline__ LpResult simplex_cta_split(const LpView &t, const Spl
             }
           }
         }
+      };
+      // HBM/L2-resident tableaus: the column cells of the first passes leave in one flight (see pivot_split)
+      constexpr int SX = (VW == 1) ? 3 : 0;
+      if constexpr (SX > 0) {
+        double vv[SX];
+#pragma unroll
+        for (int u = 0; u < SX; u++) {
+          const int r = 1 + tid + u * NT;
+          vv[u] = r < H ? A[(size_t)r * ldA + (col - 1)] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < SX; u++) {
+          const int r = 1 + tid + u * NT;
+          if (r < H) ratio_test(r, vv[u]);
+        }
       }
+      for (int r = 1 + tid + SX * NT; r < H; r += NT) ratio_test(r, A[(size_t)r * ldA + (col - 1)]);
       row = block_best<false, NW>(bi == kNone ? no_key<false>() : order_key(bv), bi, s.red, parity);
       YT_MARK(1);
       if (row == kNone) {
