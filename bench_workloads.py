@@ -174,7 +174,7 @@ def config3(torch, eng, name, n, hbm_peak, cpu_cores, l2_peak):
                      "hbm": {"achieved": achieved, "peak": hbm_peak, "frac": achieved / hbm_peak,
                              "note": "the SURVEY 8(d) bytes against the HBM peak can exceed 1: a working copy "
                                      f"({cells * 8 / 1e3:.0f} KB) stays in L2 for the ~{pivots // max(n, 1)} pivots its CTA "
-                                     "spends on it, so HBM only sees the tableau once in and once out (`traffic`)"},
+                                     "spends on it, so HBM sees far fewer bytes than the pivots touch (`traffic`: what the live copies that no longer fit L2 cost in DRAM)"},
                      "note": "R counted on the device.  The medium that serves the per-pivot bytes is L2, hence the "
                              "denominator; the kernel itself is bound by the per-pivot dependent chain of one CTA per LP"},
         "e2e": {"api": "yalps_solve_replicas (base tableau once + n*H right-hand sides from pinned host memory; "
