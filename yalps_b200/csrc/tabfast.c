@@ -22,9 +22,9 @@ typedef struct {
   int32_t *cell;
   double *val;
   Py_ssize_t n, cap;
-  int64_t limit; /* height * width: cells must stay below 2^31 (src/tableau.ts:17 uses Math.imul) */
 } Stores;
 
+/* cells must stay below 2^31: the reference indexes with Math.imul (src/tableau.ts:17) */
 static int stores_push(Stores *s, int64_t cell, double v) {
   if (cell > INT32_MAX) {
     PyErr_SetString(PyExc_OverflowError, "tableau cell index does not fit int32 (height*width must be < 2^31)");
